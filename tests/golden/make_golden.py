@@ -1,0 +1,363 @@
+"""Generate the golden fixtures by executing the REAL reference on CPU.
+
+Run in the build container only (needs /root/reference, read-only):
+
+    python tests/golden/make_golden.py
+
+The reference is imported unmodified with empty stubs for third-party modules
+that are not installed (pytorch_metric_learning, matplotlib, torch_audiomentations,
+audiomentations, librosa - none is on the paths exercised here).  Every fixture
+records inputs, the reference's outputs and (where autograd applies) the
+reference's gradients.  The GPU box has no /root/reference; tests read only the
+committed .npz files.
+"""
+import os
+import random
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("AFSL_REFERENCE", "/root/reference")
+
+
+def _stub(name, classes=()):
+    mod = types.ModuleType(name)
+    for c in classes:
+        setattr(mod, c, type(c, (), {"__init__": lambda self, *a, **k: None}))
+    sys.modules[name] = mod
+    return mod
+
+
+def import_reference():
+    pml = _stub("pytorch_metric_learning")
+    pml.losses = _stub("pytorch_metric_learning.losses", ["AngularLoss"])
+    pml.miners = _stub("pytorch_metric_learning.miners", ["AngularMiner"])
+    _stub("matplotlib").pyplot = _stub("matplotlib.pyplot")
+    _stub("torch_audiomentations",
+          "Compose Gain PolarityInversion AddColoredNoise BandPassFilter BandStopFilter HighPassFilter "
+          "LowPassFilter PitchShift Shift SpliceOut TimeInversion PeakNormalization AddBackgroundNoise".split())
+    _stub("audiomentations")
+    _stub("librosa")
+    sys.path.insert(0, REF)
+
+
+def save(name, **arrays):
+    out = {}
+    for k, v in arrays.items():
+        if torch.is_tensor(v):
+            v = v.detach().cpu().numpy()
+        out[k] = np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote", name, {k: tuple(v.shape) for k, v in out.items()})
+
+
+# ------------------------------------------------------------------ head
+HEAD_CASES = [
+    # name, ways, shots, queries-per-class, dim, views (labels repeated when > 1)
+    ("5w5s5q_d64", 5, 5, 5, 64, 1),
+    ("5w5s5q_d256", 5, 5, 5, 256, 1),
+    ("5w1s5q_d64", 5, 1, 5, 64, 1),
+    ("20w5s5q_d256", 20, 5, 5, 256, 1),
+    ("20w1s5q_d64", 20, 1, 5, 64, 1),
+    ("5w5s5q_d64_v4", 5, 5, 5, 64, 4),
+]
+
+
+def gen_head():
+    from loops.loss import FSL_Loss
+    from models.util_functions import compute_prototypes
+    for idx, (name, w, k, q, d, v) in enumerate(HEAD_CASES):
+        torch.manual_seed(100 + idx)
+        sl = torch.arange(w).repeat_interleave(k).repeat(v)
+        ql = torch.arange(w).repeat_interleave(q).repeat(v)
+        s = torch.randn(sl.numel(), d, requires_grad=True)
+        qf = torch.randn(ql.numel(), d, requires_grad=True)
+        protos = compute_prototypes(s, sl)
+        scores = -torch.cdist(qf, protos)
+        loss = FSL_Loss()(protos, qf, ql)
+        loss.backward()
+        post, pred = torch.max(scores, 1)
+        save("head_" + name, support=s, support_labels=sl, query=qf, query_labels=ql, prototypes=protos,
+             scores=scores, loss=loss, d_support=s.grad, d_query=qf.grad, pred=pred, posterior=post,
+             correct=(pred == ql).sum())
+    # ragged (multi-segment shaped) queries with shuffled support order and an exact-hit query
+    torch.manual_seed(177)
+    w, k, d = 5, 5, 64
+    sl = torch.arange(w).repeat_interleave(k)[torch.randperm(w * k)]
+    seg_counts = [1, 3, 2, 5, 1, 4, 2, 2, 3, 1, 6, 1, 2, 3, 1, 1, 2, 4, 1, 2, 3, 2, 1, 5, 2]
+    ql = torch.cat([torch.full((c,), i // 5) for i, c in enumerate(seg_counts)])
+    ids = torch.cat([torch.full((c,), i) for i, c in enumerate(seg_counts)])
+    s = torch.randn(w * k, d, requires_grad=True)
+    qf = torch.randn(ql.numel(), d)
+    with torch.no_grad():
+        qf[7] = compute_prototypes(s, sl)[int(ql[7])]            # zero distance -> zero gradient
+    qf.requires_grad_(True)
+    protos = compute_prototypes(s, sl)
+    scores = -torch.cdist(qf, protos)
+    loss = FSL_Loss()(protos, qf, ql)
+    loss.backward()
+    post, pred = torch.max(scores, 1)
+    save("head_ragged_d64", support=s, support_labels=sl, query=qf, query_labels=ql, clip_ids=ids,
+         prototypes=protos, scores=scores, loss=loss, d_support=s.grad, d_query=qf.grad, pred=pred,
+         posterior=post, correct=(pred == ql).sum())
+
+
+# ------------------------------------------------------------------ CPL
+CPL_CASES = [
+    # name, ways, per-class queries, dim, M, T, normalize prototypes first
+    ("5w5q_d256_m5", 5, 5, 256, 5, 9.2361, False),
+    ("5w5q_d256_m2", 5, 5, 256, 2, 9.2361, False),
+    ("5w20q_d64_m5", 5, 20, 64, 5, 6.0488, True),
+    ("20w5q_d256_m3", 20, 5, 256, 3, 4.081, False),
+]
+
+
+def replay_keep(labels, m):
+    """Replay the reference's randperm draws (loops/loss.py:134-165) -> keep[i, j]."""
+    uniq = labels.unique()
+    groups = {int(c): torch.where(labels == c)[0] for c in uniq}
+    n = labels.numel()
+    keep = torch.zeros(n, n, dtype=torch.bool)
+    for i in range(n):
+        for c, members in groups.items():
+            if c != int(labels[i]):
+                keep[i, members[torch.randperm(len(members))[:m]]] = True
+        keep[i, i] = True
+    return keep
+
+
+def gen_cpl():
+    from loops.loss import CPL_Loss
+    for idx, (name, w, q, d, m, t, norm) in enumerate(CPL_CASES):
+        torch.manual_seed(200 + idx)
+        labels = torch.arange(w).repeat_interleave(q)
+        protos = torch.randn(w, d)
+        if norm:
+            protos = torch.nn.functional.normalize(protos, p=2.0, dim=1, eps=1e-12)
+        protos.requires_grad_(True)
+        queries = torch.randn(w * q, d, requires_grad=True)
+        seed = 9000 + idx
+        torch.manual_seed(seed)
+        loss = CPL_Loss(T=t, M=m)(protos, queries, labels)
+        loss.backward()
+        torch.manual_seed(seed)
+        keep = replay_keep(labels, m)
+        save("cpl_" + name, prototypes=protos, queries=queries, labels=labels, keep=keep, loss=loss,
+             d_prototypes=protos.grad, d_queries=queries.grad, seed=seed, m=m, temperature=t)
+
+
+# ------------------------------------------------------------------ SpecAugment
+SPEC_CASES = [
+    ("fsd_t157", 2, 157, dict(mask_param=16, W=22, num_mask=1, mask_value=0, p=0.282)),
+    ("nsynth_t126", 2, 126, dict(mask_param=9, W=36, num_mask=1, mask_value=0, p=0.42157)),
+    ("esc_t157_2masks", 3, 157, dict(mask_param=7, W=20, num_mask=2, mask_value=-1.5, p=0.3127)),
+]
+
+
+def gen_specaug():
+    from utils.augmentations import SpecAugment
+    for idx, (name, n, t_len, sp) in enumerate(SPEC_CASES):
+        seed = 300 + idx
+        torch.manual_seed(seed)
+        x = torch.randn(n, 1, 128, t_len)
+        torch.manual_seed(seed + 50)
+        np.random.seed(seed + 50)
+        aug = SpecAugment({"specaug_params": sp})
+        views = aug.apply_augmentations(x)
+        # replay the draws to record the parameters the reference used
+        torch.manual_seed(seed + 50)
+        np.random.seed(seed + 50)
+        w = sp["W"]
+        warp_p = torch.randint(w, t_len - w, (n,))
+        warp_d = torch.randint(-w, w, (n,))
+        tm, fm = [], []
+        for _ in range(sp["num_mask"]):
+            t = np.random.randint(1, min(sp["mask_param"], int(sp["p"] * t_len)) + 1)
+            tm.append((np.random.randint(0, t_len - t), t))
+        for _ in range(sp["num_mask"]):
+            f = np.random.randint(1, sp["mask_param"] + 1)
+            fm.append((np.random.randint(0, 128 - f), f))
+        # the reference's own spline evaluation for these control points
+        xs = torch.linspace(0, t_len - 1, t_len).unsqueeze(0).expand(n, -1)
+        cx = torch.stack([torch.tensor([0]).expand(n), warp_p, torch.tensor([t_len - 1]).expand(n)], 1)
+        cy = torch.stack([torch.tensor([-1.]).expand(n), (warp_p - warp_d) * 2 / (t_len - 1) - 1,
+                          torch.tensor([1]).expand(n)], 1)
+        src_x = aug.hspline_interpolate_1D(cx, cy, xs)
+        save("specaug_" + name, x=x, warped=views[1], time_masked=views[2], freq_masked=views[3],
+             original=views[0], warp_p=warp_p, warp_d=warp_d, time_masks=np.array(tm), freq_masks=np.array(fm),
+             src_x=src_x, seed=seed + 50, **{"cfg_" + k: v for k, v in sp.items()})
+
+
+# ------------------------------------------------------------------ majority vote
+def gen_vote():
+    from loops.loops import calculate_majority_vote_accuracy
+    rng = np.random.RandomState(4242)
+    preds, ids, labels, posts, offsets, accs = [], [], [], [], [0], []
+    for case in range(120):
+        clips = rng.randint(1, 26)
+        ways = 5 if case % 2 == 0 else 20
+        seg = rng.randint(1, 9, size=clips) if case % 3 else np.minimum(36, 1 + rng.geometric(0.15, size=clips))
+        cid = np.repeat(np.arange(clips), seg)
+        if case % 5 == 0:                                   # interleave the segments of different clips
+            cid = cid[rng.permutation(cid.size)]
+        true = rng.randint(0, ways, size=clips)[cid]
+        few = rng.randint(0, min(ways, 3), size=cid.size)   # few distinct votes -> many ties
+        pred = np.where(rng.rand(cid.size) < 0.5, true, few)
+        post = -rng.rand(cid.size).astype(np.float32) * 10
+        if case % 7 == 0:
+            post = np.round(post)                           # equal posteriors among tied segments
+        row = []
+        for strat in ("", "min_label", "max_posterior"):
+            row.append(calculate_majority_vote_accuracy(torch.from_numpy(pred), torch.from_numpy(cid),
+                                                        torch.from_numpy(true), torch.from_numpy(post),
+                                                        tie_strategy=strat))
+        preds.append(pred); ids.append(cid); labels.append(true); posts.append(post)
+        offsets.append(offsets[-1] + cid.size); accs.append(row)
+    save("vote_cases", pred=np.concatenate(preds), clip_ids=np.concatenate(ids), labels=np.concatenate(labels),
+         posterior=np.concatenate(posts), offsets=np.array(offsets), accuracy=np.array(accs, dtype=np.float64))
+
+
+# ------------------------------------------------------------------ modules
+def gen_modules():
+    from models.main_modules import SelfAttention, ProjectionHead, StandardCNN, StandardHybrid
+    from models.prototypical import ContrastivePrototypicalNetworks, ContrastivePrototypicalNetworksWithoutAttention
+    mc = {"Attention": {"embed_dim": 64, "num_heads": 1, "ffn_dim": 256, "dropout": 0.0},
+          "Projection": {"input_dim": 256, "hidden_dim": 128, "output_dim": 256}}
+    torch.manual_seed(400)
+    att = SelfAttention(mc)
+    att.train()                                            # dropout 0.0 -> deterministic slow path
+    x = torch.randn(7, 4, 64, requires_grad=True)
+    y = att(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    grads = {"g_" + k: p.grad for k, p in att.named_parameters()}
+    att.eval()
+    with torch.no_grad():
+        y_eval = att(x)                                    # fused fast path
+    save("modules_fusion", x=x, y=y, gy=gy, dx=x.grad, y_eval=y_eval,
+         **{"w_" + k: v for k, v in att.state_dict().items()}, **grads)
+
+    torch.manual_seed(401)
+    proj = ProjectionHead(mc)
+    x = torch.randn(9, 256, requires_grad=True)
+    y = proj(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    save("modules_projection", x=x, y=y, gy=gy, dx=x.grad,
+         **{"w_" + k: v for k, v in proj.state_dict().items()},
+         **{"g_" + k: p.grad for k, p in proj.named_parameters() if p.grad is not None})
+
+    for enc_name, t_len in (("CNN", 157), ("Hybrid", 157), ("Hybrid", 126)):
+        torch.manual_seed(402)
+        if enc_name == "CNN":
+            enc = StandardCNN(1, (1, 1, 128, t_len), 64, [3, 3], 64)
+        else:
+            enc = StandardHybrid(1, 1, "RNN", False, 64, [3, 3], 64)
+        x = torch.randn(4, 1, 128, t_len)
+        enc.train()
+        torch.manual_seed(7)
+        for m in enc.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        y_train = enc(x)
+        enc.eval()
+        with torch.no_grad():
+            y_eval = enc(x)
+        save(f"modules_encoder_{enc_name}_t{t_len}", x=x, y_train=y_train, y_eval=y_eval,
+             keys=np.array(list(enc.state_dict().keys())),
+             **{"w_" + k: v for k, v in enc.state_dict().items()})
+
+    # model-level: fused-views model in eval mode, 5w2s3q episode on given per-view features
+    class Passthrough(torch.nn.Module):
+        def forward(self, views):
+            return list(views)
+    torch.manual_seed(403)
+    att = SelfAttention(mc).eval()
+    proj = ProjectionHead(mc).eval()
+    net = ContrastivePrototypicalNetworks(Passthrough(), att, proj).eval()
+    sl = torch.arange(5).repeat_interleave(2)
+    ql = torch.arange(5).repeat_interleave(3)
+    s_views = [torch.randn(10, 64) for _ in range(4)]
+    q_views = [torch.randn(15, 64) for _ in range(4)]
+    with torch.no_grad():
+        net.process_support_set(s_views, sl)
+        scores = net(q_views, inference=True)
+        random.seed(11)
+        cf, cp = net.contrastive_forward(True)
+    save("modules_model_fused", support_views=torch.stack(s_views), query_views=torch.stack(q_views),
+         support_labels=sl, query_labels=ql, prototypes=net.prototypes, scores=scores, contrastive_features=cf,
+         contrastive_prototypes=cp, shuffle_seed=11,
+         **{"w_att_" + k: v for k, v in att.state_dict().items()},
+         **{"w_proj_" + k: v for k, v in proj.state_dict().items()})
+    net2 = ContrastivePrototypicalNetworksWithoutAttention(Passthrough(), proj).eval()
+    with torch.no_grad():
+        net2.process_support_set([v for v in s_views], sl.repeat(4))
+        scores2 = net2([v for v in q_views], inference=True)
+    save("modules_model_concat", prototypes=net2.prototypes, scores=scores2,
+         keys_fused=np.array(list(net.state_dict().keys())), keys_concat=np.array(list(net2.state_dict().keys())))
+
+
+# ------------------------------------------------------------------ full reference training epoch
+class FakeDataset:
+    """Satisfies what datasets/batch_creation.py::sample_episode reads (:22-23,38,50,112)."""
+
+    def __init__(self, cfg, classes=6, per_class=12, t_len=157, seed=0):
+        import pandas as pd
+        g = torch.Generator().manual_seed(seed)
+        self.items = torch.randn(classes * per_class, 1, 1, 128, t_len, generator=g)   # __getitem__ -> [S=1,1,128,T]
+        names = [f"c{i}" for i in range(classes)]
+        self.class_to_label = {n: i for i, n in enumerate(names)}
+        self.data_df = pd.DataFrame({"label": [names[i // per_class] for i in range(classes * per_class)],
+                                     "index_column": list(range(classes * per_class))})
+        self.multi_segm = False
+        self.input_type = "spec"
+        self.specaug_use = cfg["specaug_params"]["use"]
+        self.waveaug_use = False
+        self.experiment_config = cfg
+
+    def __getitem__(self, i):
+        return self.items[i], 0
+
+
+def gen_epoch():
+    """Two reference training episodes + validation on a fake dataset, config-1 shaped (CNN, no views)."""
+    from loops.loops import training_epoch, evaluate_single_segment
+    from loops.loss import FSL_Loss
+    from models.main_modules import StandardCNN, ProjectionHead
+    from models.prototypical import ContrastivePrototypicalNetworksWithoutAttention
+    cfg = {"specaug_params": {"use": False, "mask_param": 16, "W": 22, "num_mask": 1, "mask_value": 0, "p": 0.282}}
+    mc = {"Projection": {"input_dim": 64, "hidden_dim": 32, "output_dim": 64}}
+    ds = FakeDataset(cfg, t_len=157, seed=5)
+
+    class Enc(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.encoder = StandardCNN(1, (1, 1, 128, 157), 64, [3, 3], 64)
+        def forward(self, views):
+            return [self.encoder(v) for v in views]
+    torch.manual_seed(500)
+    net = ContrastivePrototypicalNetworksWithoutAttention(Enc(), ProjectionHead(mc))
+    for m in net.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    init = {k: v.clone() for k, v in net.state_dict().items()}
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    random.seed(1234); np.random.seed(1234); torch.manual_seed(1234)
+    msg = training_epoch(net, ds, opt, 2, "cpu", FSL_Loss(), None, 0.0, False, False, 5, 5, 5, None, False, False)
+    random.seed(99)
+    acc = evaluate_single_segment(net, ds, 3, "cpu", 5, 5, 5, None, False)
+    after = {k: v.clone() for k, v in net.state_dict().items()}
+    save("epoch_cnn_plain", items_seed=5, items_checksum=ds.items.double().sum(), loss=msg["loss"], fsl_loss=msg["fsl_loss"],
+         val_mean=acc[0], val_std=acc[1],
+         **{"init_" + k: v for k, v in init.items()}, **{"after_" + k: v for k, v in after.items()})
+
+
+if __name__ == "__main__":
+    import_reference()
+    torch.set_num_threads(1)            # fixed reduction order for the fixtures
+    which = sys.argv[1:] or ["head", "cpl", "specaug", "vote", "modules", "epoch"]
+    for name in which:
+        globals()["gen_" + name]()
