@@ -1,0 +1,90 @@
+"""ctypes binding of libafsl.so - the only way the package reaches the GPU kernels.
+
+There is deliberately no fallback: if the shared object is missing or a call
+fails, an exception is raised (a product path that silently ran on the CPU or
+in eager PyTorch would void every parity and performance claim).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
+
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libafsl.so")
+
+_P, _I, _F = c_void_p, c_int, c_float
+
+# name -> argument ctypes, mirroring include/afsl.h exactly
+SIGNATURES = {
+    "afsl_prototypes_fwd_f32": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "afsl_prototypes_bwd_f32": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "afsl_proto_scores_fwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "afsl_proto_scores_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "afsl_proto_head_fwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "afsl_proto_head_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "afsl_l2_normalize_fwd_f32": [_P, _P, _I, _I, _F, _P],
+    "afsl_l2_normalize_bwd_f32": [_P, _P, _P, _I, _I, _F, _P],
+    "afsl_cpl_fwd_f32": [_P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _P],
+    "afsl_cpl_bwd_f32": [_P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _I, _P],
+    "afsl_specaug_views_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _I, _I, _I, _I, _I, _P],
+    "afsl_eval_vote_i32": [_P, _P, _P, _P, _P, _I, _P, _P, _I, _P],
+}
+
+_lib = None
+
+
+class AfslError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load libafsl.so (once).  Raises if it has not been built - never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AfslError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(or `python audio-few-shot-learning_b200/build.py`); there is no CPU / eager fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.afsl_version.restype = c_int
+    lib.afsl_last_error.restype = c_char_p
+    lib.afsl_launch_count.restype = c_longlong
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def launch_count() -> int:
+    """Kernel launches issued through the library so far (bench bookkeeping)."""
+    return int(load().afsl_launch_count())
+
+
+def ptr(t):
+    """Device pointer of a tensor or None; enforces the ABI's layout rules."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise AfslError("libafsl operates on CUDA tensors only (no CPU path); got a %s tensor" % t.device)
+    if not t.is_contiguous():
+        raise AfslError("libafsl needs contiguous tensors")
+    p = t.data_ptr()
+    if p % 16 and t.numel():
+        raise AfslError("libafsl needs 16-byte aligned tensors")
+    return p
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args) -> None:
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise AfslError(f"{name} failed (code {rc}): {lib.afsl_last_error().decode()}")

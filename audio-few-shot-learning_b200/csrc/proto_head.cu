@@ -1,0 +1,514 @@
+// Prototype head kernels: per-label mean of support embeddings, query->prototype Euclidean
+// distances, log-softmax / NLL, argmax / accuracy, and the fused backward.
+//
+// Reference semantics: models/util_functions.py:6-19 (compute_prototypes),
+// models/few_shot_classifier.py:108-116 (-cdist), loops/loss.py:24-37 (FSL_Loss),
+// loops/loops.py:79,271-272 (argmax, posterior, #correct).
+//
+// One CTA owns one episode at a time (persistent grid-stride loop over E).  Every support /
+// query element is read from HBM exactly once per pass with 128-bit loads; prototypes live in
+// shared memory; each query row is handled by a group of kLPR lanes holding the row in
+// registers, with warp-shuffle reductions over the embedding dimension.  fp32 throughout
+// (1e-5 parity bar; the contractions are ~1 flop/B, i.e. HBM-bound, so no tensor cores).
+#include "afsl_common.cuh"
+
+namespace afsl {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / kWarp;
+
+struct HeadParams {
+  // forward inputs
+  const float* support;     // [E,Ns,D] or null (then protos_in is used)
+  const int32_t* s_labels;  // [E,Ns]
+  const float* protos_in;   // [E,W,D] or null
+  const float* queries;     // [rows,D] or null (prototype-only call)
+  const int32_t* q_labels;  // [rows] or null
+  const int32_t* q_offsets; // [E+1] or null
+  // forward outputs (nullable)
+  float* protos_out;
+  float* scores;
+  float* loss;
+  int32_t* pred;
+  float* posterior;
+  int32_t* correct;
+  // backward
+  const float* d_loss;          // [E]
+  const float* d_scores;        // [rows,W] or null
+  const float* d_protos_extra;  // [E,W,D] or null
+  float* d_support;             // [E,Ns,D] or null
+  float* d_protos;              // [E,W,D] or null
+  float* d_queries;             // [rows,D] or null
+  int E, Ns, Nq, W, D;
+};
+
+// shared memory carve-up (floats/ints are both 4 bytes)
+struct Smem {
+  float* protos;   // [W*D]
+  float* dprotos;  // [W*D]      (backward only)
+  float* coef;     // [Nq*W]     (backward only)
+  float* score;    // [slots*W]
+  float* part;     // [slots]
+  int* lab;        // [Ns]
+  int* row;        // [Ns]
+  int* cnt;        // [W]
+  int* start;      // [W]
+  int* correct;    // [1]
+};
+
+__host__ __device__ inline size_t smem_words(int Ns, int Nq, int W, int D, int slots, bool bwd) {
+  size_t n = (size_t)W * D + (size_t)slots * W + slots + 2 * (size_t)Ns + 2 * (size_t)W + 4;
+  if (bwd) n += (size_t)W * D + (size_t)Nq * W;
+  return n;
+}
+
+__device__ inline Smem carve(float* base, int Ns, int Nq, int W, int D, int slots, bool bwd) {
+  Smem s;
+  s.protos = base;
+  base += (size_t)W * D;
+  s.dprotos = base;
+  if (bwd) base += (size_t)W * D;
+  s.coef = base;
+  if (bwd) base += (size_t)Nq * W;
+  s.score = base;
+  base += (size_t)slots * W;
+  s.part = base;
+  base += slots;
+  s.lab = reinterpret_cast<int*>(base);
+  base += Ns;
+  s.row = reinterpret_cast<int*>(base);
+  base += Ns;
+  s.cnt = reinterpret_cast<int*>(base);
+  base += W;
+  s.start = reinterpret_cast<int*>(base);
+  base += W;
+  s.correct = reinterpret_cast<int*>(base);
+  return s;
+}
+
+__device__ inline void bucket_rows(const Smem& s, const int32_t* labels, int Ns, int W) {
+  bucket_by_label(labels, Ns, W, s.lab, s.row, s.cnt, s.start);
+}
+
+// prototypes of one episode -> shared memory (and global when requested)
+__device__ inline void build_prototypes(const Smem& s, const float* support, float* protos_out, int W, int D) {
+  const int D4 = D >> 2;
+  const float4* sup4 = reinterpret_cast<const float4*>(support);
+  float4* sp4 = reinterpret_cast<float4*>(s.protos);
+  float4* out4 = reinterpret_cast<float4*>(protos_out);
+  for (int item = threadIdx.x; item < W * D4; item += kThreads) {
+    const int w = item / D4, c = item - w * D4;
+    const int n = s.cnt[w];
+    const int* rows = s.row + s.start[w];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int j = 0;
+    for (; j + 4 <= n; j += 4) {  // 4 independent 128-bit loads in flight
+      const float4 a = ldg_stream(sup4 + (size_t)rows[j] * D4 + c);
+      const float4 b = ldg_stream(sup4 + (size_t)rows[j + 1] * D4 + c);
+      const float4 d = ldg_stream(sup4 + (size_t)rows[j + 2] * D4 + c);
+      const float4 g = ldg_stream(sup4 + (size_t)rows[j + 3] * D4 + c);
+      acc.x = (((acc.x + a.x) + b.x) + d.x) + g.x;
+      acc.y = (((acc.y + a.y) + b.y) + d.y) + g.y;
+      acc.z = (((acc.z + a.z) + b.z) + d.z) + g.z;
+      acc.w = (((acc.w + a.w) + b.w) + d.w) + g.w;
+    }
+    for (; j < n; ++j) {
+      const float4 a = ldg_stream(sup4 + (size_t)rows[j] * D4 + c);
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+    const float fn = (float)n;  // n == 0 -> NaN, as the reference's empty mean
+    acc.x = __fdiv_rn(acc.x, fn); acc.y = __fdiv_rn(acc.y, fn);
+    acc.z = __fdiv_rn(acc.z, fn); acc.w = __fdiv_rn(acc.w, fn);
+    sp4[item] = acc;
+    if (protos_out) out4[item] = acc;
+  }
+}
+
+__device__ inline void load_prototypes(const Smem& s, const float* protos_in, int W, int D) {
+  const int n4 = (W * D) >> 2;
+  const float4* in4 = reinterpret_cast<const float4*>(protos_in);
+  float4* sp4 = reinterpret_cast<float4*>(s.protos);
+  for (int i = threadIdx.x; i < n4; i += kThreads) sp4[i] = __ldg(in4 + i);
+}
+
+// squared distances of the register-resident row q[] to prototype w, reduced over the lane group
+template <int kLPR, int kCPL>
+__device__ __forceinline__ float row_dist2(const float4 (&q)[kCPL], const float4* sp4, int w, int D4, int sub) {
+  float acc = 0.f;
+#pragma unroll
+  for (int u = 0; u < kCPL; ++u) {
+    const float4 p = sp4[w * D4 + sub + u * kLPR];
+    const float dx = q[u].x - p.x, dy = q[u].y - p.y, dz = q[u].z - p.z, dw = q[u].w - p.w;
+    acc = fmaf(dx, dx, acc); acc = fmaf(dy, dy, acc); acc = fmaf(dz, dz, acc); acc = fmaf(dw, dw, acc);
+  }
+  return group_sum<kLPR>(acc);
+}
+
+// Scores of one row against all prototypes -> s.score[slot*W ..]; returns (max, argmax, sumexp)
+// computed cooperatively by the lane group.
+template <int kLPR, int kCPL>
+__device__ __forceinline__ void row_scores(const float4 (&q)[kCPL], const Smem& s, int slot, int W, int D4, int sub,
+                                           float& mx, int& amx, float& sumexp) {
+  const float4* sp4 = reinterpret_cast<const float4*>(s.protos);
+  float* sc = s.score + slot * W;
+  for (int w = 0; w < W; ++w) {
+    const float d2 = row_dist2<kLPR, kCPL>(q, sp4, w, D4, sub);
+    if (sub == (w & (kLPR - 1))) sc[w] = -sqrtf(d2);
+  }
+  __syncwarp();
+  // max / first argmax over W
+  float m = -INFINITY;
+  int am = 0x7fffffff;
+  for (int w = sub; w < W; w += kLPR) {
+    const float v = sc[w];
+    if (v > m || (v == m && w < am)) { m = v; am = w; }
+    if (v != v && am == 0x7fffffff) am = w;  // NaN row: keep something defined
+  }
+#pragma unroll
+  for (int o = kLPR / 2; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+    if (om > m || (om == m && oa < am)) { m = om; am = oa; }
+  }
+  float se = 0.f;
+  for (int w = sub; w < W; w += kLPR) se += expf(sc[w] - m);
+  se = group_sum<kLPR>(se);
+  mx = m; amx = am; sumexp = se;
+}
+
+template <int kLPR, int kCPL>
+__global__ void __launch_bounds__(kThreads) head_fwd_kernel(const HeadParams p) {
+  extern __shared__ __align__(16) float smem_raw[];
+  constexpr int kGroups = kWarp / kLPR;       // rows handled concurrently by one warp
+  constexpr int kSlots = kWarps * kGroups;
+  const Smem s = carve(smem_raw, p.Ns, p.Nq, p.W, p.D, kSlots, false);
+  const int D4 = p.D >> 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & (kLPR - 1), grp = lane / kLPR;
+  const int slot = warp * kGroups + grp;
+
+  for (int e = blockIdx.x; e < p.E; e += gridDim.x) {
+    if (threadIdx.x == 0) *s.correct = 0;
+    if (p.support) {
+      bucket_rows(s, p.s_labels + (size_t)e * p.Ns, p.Ns, p.W);
+      build_prototypes(s, p.support + (size_t)e * p.Ns * p.D, p.protos_out ? p.protos_out + (size_t)e * p.W * p.D : nullptr,
+                       p.W, p.D);
+    } else {
+      load_prototypes(s, p.protos_in + (size_t)e * p.W * p.D, p.W, p.D);
+    }
+    __syncthreads();
+    if (p.queries) {
+      const int r0 = p.q_offsets ? p.q_offsets[e] : e * p.Nq;
+      const int nrows = p.q_offsets ? p.q_offsets[e + 1] - r0 : p.Nq;
+      const float4* q4 = reinterpret_cast<const float4*>(p.queries) + (size_t)r0 * D4;
+      float nll_acc = 0.f;
+      int hit = 0;
+      // every lane group walks rows slot, slot+kSlots, ...; the trip count is warp-uniform
+      const int trips = (nrows + kSlots - 1) / kSlots;
+      for (int it = 0; it < trips; ++it) {
+        const int i = it * kSlots + slot;
+        const bool live = i < nrows;
+        const int ii = live ? i : nrows - 1;  // clamp: dead groups redo the last row, results discarded
+        float4 q[kCPL];
+#pragma unroll
+        for (int u = 0; u < kCPL; ++u) q[u] = ldg_stream(q4 + (size_t)ii * D4 + sub + u * kLPR);
+        float mx, se;
+        int am;
+        row_scores<kLPR, kCPL>(q, s, slot, p.W, D4, sub, mx, am, se);
+        if (live) {
+          const float* sc = s.score + slot * p.W;
+          if (p.scores)
+            for (int w = sub; w < p.W; w += kLPR) p.scores[(size_t)(r0 + i) * p.W + w] = sc[w];
+          if (sub == 0) {
+            if (p.pred) p.pred[r0 + i] = am;
+            if (p.posterior) p.posterior[r0 + i] = mx;
+            if (p.q_labels) {
+              const int y = p.q_labels[r0 + i];
+              if (y >= 0 && y < p.W) nll_acc += -((sc[y] - mx) - logf(se));  // log_softmax then NLL
+              hit += (am == y);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (sub == 0) {
+        s.part[slot] = nll_acc;
+        if (hit) atomicAdd(s.correct, hit);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        if (p.loss) {
+          float tot = 0.f;
+          for (int k = 0; k < kSlots; ++k) tot += s.part[k];
+          p.loss[e] = tot / (float)nrows;
+        }
+        if (p.correct) p.correct[e] = *s.correct;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int kLPR, int kCPL>
+__global__ void __launch_bounds__(kThreads) head_bwd_kernel(const HeadParams p) {
+  extern __shared__ __align__(16) float smem_raw[];
+  constexpr int kGroups = kWarp / kLPR;
+  constexpr int kSlots = kWarps * kGroups;
+  const Smem s = carve(smem_raw, p.Ns, p.Nq, p.W, p.D, kSlots, true);
+  const int D4 = p.D >> 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & (kLPR - 1), grp = lane / kLPR;
+  const int slot = warp * kGroups + grp;
+  float4* sdp4 = reinterpret_cast<float4*>(s.dprotos);
+  const float4* sp4 = reinterpret_cast<const float4*>(s.protos);
+
+  for (int e = blockIdx.x; e < p.E; e += gridDim.x) {
+    if (p.support) {
+      bucket_rows(s, p.s_labels + (size_t)e * p.Ns, p.Ns, p.W);
+      if (p.queries) build_prototypes(s, p.support + (size_t)e * p.Ns * p.D, nullptr, p.W, p.D);
+    } else if (p.protos_in) {
+      load_prototypes(s, p.protos_in + (size_t)e * p.W * p.D, p.W, p.D);
+    } else {
+      bucket_rows(s, p.s_labels + (size_t)e * p.Ns, p.Ns, p.W);  // prototype-only backward
+    }
+    __syncthreads();
+    int nrows = 0, r0 = 0;
+    if (p.queries) {
+      r0 = p.q_offsets ? p.q_offsets[e] : e * p.Nq;
+      nrows = p.q_offsets ? p.q_offsets[e + 1] - r0 : p.Nq;
+      const float4* q4 = reinterpret_cast<const float4*>(p.queries) + (size_t)r0 * D4;
+      float4* dq4 = reinterpret_cast<float4*>(p.d_queries) + (size_t)r0 * D4;
+      const float dl = p.d_loss ? p.d_loss[e] / (float)nrows : 0.f;
+      const int trips = (nrows + kSlots - 1) / kSlots;
+      for (int it = 0; it < trips; ++it) {
+        const int i = it * kSlots + slot;
+        const bool live = i < nrows;
+        const int ii = live ? i : nrows - 1;
+        float4 q[kCPL];
+#pragma unroll
+        for (int u = 0; u < kCPL; ++u) q[u] = __ldg(q4 + (size_t)ii * D4 + sub + u * kLPR);
+        float mx, se;
+        int am;
+        row_scores<kLPR, kCPL>(q, s, slot, p.W, D4, sub, mx, am, se);
+        const float* sc = s.score + slot * p.W;
+        float* cf = s.coef + (size_t)ii * p.W;
+        const int y = p.q_labels ? p.q_labels[r0 + ii] : -1;
+        if (live) {
+          // dL/dscore = dl*(softmax - onehot) + d_scores ;  score = -dist  =>  dL/ddist = -dL/dscore
+          // coef = dL/ddist / dist, zero where dist == 0 (cdist backward convention)
+          for (int w = sub; w < p.W; w += kLPR) {
+            float g = dl * (expf(sc[w] - mx) / se - (w == y ? 1.f : 0.f));
+            if (p.d_scores) g += p.d_scores[(size_t)(r0 + i) * p.W + w];
+            const float dist = -sc[w];
+            cf[w] = dist > 0.f ? -g / dist : 0.f;
+          }
+        }
+        __syncwarp();
+        if (live) {
+          float4 acc[kCPL];
+#pragma unroll
+          for (int u = 0; u < kCPL; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int w = 0; w < p.W; ++w) {
+            const float c = cf[w];
+#pragma unroll
+            for (int u = 0; u < kCPL; ++u) {
+              const float4 pr = sp4[w * D4 + sub + u * kLPR];
+              acc[u].x = fmaf(c, q[u].x - pr.x, acc[u].x);
+              acc[u].y = fmaf(c, q[u].y - pr.y, acc[u].y);
+              acc[u].z = fmaf(c, q[u].z - pr.z, acc[u].z);
+              acc[u].w = fmaf(c, q[u].w - pr.w, acc[u].w);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kCPL; ++u) stg_stream(dq4 + (size_t)i * D4 + sub + u * kLPR, acc[u]);
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // dP[w] = -sum_i coef[i,w] (q_i - p_w)  (+ extra), rows in ascending order (deterministic)
+    if (p.queries || p.d_protos_extra) {
+      const float4* q4 = p.queries ? reinterpret_cast<const float4*>(p.queries) + (size_t)r0 * D4 : nullptr;
+      const float4* ex4 = p.d_protos_extra ? reinterpret_cast<const float4*>(p.d_protos_extra) + (size_t)e * p.W * D4 : nullptr;
+      float4* dpo4 = p.d_protos ? reinterpret_cast<float4*>(p.d_protos) + (size_t)e * p.W * D4 : nullptr;
+      for (int item = threadIdx.x; item < p.W * D4; item += kThreads) {
+        const int w = item / D4, c = item - w * D4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q4) {
+          const float4 pr = sp4[item];
+          for (int i = 0; i < nrows; ++i) {
+            const float cf = s.coef[(size_t)i * p.W + w];
+            const float4 qv = __ldg(q4 + (size_t)i * D4 + c);
+            acc.x = fmaf(-cf, qv.x - pr.x, acc.x);
+            acc.y = fmaf(-cf, qv.y - pr.y, acc.y);
+            acc.z = fmaf(-cf, qv.z - pr.z, acc.z);
+            acc.w = fmaf(-cf, qv.w - pr.w, acc.w);
+          }
+        }
+        if (ex4) {
+          const float4 x = __ldg(ex4 + item);
+          acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+        }
+        sdp4[item] = acc;
+        if (dpo4) dpo4[item] = acc;
+      }
+    } else if (p.d_protos_extra == nullptr && p.protos_in == nullptr && !p.queries) {
+      // unreachable: prototype-only backward always passes d_protos_extra
+    }
+    __syncthreads();
+    // dS[k] = dP[label_k] / count[label_k]   (mean backward)
+    if (p.d_support) {
+      float4* ds4 = reinterpret_cast<float4*>(p.d_support) + (size_t)e * p.Ns * D4;
+      for (int item = threadIdx.x; item < p.Ns * D4; item += kThreads) {
+        const int k = item / D4, c = item - k * D4;
+        const int w = s.lab[k];
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (w >= 0 && w < p.W) {
+          g = sdp4[w * D4 + c];
+          const float fn = (float)s.cnt[w];
+          g.x = __fdiv_rn(g.x, fn); g.y = __fdiv_rn(g.y, fn); g.z = __fdiv_rn(g.z, fn); g.w = __fdiv_rn(g.w, fn);
+        }
+        stg_stream(ds4 + item, g);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------ host dispatch
+using KernelFn = void (*)(const HeadParams);
+
+struct Variant {
+  KernelFn fwd, bwd;
+  int slots;
+};
+
+bool pick_variant(int D, Variant& v) {
+#define AFSL_VARIANT(LPR, CPL)                                                       \
+  if (D == 4 * LPR * CPL) {                                                          \
+    v.fwd = head_fwd_kernel<LPR, CPL>;                                               \
+    v.bwd = head_bwd_kernel<LPR, CPL>;                                               \
+    v.slots = kWarps * (kWarp / LPR);                                                \
+    return true;                                                                     \
+  }
+  AFSL_VARIANT(4, 1)    // D = 16
+  AFSL_VARIANT(8, 1)    // D = 32
+  AFSL_VARIANT(16, 1)   // D = 64
+  AFSL_VARIANT(32, 1)   // D = 128
+  AFSL_VARIANT(32, 2)   // D = 256
+  AFSL_VARIANT(32, 4)   // D = 512
+  AFSL_VARIANT(32, 8)   // D = 1024
+#undef AFSL_VARIANT
+  return false;
+}
+
+int launch(const HeadParams& p, bool bwd, cudaStream_t stream, const char* name) {
+  AFSL_REQUIRE(p.E >= 0 && p.W > 0 && p.D > 0, "%s: bad sizes E=%d W=%d D=%d", name, p.E, p.W, p.D);
+  if (p.E == 0) return AFSL_OK;
+  Variant v;
+  AFSL_REQUIRE(pick_variant(p.D, v), "%s: unsupported embedding dim D=%d (supported: 16,32,64,128,256,512,1024)", name, p.D);
+  const size_t bytes = smem_words(p.Ns, p.Nq, p.W, p.D, v.slots, bwd) * sizeof(float);
+  AFSL_REQUIRE(bytes <= 220 * 1024, "%s: episode does not fit shared memory (W=%d D=%d Ns=%d Nq=%d -> %zu B)", name,
+               p.W, p.D, p.Ns, p.Nq, bytes);
+  KernelFn fn = bwd ? v.bwd : v.fwd;
+  if (bytes > 48 * 1024) {
+    cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (err != cudaSuccess) {
+      set_error("%s: cannot opt in to %zu B shared memory: %s", name, bytes, cudaGetErrorString(err));
+      return AFSL_ECUDA;
+    }
+  }
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, bytes);
+  if (per_sm < 1) per_sm = 1;
+  int sms = kNumSMs;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.E < sms * per_sm ? p.E : sms * per_sm;
+  fn<<<grid, kThreads, bytes, stream>>>(p);
+  AFSL_CHECK_LAUNCH(name);
+  return AFSL_OK;
+}
+
+}  // namespace
+}  // namespace afsl
+
+using afsl::HeadParams;
+
+extern "C" int afsl_prototypes_fwd_f32(const float* support, const int32_t* labels, float* protos, int E, int Ns,
+                                        int W, int D, void* stream) {
+  AFSL_REQUIRE(support && labels && protos, "afsl_prototypes_fwd_f32: null pointer");
+  AFSL_REQUIRE(Ns > 0, "afsl_prototypes_fwd_f32: Ns=%d", Ns);
+  HeadParams p{};
+  p.support = support; p.s_labels = labels; p.protos_out = protos;
+  p.E = E; p.Ns = Ns; p.Nq = 0; p.W = W; p.D = D;
+  return afsl::launch(p, false, (cudaStream_t)stream, "afsl_prototypes_fwd_f32");
+}
+
+extern "C" int afsl_prototypes_bwd_f32(const float* d_protos, const int32_t* labels, float* d_support, int E, int Ns,
+                                        int W, int D, void* stream) {
+  AFSL_REQUIRE(d_protos && labels && d_support, "afsl_prototypes_bwd_f32: null pointer");
+  AFSL_REQUIRE(Ns > 0, "afsl_prototypes_bwd_f32: Ns=%d", Ns);
+  HeadParams p{};
+  p.s_labels = labels; p.d_protos_extra = d_protos; p.d_support = d_support;
+  p.E = E; p.Ns = Ns; p.Nq = 0; p.W = W; p.D = D;
+  return afsl::launch(p, true, (cudaStream_t)stream, "afsl_prototypes_bwd_f32");
+}
+
+extern "C" int afsl_proto_scores_fwd_f32(const float* protos, const float* queries, const int32_t* q_labels,
+                                          const int32_t* q_offsets, float* scores, float* loss, int32_t* pred,
+                                          float* posterior, int32_t* correct, int E, int Nq, int W, int D,
+                                          void* stream) {
+  AFSL_REQUIRE(protos && queries, "afsl_proto_scores_fwd_f32: null pointer");
+  AFSL_REQUIRE(q_labels || (!loss && !correct), "afsl_proto_scores_fwd_f32: loss/correct need q_labels");
+  AFSL_REQUIRE(Nq > 0, "afsl_proto_scores_fwd_f32: Nq=%d", Nq);
+  HeadParams p{};
+  p.protos_in = protos; p.queries = queries; p.q_labels = q_labels; p.q_offsets = q_offsets;
+  p.scores = scores; p.loss = loss; p.pred = pred; p.posterior = posterior; p.correct = correct;
+  p.E = E; p.Ns = 0; p.Nq = Nq; p.W = W; p.D = D;
+  return afsl::launch(p, false, (cudaStream_t)stream, "afsl_proto_scores_fwd_f32");
+}
+
+extern "C" int afsl_proto_scores_bwd_f32(const float* protos, const float* queries, const int32_t* q_labels,
+                                          const int32_t* q_offsets, const float* d_loss, const float* d_scores,
+                                          float* d_protos, float* d_queries, int E, int Nq, int W, int D,
+                                          void* stream) {
+  AFSL_REQUIRE(protos && queries && d_protos && d_queries, "afsl_proto_scores_bwd_f32: null pointer");
+  AFSL_REQUIRE(d_loss || d_scores, "afsl_proto_scores_bwd_f32: no incoming gradient");
+  AFSL_REQUIRE(!d_loss || q_labels, "afsl_proto_scores_bwd_f32: d_loss needs q_labels");
+  AFSL_REQUIRE(Nq > 0, "afsl_proto_scores_bwd_f32: Nq=%d", Nq);
+  HeadParams p{};
+  p.protos_in = protos; p.queries = queries; p.q_labels = q_labels; p.q_offsets = q_offsets;
+  p.d_loss = d_loss; p.d_scores = d_scores; p.d_protos = d_protos; p.d_queries = d_queries;
+  p.E = E; p.Ns = 0; p.Nq = Nq; p.W = W; p.D = D;
+  return afsl::launch(p, true, (cudaStream_t)stream, "afsl_proto_scores_bwd_f32");
+}
+
+extern "C" int afsl_proto_head_fwd_f32(const float* support, const int32_t* s_labels, const float* queries,
+                                        const int32_t* q_labels, const int32_t* q_offsets, float* protos, float* scores,
+                                        float* loss, int32_t* pred, float* posterior, int32_t* correct, int E, int Ns,
+                                        int Nq, int W, int D, void* stream) {
+  AFSL_REQUIRE(support && s_labels && queries, "afsl_proto_head_fwd_f32: null pointer");
+  AFSL_REQUIRE(q_labels || (!loss && !correct), "afsl_proto_head_fwd_f32: loss/correct need q_labels");
+  AFSL_REQUIRE(Ns > 0 && Nq > 0, "afsl_proto_head_fwd_f32: Ns=%d Nq=%d", Ns, Nq);
+  HeadParams p{};
+  p.support = support; p.s_labels = s_labels; p.queries = queries; p.q_labels = q_labels; p.q_offsets = q_offsets;
+  p.protos_out = protos; p.scores = scores; p.loss = loss; p.pred = pred; p.posterior = posterior; p.correct = correct;
+  p.E = E; p.Ns = Ns; p.Nq = Nq; p.W = W; p.D = D;
+  return afsl::launch(p, false, (cudaStream_t)stream, "afsl_proto_head_fwd_f32");
+}
+
+extern "C" int afsl_proto_head_bwd_f32(const float* support, const int32_t* s_labels, const float* queries,
+                                        const int32_t* q_labels, const int32_t* q_offsets, const float* d_loss,
+                                        const float* d_protos_extra, float* d_support, float* d_queries, int E, int Ns,
+                                        int Nq, int W, int D, void* stream) {
+  AFSL_REQUIRE(support && s_labels && queries && q_labels && d_loss && d_support && d_queries,
+               "afsl_proto_head_bwd_f32: null pointer");
+  AFSL_REQUIRE(Ns > 0 && Nq > 0, "afsl_proto_head_bwd_f32: Ns=%d Nq=%d", Ns, Nq);
+  HeadParams p{};
+  p.support = support; p.s_labels = s_labels; p.queries = queries; p.q_labels = q_labels; p.q_offsets = q_offsets;
+  p.d_loss = d_loss; p.d_protos_extra = d_protos_extra; p.d_support = d_support; p.d_queries = d_queries;
+  p.E = E; p.Ns = Ns; p.Nq = Nq; p.W = W; p.D = D;
+  return afsl::launch(p, true, (cudaStream_t)stream, "afsl_proto_head_bwd_f32");
+}

@@ -1,0 +1,265 @@
+"""Encoders, view fusion and projection head (host-side mirror of models/main_modules.py).
+
+Class names, constructor arguments and parameter names follow the reference so that
+its ``model.pt`` state-dicts load unchanged.  Differences, all additive:
+
+* every module also accepts a leading episode dimension (``[E, N, ...]``): the encoder
+  then keeps **per-(episode, view, set) BatchNorm statistics** - in the reference one
+  encoder call sees exactly one 25-sample set (models/main_modules.py:18-23), so
+  batching E episodes into one cuDNN call must not pool their statistics;
+* the convolutions stay PyTorch/cuDNN (north star); BatchNorm -> ReLU -> MaxPool of each
+  stage, the view fusion layer and the L2 normalisation closing the projection head go
+  through libafsl kernels when the tensors live on the GPU.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .. import ops
+
+
+def floor_power(num, divisor, power):
+    """``power`` successive floor divisions (models/main_modules.py:26-40)."""
+    for _ in range(power):
+        num = np.floor(num / divisor)
+    return num
+
+
+class GroupedBatchNorm2d(nn.BatchNorm2d):
+    """BatchNorm2d whose batch axis may hold several independent groups.
+
+    ``group_size`` consecutive samples form one group (= one encoder call of the
+    reference) with its own batch statistics in training mode; running statistics are
+    updated group by group in order, exactly as that many separate calls would.
+    With ``group_size=None`` (or a single group) this is nn.BatchNorm2d.
+    """
+
+    group_size: Optional[int] = None
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        gs = self.group_size
+        if not self.training or gs is None or x.shape[0] == gs:
+            return super().forward(x)
+        n, c, h, w = x.shape
+        if n % gs:
+            raise ValueError(f"batch of {n} samples is not a whole number of groups of {gs}")
+        g = n // gs
+        xg = x.view(g, gs, c, h, w)
+        var, mean = torch.var_mean(xg, dim=(1, 3, 4), unbiased=False, keepdim=True)      # [g,1,c,1,1]
+        y = (xg - mean) * torch.rsqrt(var + self.eps)
+        y = y.view(n, c, h, w) * self.weight.view(1, c, 1, 1) + self.bias.view(1, c, 1, 1)
+        if self.track_running_stats:
+            with torch.no_grad():
+                _update_running(self, mean.view(g, c), var.view(g, c), gs * h * w)
+        return y
+
+
+class GroupedBatchNorm1d(nn.BatchNorm1d):
+    """BatchNorm1d counterpart of :class:`GroupedBatchNorm2d` for ``[N, C]`` inputs."""
+
+    group_size: Optional[int] = None
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        gs = self.group_size
+        if not self.training or gs is None or x.shape[0] == gs:
+            return super().forward(x)
+        n, c = x.shape
+        if n % gs:
+            raise ValueError(f"batch of {n} samples is not a whole number of groups of {gs}")
+        g = n // gs
+        xg = x.view(g, gs, c)
+        var, mean = torch.var_mean(xg, dim=1, unbiased=False, keepdim=True)
+        y = ((xg - mean) * torch.rsqrt(var + self.eps)).view(n, c) * self.weight + self.bias
+        if self.track_running_stats:
+            with torch.no_grad():
+                _update_running(self, mean.view(g, c), var.view(g, c), gs)
+        return y
+
+
+def _update_running(bn, mean: torch.Tensor, var_biased: torch.Tensor, count: int) -> None:
+    """Apply ``g`` sequential momentum updates in one shot (groups in batch order)."""
+    g = mean.shape[0]
+    m = bn.momentum
+    bn.num_batches_tracked += g
+    if m is None:                                   # cumulative moving average
+        raise NotImplementedError("momentum=None is not used by the reference encoders")
+    unbiased = var_biased * (count / max(count - 1, 1))
+    decay = (1.0 - m) ** torch.arange(g - 1, -1, -1, device=mean.device, dtype=mean.dtype)   # weight of group j
+    keep = (1.0 - m) ** g
+    bn.running_mean.mul_(keep).add_((decay.unsqueeze(1) * mean).sum(0), alpha=m)
+    bn.running_var.mul_(keep).add_((decay.unsqueeze(1) * unbiased).sum(0), alpha=m)
+
+
+def conv_block(in_channels, out_channels, pool_dim):
+    """Conv3x3(pad 1) -> BatchNorm -> ReLU -> MaxPool(pool_dim) (models/main_modules.py:43-60)."""
+    return nn.Sequential(
+        nn.Conv2d(in_channels, out_channels, 3, padding=1),
+        GroupedBatchNorm2d(out_channels),
+        nn.ReLU(),
+        nn.MaxPool2d(kernel_size=pool_dim, stride=pool_dim),
+    )
+
+
+def conv_encoder(in_channels, hidden_channels, pool_dim):
+    """Four conv blocks (models/main_modules.py:63-81)."""
+    blocks = [conv_block(in_channels, hidden_channels, pool_dim)]
+    blocks += [conv_block(hidden_channels, hidden_channels, pool_dim) for _ in range(3)]
+    return nn.Sequential(*blocks)
+
+
+def _logits(features: int, out_dim: int) -> nn.Sequential:
+    return nn.Sequential(nn.Dropout(p=0.3), GroupedBatchNorm1d(features, eps=1e-05, momentum=0.1, affine=True),
+                         nn.Linear(in_features=features, out_features=out_dim))
+
+
+def _count_params(module: nn.Module) -> int:
+    return int(sum(np.prod(p.size()) for p in module.parameters() if p.requires_grad))
+
+
+class StandardCNN(nn.Module):
+    """Conv4 backbone (models/main_modules.py:84-114)."""
+
+    def __init__(self, in_channels, trial_shape, hidden_channels, pool_dim, out_dim):
+        super().__init__()
+        self.conv_encoder = conv_encoder(in_channels, hidden_channels, pool_dim)
+        num_logits = int(64 * floor_power(trial_shape[2], pool_dim[0], 4) * floor_power(trial_shape[3], pool_dim[1], 4))
+        self.logits = _logits(num_logits, out_dim)
+        self.params = _count_params(self)
+        print(f'Trainable Params: {self.params}')
+
+    def forward(self, x):
+        x = self.conv_encoder(x)
+        return self.logits(x.view(x.size(0), -1))
+
+
+class StandardHybrid(nn.Module):
+    """Conv stack + recurrent layer with skip connection (models/main_modules.py:117-198)."""
+
+    def __init__(self, in_channels, seq_layers, seq_type, bidirectional, hidden_channels, pool_dim, out_dim):
+        super().__init__()
+        self.bidirectional = bidirectional
+        self.seq_type = seq_type
+        hidden = 64
+        self.conv_encoder = conv_encoder(in_channels, hidden_channels, pool_dim)
+        if seq_type not in ['LSTM', 'GRU', 'RNN']:
+            raise ValueError('Seq type not recognised')
+        self.seq_layers = getattr(nn, seq_type)(input_size=hidden, hidden_size=hidden, num_layers=seq_layers,
+                                                bidirectional=bidirectional, batch_first=True)
+        self.logits = _logits(hidden, out_dim)
+        self.params = _count_params(self)
+        print(f'Num Layers: {seq_layers} -> Trainable Params: {self.params}')
+
+    def many_to_one(self, t, lengths):
+        return t[torch.arange(t.size(0)), lengths - 1]
+
+    def forward(self, x):
+        x = self.conv_encoder(x)
+        x = x.transpose(1, -1)                        # (batch, time, freq, channel)
+        batch, time = x.size()[:2]
+        x = x.reshape(batch, time, -1)
+        output = self.seq_layers(x)[0]
+        hs = self.seq_layers.hidden_size
+        skip = output[:, :, :hs] + x
+        if self.bidirectional:
+            skip = skip + output[:, :, hs:]
+        return self.logits(self.many_to_one(skip, skip.shape[-2]))
+
+
+def get_backbone_model(encoder_name, model_config):
+    """Build the encoder named by ``experiment_config['encoder_name']`` (models/main_modules.py:258-285).
+
+    The reference's 'CNN' branch omits StandardCNN's required ``trial_shape`` and raises
+    TypeError; here an optional ``model_config['CNN']['trial_shape']`` key supplies it (same
+    TypeError without it).
+    """
+    cfg = model_config[encoder_name]
+    if encoder_name == 'CNN':
+        kwargs = dict(in_channels=cfg['in_channels'], hidden_channels=cfg['hidden_channels'],
+                      pool_dim=cfg['pool_dim'], out_dim=cfg['out_dim'])
+        if 'trial_shape' in cfg:
+            kwargs['trial_shape'] = cfg['trial_shape']
+        return StandardCNN(**kwargs)
+    if encoder_name == 'Hybrid':
+        return StandardHybrid(in_channels=cfg['in_channels'], seq_layers=cfg['seq_layers'], seq_type=cfg['seq_type'],
+                              bidirectional=cfg['bidirectional'], hidden_channels=cfg['hidden_channels'],
+                              pool_dim=cfg['pool_dim'], out_dim=cfg['out_dim'])
+    raise UnboundLocalError(f"unknown encoder_name {encoder_name!r}")     # the reference fails the same way
+
+
+def set_group_size(module: nn.Module, group_size: Optional[int]) -> None:
+    for m in module.modules():
+        if isinstance(m, (GroupedBatchNorm2d, GroupedBatchNorm1d)):
+            m.group_size = group_size
+
+
+class EncoderModule(nn.Module):
+    """Applies the encoder to every view (models/main_modules.py:10-23).
+
+    Views shaped ``[N,1,F,T]`` are encoded one call per view like the reference.  Views shaped
+    ``[E,N,1,F,T]`` (E episodes) are encoded in ONE call for all views, with BatchNorm
+    statistics per (episode, view) group of N samples, and returned as ``[E,N,D]`` each.
+    """
+
+    def __init__(self, experiment_config, model_config, encoder: Optional[nn.Module] = None):
+        super().__init__()
+        self.experiment_config = experiment_config
+        self.encoder_str = experiment_config['encoder_name']
+        self.encoder = encoder if encoder is not None else get_backbone_model(self.encoder_str, model_config)
+
+    def forward(self, spec_list: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        first = spec_list[0]
+        if first.dim() == 4:
+            set_group_size(self.encoder, None)
+            return [self.encoder(x) for x in spec_list]
+        e, n = first.shape[:2]
+        stacked = torch.cat([x.reshape(e * n, *x.shape[2:]) for x in spec_list], dim=0)
+        set_group_size(self.encoder, n)
+        try:
+            feats = self.encoder(stacked)
+        finally:
+            set_group_size(self.encoder, None)
+        return [f.view(e, n, -1) for f in feats.chunk(len(spec_list), dim=0)]
+
+
+class SelfAttention(nn.Module):
+    """One post-norm transformer encoder layer over the V views, output ``[N, V*D]``
+    (models/main_modules.py:201-228)."""
+
+    def __init__(self, model_config):
+        super().__init__()
+        att = model_config['Attention']
+        self.embed_dim, self.num_heads = att['embed_dim'], att['num_heads']
+        self.ffn_dim, self.dropout = att['ffn_dim'], att['dropout']
+        self.encoder_layer = nn.TransformerEncoderLayer(d_model=self.embed_dim, nhead=self.num_heads,
+                                                        dim_feedforward=self.ffn_dim, dropout=self.dropout,
+                                                        batch_first=True)
+
+    def forward(self, x):
+        lead = x.shape[:-2]                            # [N] or [E, N]
+        y = self.encoder_layer(x.reshape(-1, *x.shape[-2:]))
+        return y.reshape(*lead, -1)                    # views side by side == cat(y[:, i, :])
+
+
+class ProjectionHead(nn.Module):
+    """Linear -> ReLU -> Linear -> L2 normalise (models/main_modules.py:231-255).
+    ``ln1`` / ``ln2`` exist in the state-dict but are never applied, as in the reference."""
+
+    def __init__(self, model_config):
+        super().__init__()
+        pc = model_config['Projection']
+        self.input_dim, self.hidden_dim, self.output_dim = pc['input_dim'], pc['hidden_dim'], pc['output_dim']
+        self.fc1 = nn.Linear(self.input_dim, self.hidden_dim)
+        self.ln1 = nn.LayerNorm(self.hidden_dim)
+        self.fc2 = nn.Linear(self.hidden_dim, self.output_dim)
+        self.ln2 = nn.LayerNorm(self.output_dim)
+
+    def forward(self, x):
+        x = self.fc2(F.relu(self.fc1(x)))
+        if x.is_cuda and x.shape[-1] % 4 == 0:
+            return ops.l2_normalize(x, eps=1e-12)
+        return F.normalize(x, p=2.0, dim=-1, eps=1e-12)

@@ -1,0 +1,342 @@
+"""torch.autograd bindings of the libafsl kernels.
+
+Every function takes CUDA fp32 tensors, optionally with a leading episode
+dimension E (the reference always has E = 1 and no such dimension), converts
+labels to int32 and calls the C ABI on the current stream.  There is no CPU
+implementation here on purpose (see _lib.py).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+
+TIE_STRATEGIES = {"min_label": 1, "max_posterior": 2}   # anything else -> first seen (loops/loops.py:233-234)
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _i32(t: torch.Tensor) -> torch.Tensor:
+    return t.to(dtype=torch.int32).contiguous()
+
+
+def _batched(feats: torch.Tensor, labels: Optional[torch.Tensor]):
+    """-> (feats [E,N,D], labels [E,N] or None, had_batch_dim)."""
+    if feats.dim() == 2:
+        return feats.unsqueeze(0), (labels.unsqueeze(0) if labels is not None else None), False
+    if feats.dim() == 3:
+        if labels is not None and labels.dim() == 1:
+            labels = labels.unsqueeze(0).expand(feats.shape[0], -1)
+        return feats, labels, True
+    raise ValueError("Illegal backbone or feature shape. Expected output for an image is a 1-dim tensor.")
+
+
+def infer_n_way(labels: torch.Tensor) -> int:
+    """len(torch.unique(labels)) as in models/util_functions.py:17 (synchronises when labels are on the GPU)."""
+    return int(torch.unique(labels).numel())
+
+
+# ---------------------------------------------------------------------------------- prototypes
+class _Prototypes(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, support, labels, n_way):
+        e, ns, d = support.shape
+        protos = torch.empty(e, n_way, d, device=support.device, dtype=torch.float32)
+        call("afsl_prototypes_fwd_f32", ptr(support), ptr(labels), ptr(protos), e, ns, n_way, d, stream_ptr())
+        ctx.save_for_backward(labels)
+        ctx.shape = (e, ns, n_way, d)
+        return protos
+
+    @staticmethod
+    def backward(ctx, d_protos):
+        (labels,) = ctx.saved_tensors
+        e, ns, w, d = ctx.shape
+        d_protos = _f32(d_protos)
+        d_support = torch.empty(e, ns, d, device=d_protos.device, dtype=torch.float32)
+        call("afsl_prototypes_bwd_f32", ptr(d_protos), ptr(labels), ptr(d_support), e, ns, w, d, stream_ptr())
+        return d_support, None, None
+
+
+def prototypes(support: torch.Tensor, labels: torch.Tensor, n_way: Optional[int] = None) -> torch.Tensor:
+    """Per-label mean of support rows: [Ns,D],[Ns] -> [W,D] or [E,Ns,D],[E,Ns] -> [E,W,D]."""
+    s, l, had = _batched(support, labels)
+    if n_way is None:
+        n_way = infer_n_way(l[0])
+    out = _Prototypes.apply(_f32(s), _i32(l), int(n_way))
+    return out if had else out[0]
+
+
+# ---------------------------------------------------------------------------------- scores / proto loss
+class _ProtoScores(torch.autograd.Function):
+    """(-dist, loss) given prototypes.  loss is NaN-free only when labels are given."""
+
+    @staticmethod
+    def forward(ctx, protos, queries, labels, offsets, want_scores, want_loss):
+        e, w, d = protos.shape
+        rows = queries.shape[0] * queries.shape[1] if queries.dim() == 3 else queries.shape[0]
+        nq = queries.shape[1] if queries.dim() == 3 else ctx_max_rows(offsets)
+        dev = protos.device
+        scores = torch.empty(rows, w, device=dev, dtype=torch.float32) if want_scores else None
+        loss = torch.empty(e, device=dev, dtype=torch.float32) if want_loss else None
+        call("afsl_proto_scores_fwd_f32", ptr(protos), ptr(queries), ptr(labels), ptr(offsets), ptr(scores), ptr(loss),
+             None, None, None, e, nq, w, d, stream_ptr())
+        ctx.save_for_backward(protos, queries, labels, offsets)
+        ctx.dims = (e, nq, w, d)
+        ctx.flags = (want_scores, want_loss)
+        if want_scores and queries.dim() == 3:
+            scores = scores.view(e, nq, w)
+        empty = torch.empty(0, device=dev)
+        return (scores if want_scores else empty), (loss if want_loss else empty)
+
+    @staticmethod
+    def backward(ctx, d_scores, d_loss):
+        protos, queries, labels, offsets = ctx.saved_tensors
+        e, nq, w, d = ctx.dims
+        want_scores, want_loss = ctx.flags
+        d_scores = _f32(d_scores).reshape(-1, w) if want_scores else None
+        d_loss = _f32(d_loss) if want_loss else None
+        d_protos = torch.empty_like(protos)
+        d_queries = torch.empty_like(queries)
+        call("afsl_proto_scores_bwd_f32", ptr(protos), ptr(queries), ptr(labels), ptr(offsets), ptr(d_loss),
+             ptr(d_scores), ptr(d_protos), ptr(d_queries), e, nq, w, d, stream_ptr())
+        return d_protos, d_queries, None, None, None, None
+
+
+def ctx_max_rows(offsets: torch.Tensor) -> int:
+    """Largest per-task row count of a CSR offsets tensor (host value; offsets are built on the host)."""
+    return int((offsets[1:] - offsets[:-1]).max().item())
+
+
+def l2_scores(queries: torch.Tensor, protos: torch.Tensor) -> torch.Tensor:
+    """-cdist(queries, protos): [Nq,D],[W,D] -> [Nq,W] (or with a leading E)."""
+    q, _, had = _batched(queries, None)
+    p = protos if protos.dim() == 3 else protos.unsqueeze(0)
+    scores, _ = _ProtoScores.apply(_f32(p), _f32(q), None, None, True, False)
+    return scores if had else scores[0]
+
+
+def proto_loss(protos: torch.Tensor, queries: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """FSL loss per episode: mean NLL of log_softmax(-cdist).  Returns a 0-dim tensor without E."""
+    q, l, had = _batched(queries, labels)
+    p = protos if protos.dim() == 3 else protos.unsqueeze(0)
+    _, loss = _ProtoScores.apply(_f32(p), _f32(q), _i32(l), None, False, True)
+    return loss if had else loss[0]
+
+
+# ---------------------------------------------------------------------------------- fused head
+class _ProtoHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, support, s_labels, queries, q_labels, n_way):
+        e, ns, d = support.shape
+        nq = queries.shape[1]
+        dev = support.device
+        protos = torch.empty(e, n_way, d, device=dev, dtype=torch.float32)
+        loss = torch.empty(e, device=dev, dtype=torch.float32)
+        correct = torch.empty(e, device=dev, dtype=torch.int32)
+        call("afsl_proto_head_fwd_f32", ptr(support), ptr(s_labels), ptr(queries), ptr(q_labels), None, ptr(protos), None,
+             ptr(loss), None, None, ptr(correct), e, ns, nq, n_way, d, stream_ptr())
+        ctx.save_for_backward(support, s_labels, queries, q_labels)
+        ctx.dims = (e, ns, nq, n_way, d)
+        ctx.mark_non_differentiable(correct)
+        return loss, protos, correct
+
+    @staticmethod
+    def backward(ctx, d_loss, d_protos, _d_correct):
+        support, s_labels, queries, q_labels = ctx.saved_tensors
+        e, ns, nq, w, d = ctx.dims
+        d_loss = _f32(d_loss) if d_loss is not None else torch.zeros(e, device=support.device)
+        d_protos = _f32(d_protos) if d_protos is not None else None
+        d_support = torch.empty_like(support)
+        d_queries = torch.empty_like(queries)
+        call("afsl_proto_head_bwd_f32", ptr(support), ptr(s_labels), ptr(queries), ptr(q_labels), None, ptr(d_loss),
+             ptr(d_protos), ptr(d_support), ptr(d_queries), e, ns, nq, w, d, stream_ptr())
+        return d_support, None, d_queries, None, None
+
+
+def proto_head(support, s_labels, queries, q_labels, n_way: Optional[int] = None):
+    """Fused prototypes + FSL loss (+ #correct): returns (loss [E], protos [E,W,D], correct [E])."""
+    s, sl, had = _batched(support, s_labels)
+    q, ql, _ = _batched(queries, q_labels)
+    if n_way is None:
+        n_way = infer_n_way(sl[0])
+    loss, protos, correct = _ProtoHead.apply(_f32(s), _i32(sl), _f32(q), _i32(ql), int(n_way))
+    return (loss, protos, correct) if had else (loss[0], protos[0], correct[0])
+
+
+@torch.no_grad()
+def proto_eval(support, s_labels, queries, q_labels=None, n_way: Optional[int] = None,
+               q_offsets: Optional[torch.Tensor] = None, max_rows: Optional[int] = None, want_scores: bool = False):
+    """Evaluation head: prototypes + scores -> (pred, posterior, correct, scores?).
+
+    ``queries`` is [E,Nq,D], or packed [rows,D] with CSR ``q_offsets`` [E+1] for ragged
+    multi-segment tasks (``max_rows`` = largest task, computed on the host when omitted).
+    """
+    s, sl, _ = _batched(support, s_labels)
+    e, ns, d = s.shape
+    if n_way is None:
+        n_way = infer_n_way(sl[0])
+    dev = s.device
+    if q_offsets is None:
+        q = queries if queries.dim() == 3 else queries.unsqueeze(0)
+        nq, rows = q.shape[1], q.shape[0] * q.shape[1]
+        off = None
+    else:
+        q = queries
+        rows = q.shape[0]
+        nq = int(max_rows) if max_rows is not None else ctx_max_rows(q_offsets)
+        off = _i32(q_offsets)
+    ql = _i32(q_labels.reshape(-1)) if q_labels is not None else None
+    pred = torch.empty(rows, device=dev, dtype=torch.int32)
+    post = torch.empty(rows, device=dev, dtype=torch.float32)
+    correct = torch.empty(e, device=dev, dtype=torch.int32) if ql is not None else None
+    scores = torch.empty(rows, n_way, device=dev, dtype=torch.float32) if want_scores else None
+    s32, sl32, q32 = _f32(s), _i32(sl), _f32(q)          # keep converted temporaries alive across the launch
+    call("afsl_proto_head_fwd_f32", ptr(s32), ptr(sl32), ptr(q32), ptr(ql), ptr(off), None, ptr(scores), None,
+         ptr(pred), ptr(post), ptr(correct), e, ns, nq, int(n_way), d, stream_ptr())
+    return pred, post, correct, scores
+
+
+# ---------------------------------------------------------------------------------- normalise
+class _L2Normalize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eps):
+        y = torch.empty_like(x)
+        rows, d = x.numel() // x.shape[-1], x.shape[-1]
+        call("afsl_l2_normalize_fwd_f32", ptr(x), ptr(y), rows, d, float(eps), stream_ptr())
+        ctx.save_for_backward(x)
+        ctx.eps = float(eps)
+        return y
+
+    @staticmethod
+    def backward(ctx, d_y):
+        (x,) = ctx.saved_tensors
+        d_y = _f32(d_y)
+        d_x = torch.empty_like(x)
+        rows, d = x.numel() // x.shape[-1], x.shape[-1]
+        call("afsl_l2_normalize_bwd_f32", ptr(x), ptr(d_y), ptr(d_x), rows, d, ctx.eps, stream_ptr())
+        return d_x, None
+
+
+def l2_normalize(x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    """F.normalize(x, p=2, dim=-1, eps) on the last dimension."""
+    return _L2Normalize.apply(_f32(x), eps)
+
+
+# ---------------------------------------------------------------------------------- CPL
+class _Cpl(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, protos, queries, labels, keep, temperature):
+        e, w, d = protos.shape
+        nq = queries.shape[1]
+        loss = torch.empty(e, device=protos.device, dtype=torch.float32)
+        call("afsl_cpl_fwd_f32", ptr(protos), ptr(queries), ptr(labels), ptr(keep), float(temperature), ptr(loss), e, nq, w,
+             d, stream_ptr())
+        ctx.save_for_backward(protos, queries, labels, keep)
+        ctx.temperature = float(temperature)
+        return loss
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        protos, queries, labels, keep = ctx.saved_tensors
+        e, w, d = protos.shape
+        nq = queries.shape[1]
+        d_protos, d_queries = torch.empty_like(protos), torch.empty_like(queries)
+        d_loss = _f32(d_loss)
+        call("afsl_cpl_bwd_f32", ptr(protos), ptr(queries), ptr(labels), ptr(keep), ctx.temperature, ptr(d_loss),
+             ptr(d_protos), ptr(d_queries), e, nq, w, d, stream_ptr())
+        return d_protos, d_queries, None, None, None
+
+
+def pack_keep(keep: torch.Tensor) -> torch.Tensor:
+    """bool [.., Nq, Nq] -> little-endian bit words int32 [.., Nq, ceil(Nq/32)] (host or device)."""
+    nq = keep.shape[-1]
+    words = (nq + 31) // 32
+    pad = words * 32 - nq
+    k = torch.nn.functional.pad(keep.to(torch.int64), (0, pad)).view(*keep.shape[:-1], words, 32)
+    weights = (1 << torch.arange(32, dtype=torch.int64, device=keep.device))
+    packed = (k * weights).sum(-1)
+    packed = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed)
+    return packed.to(torch.int32)
+
+
+def cpl_loss(protos, queries, labels, temperature: float, keep: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """CPL loss per episode.  ``keep``: bool [E,Nq,Nq] / [Nq,Nq] sampled-negative mask or None for
+    "all queries of the other classes" (M >= per-class count)."""
+    q, l, had = _batched(queries, labels)
+    p = protos if protos.dim() == 3 else protos.unsqueeze(0)
+    kp = None
+    if keep is not None:
+        kp = keep if keep.dim() == 3 else keep.unsqueeze(0)
+        if kp.dtype == torch.bool:
+            kp = pack_keep(kp)
+        kp = kp.to(device=q.device, dtype=torch.int32).contiguous()
+    loss = _Cpl.apply(_f32(p), _f32(q), _i32(l), kp, temperature)
+    return loss if had else loss[0]
+
+
+# ---------------------------------------------------------------------------------- SpecAugment
+_ROW_TABLES = {}
+
+
+def _row_tables(rows: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Source row / blend weight of grid_sample's y axis for grid y = linspace(-1, 1, rows)
+    (utils/augmentations.py:142-146), computed once on the host with the same fp32 ops."""
+    key = (rows, str(device))
+    if key not in _ROW_TABLES:
+        gy = torch.linspace(-1, 1, rows)
+        iy = ((gy + 1) / 2) * (rows - 1)
+        lo = torch.floor(iy)
+        _ROW_TABLES[key] = (lo.to(torch.int32).to(device), (iy - lo).to(device))
+    return _ROW_TABLES[key]
+
+
+@torch.no_grad()
+def specaug_views(x: torch.Tensor, warp_p: torch.Tensor, warp_d: torch.Tensor, time_masks: torch.Tensor,
+                  freq_masks: torch.Tensor, mask_value: float, set_size: int, src_x: Optional[torch.Tensor] = None,
+                  views_mask: int = 0b1111, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [N,1,F,T] -> views [4,N,1,F,T] (copy, time-warp, time-mask, freq-mask).
+
+    warp_p/warp_d: int [N]; time_masks/freq_masks: int [sets,num_mask,2] = (start, length) with
+    sets = N / set_size.  Views whose bit is clear in ``views_mask`` are left untouched.
+    """
+    n, c, f, t = x.shape
+    if c != 1:
+        raise ValueError("SpecAugment expects [batch, 1, freq, time]")
+    x = _f32(x)
+    dev = x.device
+    views = out if out is not None else torch.empty(4, n, 1, f, t, device=dev, dtype=torch.float32)
+    lo, w = _row_tables(f, dev)
+    tm, fm = _i32(time_masks.to(dev)), _i32(freq_masks.to(dev))
+    num_mask = tm.shape[-2] if tm.numel() else 0
+    # converted temporaries must stay referenced until the launch has been issued
+    wp, wd = _i32(warp_p.to(dev)), _i32(warp_d.to(dev))
+    sx = _f32(src_x.to(dev)) if src_x is not None else None
+    call("afsl_specaug_views_f32", ptr(x), ptr(views), ptr(wp), ptr(wd), ptr(sx), ptr(lo), ptr(w), ptr(tm), ptr(fm),
+         int(num_mask), float(mask_value), n, int(set_size), f, t, int(views_mask), stream_ptr())
+    return views
+
+
+# ---------------------------------------------------------------------------------- majority vote
+@torch.no_grad()
+def eval_vote(pred, clip_ids, labels, posterior, seg_offsets, tie_strategy: str = "min_label"):
+    """Per task (#correct clips, #clips) of the multi-segment majority vote; all inputs packed [rows]."""
+    dev = pred.device
+    off = _i32(seg_offsets.to(dev))
+    e = off.numel() - 1
+    correct = torch.empty(e, device=dev, dtype=torch.int32)
+    clips = torch.empty(e, device=dev, dtype=torch.int32)
+    pr, ci, lb, po = _i32(pred), _i32(clip_ids.to(dev)), _i32(labels.to(dev)), _f32(posterior)
+    call("afsl_eval_vote_i32", ptr(pr), ptr(ci), ptr(lb), ptr(po), ptr(off), TIE_STRATEGIES.get(tie_strategy, 0),
+         ptr(correct), ptr(clips), e, stream_ptr())
+    return correct, clips
+
+
+def launch_count() -> int:
+    return _lib.launch_count()

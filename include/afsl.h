@@ -1,0 +1,164 @@
+/*
+ * libafsl - C ABI of the B200 (sm_100a) episodic prototypical-network head.
+ *
+ * The reference (magcil/audio-few-shot-learning) is pure Python/PyTorch and has
+ * no FFI layer; its boundary for this path is the Python object API used by
+ * loops/loops.py:40-49,76-79,268-277.  Each entry point below replaces the eager
+ * ATen op chain of one reference function (cited per function) and is bound from
+ * Python with ctypes (audio-few-shot-learning_b200/_lib.py); INTEGRATION.md shows
+ * the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every pointer is DEVICE memory of the current CUDA device, owned by the
+ *    caller, contiguous, 16-byte aligned; nullable arguments are marked [opt];
+ *  - floating point is IEEE fp32, labels/indices are int32;
+ *  - a leading episode dimension E batches independent episodes / tasks
+ *    (the reference always has E = 1);
+ *  - `stream` is a cudaStream_t passed as void*; the library never allocates,
+ *    frees, synchronises or touches any RNG; all calls are re-entrant;
+ *  - host-drawn randomness (mask offsets, warp control points, CPL keep masks)
+ *    enters as explicit arrays so results are bit-reproducible;
+ *  - return value: 0 on success, otherwise an AFSL_E* code, with a thread-local
+ *    message available from afsl_last_error().
+ */
+#ifndef AFSL_H
+#define AFSL_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFSL_OK 0
+#define AFSL_EINVAL 1   /* bad shape / null pointer / unsupported size */
+#define AFSL_ECUDA 2    /* a CUDA runtime call or launch failed */
+
+#define AFSL_ABI_VERSION 1
+
+/* tie strategies of calculate_majority_vote_accuracy (loops/loops.py:216-234) */
+#define AFSL_TIE_FIRST_SEEN 0     /* any other string, e.g. the config default "" */
+#define AFSL_TIE_MIN_LABEL 1      /* "min_label" */
+#define AFSL_TIE_MAX_POSTERIOR 2  /* "max_posterior" */
+
+int afsl_version(void);
+const char* afsl_last_error(void);
+/* number of kernel launches issued by this library in this process (bench bookkeeping) */
+long long afsl_launch_count(void);
+
+/* ---------------------------------------------------------------------------
+ * Prototypes: per-label mean of the support rows.
+ * Replaces compute_prototypes, models/util_functions.py:6-19.
+ *   support [E,Ns,D], labels [E,Ns] (values 0..W-1)  ->  protos [E,W,D]
+ * bwd: d_support[e,k,:] = d_protos[e,label[e,k],:] / count[e,label[e,k]]
+ * ------------------------------------------------------------------------- */
+int afsl_prototypes_fwd_f32(const float* support, const int32_t* labels, float* protos,
+                            int E, int Ns, int W, int D, void* stream);
+int afsl_prototypes_bwd_f32(const float* d_protos, const int32_t* labels, float* d_support,
+                            int E, int Ns, int W, int D, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Scores / prototypical loss given prototypes.
+ * Replaces l2_distance_to_prototypes (models/few_shot_classifier.py:108-116),
+ * FSL_Loss.forward (loops/loss.py:24-37) and the argmax/accuracy of
+ * evaluate_on_one_task (loops/loops.py:79) and loops/loops.py:271-272.
+ *   protos [E,W,D], queries [rows,D]; episode e owns query rows
+ *   q_offsets[e]..q_offsets[e+1] when q_offsets != NULL (ragged multi-segment
+ *   tasks), else rows e*Nq..(e+1)*Nq.
+ * outputs, each [opt]:
+ *   scores [rows,W] = -||q - p||_2 ; loss [E] = mean_i NLL(log_softmax(scores_i), y_i)
+ *   pred [rows] first-index argmax ; posterior [rows] = max score ; correct [E]
+ * q_labels [opt] is required for loss / correct.
+ * ------------------------------------------------------------------------- */
+int afsl_proto_scores_fwd_f32(const float* protos, const float* queries, const int32_t* q_labels,
+                              const int32_t* q_offsets, float* scores, float* loss, int32_t* pred,
+                              float* posterior, int32_t* correct, int E, int Nq, int W, int D,
+                              void* stream);
+/* gradient of sum_e d_loss[e]*loss[e] (+ sum d_scores*scores when d_scores != NULL)
+ * w.r.t. protos and queries.  d_protos / d_queries are overwritten. */
+int afsl_proto_scores_bwd_f32(const float* protos, const float* queries, const int32_t* q_labels,
+                              const int32_t* q_offsets, const float* d_loss, const float* d_scores,
+                              float* d_protos, float* d_queries, int E, int Nq, int W, int D,
+                              void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Fused head: prototypes + distances + log-softmax + NLL (+ argmax/accuracy)
+ * in one pass over the support and query embeddings.  Replaces the chain
+ * process_support_set -> forward -> FSL_Loss of loops/loops.py:40-42 and the
+ * evaluation chain of loops/loops.py:76-79.
+ * Outputs as above plus protos [E,W,D] [opt].
+ * bwd: d_support, d_queries of sum_e d_loss[e]*loss[e]; d_protos_extra [E,W,D]
+ * [opt] is an additional gradient arriving at the prototypes from another
+ * consumer (the CPL / angular branch, loops/loops.py:44-50).
+ * ------------------------------------------------------------------------- */
+int afsl_proto_head_fwd_f32(const float* support, const int32_t* s_labels, const float* queries,
+                            const int32_t* q_labels, const int32_t* q_offsets, float* protos,
+                            float* scores, float* loss, int32_t* pred, float* posterior,
+                            int32_t* correct, int E, int Ns, int Nq, int W, int D, void* stream);
+int afsl_proto_head_bwd_f32(const float* support, const int32_t* s_labels, const float* queries,
+                            const int32_t* q_labels, const int32_t* q_offsets, const float* d_loss,
+                            const float* d_protos_extra, float* d_support, float* d_queries,
+                            int E, int Ns, int Nq, int W, int D, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Row L2 normalisation x / max(||x||, eps).  Replaces F.normalize on the
+ * prototypes, loops/loops.py:47-48 (eps 1e-12).  rows = E*W.
+ * ------------------------------------------------------------------------- */
+int afsl_l2_normalize_fwd_f32(const float* x, float* y, int rows, int D, float eps, void* stream);
+int afsl_l2_normalize_bwd_f32(const float* x, const float* d_y, float* d_x, int rows, int D, float eps,
+                              void* stream);
+
+/* ---------------------------------------------------------------------------
+ * CPL loss.  Replaces CPL_Loss.forward / similarity_sampling, loops/loss.py:118-165,
+ * in its closed form: C = cos(P,Q)/T (each vector / max(norm,1e-8)),
+ *   loss[e] = 1/Nq^2 * sum_i [ LSE_{j in keep_i} C[y_i,j] - C[y_i,i] ].
+ * keep [E,Nq,ceil(Nq/32)] is the host-drawn bit mask (bit j of row i set when
+ * query j is a sampled negative of query i, or j == i); keep == NULL selects
+ * the deterministic case M >= per-class count: keep_ij = (j == i) | (y_j != y_i).
+ *   protos [E,W,D], queries [E,Nq,D], labels [E,Nq]
+ * bwd overwrites d_protos [E,W,D], d_queries [E,Nq,D] with the gradient of
+ * sum_e d_loss[e]*loss[e].
+ * ------------------------------------------------------------------------- */
+int afsl_cpl_fwd_f32(const float* protos, const float* queries, const int32_t* labels,
+                     const uint32_t* keep, float temperature, float* loss, int E, int Nq, int W,
+                     int D, void* stream);
+int afsl_cpl_bwd_f32(const float* protos, const float* queries, const int32_t* labels,
+                     const uint32_t* keep, float temperature, const float* d_loss, float* d_protos,
+                     float* d_queries, int E, int Nq, int W, int D, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * SpecAugment views.  Replaces SpecAugment.apply_augmentations and the three
+ * transforms, utils/augmentations.py:33-157.
+ *   x [N,1,F,T]  ->  views [4,N,1,F,T] = {copy, time-warp, time-mask, freq-mask}
+ * Samples are grouped in sets of `set_size` consecutive samples (one
+ * apply_augmentations call of the reference = one set); masks are shared by a
+ * set: time_masks/freq_masks [n_sets,num_mask,2] = (start, length) int32.
+ * warp_p, warp_d [N] int32 are the per-sample control point and displacement;
+ * src_x [N,T] [opt] overrides the in-kernel Hermite spline with host-computed
+ * normalised source coordinates.  row_lo [F] int32 / row_w [F] fp32 are the
+ * source row and blend weight of grid_sample's y axis (host-computed once from
+ * linspace(-1,1,F)).  views_mask selects which of the 4 views are written
+ * (bit v), so callers can skip the plain copy.
+ * ------------------------------------------------------------------------- */
+int afsl_specaug_views_f32(const float* x, float* views, const int32_t* warp_p, const int32_t* warp_d,
+                           const float* src_x, const int32_t* row_lo, const float* row_w,
+                           const int32_t* time_masks, const int32_t* freq_masks, int num_mask,
+                           float mask_value, int N, int set_size, int F, int T, int views_mask,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Multi-segment majority vote.  Replaces calculate_majority_vote_accuracy,
+ * loops/loops.py:169-247.  Task e owns segments seg_offsets[e]..seg_offsets[e+1]
+ * of pred / clip_ids / labels / posterior.  Outputs per task the number of
+ * clips whose voted label equals the label of the clip's first segment, and the
+ * number of distinct clips (accuracy = correct/clips, divided on the host in
+ * float64 like the reference).
+ * ------------------------------------------------------------------------- */
+int afsl_eval_vote_i32(const int32_t* pred, const int32_t* clip_ids, const int32_t* labels,
+                       const float* posterior, const int32_t* seg_offsets, int tie_strategy,
+                       int32_t* correct_clips, int32_t* n_clips, int E, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFSL_H */

@@ -35,5 +35,6 @@ def golden_names(prefix):
 
 
 def t(a, dtype=None):
-    x = torch.from_numpy(np.ascontiguousarray(a))
+    a = np.asarray(a)
+    x = torch.from_numpy(np.ascontiguousarray(a)).reshape(a.shape)     # ascontiguousarray promotes 0-d to 1-d
     return x.to(dtype) if dtype is not None else x

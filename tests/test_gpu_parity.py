@@ -1,0 +1,311 @@
+"""GPU parity: libafsl kernels (through the C ABI) vs the golden fixtures of the real reference
+and vs the CPU oracle on seeded inputs.
+
+Tolerances: the north star asks for losses, distances and gradients within 1e-5 relative in fp32
+and bit-exact masks / argmax labels / per-task accuracies.  rtol below is 1e-5 with an absolute
+floor scaled to the tensor magnitude (cancellation-free 1e-5 of max|ref|).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden, t
+from oracle import head as ohead
+from oracle import specaug as ospec
+from oracle import vote as ovote
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def close(got, ref, rtol=RTOL, scale=None):
+    """rtol > 0: relative check with an absolute floor of rtol * max|ref| (or rtol * scale);
+    rtol == 0: pure absolute check with atol = scale."""
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    if rtol == 0:
+        atol = float(scale)
+    else:
+        atol = rtol * float(ref.abs().max() if scale is None else scale)
+    torch.testing.assert_close(got, ref, rtol=rtol, atol=max(atol, 1e-12))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import afsl_b200.ops as ops
+    return ops
+
+
+def dev(a, dtype=None):
+    return t(a, dtype).cuda()
+
+
+# ------------------------------------------------------------------ head vs golden (reference outputs)
+@pytest.mark.parametrize("name", golden_names("head_"))
+def test_head_vs_reference(ops, name):
+    g = load_golden(name)
+    ways = int(g["prototypes"].shape[0])
+    s = dev(g["support"]).requires_grad_(True)
+    q = dev(g["query"]).requires_grad_(True)
+    sl, ql = dev(g["support_labels"]), dev(g["query_labels"])
+    # separate ops, as the reference API composes them
+    protos = ops.prototypes(s, sl)
+    assert protos.shape == (ways, s.shape[1])
+    scores = ops.l2_scores(q, protos)
+    loss = ops.proto_loss(protos, q, ql)
+    loss.backward()
+    close(protos, t(g["prototypes"]))
+    close(scores, t(g["scores"]))
+    close(loss, t(g["loss"]))
+    close(s.grad, t(g["d_support"]))
+    close(q.grad, t(g["d_query"]))
+    # fused head
+    s2 = dev(g["support"]).requires_grad_(True)
+    q2 = dev(g["query"]).requires_grad_(True)
+    loss2, protos2, correct = ops.proto_head(s2, sl, q2, ql, n_way=ways)
+    loss2.backward()
+    close(loss2, t(g["loss"]))
+    close(protos2, t(g["prototypes"]))
+    close(s2.grad, t(g["d_support"]))
+    close(q2.grad, t(g["d_query"]))
+    assert int(correct) == int(g["correct"])
+    # evaluation head: argmax labels, posterior, #correct
+    pred, post, corr, sc = ops.proto_eval(s2.detach(), sl, q2.detach(), ql, n_way=ways, want_scores=True)
+    assert torch.equal(pred.cpu().long(), t(g["pred"]))
+    assert int(corr) == int(g["correct"])
+    close(post, t(g["posterior"]))
+    close(sc, t(g["scores"]))
+
+
+def test_head_scores_gradient_path(ops):
+    """Gradient through the scores output (-cdist) alone, vs torch autograd on CPU."""
+    g = load_golden("head_5w5s5q_d64")
+    p = dev(g["prototypes"]).requires_grad_(True)
+    q = dev(g["query"]).requires_grad_(True)
+    w = torch.randn(25, 5, generator=torch.Generator().manual_seed(1))
+    (ops.l2_scores(q, p) * w.cuda()).sum().backward()
+    pc, qc = t(g["prototypes"]).requires_grad_(True), t(g["query"]).requires_grad_(True)
+    (ohead.l2_scores(qc, pc) * w).sum().backward()
+    close(p.grad, pc.grad)
+    close(q.grad, qc.grad)
+
+
+@pytest.mark.parametrize("ways,shots,nq,dim", [(5, 5, 5, 64), (5, 5, 5, 256), (20, 5, 5, 256), (5, 1, 15, 128), (3, 2, 4, 32)])
+def test_head_batched_vs_oracle(ops, ways, shots, nq, dim):
+    """E episodes at once == the oracle applied episode by episode (incl. extra prototype gradient)."""
+    e = 37
+    gen = torch.Generator().manual_seed(ways * 1000 + dim)
+    s = torch.randn(e, ways * shots, dim, generator=gen)
+    q = torch.randn(e, ways * nq, dim, generator=gen)
+    sl = torch.stack([torch.arange(ways).repeat_interleave(shots)[torch.randperm(ways * shots, generator=gen)] for _ in range(e)])
+    ql = torch.stack([torch.arange(ways).repeat_interleave(nq)[torch.randperm(ways * nq, generator=gen)] for _ in range(e)])
+    wl = torch.rand(e, generator=gen) + 0.5
+    wp = torch.randn(e, ways, dim, generator=gen) * 0.01
+    sg, qg = s.cuda().requires_grad_(True), q.cuda().requires_grad_(True)
+    loss, protos, correct = ops.proto_head(sg, sl.cuda(), qg, ql.cuda(), n_way=ways)
+    ((loss * wl.cuda()).sum() + (protos * wp.cuda()).sum()).backward()
+    for i in range(e):
+        sc, qc = s[i].clone().requires_grad_(True), q[i].clone().requires_grad_(True)
+        pr = ohead.prototypes(sc, sl[i])
+        lo = ohead.fsl_loss(pr, qc, ql[i])
+        (lo * wl[i] + (pr * wp[i]).sum()).backward()
+        close(loss[i], lo)
+        close(protos[i], pr)
+        close(sg.grad[i], sc.grad)
+        close(qg.grad[i], qc.grad)
+        assert int(correct[i]) == ohead.evaluate_task(ohead.l2_scores(qc, pr), ql[i])[0]
+
+
+def test_head_ragged_tasks(ops):
+    """Packed multi-segment tasks with CSR offsets: labels/posteriors/#correct per task."""
+    gen = torch.Generator().manual_seed(5)
+    ways, shots, dim, tasks = 5, 5, 64, 11
+    counts = torch.randint(1, 60, (tasks,), generator=gen)
+    off = torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)])
+    s = torch.randn(tasks, ways * shots, dim, generator=gen)
+    sl = torch.arange(ways).repeat_interleave(shots).expand(tasks, -1)
+    q = torch.randn(int(off[-1]), dim, generator=gen)
+    ql = torch.randint(0, ways, (int(off[-1]),), generator=gen)
+    pred, post, correct, scores = ops.proto_eval(s.cuda(), sl.cuda(), q.cuda(), ql.cuda(), n_way=ways,
+                                                 q_offsets=off.cuda(), want_scores=True)
+    for i in range(tasks):
+        a, b = int(off[i]), int(off[i + 1])
+        sc = ohead.l2_scores(q[a:b], ohead.prototypes(s[i], sl[i]))
+        po, pr = torch.max(sc, 1)
+        assert torch.equal(pred[a:b].cpu().long(), pr)
+        close(post[a:b], po)
+        close(scores[a:b], sc)
+        assert int(correct[i]) == int((pr == ql[a:b]).sum())
+
+
+def test_l2_normalize(ops):
+    gen = torch.Generator().manual_seed(2)
+    x = torch.randn(40, 256, generator=gen)
+    x[3] = 0                                   # clamped row
+    gy = torch.randn(40, 256, generator=gen)
+    xg = x.cuda().requires_grad_(True)
+    y = ops.l2_normalize(xg)
+    y.backward(gy.cuda())
+    xc = x.clone().requires_grad_(True)
+    yc = torch.nn.functional.normalize(xc, p=2.0, dim=1, eps=1e-12)
+    yc.backward(gy)
+    close(y, yc)
+    mask = torch.ones(40, dtype=torch.bool)
+    mask[3] = False
+    close(xg.grad[mask.cuda()], xc.grad[mask])
+
+
+# ------------------------------------------------------------------ CPL
+@pytest.mark.parametrize("name", golden_names("cpl_"))
+def test_cpl_vs_reference(ops, name):
+    g = load_golden(name)
+    p = dev(g["prototypes"]).requires_grad_(True)
+    q = dev(g["queries"]).requires_grad_(True)
+    labels = dev(g["labels"])
+    keep = t(g["keep"])
+    loss = ops.cpl_loss(p, q, labels, float(g["temperature"]), keep=keep)
+    loss.backward()
+    close(loss, t(g["loss"]))
+    close(p.grad, t(g["d_prototypes"]))
+    close(q.grad, t(g["d_queries"]))
+    per_class = int((t(g["labels"]) == 0).sum())
+    if int(g["m"]) >= per_class:               # deterministic case needs no mask
+        p2 = dev(g["prototypes"]).requires_grad_(True)
+        q2 = dev(g["queries"]).requires_grad_(True)
+        loss2 = ops.cpl_loss(p2, q2, labels, float(g["temperature"]))
+        loss2.backward()
+        close(loss2, t(g["loss"]))
+        close(q2.grad, t(g["d_queries"]))
+
+
+def test_cpl_batched_vs_oracle(ops):
+    e, ways, per, dim, m, temp = 19, 5, 6, 256, 3, 2.6981
+    gen = torch.Generator().manual_seed(77)
+    p = torch.randn(e, ways, dim, generator=gen)
+    q = torch.randn(e, ways * per, dim, generator=gen)
+    labels = torch.stack([torch.arange(ways).repeat_interleave(per)[torch.randperm(ways * per, generator=gen)] for _ in range(e)])
+    torch.manual_seed(31)
+    keep = torch.stack([ohead.cpl_draw_keep(labels[i], m) for i in range(e)])
+    wl = torch.rand(e, generator=gen) + 0.5
+    pg, qg = p.cuda().requires_grad_(True), q.cuda().requires_grad_(True)
+    loss = ops.cpl_loss(pg, qg, labels.cuda(), temp, keep=keep)
+    (loss * wl.cuda()).sum().backward()
+    for i in range(e):
+        pc, qc = p[i].clone().requires_grad_(True), q[i].clone().requires_grad_(True)
+        lo = ohead.cpl_loss_closed(pc, qc, labels[i], keep[i], temp)
+        (lo * wl[i]).backward()
+        close(loss[i], lo)
+        close(pg.grad[i], pc.grad)
+        close(qg.grad[i], qc.grad)
+
+
+# ------------------------------------------------------------------ SpecAugment
+def warp_atol(x):
+    """Bound for the in-kernel spline.  torch evaluates u**2, u**3 with a 1-ulp vectorised powf that
+    cannot be reproduced bit for bit, so the normalised source coordinate may differ by <= 2 ulp(1) =
+    2.4e-7, i.e. (T-1)/2 * 2.4e-7 pixels; bilinear output then moves by at most that times the largest
+    neighbour difference (<= 2 max|x|).  close() multiplies `scale` by rtol=0 -> use it as atol via rtol arg."""
+    t_len = x.shape[-1]
+    return 2.4e-7 * (t_len - 1) / 2 * 2 * float(x.abs().max())
+
+
+@pytest.mark.parametrize("name", golden_names("specaug_"))
+def test_specaug_vs_reference(ops, name):
+    g = load_golden(name)
+    x = dev(g["x"])
+    n = x.shape[0]
+    tm = t(g["time_masks"]).view(1, -1, 2)
+    fm = t(g["freq_masks"]).view(1, -1, 2)
+    value = float(g["cfg_mask_value"])
+    # (a) spline evaluated by the reference on the host -> only the bilinear blend is ours
+    v = ops.specaug_views(x, t(g["warp_p"]), t(g["warp_d"]), tm, fm, value, set_size=n, src_x=t(g["src_x"]))
+    assert torch.equal(v[0].cpu(), t(g["original"]))
+    assert torch.equal(v[2].cpu(), t(g["time_masked"]))          # masks: bit-exact
+    assert torch.equal(v[3].cpu(), t(g["freq_masked"]))
+    close(v[1], t(g["warped"]), rtol=1e-6)
+    # (b) spline evaluated in the kernel from the host-drawn control points
+    v2 = ops.specaug_views(x, t(g["warp_p"]), t(g["warp_d"]), tm, fm, value, set_size=n)
+    close(v2[1], t(g["warped"]), rtol=0, scale=warp_atol(x))
+    assert torch.equal(v2[2], v[2]) and torch.equal(v2[3], v[3])
+
+
+def test_specaug_batched_sets_vs_oracle(ops):
+    """Several 25-sample sets in one launch, each with its own masks, vs the oracle set by set."""
+    cfg = {"specaug_params": {"mask_param": 16, "W": 22, "num_mask": 2, "mask_value": 0.25, "p": 0.282}}
+    sets, n, t_len = 5, 25, 157
+    gen = torch.Generator().manual_seed(9)
+    x = torch.randn(sets * n, 1, 128, t_len, generator=gen)
+    torch.manual_seed(123)
+    np.random.seed(123)
+    params = [ospec.draw_params(n, t_len, cfg) for _ in range(sets)]
+    wp = torch.cat([p.warp_p for p in params])
+    wd = torch.cat([p.warp_d for p in params])
+    tm = torch.tensor([p.time_masks for p in params])
+    fm = torch.tensor([p.freq_masks for p in params])
+    v = ops.specaug_views(x.cuda(), wp, wd, tm, fm, 0.25, set_size=n)
+    for i, p in enumerate(params):
+        ref = ospec.apply(x[i * n:(i + 1) * n], p, 0.25)
+        sl = slice(i * n, (i + 1) * n)
+        assert torch.equal(v[0, sl].cpu(), ref[0])
+        assert torch.equal(v[2, sl].cpu(), ref[2])
+        assert torch.equal(v[3, sl].cpu(), ref[3])
+        close(v[1, sl], ref[1], rtol=0, scale=warp_atol(x))
+
+
+# ------------------------------------------------------------------ majority vote
+def test_vote_vs_reference(ops):
+    g = load_golden("vote_cases")
+    off = torch.from_numpy(g["offsets"])
+    for k, strat in enumerate(("", "min_label", "max_posterior")):
+        correct, clips = ops.eval_vote(dev(g["pred"]), dev(g["clip_ids"]), dev(g["labels"]), dev(g["posterior"]), off, strat)
+        acc = correct.cpu().double() / clips.cpu().double()
+        assert np.array_equal(acc.numpy(), g["accuracy"][:, k]), strat
+
+
+def test_vote_random_vs_oracle(ops):
+    rng = np.random.RandomState(1)
+    preds, ids, labs, posts, offs = [], [], [], [], [0]
+    for _ in range(300):
+        clips = rng.randint(1, 30)
+        seg = rng.randint(1, 12, size=clips)
+        cid = np.repeat(rng.permutation(clips) * 3, seg)         # ids need not be 0..C-1 or sorted
+        if rng.rand() < 0.3:
+            cid = cid[rng.permutation(cid.size)]
+        true = rng.randint(0, 5, size=clips * 3)[cid]
+        pred = rng.randint(0, 4, size=cid.size)
+        post = np.round(-rng.rand(cid.size) * 4, 1).astype(np.float32)
+        preds.append(pred); ids.append(cid); labs.append(true); posts.append(post); offs.append(offs[-1] + cid.size)
+    P, I, L, Q = map(np.concatenate, (preds, ids, labs, posts))
+    for strat in ("", "min_label", "max_posterior"):
+        correct, clips = ops.eval_vote(dev(P), dev(I), dev(L), dev(Q), torch.tensor(offs), strat)
+        got = (correct.cpu().double() / clips.cpu().double()).numpy()
+        want = np.array([ovote.majority_vote_accuracy(preds[i], ids[i], labs[i], posts[i], strat) for i in range(300)])
+        assert np.array_equal(got, want), strat
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_full_size_properties(ops):
+    """BASELINE-scale batch (E = 16384 episodes, 5w5s5q, D = 256): size-independent properties."""
+    e, ways, shots, nq, dim = 16384, 5, 5, 5, 256
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    s = torch.randn(e, ways * shots, dim, device="cuda", generator=gen)
+    q = torch.randn(e, ways * nq, dim, device="cuda", generator=gen)
+    sl = torch.arange(ways, device="cuda").repeat_interleave(shots).expand(e, -1).contiguous()
+    ql = torch.arange(ways, device="cuda").repeat_interleave(nq).expand(e, -1).contiguous()
+    loss, protos, correct = ops.proto_head(s, sl, q, ql, n_way=ways)
+    # (1) prototypes are the class means: linear in the support set
+    close(protos, s.view(e, ways, shots, dim).mean(2), rtol=1e-5)
+    # (2) permuting episodes permutes the outputs (no cross-episode leakage), bit-exactly
+    perm = torch.randperm(e, device="cuda")
+    loss_p, _, correct_p = ops.proto_head(s[perm].contiguous(), sl, q[perm].contiguous(), ql, n_way=ways)
+    assert torch.equal(loss_p, loss[perm]) and torch.equal(correct_p, correct[perm])
+    # (3) a query placed exactly on its own prototype is classified correctly with posterior 0
+    q2 = protos[:, ql[0]].contiguous()
+    pred, post, corr, _ = ops.proto_eval(s, sl, q2, ql, n_way=ways)
+    assert torch.equal(pred.view(e, -1).long(), ql) and bool((post == 0).all()) and bool((corr == ways * nq).all())
+    # (4) translation invariance of distances: shifting support and queries together leaves the loss unchanged
+    shift = torch.randn(e, 1, dim, device="cuda", generator=gen)
+    loss_s, _, _ = ops.proto_head(s + shift, sl, q + shift, ql, n_way=ways)
+    close(loss_s, loss, rtol=1e-4)
+    # (5) idempotence / determinism
+    loss_again, _, _ = ops.proto_head(s, sl, q, ql, n_way=ways)
+    assert torch.equal(loss_again, loss)
