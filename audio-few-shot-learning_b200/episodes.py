@@ -1,0 +1,200 @@
+"""Batched episode steps: E independent episodes per launch.
+
+The reference runs one episode per optimizer step (loops/loops.py:26-61) and one task per
+evaluation call (:66-81, :250-277).  Episodes are independent (prototypes, losses, BatchNorm
+batch statistics and votes are all per episode), so this module runs E of them at once:
+
+* ``EpisodeBatch``      - E episodes of spectrograms + labels, on the host (pinned) or the device;
+* ``EpisodeRunner``     - ``train_step`` (SpecAugment views -> encoder -> view fusion -> fused
+                          prototype head + CPL/angular loss -> backward -> optimizer step) and
+                          ``eval_step`` (single-segment accuracy or multi-segment vote);
+  per-episode arithmetic equals the reference's; the optimizer step uses the mean loss over the E
+  episodes (E = 1 reproduces the reference's one-step-per-episode schedule exactly).
+"""
+from __future__ import annotations
+
+import random
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .loops.loss import draw_keep_reference, draw_keep_vectorised
+from .utils.augmentations import SpecAugment
+
+
+@dataclass
+class EpisodeBatch:
+    support: torch.Tensor          # [E, Ns, 1, F, T] fp32
+    support_labels: torch.Tensor   # [E, Ns] int64, values 0..W-1
+    query: torch.Tensor            # [E, Nq, 1, F, T]
+    query_labels: torch.Tensor     # [E, Nq]
+    n_way: int
+
+    @property
+    def episodes(self) -> int:
+        return self.support.shape[0]
+
+    def pin(self) -> "EpisodeBatch":
+        return EpisodeBatch(self.support.pin_memory(), self.support_labels.pin_memory(), self.query.pin_memory(),
+                            self.query_labels.pin_memory(), self.n_way)
+
+    def to(self, device, non_blocking: bool = True) -> "EpisodeBatch":
+        mv = lambda t: t.to(device, non_blocking=non_blocking)
+        return EpisodeBatch(mv(self.support), mv(self.support_labels), mv(self.query), mv(self.query_labels), self.n_way)
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.support, self.support_labels, self.query, self.query_labels))
+
+
+def synthetic_batch(episodes: int, n_way: int, k_shot: int, k_query: int, t_len: int, seed: int = 1234,
+                    device: str = "cpu", mels: int = 128) -> EpisodeBatch:
+    """N(0,1) spectrograms of the dataset's shape with labels arange(W).repeat_interleave(K)."""
+    gen = torch.Generator(device=device).manual_seed(seed)
+    ns, nq = n_way * k_shot, n_way * k_query
+    support = torch.randn(episodes, ns, 1, mels, t_len, generator=gen, device=device)
+    query = torch.randn(episodes, nq, 1, mels, t_len, generator=gen, device=device)
+    sl = torch.arange(n_way, device=device).repeat_interleave(k_shot).expand(episodes, -1).contiguous()
+    ql = torch.arange(n_way, device=device).repeat_interleave(k_query).expand(episodes, -1).contiguous()
+    return EpisodeBatch(support, sl, query, ql, n_way)
+
+
+class EpisodeRunner:
+    """Runs batches of episodes through a few-shot model according to ``experiment_config``.
+
+    Config keys honoured (same meaning as src/train_test.py:47-80 and loops/loops.py:19-50):
+    ``use_contrastive``, ``loss.l_param``, ``loss.cpl.{use,m_param,t_param}``,
+    ``loss.angular.{use,angle,prototypes_as_anchors}``, ``project_prototypes`` (overrides
+    ``normalize_prototypes``), ``train_query_augmentations``, ``specaug_params.*``.
+    ``replay_reference_rng`` makes every host-side draw (SpecAugment parameters, view shuffle, CPL
+    negatives) follow the reference's generators and order episode by episode.
+    """
+
+    def __init__(self, model, experiment_config: dict, optimizer: Optional[torch.optim.Optimizer] = None,
+                 replay_reference_rng: bool = False):
+        self.model = model
+        self.cfg = experiment_config
+        self.optimizer = optimizer
+        self.replay = replay_reference_rng
+        self.specaug = SpecAugment(experiment_config) if experiment_config["specaug_params"]["use"] else None
+        self.concat_views = type(model).__name__ == "ContrastivePrototypicalNetworksWithoutAttention"
+        self.grad_sync = None          # set by parallel.EpisodeDataParallel: all-reduce of the flat gradient
+
+    # ------------------------------------------------------------------ views
+    def _views(self, spec: torch.Tensor, augment: bool) -> List[torch.Tensor]:
+        """[E,N,1,F,T] -> list of V tensors [E,N,1,F,T] (datasets/batch_creation.py:111-121)."""
+        if self.specaug is None or not augment:
+            return [spec]
+        e, n = spec.shape[:2]
+        params = self.specaug.draw_batch(e, n, spec.shape[-1], replay_reference_rng=self.replay)
+        views = self.specaug.apply_batch(spec.reshape(e * n, *spec.shape[2:]), params, exact_spline=self.replay)
+        return [views[v].view(e, n, *spec.shape[2:]) for v in range(4)]
+
+    # ------------------------------------------------------------------ training
+    def train_step(self, batch: EpisodeBatch) -> Dict[str, torch.Tensor]:
+        """One optimizer step on E episodes.  Returns per-episode losses (device tensors)."""
+        cfg, model = self.cfg, self.model
+        model.train()
+        batch = batch.to(next(model.parameters()).device)
+        model.n_way = batch.n_way
+        s_views = self._views(batch.support, True)
+        q_views = self._views(batch.query, cfg["train_query_augmentations"])
+        sl, ql = batch.support_labels, batch.query_labels
+        if self.concat_views:                                   # loops/loops.py:33-37
+            sl, ql = sl.repeat(1, len(s_views)), ql.repeat(1, len(q_views))
+        if self.optimizer is not None:
+            self.optimizer.zero_grad(set_to_none=True)
+        # support + query features, then the fused head: prototypes + FSL loss in one kernel
+        support_features = model.compute_features(s_views)
+        query_features = model(q_views)
+        fsl, protos, _ = ops.proto_head(support_features, sl, query_features, ql, n_way=batch.n_way)
+        model.prototypes, model.support_features, model.support_labels = protos, support_features, sl
+        out = {"fsl_loss": fsl}
+        total = fsl
+        if cfg["use_contrastive"]:
+            project = cfg["project_prototypes"]
+            cfeats, cprotos = self._contrastive_forward_batched(project)
+            if not project and cfg["normalize_prototypes"]:     # loops/loops.py:45-48
+                cprotos = ops.l2_normalize(cprotos, eps=1e-12)
+            extra = self._extra_loss(cprotos, cfeats, ql, batch.n_way)
+            total = fsl + cfg["loss"]["l_param"] * extra
+            out["cpl_loss"] = extra
+        out["loss"] = total
+        total.mean().backward()
+        if self.grad_sync is not None:
+            self.grad_sync()
+        if self.optimizer is not None:
+            self.optimizer.step()
+        return {k: v.detach() for k, v in out.items()}
+
+    def _contrastive_forward_batched(self, project: bool):
+        """contrastive_forward for E episodes with an independent view permutation per episode.
+
+        The reference shuffles views 1..V-1 with ``random.shuffle`` once per episode
+        (prototypical.py:66-70).  Here the E permutations are drawn up front (same Python ``random``
+        stream, one ``shuffle`` of a (V-1)-list per episode) and applied with one gather."""
+        model = self.model
+        if not hasattr(model, "attention_model"):
+            return model.contrastive_forward(project)
+        feats = torch.stack(model.query_feature_list, dim=-2)            # [E, N, V, D]
+        e, n, v, d = feats.shape
+        perms = []
+        for _ in range(e):
+            rest = list(range(1, v))
+            random.shuffle(rest)
+            perms.append([0] + rest)
+        idx = torch.tensor(perms, device=feats.device).view(e, 1, v, 1).expand(e, n, v, d)
+        shuffled = model.attention_model(torch.gather(feats, 2, idx))
+        projected = model.projection_head(shuffled)
+        protos = model.projection_head(model.prototypes) if project else model.prototypes
+        return projected, protos
+
+    def _extra_loss(self, protos, feats, labels, n_way):
+        lc = self.cfg["loss"]
+        if lc["cpl"]["use"]:
+            m, temp = int(lc["cpl"]["m_param"]), float(lc["cpl"]["t_param"])
+            if self.replay:
+                keep = torch.stack([draw_keep_reference(row, m) for row in labels.cpu()])
+            else:
+                per_class = labels.shape[1] // n_way          # balanced synthetic / sampled episodes
+                keep = None if m >= per_class else draw_keep_vectorised(labels, m, n_way)
+            return ops.cpl_loss(protos, feats, labels, temp, keep=keep)
+        if lc["angular"]["use"]:
+            return ops.angular_loss(protos, feats, labels, float(lc["angular"]["angle"]), 40.0,
+                                    bool(lc["angular"]["prototypes_as_anchors"]), False)
+        raise ValueError("use_contrastive is set but neither loss.cpl.use nor loss.angular.use")
+
+    # ------------------------------------------------------------------ evaluation
+    @torch.no_grad()
+    def eval_step(self, batch: EpisodeBatch, augment_query: bool = False, clip_ids: Optional[torch.Tensor] = None,
+                  seg_offsets: Optional[torch.Tensor] = None, tie_strategy: str = "") -> np.ndarray:
+        """Per-task accuracies (float64 numpy, ``correct/total`` like loops/loops.py:114,277).
+
+        Single-segment: ``batch.query`` is [E,Nq,...].  Multi-segment: ``batch.query`` is
+        [1,rows,...] packed over tasks, with ``seg_offsets`` [E+1] and ``clip_ids`` [rows]."""
+        model = self.model
+        model.eval()
+        batch = batch.to(next(model.parameters()).device)
+        model.n_way = batch.n_way
+        s_views = self._views(batch.support, True)
+        sl = batch.support_labels
+        if self.concat_views:
+            sl = sl.repeat(1, len(s_views))
+        support_features = model.compute_features(s_views)
+        if seg_offsets is None:
+            q_views = self._views(batch.query, augment_query)
+            ql = batch.query_labels.repeat(1, len(q_views)) if self.concat_views else batch.query_labels
+            feats = model(q_views)
+            _, _, correct, _ = ops.proto_eval(support_features, sl, feats, ql, n_way=batch.n_way)
+            return correct.cpu().numpy().astype(np.float64) / ql.shape[1]
+        q_views = self._views(batch.query, augment_query)
+        feats = model(q_views)[0]                                # packed rows
+        ql = batch.query_labels[0]
+        max_rows = int((seg_offsets[1:] - seg_offsets[:-1]).max())
+        pred, post, _, _ = ops.proto_eval(support_features, sl, feats, ql, n_way=batch.n_way,
+                                          q_offsets=seg_offsets.to(feats.device), max_rows=max_rows)
+        correct, clips = ops.eval_vote(pred, clip_ids, ql, post, seg_offsets, tie_strategy)
+        return correct.cpu().numpy().astype(np.float64) / clips.cpu().numpy().astype(np.float64)

@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Benchmark of the episodic prototypical-network hot path (BASELINE.json metric: episodes/s, train fwd+bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--episodes E] [--impl b200|reference]
+
+Workload = BASELINE.json configs[1]: Hybrid encoder + self-attention view fusion + CPL loss
+(M=5, T=9.2361, l=2.022308) with SpecAugment support and query views, FSD2018-shaped 5-way 5-shot
+5-query episodes of [1,128,157] synthetic N(0,1) log-mel spectrograms, random-init weights.
+A step = one optimizer step over E episodes per GPU (SpecAugment views -> encoder -> view fusion ->
+fused prototype head + CPL -> backward -> Adam).  ``value`` is measured with inputs resident in HBM,
+``e2e`` through EpisodeRunner.train_step with pinned HOST inputs (H2D copy of the spectrograms and D2H
+read of the loss inside the timed region).  N > 1: one process per GPU (torchrun), episodes sharded
+across ranks (weak scaling), one NCCL all-reduce of the flat gradient per step.
+
+``--impl reference`` times the reference's algorithm on the host cores: the CPU oracle port
+(oracle/episode.py - a torch-CPU restatement of loops/loops.py:26-61 pinned to the real reference by
+tests/golden), one episode per optimizer step exactly as the reference does, all host threads.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOAD = ("config2: Hybrid encoder + self-attention view fusion + CPL(M=5,T=9.2361,l=2.022308) + SpecAugment "
+            "support/query views, FSD2018-shaped 5-way 5-shot 5-query, spectrograms [1,128,157]")
+N_WAY, K_SHOT, K_QUERY, T_LEN, MELS = 5, 5, 5, 157, 128
+
+EXPERIMENT_CONFIG = {
+    "encoder_name": "Hybrid", "use_attention": True, "use_contrastive": True, "input_type": "spec",
+    "train_query_augmentations": True, "project_prototypes": True, "normalize_prototypes": True,
+    "loss": {"l_param": 2.022308, "cpl": {"use": True, "m_param": 5, "t_param": 9.2361},
+             "angular": {"use": False, "angle": 0, "prototypes_as_anchors": True}},
+    "specaug_params": {"use": True, "mask_param": 16, "W": 22, "num_mask": 1, "mask_value": 0, "p": 0.282},
+    "lr": 0.0007,
+}
+MODEL_CONFIG = {
+    "Hybrid": {"in_channels": 1, "seq_layers": 1, "seq_type": "RNN", "bidirectional": False, "hidden_channels": 64,
+               "pool_dim": [3, 3], "out_dim": 64},
+    "Attention": {"embed_dim": 64, "num_heads": 1, "ffn_dim": 256, "dropout": 0.1},
+    "Projection": {"input_dim": 256, "hidden_dim": 512, "output_dim": 256},
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc = index, None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        self.summary = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[2:6]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            self.summary = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                            "samples": len(sm)}
+
+
+def build_model(device):
+    from afsl_b200.models.main_modules import EncoderModule, ProjectionHead, SelfAttention
+    from afsl_b200.models.prototypical import ContrastivePrototypicalNetworks
+    torch.manual_seed(1234)
+    model = ContrastivePrototypicalNetworks(EncoderModule(EXPERIMENT_CONFIG, MODEL_CONFIG), SelfAttention(MODEL_CONFIG),
+                                            ProjectionHead(MODEL_CONFIG)).to(device)
+    return model
+
+
+def kernel_rooflines(device, peak_gbs, episodes):
+    """CUDA-event timing of the custom kernels alone, on buffers larger than L2, vs their algorithmic bytes."""
+    import afsl_b200.ops as ops
+    from afsl_b200.utils.augmentations import SpecAugment
+    out = {}
+
+    def timed(fn, reps=10):
+        fn(); fn()
+        torch.cuda.synchronize()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(reps):
+            fn()
+        end.record()
+        torch.cuda.synchronize()
+        return start.elapsed_time(end) / reps * 1e-3
+
+    # SpecAugment: sets of 25 samples, 4 views written; algorithmic bytes 4*N*F*T*(1+V)   
+    sets = max(2 * episodes, 64)
+    n = sets * 25
+    x = torch.randn(n, 1, MELS, T_LEN, device=device)
+    aug = SpecAugment(EXPERIMENT_CONFIG)
+    params = aug.draw_batch(sets, 25, T_LEN, replay_reference_rng=False)
+    views = torch.empty(4, n, 1, MELS, T_LEN, device=device)
+    sec = timed(lambda: aug.apply_batch(x, params, out=views))
+    bytes_ = 4.0 * n * MELS * T_LEN * 5
+    out["specaug_views"] = {"bound": "hbm", "achieved": bytes_ / sec / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                            "frac": bytes_ / sec / 1e9 / peak_gbs, "traffic": None, "ms": sec * 1e3,
+                            "units": f"{sets} sets x 25 samples", "bytes_per_launch": bytes_}
+    del x, views
+    # fused head fwd+bwd, D=256, 5w5s5q: 4*D*[3*(Ns+Nq)+W] + 4*(Ns+Nq) + 4 B/episode (158.9 KB)
+    e, d, ns, nq = 16384, 256, 25, 25
+    s = torch.randn(e, ns, d, device=device, requires_grad=True)
+    q = torch.randn(e, nq, d, device=device, requires_grad=True)
+    sl = torch.arange(N_WAY, device=device).repeat_interleave(K_SHOT).expand(e, -1).contiguous()
+    ql = torch.arange(N_WAY, device=device).repeat_interleave(K_QUERY).expand(e, -1).contiguous()
+    w = torch.full((e,), 1.0 / e, device=device)
+
+    def head():
+        loss, _, _ = ops.proto_head(s, sl, q, ql, n_way=N_WAY)
+        s.grad = q.grad = None
+        loss.backward(w)
+    sec = timed(head)
+    per_ep = 4.0 * d * (3 * (ns + nq) + N_WAY) + 4 * (ns + nq) + 4
+    out["proto_head_fwd_bwd"] = {"bound": "hbm", "achieved": per_ep * e / sec / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                                 "frac": per_ep * e / sec / 1e9 / peak_gbs, "traffic": None, "ms": sec * 1e3,
+                                 "units": f"{e} episodes", "bytes_per_launch": per_ep * e}
+    # CPL fwd+bwd, Dp=256, Nq=25: 4*Dp*3*(Nq+W) + Nq^2/8 B/episode (92.2 KB)
+    p = torch.randn(e, N_WAY, d, device=device, requires_grad=True)
+
+    def cpl():
+        loss = ops.cpl_loss(p, q, ql, 9.2361)
+        p.grad = q.grad = None
+        loss.backward(w)
+    sec = timed(cpl)
+    per_ep = 4.0 * d * 3 * (nq + N_WAY) + nq * nq / 8
+    out["cpl_fwd_bwd"] = {"bound": "hbm", "achieved": per_ep * e / sec / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                          "frac": per_ep * e / sec / 1e9 / peak_gbs, "traffic": None, "ms": sec * 1e3,
+                          "units": f"{e} episodes", "bytes_per_launch": per_ep * e}
+    # evaluation head, 5w5s D=256: 4*D*(Ns+Nq) + 4*(Ns+Nq) + 8 B/task (51.4 KB)
+    sd, qd = s.detach(), q.detach()
+    sec = timed(lambda: ops.proto_eval(sd, sl, qd, ql, n_way=N_WAY))
+    per_task = 4.0 * d * (ns + nq) + 4 * (ns + nq) + 8
+    out["eval_head"] = {"bound": "hbm", "achieved": per_task * e / sec / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                        "frac": per_task * e / sec / 1e9 / peak_gbs, "traffic": None, "ms": sec * 1e3,
+                        "units": f"{e} tasks", "tasks_per_s": e / sec, "bytes_per_launch": per_task * e}
+    return out
+
+
+def cpu_episode_runner(threads):
+    """The CPU oracle port of one reference training episode (config 2)."""
+    from oracle import episode as oep
+    from oracle import modules as om
+    torch.set_num_threads(threads)
+    torch.manual_seed(1234)
+    net = om.FusedViewsNet(om.ViewEncoder(om.build_encoder("Hybrid", T_LEN)), om.ViewFusion(64, 1, 256, 0.1),
+                           om.Projection(256, 512, 256))
+    opt = torch.optim.Adam(net.parameters(), lr=EXPERIMENT_CONFIG["lr"])
+    gen = torch.Generator().manual_seed(99)
+    sl = torch.arange(N_WAY).repeat_interleave(K_SHOT)
+    ql = torch.arange(N_WAY).repeat_interleave(K_QUERY)
+
+    def one_episode():
+        s = torch.randn(N_WAY * K_SHOT, 1, MELS, T_LEN, generator=gen)
+        q = torch.randn(N_WAY * K_QUERY, 1, MELS, T_LEN, generator=gen)
+        return oep.train_step(net, opt, s, sl, q, ql, EXPERIMENT_CONFIG)
+    return one_episode
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    step = cpu_episode_runner(threads)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = args.steps / dt
+    line = {"impl": "reference", "metric": "episodes/sec (train fwd+bwd)", "value": value, "unit": "episodes/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "episodes_per_step": 1, "device": "cpu"},
+            "cpu_baseline": {"value": value, "unit": "episodes/s", "cores": threads, "kind": "port",
+                             "sample": f"{args.steps} episodes, one optimizer step each (reference schedule), "
+                                       "oracle/episode.py torch-CPU port of loops/loops.py:26-61"},
+            "e2e": {"value": value, "unit": "episodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    import afsl_b200.ops as ops
+    from afsl_b200 import parallel
+    from afsl_b200.episodes import EpisodeRunner, synthetic_batch
+
+    rank, world, local = parallel.init_from_env("nccl")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    torch.backends.cudnn.benchmark = True
+    pk, pk_src = peaks()
+    E = args.episodes
+
+    model = build_model(device)
+    opt = torch.optim.Adam(model.parameters(), lr=EXPERIMENT_CONFIG["lr"])
+    runner = EpisodeRunner(model, EXPERIMENT_CONFIG, opt, replay_reference_rng=False)
+    dp = parallel.EpisodeDataParallel(model)
+    runner.grad_sync = dp.sync_gradients if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # rotate over several distinct input batches; per-step activations (GBs) exceed the 126 MB L2 anyway
+    n_rot = 3
+    host = [synthetic_batch(E, N_WAY, K_SHOT, K_QUERY, T_LEN, seed=1234 + rank * 100 + i).pin() for i in range(n_rot)]
+    resident = [b.to(device) for b in host]
+    torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for i in range(args.warmup):
+        runner.train_step(resident[i % n_rot])
+    barrier()
+    launches0 = ops.launch_count()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        start.record()
+        for i in range(args.steps):
+            runner.train_step(resident[i % n_rot])
+        end.record()
+        barrier()
+    ms = start.elapsed_time(end)
+    launches = ops.launch_count() - launches0
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * E * args.steps / (ms * 1e-3)
+
+    # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the loss
+    del resident
+    for i in range(max(1, args.warmup // 2)):
+        float(runner.train_step(host[i % n_rot])["loss"].mean().item())
+    barrier()
+    t0 = time.perf_counter()
+    start.record()
+    for i in range(args.steps):
+        out = runner.train_step(host[i % n_rot])
+        loss_host = out["loss"].cpu()              # D2H of the per-episode losses
+    end.record()
+    barrier()
+    e2e_ms = start.elapsed_time(end)
+    t = torch.tensor([e2e_ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = world * E * args.steps / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    roofs = kernel_rooflines(device, pk["hbm_gbs"], E) if not args.skip_kernels else {}
+    cpu = None
+    if world == 1 and not args.skip_cpu:
+        threads = os.cpu_count() or 1
+        step = cpu_episode_runner(threads)
+        step()
+        t0 = time.perf_counter()
+        n_cpu = 4
+        for _ in range(n_cpu):
+            step()
+        dt = time.perf_counter() - t0
+        cpu = {"value": n_cpu / dt, "unit": "episodes/s", "cores": threads, "kind": "port",
+               "sample": f"{n_cpu} episodes after 1 warm-up, one optimizer step each; oracle/episode.py (torch-CPU port "
+                         "of loops/loops.py:26-61, pinned to the reference by tests/golden)"}
+    line = {
+        "metric": "episodes/sec (train fwd+bwd)", "value": value, "unit": "episodes/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "episodes_per_step_per_gpu": E, "global_episodes_per_step": world * E,
+                   "parallelism": f"episode-sharded dp{world}", "cudnn_conv_tf32": torch.backends.cudnn.allow_tf32,
+                   "l2": f"inputs rotate over {n_rot} batches; per-step activations exceed the 126 MB L2",
+                   "peaks": pk_src},
+        "e2e": {"value": e2e_value, "unit": "episodes/s", "h2d_bytes_per_step": host[0].nbytes(),
+                "d2h_bytes_per_step": int(loss_host.numel() * 4), "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary,
+        "roofline": roofs.get("specaug_views"),
+        "kernels": roofs,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--episodes", type=int, default=16, help="episodes per step per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-kernels", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback "
+                             "(use --impl reference for the CPU oracle port)")
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
