@@ -29,6 +29,8 @@ SIGNATURES = {
     "afsl_l2_normalize_bwd_f32": [_P, _P, _P, _I, _I, _F, _P],
     "afsl_cpl_fwd_f32": [_P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _P],
     "afsl_cpl_bwd_f32": [_P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _I, _P],
+    "afsl_angular_fwd_f32": [_P, _P, _P, _F, _F, _I, _I, _P, _I, _I, _I, _I, _P],
+    "afsl_angular_bwd_f32": [_P, _P, _P, _F, _F, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P],
     "afsl_specaug_views_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _I, _I, _I, _I, _I, _P],
     "afsl_eval_vote_i32": [_P, _P, _P, _P, _P, _I, _P, _P, _I, _P],
 }

@@ -1,0 +1,333 @@
+// Angular loss with angular mining, forward and backward, batched over episodes.
+//
+// Reference: AngularLossClass.forward, loops/loss.py:48-97, which delegates to
+// pytorch_metric_learning: AngularMiner(angle) keeps the triplets (a,p,n) with
+// atan(|a^-p^| / (2|n^-c^|)) > angle (c = (a+p)/2, every vector L2-normalised, F.pairwise_distance
+// adds eps = 1e-6 to the difference), and AngularLoss(alpha = 40 deg) evaluates
+//   log(1 + sum_k exp(4 tan^2(alpha) (a^+p^).x_k - 2 (1+tan^2(alpha)) a^.p^))
+// over (anchor, positive) pairs against all other-label reference rows, averaged over pairs.
+// PML is not vendored by the reference and not installed here: parity for this kernel is against
+// the restatement in oracle/angular.py (see its header), not against PML itself.
+//
+// The reference materialises a [pairs x refs] matrix (4e8 B per episode at angle 0).  Here the
+// episode's W prototypes and Nq queries are pooled into N = W+Nq normalised rows; everything the
+// miner and the loss need is a function of their N x N Gram matrix, the raw norms and the label
+// vector, so one CTA per episode keeps it all in shared memory:
+//   anchors branch (loss.py:68-83): pairs (a in P, p in Q, y_p = a) weighted m_a * w_p, negatives
+//     k in Q weighted w_k, where m_a = #mined triplets of anchor a and w_q = #times q was mined as
+//     positive or negative (the reference duplicates rows instead of weighting them);
+//   pooled branch (loss.py:84-96): pairs (a,p) in P u Q with equal label weighted by their number
+//     of mined negatives; negatives are all other-label rows with weight 1.
+#include "afsl_common.cuh"
+
+namespace afsl {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / kWarp;
+constexpr float kNormEps = 1e-12f;   // F.normalize
+constexpr float kPairEps = 1e-6f;    // F.pairwise_distance
+
+struct AngParams {
+  const float* protos;    // [E,W,D]
+  const float* queries;   // [E,Nq,D]
+  const int32_t* labels;  // [E,Nq]
+  float miner_angle;      // radians
+  float t2;               // tan^2(alpha)
+  int anchors, normalize_ref;
+  float* loss;            // [E]
+  const float* d_loss;    // [E]      (backward)
+  float* d_protos;        // [E,W,D]
+  float* d_queries;       // [E,Nq,D]
+  int E, Nq, W, D;
+};
+
+struct Smem {
+  float* gram;   // [N*N]
+  float* xhat;   // [N*(D+1)]   union with dgram/cnt (dead after the Gram matrix is built)
+  float* dgram;  // [N*N]
+  int* cnt;      // [N*N] mined negatives per (anchor, positive) pair
+  float* norm;   // [N] raw norms
+  float* csum;   // [N] component sum of the normalised row
+  float* nu;     // [N] negative weight
+  float* drho;   // [N]
+  float* red;    // [2*kWarps]
+  int* lab;      // [N]
+  int* wneg;     // [N] times mined as negative
+  int* manc;     // [N] mined triplets per anchor
+};
+
+inline size_t smem_words(int N, int D) {
+  const size_t uni = (size_t)N * (D + 1) > 2 * (size_t)N * N ? (size_t)N * (D + 1) : 2 * (size_t)N * N;
+  return (size_t)N * N + uni + 7 * (size_t)N + 2 * kWarps + 8;
+}
+
+__device__ inline Smem carve(float* b, int N, int D) {
+  Smem s;
+  const size_t uni = (size_t)N * (D + 1) > 2 * (size_t)N * N ? (size_t)N * (D + 1) : 2 * (size_t)N * N;
+  s.gram = b; b += (size_t)N * N;
+  s.xhat = b; s.dgram = b; s.cnt = reinterpret_cast<int*>(b + (size_t)N * N); b += uni;
+  s.norm = b; b += N;
+  s.csum = b; b += N;
+  s.nu = b; b += N;
+  s.drho = b; b += N;
+  s.red = b; b += 2 * kWarps;
+  s.lab = reinterpret_cast<int*>(b); b += N;
+  s.wneg = reinterpret_cast<int*>(b); b += N;
+  s.manc = reinterpret_cast<int*>(b);
+  return s;
+}
+
+__device__ __forceinline__ const float* row_ptr(const AngParams& p, int e, int i) {
+  return i < p.W ? p.protos + ((size_t)e * p.W + i) * p.D : p.queries + ((size_t)e * p.Nq + (i - p.W)) * p.D;
+}
+
+__device__ __forceinline__ bool is_pair(const AngParams& p, const int* lab, int a, int q) {
+  if (p.anchors) return a < p.W && q >= p.W && lab[q] == a;
+  return a != q && lab[a] == lab[q];
+}
+__device__ __forceinline__ bool is_negative(const AngParams& p, const int* lab, int a, int k) {
+  if (p.anchors) return k >= p.W && lab[k] != lab[a];
+  return lab[k] != lab[a];
+}
+
+// per pair: max and normalised sum of the masked, weighted log-sum-exp with the appended zero
+__device__ __forceinline__ void pair_lse(const AngParams& p, const Smem& s, int N, int a, int q, float& m, float& tot) {
+  const float base = -2.f * (1.f + p.t2) * s.gram[a * N + q];
+  float mx = 0.f;
+  for (int k = 0; k < N; ++k) {
+    if (!is_negative(p, s.lab, a, k) || s.nu[k] <= 0.f) continue;
+    const float rho = p.normalize_ref ? 1.f : s.norm[k];
+    mx = fmaxf(mx, fmaf(4.f * p.t2 * rho, s.gram[a * N + k] + s.gram[q * N + k], base));
+  }
+  float acc = expf(-mx);
+  for (int k = 0; k < N; ++k) {
+    if (!is_negative(p, s.lab, a, k) || s.nu[k] <= 0.f) continue;
+    const float rho = p.normalize_ref ? 1.f : s.norm[k];
+    const float f = fmaf(4.f * p.t2 * rho, s.gram[a * N + k] + s.gram[q * N + k], base);
+    acc = fmaf(s.nu[k], expf(f - mx), acc);
+  }
+  m = mx;
+  tot = acc;
+}
+
+__device__ inline float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int k = 0; k < kWarps; ++k) t += red[k];
+  return t;
+}
+
+template <bool kBackward>
+__global__ void __launch_bounds__(kThreads) angular_kernel(const AngParams p) {
+  extern __shared__ __align__(16) float smem_raw[];
+  const int N = p.W + p.Nq, D = p.D, ld = D + 1;
+  const Smem s = carve(smem_raw, N, D);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  for (int e = blockIdx.x; e < p.E; e += gridDim.x) {
+    // ---- labels, normalised rows, norms
+    for (int i = threadIdx.x; i < N; i += kThreads) {
+      s.lab[i] = i < p.W ? i : p.labels[(size_t)e * p.Nq + (i - p.W)];
+      s.wneg[i] = 0;
+      s.manc[i] = 0;
+    }
+    for (int i = warp; i < N; i += kWarps) {
+      const float* x = row_ptr(p, e, i);
+      float ss = 0.f;
+      for (int c = lane; c < D; c += 32) { const float v = __ldg(x + c); ss = fmaf(v, v, ss); }
+      ss = warp_sum(ss);
+      const float nrm = sqrtf(ss), den = fmaxf(nrm, kNormEps);
+      float cs = 0.f;
+      for (int c = lane; c < D; c += 32) {
+        const float v = __fdiv_rn(__ldg(x + c), den);
+        s.xhat[i * ld + c] = v;
+        cs += v;
+      }
+      cs = warp_sum(cs);
+      if (lane == 0) { s.norm[i] = nrm; s.csum[i] = cs; }
+    }
+    __syncthreads();
+    // ---- Gram matrix of the normalised rows (upper triangle, mirrored)
+    for (int item = threadIdx.x; item < N * N; item += kThreads) {
+      const int i = item / N, j = item - i * N;
+      if (j < i) continue;
+      float dot = 0.f;
+      for (int c = 0; c < D; ++c) dot = fmaf(s.xhat[i * ld + c], s.xhat[j * ld + c], dot);
+      s.gram[i * N + j] = dot;
+      s.gram[j * N + i] = dot;
+    }
+    __syncthreads();
+    // ---- mining: count passing negatives per pair (xhat region is dead from here on)
+    const float deps = (float)D * kPairEps * kPairEps;
+    for (int item = threadIdx.x; item < N * N; item += kThreads) {
+      const int a = item / N, q = item - a * N;
+      int count = 0;
+      if (is_pair(p, s.lab, a, q)) {
+        const float gaq = s.gram[a * N + q];
+        const float ap2 = s.gram[a * N + a] + s.gram[q * N + q] - 2.f * gaq + 2.f * kPairEps * (s.csum[a] - s.csum[q]) + deps;
+        const float ap = sqrtf(fmaxf(ap2, 0.f));
+        const float ra = s.norm[a], rq = s.norm[q];
+        const float sum_norm = sqrtf(fmaxf(ra * ra + rq * rq + 2.f * ra * rq * gaq, 0.f));
+        const float inv = 1.f / fmaxf(sum_norm, kNormEps);
+        const float cc = sum_norm > kNormEps ? 1.f : (sum_norm * inv) * (sum_norm * inv);
+        const float csum_c = (ra * s.csum[a] + rq * s.csum[q]) * inv;
+        for (int k = 0; k < N; ++k) {
+          if (!is_negative(p, s.lab, a, k)) continue;
+          const float dot = (ra * s.gram[k * N + a] + rq * s.gram[k * N + q]) * inv;
+          const float nc2 = s.gram[k * N + k] + cc - 2.f * dot + 2.f * kPairEps * (s.csum[k] - csum_c) + deps;
+          const float nc = sqrtf(fmaxf(nc2, 0.f));
+          if (atanf(ap / (2.f * nc)) > p.miner_angle) {
+            ++count;
+            atomicAdd(&s.wneg[k], 1);
+          }
+        }
+        if (count) atomicAdd(&s.manc[a], count);
+      }
+      s.cnt[item] = count;
+    }
+    __syncthreads();
+    // ---- weights
+    for (int k = threadIdx.x; k < N; k += kThreads) {
+      float w = 1.f;
+      if (p.anchors) w = k >= p.W ? (float)(s.cnt[s.lab[k] * N + k] + s.wneg[k]) : 0.f;
+      s.nu[k] = w;
+    }
+    __syncthreads();
+    // ---- forward: sum of pair weights and weighted pair losses
+    float num = 0.f, den = 0.f;
+    for (int item = threadIdx.x; item < N * N; item += kThreads) {
+      const int a = item / N, q = item - a * N;
+      if (s.cnt[item] == 0 && !p.anchors) continue;
+      if (!is_pair(p, s.lab, a, q)) continue;
+      const float omega = p.anchors ? (float)s.manc[a] * s.nu[q] : (float)s.cnt[item];
+      if (omega <= 0.f) continue;
+      float m, tot;
+      pair_lse(p, s, N, a, q, m, tot);
+      num = fmaf(omega, m + logf(tot), num);
+      den += omega;
+    }
+    num = block_sum(num, s.red);
+    den = block_sum(den, s.red + kWarps);
+    if (!kBackward) {
+      if (threadIdx.x == 0) p.loss[e] = den > 0.f ? num / den : 0.f;
+      __syncthreads();
+      continue;
+    }
+    // ---- backward
+    for (int item = threadIdx.x; item < N * N; item += kThreads) s.dgram[item] = 0.f;
+    __syncthreads();
+    const float scale = den > 0.f ? p.d_loss[e] / den : 0.f;
+    // pass A: rows owned by the anchor.  pass B: rows owned by the positive.
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int i = threadIdx.x; i < N; i += kThreads) {
+        for (int j = 0; j < N; ++j) {
+          const int a = pass == 0 ? i : j, q = pass == 0 ? j : i;
+          if (!is_pair(p, s.lab, a, q)) continue;
+          const float omega = p.anchors ? (float)s.manc[a] * s.nu[q] : (float)s.cnt[a * N + q];
+          if (omega <= 0.f) continue;
+          float m, tot;
+          pair_lse(p, s, N, a, q, m, tot);
+          const float base = -2.f * (1.f + p.t2) * s.gram[a * N + q];
+          const float coef = scale * omega / tot;
+          float gsum = 0.f;
+          for (int k = 0; k < N; ++k) {
+            if (!is_negative(p, s.lab, a, k) || s.nu[k] <= 0.f) continue;
+            const float rho = p.normalize_ref ? 1.f : s.norm[k];
+            const float f = fmaf(4.f * p.t2 * rho, s.gram[a * N + k] + s.gram[q * N + k], base);
+            const float g = coef * s.nu[k] * expf(f - m);
+            gsum += g;
+            s.dgram[i * N + k] += 4.f * p.t2 * rho * g;
+          }
+          if (pass == 0) s.dgram[a * N + q] += -2.f * (1.f + p.t2) * gsum;
+        }
+      }
+      __syncthreads();
+    }
+    // d rho_k = sum_i G[i,k] dG[i,k] / rho_k over rows i of another label (those entries hold only 4 t2 rho g sums)
+    for (int k = threadIdx.x; k < N; k += kThreads) {
+      float acc = 0.f;
+      if (!p.normalize_ref && s.norm[k] > 0.f) {
+        for (int i = 0; i < N; ++i)
+          if (s.lab[i] != s.lab[k]) acc = fmaf(s.gram[i * N + k], s.dgram[i * N + k], acc);
+        acc /= s.norm[k];
+      }
+      s.drho[k] = acc;
+    }
+    __syncthreads();
+    // d x^_i = sum_j (dG[i,j] + dG[j,i]) x^_j ;  d x_i = (d x^_i - x^_i <x^_i, d x^_i>) / |x_i| + d rho_i x^_i
+    for (int i = warp; i < N; i += kWarps) {
+      const float inv_i = 1.f / fmaxf(s.norm[i], kNormEps);
+      const bool clamped = !(s.norm[i] > kNormEps);
+      const float* xi = row_ptr(p, e, i);
+      float* out = i < p.W ? p.d_protos + ((size_t)e * p.W + i) * D : p.d_queries + ((size_t)e * p.Nq + (i - p.W)) * D;
+      float dot = 0.f;
+      // two sweeps over the columns: first the projection <x^_i, d x^_i>, then the result
+      for (int sweep = 0; sweep < 2; ++sweep) {
+        for (int c = lane; c < D; c += 32) {
+          float acc = 0.f;
+          for (int j = 0; j < N; ++j) {
+            const float w = s.dgram[i * N + j] + s.dgram[j * N + i];
+            if (w != 0.f) acc = fmaf(w / fmaxf(s.norm[j], kNormEps), __ldg(row_ptr(p, e, j) + c), acc);
+          }
+          const float xh = __ldg(xi + c) * inv_i;
+          if (sweep == 0) dot = fmaf(acc, xh, dot);
+          else out[c] = (acc - (clamped ? 0.f : xh * dot)) * inv_i + s.drho[i] * xh;
+        }
+        if (sweep == 0) dot = warp_sum(dot);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int launch(const AngParams& p, bool bwd, cudaStream_t stream, const char* name) {
+  AFSL_REQUIRE(p.protos && p.queries && p.labels, "%s: null pointer", name);
+  AFSL_REQUIRE(p.E >= 0 && p.Nq > 0 && p.W > 0 && p.D > 0, "%s: bad sizes E=%d Nq=%d W=%d D=%d", name, p.E, p.Nq, p.W, p.D);
+  if (p.E == 0) return AFSL_OK;
+  const size_t bytes = smem_words(p.W + p.Nq, p.D) * sizeof(float);
+  auto fn = bwd ? angular_kernel<true> : angular_kernel<false>;
+  if (int rc = opt_in_smem(fn, bytes, name)) return rc;
+  const int grid = persistent_grid(fn, kThreads, bytes, p.E);
+  fn<<<grid, kThreads, bytes, stream>>>(p);
+  AFSL_CHECK_LAUNCH(name);
+  return AFSL_OK;
+}
+
+AngParams make(const float* protos, const float* queries, const int32_t* labels, float miner_angle_deg, float alpha_deg,
+               int anchors, int normalize_ref, int E, int Nq, int W, int D) {
+  AngParams p{};
+  p.protos = protos; p.queries = queries; p.labels = labels;
+  p.miner_angle = (float)((double)miner_angle_deg * 3.14159265358979323846 / 180.0);
+  const double t = tan((double)alpha_deg * 3.14159265358979323846 / 180.0);
+  p.t2 = (float)(t * t);
+  p.anchors = anchors; p.normalize_ref = normalize_ref;
+  p.E = E; p.Nq = Nq; p.W = W; p.D = D;
+  return p;
+}
+
+}  // namespace
+}  // namespace afsl
+
+extern "C" int afsl_angular_fwd_f32(const float* protos, const float* queries, const int32_t* labels,
+                                     float miner_angle_deg, float alpha_deg, int anchors, int normalize_ref, float* loss,
+                                     int E, int Nq, int W, int D, void* stream) {
+  AFSL_REQUIRE(loss, "afsl_angular_fwd_f32: null loss");
+  afsl::AngParams p = afsl::make(protos, queries, labels, miner_angle_deg, alpha_deg, anchors, normalize_ref, E, Nq, W, D);
+  p.loss = loss;
+  return afsl::launch(p, false, (cudaStream_t)stream, "afsl_angular_fwd_f32");
+}
+
+extern "C" int afsl_angular_bwd_f32(const float* protos, const float* queries, const int32_t* labels,
+                                     float miner_angle_deg, float alpha_deg, int anchors, int normalize_ref,
+                                     const float* d_loss, float* d_protos, float* d_queries, int E, int Nq, int W, int D,
+                                     void* stream) {
+  AFSL_REQUIRE(d_loss && d_protos && d_queries, "afsl_angular_bwd_f32: null pointer");
+  afsl::AngParams p = afsl::make(protos, queries, labels, miner_angle_deg, alpha_deg, anchors, normalize_ref, E, Nq, W, D);
+  p.d_loss = d_loss; p.d_protos = d_protos; p.d_queries = d_queries;
+  return afsl::launch(p, true, (cudaStream_t)stream, "afsl_angular_bwd_f32");
+}

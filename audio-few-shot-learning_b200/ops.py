@@ -281,6 +281,40 @@ def cpl_loss(protos, queries, labels, temperature: float, keep: Optional[torch.T
     return loss if had else loss[0]
 
 
+# ---------------------------------------------------------------------------------- angular
+class _Angular(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, protos, queries, labels, angle, alpha, anchors, normalize_ref):
+        e, w, d = protos.shape
+        nq = queries.shape[1]
+        loss = torch.empty(e, device=protos.device, dtype=torch.float32)
+        call("afsl_angular_fwd_f32", ptr(protos), ptr(queries), ptr(labels), float(angle), float(alpha), int(anchors),
+             int(normalize_ref), ptr(loss), e, nq, w, d, stream_ptr())
+        ctx.save_for_backward(protos, queries, labels)
+        ctx.args = (float(angle), float(alpha), int(anchors), int(normalize_ref))
+        return loss
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        protos, queries, labels = ctx.saved_tensors
+        e, w, d = protos.shape
+        nq = queries.shape[1]
+        d_loss = _f32(d_loss)
+        d_protos, d_queries = torch.empty_like(protos), torch.empty_like(queries)
+        call("afsl_angular_bwd_f32", ptr(protos), ptr(queries), ptr(labels), *ctx.args, ptr(d_loss), ptr(d_protos),
+             ptr(d_queries), e, nq, w, d, stream_ptr())
+        return d_protos, d_queries, None, None, None, None, None
+
+
+def angular_loss(protos, queries, labels, miner_angle_deg: float, alpha_deg: float = 40.0,
+                 prototypes_as_anchors: bool = True, normalize_ref: bool = False) -> torch.Tensor:
+    """Angular loss with angular mining per episode (AngularLossClass, loops/loss.py:39-97)."""
+    q, l, had = _batched(queries, labels)
+    p = protos if protos.dim() == 3 else protos.unsqueeze(0)
+    loss = _Angular.apply(_f32(p), _f32(q), _i32(l), miner_angle_deg, alpha_deg, prototypes_as_anchors, normalize_ref)
+    return loss if had else loss[0]
+
+
 # ---------------------------------------------------------------------------------- SpecAugment
 _ROW_TABLES = {}
 

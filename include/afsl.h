@@ -127,6 +127,23 @@ int afsl_cpl_bwd_f32(const float* protos, const float* queries, const int32_t* l
                      float* d_queries, int E, int Nq, int W, int D, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Angular loss.  Replaces AngularLossClass.forward, loops/loss.py:48-97
+ * (pytorch_metric_learning AngularMiner(angle) -> AngularLoss(alpha=40 deg)),
+ * mining included, in the multiplicity-weighted closed form.
+ * anchors != 0: prototypes_as_anchors=True branch (loss.py:68-83);
+ * anchors == 0: prototypes and queries pooled (loss.py:84-96).
+ * normalize_ref selects whether the reference rows inside the loss are
+ * L2-normalised (identical for unit-norm inputs).
+ * ------------------------------------------------------------------------- */
+int afsl_angular_fwd_f32(const float* protos, const float* queries, const int32_t* labels,
+                         float miner_angle_deg, float alpha_deg, int anchors, int normalize_ref,
+                         float* loss, int E, int Nq, int W, int D, void* stream);
+int afsl_angular_bwd_f32(const float* protos, const float* queries, const int32_t* labels,
+                         float miner_angle_deg, float alpha_deg, int anchors, int normalize_ref,
+                         const float* d_loss, float* d_protos, float* d_queries, int E, int Nq,
+                         int W, int D, void* stream);
+
+/* ---------------------------------------------------------------------------
  * SpecAugment views.  Replaces SpecAugment.apply_augmentations and the three
  * transforms, utils/augmentations.py:33-157.
  *   x [N,1,F,T]  ->  views [4,N,1,F,T] = {copy, time-warp, time-mask, freq-mask}

@@ -198,6 +198,33 @@ def test_cpl_batched_vs_oracle(ops):
         close(qg.grad[i], qc.grad)
 
 
+# ------------------------------------------------------------------ angular (restated-oracle parity: PML unpinned)
+@pytest.mark.parametrize("anchors", [True, False])
+@pytest.mark.parametrize("angle", [0.0, 15.0, 30.0])
+@pytest.mark.parametrize("unit_protos", [True, False])
+def test_angular_vs_restated_oracle(ops, anchors, angle, unit_protos):
+    from oracle import angular as oang
+    e, ways, per, dim = 6, 5, 5, 64
+    gen = torch.Generator().manual_seed(int(angle) * 10 + int(anchors) + 100 * int(unit_protos))
+    protos = torch.randn(e, ways, dim, generator=gen)
+    if unit_protos:
+        protos = torch.nn.functional.normalize(protos, dim=-1)
+    queries = torch.nn.functional.normalize(torch.randn(e, ways * per, dim, generator=gen) + 0.5 * protos.repeat_interleave(per, 1), dim=-1)
+    labels = torch.arange(ways).repeat_interleave(per).expand(e, -1).contiguous()
+    wl = torch.rand(e, generator=gen) + 0.5
+    pg, qg = protos.cuda().requires_grad_(True), queries.cuda().requires_grad_(True)
+    loss = ops.angular_loss(pg, qg, labels.cuda(), angle, 40.0, anchors, False)
+    (loss * wl.cuda()).sum().backward()
+    for i in range(e):
+        pc, qc = protos[i].clone().requires_grad_(True), queries[i].clone().requires_grad_(True)
+        lo = oang.angular_loss_class(pc, qc, labels[i], angle, anchors)
+        (lo * wl[i]).backward()
+        close(loss[i], lo, rtol=2e-5)
+        zero = lambda g, like: torch.zeros_like(like) if g is None else g      # nothing mined -> constant zero loss
+        close(pg.grad[i], zero(pc.grad, pc), rtol=1e-4)
+        close(qg.grad[i], zero(qc.grad, qc), rtol=1e-4)
+
+
 # ------------------------------------------------------------------ SpecAugment
 def warp_atol(x):
     """Bound for the in-kernel spline.  torch evaluates u**2, u**3 with a 1-ulp vectorised powf that
