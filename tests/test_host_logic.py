@@ -1,0 +1,200 @@
+"""CPU tests of the host-side logic: RNG replay, mask packing, grouped BatchNorm, state-dict
+compatibility, episode sharding and the world-size-2 gloo path."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import golden_names, load_golden, t
+from oracle import head as ohead
+from oracle import modules as omod
+from oracle import specaug as ospec
+
+CFG = {"specaug_params": {"use": True, "mask_param": 16, "W": 22, "num_mask": 2, "mask_value": 0, "p": 0.282}}
+
+
+def test_specaug_draws_replay_reference_order():
+    from afsl_b200.utils.augmentations import SpecAugment
+    torch.manual_seed(5); np.random.seed(5)
+    want = [ospec.draw_params(25, 157, CFG) for _ in range(3)]
+    torch.manual_seed(5); np.random.seed(5)
+    got = SpecAugment(CFG).draw_batch(3, 25, 157, replay_reference_rng=True)
+    assert torch.equal(got.warp_p, torch.cat([w.warp_p for w in want]))
+    assert torch.equal(got.warp_d, torch.cat([w.warp_d for w in want]))
+    assert got.time_masks.tolist() == [[list(m) for m in w.time_masks] for w in want]
+    assert got.freq_masks.tolist() == [[list(m) for m in w.freq_masks] for w in want]
+
+
+def test_specaug_vectorised_draws_in_range():
+    from afsl_b200.utils.augmentations import SpecAugment
+    p = SpecAugment(CFG).draw_batch(2000, 25, 157, replay_reference_rng=False)
+    assert p.warp_p.min() >= 22 and p.warp_p.max() < 157 - 22 and p.warp_d.min() >= -22 and p.warp_d.max() < 22
+    t0, tl = p.time_masks[..., 0], p.time_masks[..., 1]
+    assert tl.min() >= 1 and tl.max() <= min(16, int(0.282 * 157)) and t0.min() >= 0 and bool((t0 + tl <= 156).all())
+    f0, fl = p.freq_masks[..., 0], p.freq_masks[..., 1]
+    assert fl.min() >= 1 and fl.max() <= 16 and f0.min() >= 0 and bool((f0 + fl <= 127).all())
+    assert set(tl.unique().tolist()) == set(range(1, 17))          # every length is reachable
+
+
+@pytest.mark.parametrize("name", golden_names("specaug_"))
+def test_host_spline_matches_reference(name):
+    from afsl_b200.utils.augmentations import warp_source_x
+    g = load_golden(name)
+    assert torch.equal(warp_source_x(t(g["warp_p"]), t(g["warp_d"]), g["x"].shape[-1]), t(g["src_x"]))
+
+
+@pytest.mark.parametrize("name", golden_names("cpl_"))
+def test_cpl_keep_replay_matches_reference(name):
+    from afsl_b200.loops.loss import draw_keep_reference
+    from afsl_b200.ops import pack_keep
+    g = load_golden(name)
+    torch.manual_seed(int(g["seed"]))
+    keep = draw_keep_reference(t(g["labels"]), int(g["m"]))
+    assert torch.equal(keep, t(g["keep"]))
+    packed = pack_keep(keep)
+    n = keep.shape[0]
+    for i in (0, n // 2, n - 1):
+        for j in range(n):
+            assert bool((int(packed[i, j // 32]) >> (j % 32)) & 1) == bool(keep[i, j])
+
+
+def test_cpl_keep_vectorised_distribution():
+    from afsl_b200.loops.loss import draw_keep_vectorised
+    labels = torch.arange(5).repeat_interleave(8)[torch.randperm(40)].expand(6, -1)
+    keep = draw_keep_vectorised(labels, 3, 5)
+    same = labels.unsqueeze(2) == labels.unsqueeze(1)
+    eye = torch.eye(40, dtype=torch.bool)
+    assert bool((keep & same == eye).all())                        # own class: only the query itself
+    for c in range(5):                                             # exactly M from every other class
+        cols = (labels == c).unsqueeze(1)
+        cnt = (keep & cols).sum(2)
+        rows_other = labels != c
+        assert bool((cnt[rows_other] == 3).all())
+
+
+def test_grouped_batchnorm_equals_sequential_calls():
+    from afsl_b200.models.main_modules import GroupedBatchNorm1d, GroupedBatchNorm2d
+    torch.manual_seed(0)
+    for grouped_cls, ref_cls, shape in ((GroupedBatchNorm2d, torch.nn.BatchNorm2d, (6, 8, 5, 7)),
+                                        (GroupedBatchNorm1d, torch.nn.BatchNorm1d, (6, 8))):
+        g, r = grouped_cls(8), ref_cls(8)
+        with torch.no_grad():
+            g.weight.uniform_(0.5, 1.5); g.bias.uniform_(-1, 1)
+            r.weight.copy_(g.weight); r.bias.copy_(g.bias)
+        x = torch.randn(4 * shape[0], *shape[1:], requires_grad=True)
+        xr = x.detach().clone().requires_grad_(True)
+        g.group_size = shape[0]
+        yg = g(x)
+        yr = torch.cat([r(xr[i * shape[0]:(i + 1) * shape[0]]) for i in range(4)])
+        torch.testing.assert_close(yg, yr, rtol=1e-5, atol=1e-6)
+        w = torch.randn_like(yg)
+        (yg * w).sum().backward(); (yr * w).sum().backward()
+        torch.testing.assert_close(x.grad, xr.grad, rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(g.weight.grad, r.weight.grad, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(g.running_mean, r.running_mean, rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(g.running_var, r.running_var, rtol=1e-5, atol=1e-7)
+        assert int(g.num_batches_tracked) == int(r.num_batches_tracked) == 4
+
+
+def test_batched_encoder_equals_per_episode_calls():
+    """[E,N,1,F,T] views through EncoderModule == the reference's one call per (episode, view)."""
+    from afsl_b200.models.main_modules import EncoderModule, StandardCNN
+    torch.manual_seed(1)
+    enc = EncoderModule({"encoder_name": "CNN"}, {}, encoder=StandardCNN(1, (1, 1, 32, 40), 64, [2, 2], 16))
+    for m in enc.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    enc.train()
+    views = [torch.randn(3, 4, 1, 32, 40) for _ in range(2)]
+    got = enc(views)
+    import copy
+    ref = copy.deepcopy(enc)
+    for v in range(2):
+        for e in range(3):
+            want = ref([views[v][e]])[0]
+            torch.testing.assert_close(got[v][e], want, rtol=1e-4, atol=1e-5)
+
+
+def test_state_dict_keys_match_reference():
+    from afsl_b200.models.main_modules import EncoderModule, ProjectionHead, SelfAttention
+    from afsl_b200.models.prototypical import (ContrastivePrototypicalNetworks,
+                                               ContrastivePrototypicalNetworksWithoutAttention)
+    import bench
+    g = load_golden("modules_model_concat")
+    att, proj = SelfAttention(bench.MODEL_CONFIG), ProjectionHead({"Projection": {"input_dim": 256, "hidden_dim": 128, "output_dim": 256}})
+    ident = torch.nn.Identity()
+    fused = ContrastivePrototypicalNetworks(ident, att, proj)
+    concat = ContrastivePrototypicalNetworksWithoutAttention(ident, proj)
+    assert list(fused.state_dict().keys()) == [str(k) for k in g["keys_fused"]]
+    assert list(concat.state_dict().keys()) == [str(k) for k in g["keys_concat"]]
+    for name in golden_names("modules_encoder_"):
+        ge = load_golden(name)
+        kind = name.split("_")[2]
+        mc = dict(bench.MODEL_CONFIG)
+        mc["CNN"] = {"in_channels": 1, "hidden_channels": 64, "pool_dim": [3, 3], "out_dim": 64,
+                     "trial_shape": (1, 1, 128, int(name.split("_t")[-1]))}
+        enc = EncoderModule({"encoder_name": kind}, mc)
+        assert list(enc.encoder.state_dict().keys()) == [str(k) for k in ge["keys"]]
+        enc.encoder.load_state_dict({k[2:]: t(v) for k, v in ge.items() if k.startswith("w_")})
+        enc.eval()
+        with torch.no_grad():                      # cuDNN-free CPU check of the mirrored architecture
+            torch.testing.assert_close(enc([t(ge["x"])])[0], t(ge["y_eval"]), rtol=1e-5, atol=1e-6)
+    with pytest.raises(TypeError):                 # the reference's 'CNN' branch fails the same way
+        from afsl_b200.models.main_modules import get_backbone_model
+        get_backbone_model("CNN", {"CNN": {"in_channels": 1, "hidden_channels": 64, "pool_dim": [3, 3], "out_dim": 64}})
+
+
+def test_shard_range_partitions():
+    from afsl_b200.parallel import shard_range
+    for total in (0, 1, 7, 2000, 65536):
+        for world in (1, 2, 3, 8):
+            blocks = [shard_range(total, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == total
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from afsl_b200 import parallel
+    r, w, _ = parallel.init_from_env("gloo")
+    torch.manual_seed(100 + rank)                      # replicas start different; broadcast must fix that
+    net = torch.nn.Sequential(torch.nn.Linear(6, 4), torch.nn.BatchNorm1d(4), torch.nn.Linear(4, 2))
+    dp = parallel.EpisodeDataParallel(net)
+    # every rank owns a contiguous block of the step's episodes
+    total = 7
+    lo, hi = parallel.shard_range(total, r, w)
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(total, 5, 6, generator=gen)
+    loss = torch.stack([net(x[i]).pow(2).mean() for i in range(lo, hi)]).sum() / total * w   # mean over ALL episodes, times world
+    loss.backward()
+    dp.sync_gradients()
+    flat = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+    acc = parallel.gather_accuracies(np.arange(lo, hi, dtype=np.float64) / 10.0, total)
+    if rank == 0:
+        torch.save({"grad": flat, "acc": acc, "w0": net[0].weight.detach().clone()}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_two_ranks_match_single_process(tmp_path):
+    port = 29500 + random.randint(0, 2000)
+    out = str(tmp_path / "rank0.pt")
+    mp.spawn(_gloo_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out, weights_only=False)
+    # single process reference: rank 0's initial weights, all 7 episodes
+    torch.manual_seed(100)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 4), torch.nn.BatchNorm1d(4), torch.nn.Linear(4, 2))
+    assert torch.equal(net[0].weight, got["w0"])
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(7, 5, 6, generator=gen)
+    torch.stack([net(x[i]).pow(2).mean() for i in range(7)]).mean().backward()
+    want = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+    torch.testing.assert_close(got["grad"], want, rtol=1e-5, atol=1e-7)
+    assert np.array_equal(got["acc"], np.arange(7, dtype=np.float64) / 10.0)
