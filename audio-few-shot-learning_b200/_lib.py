@@ -32,6 +32,9 @@ SIGNATURES = {
     "afsl_angular_fwd_f32": [_P, _P, _P, _F, _F, _I, _I, _P, _I, _I, _I, _I, _P],
     "afsl_angular_bwd_f32": [_P, _P, _P, _F, _F, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P],
     "afsl_specaug_views_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _I, _I, _I, _I, _I, _P],
+    "afsl_gbn_stats_f32": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "afsl_gbn_relu_pool_fwd_f32": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "afsl_gbn_relu_pool_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "afsl_eval_vote_i32": [_P, _P, _P, _P, _P, _I, _P, _P, _I, _P],
 }
 

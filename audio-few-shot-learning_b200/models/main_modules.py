@@ -95,9 +95,38 @@ def _update_running(bn, mean: torch.Tensor, var_biased: torch.Tensor, count: int
     bn.running_var.mul_(keep).add_((decay.unsqueeze(1) * unbiased).sum(0), alpha=m)
 
 
+class ConvBlock(nn.Sequential):
+    """Conv3x3(pad 1) -> BatchNorm -> ReLU -> MaxPool(pool_dim) (models/main_modules.py:43-60).
+
+    Same children (and state-dict keys ``0.*`` / ``1.*``) as the reference's nn.Sequential.  On the GPU
+    with the reference's 3x3 pooling, BatchNorm -> ReLU -> MaxPool run as ONE libafsl kernel per pass
+    (per-group statistics included); the convolution is cuDNN.  Other pool sizes, or CPU tensors in the
+    unit tests, take the stock module chain - the encoder is the part of the model that stays PyTorch.
+    """
+
+    def forward(self, x):
+        conv, bn, relu, pool = self[0], self[1], self[2], self[3]
+        is3 = _all_equal(pool.kernel_size, 3) and _all_equal(pool.stride, 3) and _all_equal(pool.padding, 0)
+        if x.is_cuda and is3 and FUSED_STAGES:
+            # bias-free cuDNN convolution; the bias is folded into the BatchNorm statistics by the kernel
+            u = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+            if u.shape[-1] >= 3 and u.shape[-2] >= 3:
+                return ops.gbn_relu_pool(u, bn, getattr(bn, "group_size", None), conv_bias=conv.bias)
+            x = u if conv.bias is None else u + conv.bias.view(1, -1, 1, 1)
+        else:
+            x = conv(x)
+        return pool(relu(bn(x)))
+
+
+def _all_equal(v, k) -> bool:
+    return v == k if isinstance(v, int) else all(int(e) == k for e in v)
+
+
+FUSED_STAGES = True     # switch for A/B measurements of the fused BatchNorm-ReLU-MaxPool kernels
+
+
 def conv_block(in_channels, out_channels, pool_dim):
-    """Conv3x3(pad 1) -> BatchNorm -> ReLU -> MaxPool(pool_dim) (models/main_modules.py:43-60)."""
-    return nn.Sequential(
+    return ConvBlock(
         nn.Conv2d(in_channels, out_channels, 3, padding=1),
         GroupedBatchNorm2d(out_channels),
         nn.ReLU(),

@@ -357,6 +357,81 @@ def specaug_views(x: torch.Tensor, warp_p: torch.Tensor, warp_d: torch.Tensor, t
     return views
 
 
+# ---------------------------------------------------------------------------------- grouped BN + ReLU + pool
+class _GbnReluPool(torch.autograd.Function):
+    """y = MaxPool3(ReLU(BN(u + conv_bias))) with u the bias-free convolution output.
+
+    mean/rstd refer to u (training: batch statistics of u per group; eval: running_mean - conv_bias),
+    so the convolution bias never has to be added to the full-resolution tensor."""
+
+    @staticmethod
+    def forward(ctx, u, gamma, beta, conv_bias, mean, rstd, groups, group, per_group):
+        n, c, h, w = u.shape
+        y = torch.empty(n, c, h // 3, w // 3, device=u.device, dtype=torch.float32)
+        call("afsl_gbn_relu_pool_fwd_f32", ptr(u), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(y), groups, group, c, h, w,
+             int(per_group), stream_ptr())
+        ctx.save_for_backward(u, gamma, beta, mean, rstd)
+        ctx.dims = (groups, group, int(per_group))
+        ctx.has_bias = conv_bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, d_y):
+        u, gamma, beta, mean, rstd = ctx.saved_tensors
+        groups, group, per_group = ctx.dims
+        n, c, h, w = u.shape
+        d_y = _f32(d_y)
+        d_u = torch.empty_like(u)
+        sums = torch.empty(groups, c, 2, device=u.device, dtype=torch.float32)
+        call("afsl_gbn_relu_pool_bwd_f32", ptr(u), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(d_y), ptr(d_u), ptr(sums),
+             groups, group, c, h, w, per_group, stream_ptr())
+        totals = sums.sum(0)
+        d_gamma, d_beta = totals[:, 1].contiguous(), totals[:, 0].contiguous()
+        d_bias = None
+        if ctx.has_bias:
+            # batch statistics remove any per-channel constant: the gradient is exactly zero (the eager
+            # chain obtains round-off noise by summing d_u); with running statistics it is gamma*rstd*sum(dz)
+            d_bias = torch.zeros_like(gamma) if per_group else gamma * rstd * d_beta
+        return d_u, d_gamma, d_beta, d_bias, None, None, None, None, None
+
+
+def gbn_relu_pool(u: torch.Tensor, bn: torch.nn.BatchNorm2d, group_size: Optional[int] = None,
+                  conv_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """MaxPool3(ReLU(BatchNorm(u + conv_bias))) for a convolution output ``u [N,C,H,W]``.
+
+    Training mode: batch statistics per group of ``group_size`` consecutive samples (default: the
+    whole batch), running statistics updated group by group like that many separate module calls.
+    Eval mode: running statistics.  ``conv_bias`` (per channel) is folded into the statistics instead
+    of being added to the tensor.  One libafsl launch per pass instead of the eager chain.
+    """
+    u = _f32(u)
+    n, c, h, w = u.shape
+    gamma, beta = _f32(bn.weight), _f32(bn.bias)
+    use_batch_stats = bn.training or not bn.track_running_stats
+    if use_batch_stats:
+        group = int(group_size) if group_size else n
+        if n % group:
+            raise ValueError(f"batch of {n} samples is not a whole number of groups of {group}")
+        groups = n // group
+        mean = torch.empty(groups, c, device=u.device, dtype=torch.float32)
+        rstd, var = torch.empty_like(mean), torch.empty_like(mean)
+        call("afsl_gbn_stats_f32", ptr(u), ptr(mean), ptr(rstd), ptr(var), groups, group, c, h, w, float(bn.eps), stream_ptr())
+        if bn.training and bn.track_running_stats:
+            with torch.no_grad():
+                count = group * h * w
+                m = bn.momentum
+                bn.num_batches_tracked += groups
+                decay = (1.0 - m) ** torch.arange(groups - 1, -1, -1, device=u.device, dtype=torch.float32)
+                keep = (1.0 - m) ** groups
+                true_mean = mean if conv_bias is None else mean + conv_bias
+                bn.running_mean.mul_(keep).add_((decay.unsqueeze(1) * true_mean).sum(0), alpha=m)
+                bn.running_var.mul_(keep).add_((decay.unsqueeze(1) * var).sum(0), alpha=m * count / max(count - 1, 1))
+        return _GbnReluPool.apply(u, gamma, beta, conv_bias, mean, rstd, groups, group, True)
+    mean = _f32(bn.running_mean) if conv_bias is None else _f32(bn.running_mean - conv_bias)
+    rstd = torch.rsqrt(bn.running_var.float() + bn.eps)
+    return _GbnReluPool.apply(u, gamma, beta, conv_bias, mean, rstd, 1, n, False)
+
+
 # ---------------------------------------------------------------------------------- majority vote
 @torch.no_grad()
 def eval_vote(pred, clip_ids, labels, posterior, seg_offsets, tie_strategy: str = "min_label"):

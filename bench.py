@@ -106,9 +106,11 @@ class ClockSampler:
 def build_model(device):
     from afsl_b200.models.main_modules import EncoderModule, ProjectionHead, SelfAttention
     from afsl_b200.models.prototypical import ContrastivePrototypicalNetworks
+    import contextlib
     torch.manual_seed(1234)
-    model = ContrastivePrototypicalNetworks(EncoderModule(EXPERIMENT_CONFIG, MODEL_CONFIG), SelfAttention(MODEL_CONFIG),
-                                            ProjectionHead(MODEL_CONFIG)).to(device)
+    with contextlib.redirect_stdout(sys.stderr):          # the encoder prints its parameter count like the reference
+        model = ContrastivePrototypicalNetworks(EncoderModule(EXPERIMENT_CONFIG, MODEL_CONFIG),
+                                                SelfAttention(MODEL_CONFIG), ProjectionHead(MODEL_CONFIG)).to(device)
     return model
 
 
@@ -342,7 +344,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--episodes", type=int, default=16, help="episodes per step per GPU")
+    ap.add_argument("--episodes", type=int, default=32, help="episodes per step per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-kernels", action="store_true")

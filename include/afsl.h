@@ -175,6 +175,28 @@ int afsl_eval_vote_i32(const int32_t* pred, const int32_t* clip_ids, const int32
                        const float* posterior, const int32_t* seg_offsets, int tie_strategy,
                        int32_t* correct_clips, int32_t* n_clips, int E, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Grouped BatchNorm + ReLU + MaxPool(3, stride 3) over convolution outputs whose
+ * batch axis holds G groups of `group` consecutive samples with independent batch
+ * statistics - one group = one encoder call of the reference (conv_block,
+ * models/main_modules.py:43-60, applied per view per set per episode, :18-23), so
+ * batching E episodes keeps the per-(episode, set, view) statistics.
+ *   x [G*group,C,H,W] NCHW -> y [G*group,C,H/3,W/3]
+ * stats: mean / rstd = 1/sqrt(var_biased + eps) / var_biased, each [G,C].
+ * fwd / bwd take mean, rstd as [G,C] (stats_per_group = 1, training) or [C]
+ * (stats_per_group = 0, running statistics in eval mode).
+ * bwd writes d_x (like x) and sums [G,C,2] = (sum dz, sum dz*xhat) per slab, from
+ * which d_beta[c] = sum_g sums[g,c,0], d_gamma[c] = sum_g sums[g,c,1].
+ * ------------------------------------------------------------------------- */
+int afsl_gbn_stats_f32(const float* x, float* mean, float* rstd, float* var_biased, int G, int group,
+                       int C, int H, int W, float eps, void* stream);
+int afsl_gbn_relu_pool_fwd_f32(const float* x, const float* mean, const float* rstd, const float* gamma,
+                               const float* beta, float* y, int G, int group, int C, int H, int W,
+                               int stats_per_group, void* stream);
+int afsl_gbn_relu_pool_bwd_f32(const float* x, const float* mean, const float* rstd, const float* gamma,
+                               const float* beta, const float* d_y, float* d_x, float* sums, int G,
+                               int group, int C, int H, int W, int stats_per_group, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

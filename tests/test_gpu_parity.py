@@ -336,3 +336,85 @@ def test_full_size_properties(ops):
     # (5) idempotence / determinism
     loss_again, _, _ = ops.proto_head(s, sl, q, ql, n_way=ways)
     assert torch.equal(loss_again, loss)
+
+
+# ------------------------------------------------------------------ grouped BatchNorm + ReLU + MaxPool
+@pytest.mark.parametrize("shape,group", [((50, 8, 20, 25), 25), ((12, 64, 42, 52), 4), ((6, 16, 14, 17), 3),
+                                          ((10, 64, 4, 5), 5), ((4, 4, 128, 157), 2)])
+def test_gbn_relu_pool_vs_torch(ops, shape, group):
+    """Fused kernels vs the eager fp32 chain (per-group nn.BatchNorm2d -> ReLU -> MaxPool2d(3)) on the GPU."""
+    n, c, h, w = shape
+    gen = torch.Generator().manual_seed(n * c + h)
+    x = (torch.randn(shape, generator=gen) * 2 + 0.7).cuda()
+    bn = torch.nn.BatchNorm2d(c).cuda()
+    ref = torch.nn.BatchNorm2d(c).cuda()
+    with torch.no_grad():
+        bn.weight.uniform_(-1.5, 1.5); bn.bias.uniform_(-0.5, 0.5)        # negative gammas included
+        ref.weight.copy_(bn.weight); ref.bias.copy_(bn.bias)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    cb = (torch.randn(c, generator=gen) * 0.3).cuda().requires_grad_(True)       # convolution bias, folded by the kernel
+    cbr = cb.detach().clone().requires_grad_(True)
+    y = ops.gbn_relu_pool(xa, bn, group, conv_bias=cb)
+    yr = torch.cat([torch.nn.functional.max_pool2d(torch.relu(ref(xb[i:i + group] + cbr.view(1, -1, 1, 1))), 3, 3)
+                    for i in range(0, n, group)])
+    close(y, yr, rtol=1e-5)
+    gy = torch.randn(y.shape, generator=gen).cuda()
+    y.backward(gy); yr.backward(gy)
+    close(xa.grad, xb.grad, rtol=1e-4)
+    close(bn.weight.grad, ref.weight.grad, rtol=1e-4)
+    close(bn.bias.grad, ref.bias.grad, rtol=1e-4)
+    close(bn.running_mean, ref.running_mean, rtol=1e-5)
+    close(bn.running_var, ref.running_var, rtol=1e-5)
+    assert int(bn.num_batches_tracked) == int(ref.num_batches_tracked) == n // group
+    close(cb.grad, cbr.grad, rtol=0, scale=1e-4 * float(xb.grad.abs().max()) * h * w)     # exactly 0 vs round-off
+    # eval mode: running statistics, gradients included
+    bn.eval(); ref.eval()
+    for tns in (xa, xb, cb, cbr, bn.weight, bn.bias, ref.weight, ref.bias):
+        tns.grad = None
+    ye = ops.gbn_relu_pool(xa, bn, group, conv_bias=cb)
+    yer = torch.nn.functional.max_pool2d(torch.relu(ref(xb + cbr.view(1, -1, 1, 1))), 3, 3)
+    close(ye, yer, rtol=1e-5)
+    ye.backward(gy); yer.backward(gy)
+    close(xa.grad, xb.grad, rtol=1e-4)
+    close(cb.grad, cbr.grad, rtol=1e-4)
+    close(bn.weight.grad, ref.weight.grad, rtol=1e-4)
+    close(bn.bias.grad, ref.bias.grad, rtol=1e-4)
+
+
+def test_batched_encoder_fused_vs_per_episode(ops):
+    """Hybrid encoder on [E,N,1,128,157] views (fused stages, grouped statistics) == one eager call per (episode, view)."""
+    import copy
+    import afsl_b200.models.main_modules as mm
+    torch.manual_seed(3)
+    enc = mm.EncoderModule({"encoder_name": "Hybrid"}, {"Hybrid": {"in_channels": 1, "seq_layers": 1, "seq_type": "RNN",
+                           "bidirectional": False, "hidden_channels": 64, "pool_dim": [3, 3], "out_dim": 64}}).cuda()
+    for m in enc.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    ref = copy.deepcopy(enc)
+    enc.train(); ref.train()
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        views = [torch.randn(2, 5, 1, 128, 157, device="cuda") for _ in range(2)]
+        got = enc(views)
+        (sum(g.square().sum() for g in got)).backward()
+        mm.FUSED_STAGES = False
+        want = [[ref([views[v][e]])[0] for e in range(2)] for v in range(2)]
+        (sum(w.square().sum() for row in want for w in row)).backward()
+    finally:
+        mm.FUSED_STAGES = True
+        torch.backends.cudnn.allow_tf32 = True
+    for v in range(2):
+        for e in range(2):
+            close(got[v][e], want[v][e], rtol=2e-4)
+    params, refs = dict(enc.named_parameters()), dict(ref.named_parameters())
+    for k, a in params.items():
+        if k.startswith("encoder.conv_encoder") and k.endswith(".0.bias"):
+            # a convolution bias feeding batch-statistics BatchNorm has an exactly zero gradient; the eager
+            # chain returns round-off noise (sum of d_u), so compare against the weight-gradient scale
+            scale = float(refs[k.replace("bias", "weight")].grad.abs().max())
+            close(a.grad, refs[k].grad, rtol=0, scale=1e-4 * scale)
+        else:
+            close(a.grad, refs[k].grad, rtol=2e-3)
+    for (k, a), (_, b) in zip(enc.named_buffers(), ref.named_buffers()):
+        close(a.float(), b.float(), rtol=1e-4)
