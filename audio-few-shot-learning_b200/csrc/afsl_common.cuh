@@ -55,6 +55,31 @@ __device__ __forceinline__ float group_sum(float v) {
   return v;
 }
 
+// packed fp32x2 arithmetic (Blackwell FADD2 / FFMA2): two IEEE fp32 operations per issued instruction,
+// bit-identical to the scalar sub / fma they replace
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ float sum2(f32x2 v) {
+  float lo, hi;
+  unpack2(v, lo, hi);
+  return lo + hi;
+}
+
 // streaming 128-bit global accesses: data touched once, keep it out of L1
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   float4 r;
@@ -69,6 +94,36 @@ __device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
                : "memory");
 }
 
+
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier: global -> shared without register staging
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// make barrier initialisation / prior generic-proxy accesses visible to the async proxy
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
 
 // Stable bucket of rows by label, whole CTA cooperating: on return (after the trailing barrier)
 // row[start[w] .. start[w]+cnt[w]) lists the rows whose label is w in ascending row order - the order

@@ -10,6 +10,8 @@
 // shared memory; each query row is handled by a group of kLPR lanes holding the row in
 // registers, with warp-shuffle reductions over the embedding dimension.  fp32 throughout
 // (1e-5 parity bar; the contractions are ~1 flop/B, i.e. HBM-bound, so no tensor cores).
+#include <cstdlib>
+
 #include "afsl_common.cuh"
 
 namespace afsl {
@@ -17,6 +19,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / kWarp;
+constexpr bool kStagedByDefault = false;  // measured on B200: occupancy (8 CTAs/SM) beats staging (2 CTAs/SM) at 5w5s5q
 
 struct HeadParams {
   // forward inputs
@@ -91,7 +94,21 @@ __device__ inline void bucket_rows(const Smem& s, const int32_t* labels, int Ns,
   bucket_by_label(labels, Ns, W, s.lab, s.row, s.cnt, s.start);
 }
 
+// kStaged: the episode's support / query blocks were brought into shared memory by a TMA bulk copy, so
+// they are read with plain shared loads; otherwise they are streamed from global memory.
+template <bool kStaged>
+__device__ __forceinline__ float4 ld_row(const float4* p) {
+  if (kStaged) return *p;
+  return ldg_stream(p);
+}
+template <bool kStaged>
+__device__ __forceinline__ float4 ld_row_cached(const float4* p) {
+  if (kStaged) return *p;
+  return __ldg(p);
+}
+
 // prototypes of one episode -> shared memory (and global when requested)
+template <bool kStaged>
 __device__ inline void build_prototypes(const Smem& s, const float* support, float* protos_out, int W, int D) {
   const int D4 = D >> 2;
   const float4* sup4 = reinterpret_cast<const float4*>(support);
@@ -104,17 +121,17 @@ __device__ inline void build_prototypes(const Smem& s, const float* support, flo
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int j = 0;
     for (; j + 4 <= n; j += 4) {  // 4 independent 128-bit loads in flight
-      const float4 a = ldg_stream(sup4 + (size_t)rows[j] * D4 + c);
-      const float4 b = ldg_stream(sup4 + (size_t)rows[j + 1] * D4 + c);
-      const float4 d = ldg_stream(sup4 + (size_t)rows[j + 2] * D4 + c);
-      const float4 g = ldg_stream(sup4 + (size_t)rows[j + 3] * D4 + c);
+      const float4 a = ld_row<kStaged>(sup4 + (size_t)rows[j] * D4 + c);
+      const float4 b = ld_row<kStaged>(sup4 + (size_t)rows[j + 1] * D4 + c);
+      const float4 d = ld_row<kStaged>(sup4 + (size_t)rows[j + 2] * D4 + c);
+      const float4 g = ld_row<kStaged>(sup4 + (size_t)rows[j + 3] * D4 + c);
       acc.x = (((acc.x + a.x) + b.x) + d.x) + g.x;
       acc.y = (((acc.y + a.y) + b.y) + d.y) + g.y;
       acc.z = (((acc.z + a.z) + b.z) + d.z) + g.z;
       acc.w = (((acc.w + a.w) + b.w) + d.w) + g.w;
     }
     for (; j < n; ++j) {
-      const float4 a = ldg_stream(sup4 + (size_t)rows[j] * D4 + c);
+      const float4 a = ld_row<kStaged>(sup4 + (size_t)rows[j] * D4 + c);
       acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
     }
     const float fn = (float)n;  // n == 0 -> NaN, as the reference's empty mean
@@ -132,29 +149,44 @@ __device__ inline void load_prototypes(const Smem& s, const float* protos_in, in
   for (int i = threadIdx.x; i < n4; i += kThreads) sp4[i] = __ldg(in4 + i);
 }
 
-// squared distances of the register-resident row q[] to prototype w, reduced over the lane group
-template <int kLPR, int kCPL>
-__device__ __forceinline__ float row_dist2(const float4 (&q)[kCPL], const float4* sp4, int w, int D4, int sub) {
-  float acc = 0.f;
+// Squared distances of the register-resident row q[] to kWB consecutive prototypes, reduced over the
+// lane group.  The prototype block is unrolled so the row is read once per block, the arithmetic is
+// packed (FADD2 + FFMA2: the same IEEE sub / fma as the scalar form, two per instruction).
+template <int kLPR, int kCPL, int kWB>
+__device__ __forceinline__ void row_dist2_block(const float4 (&q)[kCPL], const float4* sp4, int w0, int D4, int sub,
+                                                float (&d2)[kWB]) {
+  f32x2 acc[kWB][2];
+#pragma unroll
+  for (int b = 0; b < kWB; ++b) acc[b][0] = acc[b][1] = 0ull;
 #pragma unroll
   for (int u = 0; u < kCPL; ++u) {
-    const float4 p = sp4[w * D4 + sub + u * kLPR];
-    const float dx = q[u].x - p.x, dy = q[u].y - p.y, dz = q[u].z - p.z, dw = q[u].w - p.w;
-    acc = fmaf(dx, dx, acc); acc = fmaf(dy, dy, acc); acc = fmaf(dz, dz, acc); acc = fmaf(dw, dw, acc);
+    const f32x2 qa = pack2(q[u].x, q[u].y), qb = pack2(q[u].z, q[u].w);
+#pragma unroll
+    for (int b = 0; b < kWB; ++b) {
+      const float4 pr = sp4[(w0 + b) * D4 + sub + u * kLPR];
+      const f32x2 da = sub2(qa, pack2(pr.x, pr.y)), db = sub2(qb, pack2(pr.z, pr.w));
+      acc[b][0] = fma2(da, da, acc[b][0]);
+      acc[b][1] = fma2(db, db, acc[b][1]);
+    }
   }
-  return group_sum<kLPR>(acc);
+#pragma unroll
+  for (int b = 0; b < kWB; ++b) d2[b] = group_sum<kLPR>(sum2(acc[b][0]) + sum2(acc[b][1]));
 }
 
 // Scores of one row against all prototypes -> s.score[slot*W ..]; returns (max, argmax, sumexp)
-// computed cooperatively by the lane group.
-template <int kLPR, int kCPL>
+// computed cooperatively by the lane group.  W must be a multiple of kWB.
+template <int kLPR, int kCPL, int kWB>
 __device__ __forceinline__ void row_scores(const float4 (&q)[kCPL], const Smem& s, int slot, int W, int D4, int sub,
                                            float& mx, int& amx, float& sumexp) {
   const float4* sp4 = reinterpret_cast<const float4*>(s.protos);
   float* sc = s.score + slot * W;
-  for (int w = 0; w < W; ++w) {
-    const float d2 = row_dist2<kLPR, kCPL>(q, sp4, w, D4, sub);
-    if (sub == (w & (kLPR - 1))) sc[w] = -sqrtf(d2);
+  for (int w0 = 0; w0 < W; w0 += kWB) {
+    float d2[kWB];
+    row_dist2_block<kLPR, kCPL, kWB>(q, sp4, w0, D4, sub, d2);
+    if (sub == 0) {
+#pragma unroll
+      for (int b = 0; b < kWB; ++b) sc[w0 + b] = -sqrtf(d2[b]);
+    }
   }
   __syncwarp();
   // max / first argmax over W
@@ -177,31 +209,89 @@ __device__ __forceinline__ void row_scores(const float4 (&q)[kCPL], const Smem& 
   mx = m; amx = am; sumexp = se;
 }
 
-template <int kLPR, int kCPL>
+// ---- TMA staging: double-buffered bulk copies of the episode's support / query blocks
+struct Staging {
+  float* buf;       // [2][(Ns + Nq) * D]
+  uint64_t* bars;   // [2]
+  int sup_floats, qry_floats;
+};
+
+__host__ __device__ inline size_t align4(size_t words) { return (words + 3) & ~(size_t)3; }
+
+__device__ inline Staging carve_staging(float* smem_raw, size_t base_words, int Ns, int Nq, int D) {
+  Staging g;
+  g.buf = smem_raw + align4(base_words);
+  g.sup_floats = Ns * D;
+  g.qry_floats = Nq * D;
+  g.bars = reinterpret_cast<uint64_t*>(g.buf + 2 * (size_t)(g.sup_floats + g.qry_floats));
+  return g;
+}
+
+__device__ inline void query_rows(const HeadParams& p, int e, int& r0, int& nrows) {
+  r0 = p.q_offsets ? p.q_offsets[e] : e * p.Nq;
+  nrows = p.q_offsets ? p.q_offsets[e + 1] - r0 : p.Nq;
+}
+
+// one thread: start the bulk copies of episode e into stage st
+__device__ inline void stage_issue(const HeadParams& p, const Staging& g, int e, int st) {
+  float* dst = g.buf + (size_t)st * (g.sup_floats + g.qry_floats);
+  uint32_t sup_bytes = p.support ? (uint32_t)g.sup_floats * 4u : 0u;
+  uint32_t qry_bytes = 0;
+  int r0 = 0, nrows = 0;
+  if (p.queries) {
+    query_rows(p, e, r0, nrows);
+    qry_bytes = (uint32_t)nrows * (uint32_t)p.D * 4u;
+  }
+  mbar_arrive_expect_tx(&g.bars[st], sup_bytes + qry_bytes);
+  if (sup_bytes) bulk_copy_g2s(dst, p.support + (size_t)e * g.sup_floats, sup_bytes, &g.bars[st]);
+  if (qry_bytes) bulk_copy_g2s(dst + g.sup_floats, p.queries + (size_t)r0 * p.D, qry_bytes, &g.bars[st]);
+}
+
+template <int kLPR, int kCPL, int kWB, bool kStaged>
 __global__ void __launch_bounds__(kThreads) head_fwd_kernel(const HeadParams p) {
   extern __shared__ __align__(16) float smem_raw[];
   constexpr int kGroups = kWarp / kLPR;       // rows handled concurrently by one warp
   constexpr int kSlots = kWarps * kGroups;
   const Smem s = carve(smem_raw, p.Ns, p.Nq, p.W, p.D, kSlots, false);
+  const Staging g = carve_staging(smem_raw, smem_words(p.Ns, p.Nq, p.W, p.D, kSlots, false), p.Ns, p.Nq, p.D);
   const int D4 = p.D >> 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane & (kLPR - 1), grp = lane / kLPR;
   const int slot = warp * kGroups + grp;
+  if (kStaged) {
+    if (threadIdx.x == 0) {
+      mbar_init(&g.bars[0], 1);
+      mbar_init(&g.bars[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && blockIdx.x < p.E) stage_issue(p, g, blockIdx.x, 0);
+  }
 
-  for (int e = blockIdx.x; e < p.E; e += gridDim.x) {
+  int it = 0;
+  for (int e = blockIdx.x; e < p.E; e += gridDim.x, ++it) {
+    const int st = it & 1;
+    const float* stage = g.buf + (size_t)st * (g.sup_floats + g.qry_floats);
+    if (kStaged && threadIdx.x == 0 && e + (int)gridDim.x < p.E) {
+      fence_async_proxy();               // the other stage was last read before the barrier ending the previous episode
+      stage_issue(p, g, e + gridDim.x, st ^ 1);
+    }
     if (threadIdx.x == 0) *s.correct = 0;
     if (p.support) {
       bucket_rows(s, p.s_labels + (size_t)e * p.Ns, p.Ns, p.W);
-      build_prototypes(s, p.support + (size_t)e * p.Ns * p.D, p.protos_out ? p.protos_out + (size_t)e * p.W * p.D : nullptr,
-                       p.W, p.D);
+      if (kStaged) mbar_wait(&g.bars[st], (it >> 1) & 1);
+      build_prototypes<kStaged>(s, kStaged ? stage : p.support + (size_t)e * p.Ns * p.D,
+                                p.protos_out ? p.protos_out + (size_t)e * p.W * p.D : nullptr, p.W, p.D);
     } else {
       load_prototypes(s, p.protos_in + (size_t)e * p.W * p.D, p.W, p.D);
+      if (kStaged) mbar_wait(&g.bars[st], (it >> 1) & 1);
     }
     __syncthreads();
     if (p.queries) {
-      const int r0 = p.q_offsets ? p.q_offsets[e] : e * p.Nq;
-      const int nrows = p.q_offsets ? p.q_offsets[e + 1] - r0 : p.Nq;
-      const float4* q4 = reinterpret_cast<const float4*>(p.queries) + (size_t)r0 * D4;
+      int r0, nrows;
+      query_rows(p, e, r0, nrows);
+      const float4* q4 = kStaged ? reinterpret_cast<const float4*>(stage + g.sup_floats)
+                                 : reinterpret_cast<const float4*>(p.queries) + (size_t)r0 * D4;
       float nll_acc = 0.f;
       int hit = 0;
       // every lane group walks rows slot, slot+kSlots, ...; the trip count is warp-uniform
@@ -212,10 +302,10 @@ __global__ void __launch_bounds__(kThreads) head_fwd_kernel(const HeadParams p) 
         const int ii = live ? i : nrows - 1;  // clamp: dead groups redo the last row, results discarded
         float4 q[kCPL];
 #pragma unroll
-        for (int u = 0; u < kCPL; ++u) q[u] = ldg_stream(q4 + (size_t)ii * D4 + sub + u * kLPR);
+        for (int u = 0; u < kCPL; ++u) q[u] = ld_row<kStaged>(q4 + (size_t)ii * D4 + sub + u * kLPR);
         float mx, se;
         int am;
-        row_scores<kLPR, kCPL>(q, s, slot, p.W, D4, sub, mx, am, se);
+        row_scores<kLPR, kCPL, kWB>(q, s, slot, p.W, D4, sub, mx, am, se);
         if (live) {
           const float* sc = s.score + slot * p.W;
           if (p.scores)
@@ -250,34 +340,55 @@ __global__ void __launch_bounds__(kThreads) head_fwd_kernel(const HeadParams p) 
   }
 }
 
-template <int kLPR, int kCPL>
+template <int kLPR, int kCPL, int kWB, bool kStaged>
 __global__ void __launch_bounds__(kThreads) head_bwd_kernel(const HeadParams p) {
   extern __shared__ __align__(16) float smem_raw[];
   constexpr int kGroups = kWarp / kLPR;
   constexpr int kSlots = kWarps * kGroups;
   const Smem s = carve(smem_raw, p.Ns, p.Nq, p.W, p.D, kSlots, true);
+  const Staging g = carve_staging(smem_raw, smem_words(p.Ns, p.Nq, p.W, p.D, kSlots, true), p.Ns, p.Nq, p.D);
   const int D4 = p.D >> 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane & (kLPR - 1), grp = lane / kLPR;
   const int slot = warp * kGroups + grp;
   float4* sdp4 = reinterpret_cast<float4*>(s.dprotos);
   const float4* sp4 = reinterpret_cast<const float4*>(s.protos);
+  if (kStaged) {
+    if (threadIdx.x == 0) {
+      mbar_init(&g.bars[0], 1);
+      mbar_init(&g.bars[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && blockIdx.x < p.E) stage_issue(p, g, blockIdx.x, 0);
+  }
 
-  for (int e = blockIdx.x; e < p.E; e += gridDim.x) {
+  int it = 0;
+  for (int e = blockIdx.x; e < p.E; e += gridDim.x, ++it) {
+    const int st = it & 1;
+    const float* stage = g.buf + (size_t)st * (g.sup_floats + g.qry_floats);
+    if (kStaged && threadIdx.x == 0 && e + (int)gridDim.x < p.E) {
+      fence_async_proxy();
+      stage_issue(p, g, e + gridDim.x, st ^ 1);
+    }
     if (p.support) {
       bucket_rows(s, p.s_labels + (size_t)e * p.Ns, p.Ns, p.W);
-      if (p.queries) build_prototypes(s, p.support + (size_t)e * p.Ns * p.D, nullptr, p.W, p.D);
+      if (kStaged) mbar_wait(&g.bars[st], (it >> 1) & 1);
+      if (p.queries)
+        build_prototypes<kStaged>(s, kStaged ? stage : p.support + (size_t)e * p.Ns * p.D, nullptr, p.W, p.D);
     } else if (p.protos_in) {
       load_prototypes(s, p.protos_in + (size_t)e * p.W * p.D, p.W, p.D);
+      if (kStaged) mbar_wait(&g.bars[st], (it >> 1) & 1);
     } else {
       bucket_rows(s, p.s_labels + (size_t)e * p.Ns, p.Ns, p.W);  // prototype-only backward
     }
     __syncthreads();
     int nrows = 0, r0 = 0;
+    const float4* q4 = nullptr;
     if (p.queries) {
-      r0 = p.q_offsets ? p.q_offsets[e] : e * p.Nq;
-      nrows = p.q_offsets ? p.q_offsets[e + 1] - r0 : p.Nq;
-      const float4* q4 = reinterpret_cast<const float4*>(p.queries) + (size_t)r0 * D4;
+      query_rows(p, e, r0, nrows);
+      q4 = kStaged ? reinterpret_cast<const float4*>(stage + g.sup_floats)
+                   : reinterpret_cast<const float4*>(p.queries) + (size_t)r0 * D4;
       float4* dq4 = reinterpret_cast<float4*>(p.d_queries) + (size_t)r0 * D4;
       const float dl = p.d_loss ? p.d_loss[e] / (float)nrows : 0.f;
       const int trips = (nrows + kSlots - 1) / kSlots;
@@ -287,10 +398,10 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(const HeadParams p) 
         const int ii = live ? i : nrows - 1;
         float4 q[kCPL];
 #pragma unroll
-        for (int u = 0; u < kCPL; ++u) q[u] = __ldg(q4 + (size_t)ii * D4 + sub + u * kLPR);
+        for (int u = 0; u < kCPL; ++u) q[u] = ld_row_cached<kStaged>(q4 + (size_t)ii * D4 + sub + u * kLPR);
         float mx, se;
         int am;
-        row_scores<kLPR, kCPL>(q, s, slot, p.W, D4, sub, mx, am, se);
+        row_scores<kLPR, kCPL, kWB>(q, s, slot, p.W, D4, sub, mx, am, se);
         const float* sc = s.score + slot * p.W;
         float* cf = s.coef + (size_t)ii * p.W;
         const int y = p.q_labels ? p.q_labels[r0 + ii] : -1;
@@ -306,22 +417,29 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(const HeadParams p) 
         }
         __syncwarp();
         if (live) {
-          float4 acc[kCPL];
+          f32x2 acc[kCPL][2];
 #pragma unroll
-          for (int u = 0; u < kCPL; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int w = 0; w < p.W; ++w) {
-            const float c = cf[w];
+          for (int u = 0; u < kCPL; ++u) acc[u][0] = acc[u][1] = 0ull;
+          for (int w0 = 0; w0 < p.W; w0 += kWB) {
 #pragma unroll
-            for (int u = 0; u < kCPL; ++u) {
-              const float4 pr = sp4[w * D4 + sub + u * kLPR];
-              acc[u].x = fmaf(c, q[u].x - pr.x, acc[u].x);
-              acc[u].y = fmaf(c, q[u].y - pr.y, acc[u].y);
-              acc[u].z = fmaf(c, q[u].z - pr.z, acc[u].z);
-              acc[u].w = fmaf(c, q[u].w - pr.w, acc[u].w);
+            for (int b = 0; b < kWB; ++b) {
+              const float c = cf[w0 + b];
+              const f32x2 c2 = pack2(c, c);
+#pragma unroll
+              for (int u = 0; u < kCPL; ++u) {
+                const float4 pr = sp4[(w0 + b) * D4 + sub + u * kLPR];
+                acc[u][0] = fma2(c2, sub2(pack2(q[u].x, q[u].y), pack2(pr.x, pr.y)), acc[u][0]);
+                acc[u][1] = fma2(c2, sub2(pack2(q[u].z, q[u].w), pack2(pr.z, pr.w)), acc[u][1]);
+              }
             }
           }
 #pragma unroll
-          for (int u = 0; u < kCPL; ++u) stg_stream(dq4 + (size_t)i * D4 + sub + u * kLPR, acc[u]);
+          for (int u = 0; u < kCPL; ++u) {
+            float4 o;
+            unpack2(acc[u][0], o.x, o.y);
+            unpack2(acc[u][1], o.z, o.w);
+            stg_stream(dq4 + (size_t)i * D4 + sub + u * kLPR, o);
+          }
         }
         __syncwarp();
       }
@@ -329,7 +447,6 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(const HeadParams p) 
     __syncthreads();
     // dP[w] = -sum_i coef[i,w] (q_i - p_w)  (+ extra), rows in ascending order (deterministic)
     if (p.queries || p.d_protos_extra) {
-      const float4* q4 = p.queries ? reinterpret_cast<const float4*>(p.queries) + (size_t)r0 * D4 : nullptr;
       const float4* ex4 = p.d_protos_extra ? reinterpret_cast<const float4*>(p.d_protos_extra) + (size_t)e * p.W * D4 : nullptr;
       float4* dpo4 = p.d_protos ? reinterpret_cast<float4*>(p.d_protos) + (size_t)e * p.W * D4 : nullptr;
       for (int item = threadIdx.x; item < p.W * D4; item += kThreads) {
@@ -337,14 +454,18 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(const HeadParams p) 
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         if (q4) {
           const float4 pr = sp4[item];
+          const f32x2 pa = pack2(pr.x, pr.y), pb = pack2(pr.z, pr.w);
+          f32x2 a0 = 0ull, a1 = 0ull;
+#pragma unroll 5
           for (int i = 0; i < nrows; ++i) {
-            const float cf = s.coef[(size_t)i * p.W + w];
-            const float4 qv = __ldg(q4 + (size_t)i * D4 + c);
-            acc.x = fmaf(-cf, qv.x - pr.x, acc.x);
-            acc.y = fmaf(-cf, qv.y - pr.y, acc.y);
-            acc.z = fmaf(-cf, qv.z - pr.z, acc.z);
-            acc.w = fmaf(-cf, qv.w - pr.w, acc.w);
+            const float cf = -s.coef[(size_t)i * p.W + w];
+            const f32x2 c2 = pack2(cf, cf);
+            const float4 qv = ld_row_cached<kStaged>(q4 + (size_t)i * D4 + c);
+            a0 = fma2(c2, sub2(pack2(qv.x, qv.y), pa), a0);
+            a1 = fma2(c2, sub2(pack2(qv.z, qv.w), pb), a1);
           }
+          unpack2(a0, acc.x, acc.y);
+          unpack2(a1, acc.z, acc.w);
         }
         if (ex4) {
           const float4 x = __ldg(ex4 + item);
@@ -380,38 +501,61 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(const HeadParams p) 
 using KernelFn = void (*)(const HeadParams);
 
 struct Variant {
-  KernelFn fwd, bwd;
+  KernelFn fwd, bwd, fwd_staged, bwd_staged;
   int slots;
 };
 
-bool pick_variant(int D, Variant& v) {
-#define AFSL_VARIANT(LPR, CPL)                                                       \
-  if (D == 4 * LPR * CPL) {                                                          \
-    v.fwd = head_fwd_kernel<LPR, CPL>;                                               \
-    v.bwd = head_bwd_kernel<LPR, CPL>;                                               \
-    v.slots = kWarps * (kWarp / LPR);                                                \
-    return true;                                                                     \
+template <int kLPR, int kCPL>
+void fill_variant(int W, Variant& v) {
+  v.slots = kWarps * (kWarp / kLPR);
+#define AFSL_WB(WB)                                          \
+  {                                                          \
+    v.fwd = head_fwd_kernel<kLPR, kCPL, WB, false>;          \
+    v.bwd = head_bwd_kernel<kLPR, kCPL, WB, false>;          \
+    v.fwd_staged = head_fwd_kernel<kLPR, kCPL, WB, true>;    \
+    v.bwd_staged = head_bwd_kernel<kLPR, kCPL, WB, true>;    \
   }
-  AFSL_VARIANT(4, 1)    // D = 16
-  AFSL_VARIANT(8, 1)    // D = 32
-  AFSL_VARIANT(16, 1)   // D = 64
-  AFSL_VARIANT(32, 1)   // D = 128
-  AFSL_VARIANT(32, 2)   // D = 256
-  AFSL_VARIANT(32, 4)   // D = 512
-  AFSL_VARIANT(32, 8)   // D = 1024
-#undef AFSL_VARIANT
-  return false;
+  if (W % 5 == 0) AFSL_WB(5) else if (W % 4 == 0) AFSL_WB(4) else AFSL_WB(1)
+#undef AFSL_WB
+}
+
+// lane group per query row: 8 lanes up to D = 256 (4 rows per warp), wider groups beyond
+bool pick_variant(int D, int W, Variant& v) {
+  switch (D) {
+    case 16: fill_variant<4, 1>(W, v); return true;
+    case 32: fill_variant<8, 1>(W, v); return true;
+    case 64: fill_variant<8, 2>(W, v); return true;
+    case 128: fill_variant<8, 4>(W, v); return true;
+    case 256: fill_variant<8, 8>(W, v); return true;
+    case 512: fill_variant<16, 8>(W, v); return true;
+    case 1024: fill_variant<32, 8>(W, v); return true;
+    default: return false;
+  }
 }
 
 int launch(const HeadParams& p, bool bwd, cudaStream_t stream, const char* name) {
   AFSL_REQUIRE(p.E >= 0 && p.W > 0 && p.D > 0, "%s: bad sizes E=%d W=%d D=%d", name, p.E, p.W, p.D);
   if (p.E == 0) return AFSL_OK;
   Variant v;
-  AFSL_REQUIRE(pick_variant(p.D, v), "%s: unsupported embedding dim D=%d (supported: 16,32,64,128,256,512,1024)", name, p.D);
-  const size_t bytes = smem_words(p.Ns, p.Nq, p.W, p.D, v.slots, bwd) * sizeof(float);
+  AFSL_REQUIRE(pick_variant(p.D, p.W, v), "%s: unsupported embedding dim D=%d (supported: 16,32,64,128,256,512,1024)", name, p.D);
+  size_t bytes = smem_words(p.Ns, p.Nq, p.W, p.D, v.slots, bwd) * sizeof(float);
   AFSL_REQUIRE(bytes <= 220 * 1024, "%s: episode does not fit shared memory (W=%d D=%d Ns=%d Nq=%d -> %zu B)", name,
                p.W, p.D, p.Ns, p.Nq, bytes);
   KernelFn fn = bwd ? v.bwd : v.fwd;
+  // TMA-staged variant: double-buffered bulk copies of the support / query blocks, when two stages fit
+  // next to the working set with room for at least two CTAs per SM
+  const size_t staged_bytes = align4(bytes / sizeof(float)) * sizeof(float) +
+                              2 * (size_t)(p.Ns + p.Nq) * p.D * sizeof(float) + 2 * sizeof(uint64_t);
+  const bool has_blocks = (p.support != nullptr || p.queries != nullptr) && (p.Ns + p.Nq) > 0;
+  static const int staged_mode = [] {   // AFSL_HEAD_STAGED=0 / 1 overrides the default choice (measurement switch)
+    const char* e = getenv("AFSL_HEAD_STAGED");
+    return e ? atoi(e) : -1;
+  }();
+  const bool want_staged = staged_mode < 0 ? kStagedByDefault : staged_mode != 0;
+  if (want_staged && has_blocks && staged_bytes <= 110 * 1024 && (size_t)(p.Ns + p.Nq) * p.D * 4 < (1u << 20)) {
+    fn = bwd ? v.bwd_staged : v.fwd_staged;
+    bytes = staged_bytes;
+  }
   if (bytes > 48 * 1024) {
     cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (err != cudaSuccess) {

@@ -8,10 +8,11 @@
 // mask views are bit-exact and the warp view differs only by fp32 rounding of the spline.
 //
 // HBM-bound streaming kernel (algorithmic traffic 4 B x (1 read + up to 4 writes) per element).
-// One CTA handles kRows consecutive mel rows of one sample: the tile is contiguous in memory, so
-// loads/stores are flat 128-bit accesses even though T (157, 126) is not a multiple of 4.  The tile
-// (+1 halo row each side, needed because grid_sample's y coordinate is f +- 1ulp) is staged in
-// shared memory for the time-warp gather.
+// One CTA handles kRows consecutive mel rows of one sample, one warp per row.  T (157, 126) is not a
+// multiple of 4, so rows are not 16-byte aligned: accesses are 4 B per lane / 128 B per warp
+// instruction, which keeps every 32 B sector fully used.  The tile (+1 halo row each side, needed
+// because grid_sample's y coordinate is f +- 1 ulp for 36 of the 128 rows) is staged in shared
+// memory for the time-warp gather.
 #include "afsl_common.cuh"
 
 namespace afsl {
@@ -32,7 +33,7 @@ struct SpecParams {
   const int32_t* freq_masks;  // [sets,num_mask,2]
   int num_mask;
   float mask_value;
-  int N, set_size, F, T, views_mask;
+  int N, set_size, F, T, views_mask, split;
 };
 
 // Normalised source x of output column t, following hspline_interpolate_1D
@@ -63,109 +64,130 @@ __device__ __forceinline__ float spline_source_x(int t, int p, int d, int T) {
   return r;
 }
 
+// One warp per mel row: lane l owns columns l, l+32, ... (kTJ of them), so everything that depends
+// only on the column (warp source column / weight, time-mask flag) lives in registers for the whole
+// tile and everything that depends only on the row (frequency-mask flag, y blend) is warp-uniform.
+// Global accesses are 4-byte per lane, 128 B per warp instruction, fully coalesced for any T.
+template <int kTJ>
 __global__ void __launch_bounds__(kThreads) specaug_kernel(const SpecParams p) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(16) float tile[];          // [(kRows+2) * T], row 0 = halo above
   const int T = p.T, F = p.F;
-  float* tile = smem;                                   // [(kRows+2) * T], row 0 = halo above
-  int* col_lo = reinterpret_cast<int*>(tile + (kRows + 2) * T);   // [T]
-  float* col_w = reinterpret_cast<float*>(col_lo + T);            // [T]
-
-  const int tiles_per_sample = (F + kRows - 1) / kRows;
-  const long long total_tiles = (long long)p.N * tiles_per_sample;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kWarpsPerCta = kThreads / 32;
   const size_t plane = (size_t)p.N * F * T;
-  for (long long tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x) {
-    const int n = (int)(tile_id / tiles_per_sample);
-    const int f0 = (int)(tile_id - (long long)n * tiles_per_sample) * kRows;
-    const int rows = min(kRows, F - f0);
+  const bool want_copy = p.views_mask & 1, want_warp = p.views_mask & 2, want_tm = p.views_mask & 4,
+             want_fm = p.views_mask & 8;
+
+  // work item = kSplit-th part of one sample (a run of row tiles): the per-column tables below are
+  // computed once per item and reused for all its rows
+  const int tiles_per_sample = (F + kRows - 1) / kRows;
+  const int tiles_per_item = (tiles_per_sample + p.split - 1) / p.split;
+  const long long total_items = (long long)p.N * p.split;
+  for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
+    const int n = (int)(item / p.split);
+    const int part = (int)(item - (long long)n * p.split);
     const int set = n / p.set_size;
     const float* xs = p.x + (size_t)n * F * T;
-    const bool want_warp = (p.views_mask & 2) != 0;
+    const int32_t* tmk = p.time_masks + (size_t)set * p.num_mask * 2;
+    const int32_t* fmk = p.freq_masks + (size_t)set * p.num_mask * 2;
 
-    if (want_warp) {
-      for (int t = threadIdx.x; t < T; t += kThreads) {
-        const float gx = p.src_x ? p.src_x[(size_t)n * T + t] : spline_source_x(t, p.warp_p[n], p.warp_d[n], T);
-        // grid_sampler_unnormalize, align_corners=True: ((g + 1) / 2) * (size - 1)
-        const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), (float)(T - 1));
-        const float fl = floorf(ix);
-        col_lo[t] = (int)fl;
-        col_w[t] = __fsub_rn(ix, fl);
-      }
-      // halo rows f0-1 and f0+rows (zero when outside the image: zeros padding)
-      for (int t = threadIdx.x; t < 2 * T; t += kThreads) {
-        const bool below = t >= T;
-        const int tt = below ? t - T : t;
-        const int f = below ? f0 + rows : f0 - 1;
-        tile[(below ? rows + 1 : 0) * T + tt] = (f >= 0 && f < F) ? __ldg(xs + (size_t)f * T + tt) : 0.f;
+    // per-column registers
+    int col_lo[kTJ];
+    float col_w[kTJ];
+    unsigned tmask_bits = 0;
+#pragma unroll
+    for (int j = 0; j < kTJ; ++j) {
+      const int t = lane + 32 * j;
+      col_lo[j] = 0;
+      col_w[j] = 0.f;
+      if (t < T) {
+        if (want_warp) {
+          const float gx = p.src_x ? __ldg(p.src_x + (size_t)n * T + t)
+                                   : spline_source_x(t, __ldg(p.warp_p + n), __ldg(p.warp_d + n), T);
+          // grid_sampler_unnormalize, align_corners=True: ((g + 1) / 2) * (size - 1)
+          const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), (float)(T - 1));
+          const float fl = floorf(ix);
+          col_lo[j] = (int)fl;
+          col_w[j] = __fsub_rn(ix, fl);
+        }
+        if (want_tm)
+          for (int m = 0; m < p.num_mask; ++m) {
+            const int t0 = __ldg(tmk + 2 * m), len = __ldg(tmk + 2 * m + 1);
+            if (t >= t0 && t < t0 + len) tmask_bits |= 1u << j;
+          }
       }
     }
-    // body: flat 128-bit loads; keep a copy in registers for the copy / mask views
-    const int n4 = (rows * T) >> 2;
-    const float4* src4 = reinterpret_cast<const float4*>(xs + (size_t)f0 * T);
-    for (int q = threadIdx.x; q < n4; q += kThreads) {
-      const float4 v = ldg_stream(src4 + q);
-      if (want_warp) {
-        // tile + T is 16-byte aligned only when T % 4 == 0, so the shared copy is written as scalars
-        float* dst = tile + T + 4 * q;
-        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
-      }
-      const int e0 = 4 * q;
-      const size_t out_off = (size_t)n * F * T + (size_t)f0 * T + e0;
-      if (p.views_mask & 1) stg_stream(reinterpret_cast<float4*>(p.views + out_off), v);
-      if (p.views_mask & (4 | 8)) {
-        float tm[4] = {v.x, v.y, v.z, v.w}, fm[4] = {v.x, v.y, v.z, v.w};
+    for (int tl = part * tiles_per_item; tl < min((part + 1) * tiles_per_item, tiles_per_sample); ++tl) {
+    const int f0 = tl * kRows;
+    const int rows = min(kRows, F - f0);
+    // pass 1: rows (with halo when warping) -> shared tile; copy / mask views straight from registers
+    const int r_begin = want_warp ? 0 : 1, r_end = want_warp ? rows + 2 : rows + 1;
+    for (int r = r_begin + warp; r < r_end; r += kWarpsPerCta) {
+      const int f = f0 - 1 + r;
+      const bool inside = f >= 0 && f < F;
+      const bool body = r >= 1 && r <= rows;
+      bool frow = false;
+      if (body && want_fm)
+        for (int m = 0; m < p.num_mask; ++m) {
+          const int a = __ldg(fmk + 2 * m), len = __ldg(fmk + 2 * m + 1);
+          frow |= (f >= a && f < a + len);
+        }
+      const float* src = xs + (size_t)f * T;
+      const size_t out_off = (size_t)n * F * T + (size_t)f * T;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int e = e0 + k;
-          const int r = e / T, t = e - r * T;
-          const int f = f0 + r;
-          for (int m = 0; m < p.num_mask; ++m) {
-            const int* tmk = p.time_masks + ((size_t)set * p.num_mask + m) * 2;
-            const int* fmk = p.freq_masks + ((size_t)set * p.num_mask + m) * 2;
-            if (t >= tmk[0] && t < tmk[0] + tmk[1]) tm[k] = p.mask_value;
-            if (f >= fmk[0] && f < fmk[0] + fmk[1]) fm[k] = p.mask_value;
+      for (int j = 0; j < kTJ; ++j) {
+        const int t = lane + 32 * j;
+        if (t < T) {
+          const float v = inside ? __ldg(src + t) : 0.f;
+          if (want_warp) tile[r * T + t] = v;
+          if (body) {
+            if (want_copy) p.views[out_off + t] = v;
+            if (want_tm) p.views[2 * plane + out_off + t] = ((tmask_bits >> j) & 1u) ? p.mask_value : v;
+            if (want_fm) p.views[3 * plane + out_off + t] = frow ? p.mask_value : v;
           }
         }
-        if (p.views_mask & 4)
-          stg_stream(reinterpret_cast<float4*>(p.views + 2 * plane + out_off), make_float4(tm[0], tm[1], tm[2], tm[3]));
-        if (p.views_mask & 8)
-          stg_stream(reinterpret_cast<float4*>(p.views + 3 * plane + out_off), make_float4(fm[0], fm[1], fm[2], fm[3]));
       }
     }
     if (want_warp) {
       __syncthreads();
-      for (int q = threadIdx.x; q < n4; q += kThreads) {
-        float o[4];
+      for (int r = 1 + warp; r <= rows; r += kWarpsPerCta) {
+        const int f = f0 - 1 + r;
+        const int yn = __ldg(p.row_lo + f);
+        const float wn = __ldg(p.row_w + f);          // n = iy - floor(iy); s = 1 - n
+        const float ws = __fsub_rn(1.f, wn);
+        const int rr = yn - (f0 - 1);
+        const bool north_in = yn >= 0 && yn < F, south_in = yn + 1 >= 0 && yn + 1 < F;
+        const bool staged = rr >= 0 && rr + 1 < rows + 2;
+        const float* north = tile + rr * T;
+        const float* south = north + T;
+        const size_t out_off = plane + (size_t)n * F * T + (size_t)f * T;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int e = 4 * q + k;
-          const int r = e / T, t = e - r * T;
-          const int f = f0 + r;
-          const int yn = p.row_lo[f];
-          const float wn = p.row_w[f];           // n = iy - floor(iy)
-          const float ws = __fsub_rn(1.f, wn);   // s
-          const int xw = col_lo[t];
-          const float ww = col_w[t];             // w = ix - floor(ix)
-          const float we = __fsub_rn(1.f, ww);   // e
-          // corner fetch: shared tile when the row is inside [f0-1, f0+rows], else global; zero outside the image
-          auto fetch = [&](int yy, int xx) -> float {
-            if (xx < 0 || xx >= T || yy < 0 || yy >= F) return 0.f;
-            const int rr = yy - (f0 - 1);
-            if (rr >= 0 && rr < rows + 2) return tile[rr * T + xx];
-            return __ldg(xs + (size_t)yy * T + xx);
-          };
-          const float v_nw = fetch(yn, xw), v_ne = fetch(yn, xw + 1);
-          const float v_sw = fetch(yn + 1, xw), v_se = fetch(yn + 1, xw + 1);
-          float acc = __fmul_rn(v_nw, __fmul_rn(ws, we));
-          acc = __fadd_rn(acc, __fmul_rn(v_ne, __fmul_rn(ws, ww)));
-          acc = __fadd_rn(acc, __fmul_rn(v_sw, __fmul_rn(wn, we)));
-          acc = __fadd_rn(acc, __fmul_rn(v_se, __fmul_rn(wn, ww)));
-          o[k] = acc;
+        for (int j = 0; j < kTJ; ++j) {
+          const int t = lane + 32 * j;
+          if (t < T) {
+            const int xw = col_lo[j];
+            const float ww = col_w[j], we = __fsub_rn(1.f, ww);
+            const bool west_in = xw >= 0 && xw < T, east_in = xw + 1 >= 0 && xw + 1 < T;
+            float v_nw = 0.f, v_ne = 0.f, v_sw = 0.f, v_se = 0.f;
+            if (staged) {
+              if (north_in) { if (west_in) v_nw = north[xw]; if (east_in) v_ne = north[xw + 1]; }
+              if (south_in && wn != 0.f) { if (west_in) v_sw = south[xw]; if (east_in) v_se = south[xw + 1]; }
+            } else {  // generic row tables: fall back to global memory
+              if (north_in) { if (west_in) v_nw = __ldg(xs + (size_t)yn * T + xw); if (east_in) v_ne = __ldg(xs + (size_t)yn * T + xw + 1); }
+              if (south_in) { if (west_in) v_sw = __ldg(xs + (size_t)(yn + 1) * T + xw); if (east_in) v_se = __ldg(xs + (size_t)(yn + 1) * T + xw + 1); }
+            }
+            // out = nw*(s*e) + ne*(s*w) + sw*(n*e) + se*(n*w), each product and sum rounded (grid_sampler order)
+            float acc = __fmul_rn(v_nw, __fmul_rn(ws, we));
+            acc = __fadd_rn(acc, __fmul_rn(v_ne, __fmul_rn(ws, ww)));
+            acc = __fadd_rn(acc, __fmul_rn(v_sw, __fmul_rn(wn, we)));
+            acc = __fadd_rn(acc, __fmul_rn(v_se, __fmul_rn(wn, ww)));
+            p.views[out_off + t] = acc;
+          }
         }
-        const size_t out_off = (size_t)n * F * T + (size_t)f0 * T + 4 * q;
-        stg_stream(reinterpret_cast<float4*>(p.views + plane + out_off), make_float4(o[0], o[1], o[2], o[3]));
       }
       __syncthreads();
     }
+    }  // row tiles of the item
   }
 }
 
@@ -181,7 +203,6 @@ extern "C" int afsl_specaug_views_f32(const float* x, float* views, const int32_
   AFSL_REQUIRE(x && views, "afsl_specaug_views_f32: null pointer");
   AFSL_REQUIRE(N >= 0 && F > 0 && T > 1 && set_size > 0, "afsl_specaug_views_f32: bad sizes N=%d F=%d T=%d set=%d", N, F, T,
                set_size);
-  AFSL_REQUIRE(F % 4 == 0, "afsl_specaug_views_f32: F=%d must be a multiple of 4 (128-bit tiles)", F);
   AFSL_REQUIRE(views_mask > 0 && views_mask < 16, "afsl_specaug_views_f32: views_mask=%d", views_mask);
   if (views_mask & 2) {
     AFSL_REQUIRE(row_lo && row_w, "afsl_specaug_views_f32: time-warp view needs row_lo/row_w");
@@ -196,12 +217,21 @@ extern "C" int afsl_specaug_views_f32(const float* x, float* views, const int32_
   p.x = x; p.views = views; p.warp_p = warp_p; p.warp_d = warp_d; p.src_x = src_x; p.row_lo = row_lo; p.row_w = row_w;
   p.time_masks = time_masks; p.freq_masks = freq_masks; p.num_mask = num_mask; p.mask_value = mask_value;
   p.N = N; p.set_size = set_size; p.F = F; p.T = T; p.views_mask = views_mask;
-  const size_t bytes = ((size_t)(kRows + 2) * T + 2 * (size_t)T) * sizeof(float);
-  if (int rc = opt_in_smem(specaug_kernel, bytes, "afsl_specaug_views_f32")) return rc;
-  const long long tiles = (long long)N * ((F + kRows - 1) / kRows);
-  const int cap = persistent_grid(specaug_kernel, kThreads, bytes, 1 << 30);
-  const int grid = (int)(tiles < cap ? tiles : cap);
-  specaug_kernel<<<grid, kThreads, bytes, (cudaStream_t)stream>>>(p);
+  const size_t bytes = (size_t)(kRows + 2) * T * sizeof(float);
+  const int tj = (T + 31) / 32;
+  AFSL_REQUIRE(tj <= 16, "afsl_specaug_views_f32: T=%d too long (max 512 columns)", T);
+  void (*fn)(const SpecParams) = tj <= 4 ? specaug_kernel<4> : tj <= 5 ? specaug_kernel<5> : tj <= 8 ? specaug_kernel<8>
+                                                                                          : specaug_kernel<16>;
+  if (int rc = opt_in_smem(fn, bytes, "afsl_specaug_views_f32")) return rc;
+  // whole samples per CTA when there are enough of them to fill the machine twice, else split samples
+  const int cap = persistent_grid(fn, kThreads, bytes, 1 << 30);
+  const int tiles_per_sample = (F + kRows - 1) / kRows;
+  int split = 1;
+  while ((long long)N * split < 2LL * cap && split < tiles_per_sample) split *= 2;
+  p.split = split;
+  const long long items = (long long)N * split;
+  const int grid = (int)(items < cap ? items : cap);
+  fn<<<grid, kThreads, bytes, (cudaStream_t)stream>>>(p);
   AFSL_CHECK_LAUNCH("afsl_specaug_views_f32");
   return AFSL_OK;
 }

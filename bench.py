@@ -115,13 +115,15 @@ def build_model(device):
 
 
 def kernel_rooflines(device, peak_gbs, episodes):
-    """CUDA-event timing of the custom kernels alone, on buffers larger than L2, vs their algorithmic bytes."""
-    import afsl_b200.ops as ops
-    from afsl_b200.utils.augmentations import SpecAugment
+    """CUDA-event timing of each libafsl kernel alone (direct C-ABI launches on preallocated buffers larger
+    than the 126 MB L2, current stream) against its algorithmic bytes (SURVEY 8d / DESIGN.md)."""
+    from afsl_b200._lib import call, ptr, stream_ptr
+    from afsl_b200.ops import _row_tables
     out = {}
 
-    def timed(fn, reps=10):
-        fn(); fn()
+    def timed(fn, reps=20):
+        for _ in range(3):
+            fn()
         torch.cuda.synchronize()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
@@ -131,55 +133,83 @@ def kernel_rooflines(device, peak_gbs, episodes):
         torch.cuda.synchronize()
         return start.elapsed_time(end) / reps * 1e-3
 
-    # SpecAugment: sets of 25 samples, 4 views written; algorithmic bytes 4*N*F*T*(1+V)   
-    sets = max(2 * episodes, 64)
-    n = sets * 25
+    def entry(name, bytes_per_launch, sec, units, launches=1, **extra):
+        out[name] = {"bound": "hbm", "achieved": bytes_per_launch / sec / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": bytes_per_launch / sec / 1e9 / peak_gbs, "traffic": None, "ms": sec * 1e3, "units": units,
+                     "bytes_per_launch": bytes_per_launch, "launches": launches, **extra}
+
+    st = stream_ptr()
+    # ---- SpecAugment: 4 views written; algorithmic bytes 4*N*F*T*(1+V) per launch (10.05 MB / 25-sample set)
+    sets, n = 256, 256 * 25
     x = torch.randn(n, 1, MELS, T_LEN, device=device)
-    aug = SpecAugment(EXPERIMENT_CONFIG)
-    params = aug.draw_batch(sets, 25, T_LEN, replay_reference_rng=False)
     views = torch.empty(4, n, 1, MELS, T_LEN, device=device)
-    sec = timed(lambda: aug.apply_batch(x, params, out=views))
-    bytes_ = 4.0 * n * MELS * T_LEN * 5
-    out["specaug_views"] = {"bound": "hbm", "achieved": bytes_ / sec / 1e9, "peak": peak_gbs, "unit": "GB/s",
-                            "frac": bytes_ / sec / 1e9 / peak_gbs, "traffic": None, "ms": sec * 1e3,
-                            "units": f"{sets} sets x 25 samples", "bytes_per_launch": bytes_}
+    wp = torch.randint(22, T_LEN - 22, (n,), device=device, dtype=torch.int32)
+    wd = torch.randint(-22, 22, (n,), device=device, dtype=torch.int32)
+    tm = torch.tensor([[[40, 12]]], device=device, dtype=torch.int32).repeat(sets, 1, 1).contiguous()
+    fm = torch.tensor([[[60, 9]]], device=device, dtype=torch.int32).repeat(sets, 1, 1).contiguous()
+    lo, w = _row_tables(MELS, device)
+    sec = timed(lambda: call("afsl_specaug_views_f32", ptr(x), ptr(views), ptr(wp), ptr(wd), None, ptr(lo), ptr(w), ptr(tm),
+                             ptr(fm), 1, 0.0, n, 25, MELS, T_LEN, 15, st))
+    entry("specaug_views", 4.0 * n * MELS * T_LEN * 5, sec, f"{sets} sets x 25 samples [1,128,157]")
     del x, views
-    # fused head fwd+bwd, D=256, 5w5s5q: 4*D*[3*(Ns+Nq)+W] + 4*(Ns+Nq) + 4 B/episode (158.9 KB)
-    e, d, ns, nq = 16384, 256, 25, 25
-    s = torch.randn(e, ns, d, device=device, requires_grad=True)
-    q = torch.randn(e, nq, d, device=device, requires_grad=True)
-    sl = torch.arange(N_WAY, device=device).repeat_interleave(K_SHOT).expand(e, -1).contiguous()
-    ql = torch.arange(N_WAY, device=device).repeat_interleave(K_QUERY).expand(e, -1).contiguous()
-    w = torch.full((e,), 1.0 / e, device=device)
-
-    def head():
-        loss, _, _ = ops.proto_head(s, sl, q, ql, n_way=N_WAY)
-        s.grad = q.grad = None
-        loss.backward(w)
-    sec = timed(head)
-    per_ep = 4.0 * d * (3 * (ns + nq) + N_WAY) + 4 * (ns + nq) + 4
-    out["proto_head_fwd_bwd"] = {"bound": "hbm", "achieved": per_ep * e / sec / 1e9, "peak": peak_gbs, "unit": "GB/s",
-                                 "frac": per_ep * e / sec / 1e9 / peak_gbs, "traffic": None, "ms": sec * 1e3,
-                                 "units": f"{e} episodes", "bytes_per_launch": per_ep * e}
-    # CPL fwd+bwd, Dp=256, Nq=25: 4*Dp*3*(Nq+W) + Nq^2/8 B/episode (92.2 KB)
-    p = torch.randn(e, N_WAY, d, device=device, requires_grad=True)
-
-    def cpl():
-        loss = ops.cpl_loss(p, q, ql, 9.2361)
-        p.grad = q.grad = None
-        loss.backward(w)
-    sec = timed(cpl)
-    per_ep = 4.0 * d * 3 * (nq + N_WAY) + nq * nq / 8
-    out["cpl_fwd_bwd"] = {"bound": "hbm", "achieved": per_ep * e / sec / 1e9, "peak": peak_gbs, "unit": "GB/s",
-                          "frac": per_ep * e / sec / 1e9 / peak_gbs, "traffic": None, "ms": sec * 1e3,
-                          "units": f"{e} episodes", "bytes_per_launch": per_ep * e}
-    # evaluation head, 5w5s D=256: 4*D*(Ns+Nq) + 4*(Ns+Nq) + 8 B/task (51.4 KB)
-    sd, qd = s.detach(), q.detach()
-    sec = timed(lambda: ops.proto_eval(sd, sl, qd, ql, n_way=N_WAY))
-    per_task = 4.0 * d * (ns + nq) + 4 * (ns + nq) + 8
-    out["eval_head"] = {"bound": "hbm", "achieved": per_task * e / sec / 1e9, "peak": peak_gbs, "unit": "GB/s",
-                        "frac": per_task * e / sec / 1e9 / peak_gbs, "traffic": None, "ms": sec * 1e3,
-                        "units": f"{e} tasks", "tasks_per_s": e / sec, "bytes_per_launch": per_task * e}
+    # ---- fused head, D=256, 5w5s5q
+    e, d, ns, nq, ways = 16384, 256, 25, 25, N_WAY
+    s = torch.randn(e, ns, d, device=device)
+    q = torch.randn(e, nq, d, device=device)
+    sl = torch.arange(ways, device=device, dtype=torch.int32).repeat_interleave(K_SHOT).expand(e, -1).contiguous()
+    ql = torch.arange(ways, device=device, dtype=torch.int32).repeat_interleave(K_QUERY).expand(e, -1).contiguous()
+    protos = torch.empty(e, ways, d, device=device)
+    loss = torch.empty(e, device=device)
+    correct = torch.empty(e, device=device, dtype=torch.int32)
+    pred = torch.empty(e * nq, device=device, dtype=torch.int32)
+    post = torch.empty(e * nq, device=device)
+    dl = torch.full((e,), 1.0 / e, device=device)
+    ds, dq = torch.empty_like(s), torch.empty_like(q)
+    fwd = lambda: call("afsl_proto_head_fwd_f32", ptr(s), ptr(sl), ptr(q), ptr(ql), None, ptr(protos), None, ptr(loss), None,
+                       None, ptr(correct), e, ns, nq, ways, d, st)
+    bwd = lambda: call("afsl_proto_head_bwd_f32", ptr(s), ptr(sl), ptr(q), ptr(ql), None, ptr(dl), None, ptr(ds), ptr(dq), e,
+                       ns, nq, ways, d, st)
+    t_f, t_b = timed(fwd), timed(bwd)
+    b_f = (4.0 * d * (ns + nq + ways) + 4 * (ns + nq) + 8) * e            # read S,Q ; write prototypes, loss, correct
+    b_b = (4.0 * d * 2 * (ns + nq) + 4 * (ns + nq) + 4) * e                # re-read S,Q ; write dS,dQ
+    entry("proto_head_fwd", b_f, t_f, f"{e} episodes 5w5s5q D=256")
+    entry("proto_head_bwd", b_b, t_b, f"{e} episodes 5w5s5q D=256")
+    # SURVEY 8d unit: 4*D*[3*(Ns+Nq)+W] + 4*(Ns+Nq) + 4 = 158.9 KB per episode for fwd+bwd
+    entry("proto_head_fwd_bwd", (4.0 * d * (3 * (ns + nq) + ways) + 4 * (ns + nq) + 4) * e, t_f + t_b,
+          f"{e} episodes 5w5s5q D=256", launches=2, episodes_per_s=e / (t_f + t_b))
+    # ---- evaluation head (prototypes + distances + argmax + accuracy): 4*D*(Ns+Nq) + 4*(Ns+Nq) + 8 B per task
+    ev = lambda: call("afsl_proto_head_fwd_f32", ptr(s), ptr(sl), ptr(q), ptr(ql), None, None, None, None, ptr(pred), ptr(post),
+                      ptr(correct), e, ns, nq, ways, d, st)
+    t_e = timed(ev)
+    entry("eval_head", (4.0 * d * (ns + nq) + 4 * (ns + nq) + 8) * e, t_e, f"{e} tasks 5w5s5q D=256", tasks_per_s=e / t_e)
+    # ---- CPL fwd+bwd, Dp=256, Nq=25: 4*Dp*3*(Nq+W) + Nq^2/8 B per episode (92.2 KB)
+    p = torch.randn(e, ways, d, device=device)
+    dp = torch.empty_like(p)
+    cf = lambda: call("afsl_cpl_fwd_f32", ptr(p), ptr(q), ptr(ql), None, 9.2361, ptr(loss), e, nq, ways, d, st)
+    cb = lambda: call("afsl_cpl_bwd_f32", ptr(p), ptr(q), ptr(ql), None, 9.2361, ptr(dl), ptr(dp), ptr(dq), e, nq, ways, d, st)
+    t_cf, t_cb = timed(cf), timed(cb)
+    entry("cpl_fwd", (4.0 * d * (nq + ways) + 4 * nq + 4) * e, t_cf, f"{e} episodes Nq=25 Dp=256")
+    entry("cpl_bwd", (4.0 * d * 2 * (nq + ways) + 4 * nq + 4) * e, t_cb, f"{e} episodes Nq=25 Dp=256")
+    entry("cpl_fwd_bwd", (4.0 * d * 3 * (nq + ways) + nq * nq / 8) * e, t_cf + t_cb, f"{e} episodes Nq=25 Dp=256", launches=2)
+    del s, q, ds, dq, p, dp
+    # ---- grouped BN + ReLU + MaxPool, stage-1 shape [G*25, 64, 128, 157]
+    g, grp, c, h, wd_ = 16, 25, 64, MELS, T_LEN
+    xx = torch.randn(g * grp, c, h, wd_, device=device)
+    mean, rstd, var = (torch.empty(g, c, device=device) for _ in range(3))
+    gamma, beta = torch.ones(c, device=device), torch.zeros(c, device=device)
+    yy = torch.empty(g * grp, c, h // 3, wd_ // 3, device=device)
+    dyy = torch.randn_like(yy)
+    dxx = torch.empty_like(xx)
+    sums = torch.empty(g, c, 2, device=device)
+    t_s = timed(lambda: call("afsl_gbn_stats_f32", ptr(xx), ptr(mean), ptr(rstd), ptr(var), g, grp, c, h, wd_, 1e-5, st), reps=5)
+    t_gf = timed(lambda: call("afsl_gbn_relu_pool_fwd_f32", ptr(xx), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(yy), g, grp,
+                              c, h, wd_, 1, st), reps=5)
+    t_gb = timed(lambda: call("afsl_gbn_relu_pool_bwd_f32", ptr(xx), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(dyy),
+                              ptr(dxx), ptr(sums), g, grp, c, h, wd_, 1, st), reps=5)
+    nx, ny = xx.numel() * 4.0, yy.numel() * 4.0
+    entry("gbn_stats", nx, t_s, f"{g} groups x 25 x [64,128,157]")
+    entry("gbn_relu_pool_fwd", nx + ny, t_gf, f"{g} groups x 25 x [64,128,157]")
+    entry("gbn_relu_pool_bwd", 2 * (nx + ny) + nx, t_gb, f"{g} groups x 25 x [64,128,157]", launches=2)
     return out
 
 
