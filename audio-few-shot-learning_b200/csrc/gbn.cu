@@ -144,6 +144,27 @@ __device__ __forceinline__ void window_max(const float* __restrict__ pl, int W, 
   }
 }
 
+// same, on 9 values already in registers (row-major); also returns x at the argmax
+__device__ __forceinline__ void window_load(const float* __restrict__ pl, int W, int ph, int pw, float (&xv)[9]) {
+  const float* base = pl + (size_t)(3 * ph) * W + 3 * pw;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int q = 0; q < 3; ++q) xv[r * 3 + q] = __ldg(base + r * W + q);
+}
+__device__ __forceinline__ void window_pick(const float (&xv)[9], const Affine& f, float& zmax, int& arg, float& xmax) {
+  zmax = -INFINITY;
+  arg = 0;
+  xmax = xv[0];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const float z = fmaf(f.a, xv[k], f.b);
+    if (z > zmax || z != z) {
+      if (!(zmax != zmax)) { zmax = z; arg = k; xmax = xv[k]; }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- forward
 __global__ void __launch_bounds__(kThreads) gbn_fwd_kernel(const GbnParams p) {
   const int hw = p.H * p.W, phw = p.PH * p.PW;
@@ -181,14 +202,16 @@ __global__ void __launch_bounds__(kThreads) gbn_bwd_reduce_kernel(const GbnParam
       const int i = o / phw, rem = o - i * phw;
       const int ph = rem / p.PW, pw = rem - ph * p.PW;
       const float* pl = x0 + (size_t)i * plane_stride;
-      float zmax;
+      // all ten loads of the window are independent: issue them together, then decide
+      const float dyv = __ldg(dy0 + (size_t)i * pplane_stride + rem);
+      float xv[9];
+      window_load(pl, p.W, ph, pw, xv);
+      float zmax, xmax;
       int arg;
-      window_max(pl, p.W, ph, pw, f, zmax, arg);
+      window_pick(xv, f, zmax, arg, xmax);
       if (zmax > 0.f) {  // ReLU gate
-        const float dz = __ldg(dy0 + (size_t)i * pplane_stride + rem);
-        const float xv = __ldg(pl + (size_t)(3 * ph + arg / 3) * p.W + 3 * pw + arg % 3);
-        s1 += dz;
-        s2 = fmaf(dz, (xv - f.mean) * f.rstd, s2);
+        s1 += dyv;
+        s2 = fmaf(dyv, (xmax - f.mean) * f.rstd, s2);
       }
     }
     const double t1 = block_sum_d((double)s1, red);
@@ -226,16 +249,19 @@ __global__ void __launch_bounds__(kThreads) gbn_bwd_dx_kernel(const GbnParams p)
       const int ph = rem / p.PW, pw = rem - ph * p.PW;
       const float* pl = x0 + (size_t)i * plane_stride;
       float* dpl = dx0 + (size_t)i * plane_stride;
-      float zmax;
+      const float dyv = __ldg(dy0 + (size_t)i * pplane_stride + rem);
+      float xv[9];
+      window_load(pl, p.W, ph, pw, xv);
+      float zmax, xmax;
       int arg;
-      window_max(pl, p.W, ph, pw, f, zmax, arg);
-      const float dz = zmax > 0.f ? __ldg(dy0 + (size_t)i * pplane_stride + rem) : 0.f;
+      window_pick(xv, f, zmax, arg, xmax);
+      const float dz = zmax > 0.f ? dyv : 0.f;
       const size_t base = (size_t)(3 * ph) * p.W + 3 * pw;
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-          const float xhat = (__ldg(pl + base + r * p.W + q) - f.mean) * f.rstd;
+          const float xhat = (xv[r * 3 + q] - f.mean) * f.rstd;
           const float d = (r * 3 + q == arg) ? dz : 0.f;
           dpl[base + r * p.W + q] = f.a * (d - m1 - xhat * m2);
         }
