@@ -32,6 +32,9 @@ SIGNATURES = {
     "afsl_angular_fwd_f32": [_P, _P, _P, _F, _F, _I, _I, _P, _I, _I, _I, _I, _P],
     "afsl_angular_bwd_f32": [_P, _P, _P, _F, _F, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P],
     "afsl_specaug_views_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _I, _I, _I, _I, _I, _P],
+    "afsl_view_fusion_grid": [_I, _I],
+    "afsl_view_fusion_fwd_f32": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "afsl_view_fusion_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "afsl_gbn_stats_f32": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "afsl_gbn_relu_pool_fwd_f32": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "afsl_gbn_relu_pool_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
@@ -57,6 +60,8 @@ def load() -> ctypes.CDLL:
     lib.afsl_version.restype = c_int
     lib.afsl_last_error.restype = c_char_p
     lib.afsl_launch_count.restype = c_longlong
+    lib.afsl_view_fusion_weight_floats.restype = c_int
+    lib.afsl_view_fusion_param_floats.restype = c_int
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

@@ -122,6 +122,7 @@ def _all_equal(v, k) -> bool:
     return v == k if isinstance(v, int) else all(int(e) == k for e in v)
 
 
+FUSED_VIEW_FUSION = True
 FUSED_STAGES = True     # switch for A/B measurements of the fused BatchNorm-ReLU-MaxPool kernels
 
 
@@ -270,7 +271,10 @@ class SelfAttention(nn.Module):
 
     def forward(self, x):
         lead = x.shape[:-2]                            # [N] or [E, N]
-        y = self.encoder_layer(x.reshape(-1, *x.shape[-2:]))
+        if x.is_cuda and FUSED_VIEW_FUSION and ops.view_fusion_supported(self.encoder_layer, x.shape[-2]):
+            y = ops.view_fusion(x, self.encoder_layer)                 # libafsl kernel (fwd + bwd)
+        else:                                          # other layer shapes / CPU unit tests: stock module
+            y = self.encoder_layer(x.reshape(-1, *x.shape[-2:]))
         return y.reshape(*lead, -1)                    # views side by side == cat(y[:, i, :])
 
 

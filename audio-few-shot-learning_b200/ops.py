@@ -357,6 +357,88 @@ def specaug_views(x: torch.Tensor, warp_p: torch.Tensor, warp_d: torch.Tensor, t
     return views
 
 
+# ---------------------------------------------------------------------------------- view fusion
+_FUSION_PARAMS = ("self_attn.in_proj_weight", "self_attn.in_proj_bias", "self_attn.out_proj.weight", "self_attn.out_proj.bias",
+                  "linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias", "norm1.weight", "norm1.bias",
+                  "norm2.weight", "norm2.bias")
+
+
+class _ViewFusion(torch.autograd.Function):
+    """x [N,V,64] -> y [N,V,64] through the packed encoder-layer weights (see include/afsl.h)."""
+
+    @staticmethod
+    def forward(ctx, x, masks, *params):
+        n, v, d = x.shape
+        ffn = params[4].shape[0]
+        flat = [p.detach().reshape(-1) for p in params]
+        transposed = [params[0].detach().t().reshape(-1), params[2].detach().t().reshape(-1),
+                      params[4].detach().t().reshape(-1), params[6].detach().t().reshape(-1)]
+        packed = torch.cat(flat + transposed).float().contiguous()
+        y = torch.empty_like(x)
+        m = [None if t is None else _f32(t) for t in masks]
+        call("afsl_view_fusion_fwd_f32", ptr(x), ptr(packed), ptr(y), ptr(m[0]), ptr(m[1]), ptr(m[2]), ptr(m[3]), n, v, d, ffn,
+             stream_ptr())
+        ctx.save_for_backward(x, packed, *[t for t in m if t is not None])
+        ctx.mask_present = [t is not None for t in m]
+        ctx.shapes = [p.shape for p in params]
+        ctx.dims = (n, v, d, ffn)
+        return y
+
+    @staticmethod
+    def backward(ctx, d_y):
+        x, packed, *present = ctx.saved_tensors
+        it = iter(present)
+        m = [next(it) if has else None for has in ctx.mask_present]
+        n, v, d, ffn = ctx.dims
+        lib = _lib.load()
+        count = int(lib.afsl_view_fusion_param_floats())
+        grid = int(lib.afsl_view_fusion_grid(n, v))
+        d_y = _f32(d_y)
+        d_x = torch.empty_like(x)
+        partial = torch.zeros(grid, count, device=x.device, dtype=torch.float32)
+        call("afsl_view_fusion_bwd_f32", ptr(x), ptr(packed), ptr(d_y), ptr(m[0]), ptr(m[1]), ptr(m[2]), ptr(m[3]), ptr(d_x),
+             ptr(partial), n, v, d, ffn, stream_ptr())
+        total = partial.sum(0)
+        grads, off = [], 0
+        for shape in ctx.shapes:
+            k = int(torch.Size(shape).numel())
+            grads.append(total[off:off + k].view(shape))
+            off += k
+        return (d_x, None, *grads)
+
+
+def view_fusion_supported(layer: torch.nn.TransformerEncoderLayer, views: int) -> bool:
+    att = layer.self_attn
+    return (att.embed_dim == 64 and att.num_heads == 1 and layer.linear1.out_features == 256 and not layer.norm_first
+            and views in (1, 2, 4, 8) and getattr(layer, "activation_relu_or_gelu", 1) == 1
+            and abs(layer.norm1.eps - 1e-5) < 1e-12 and att.in_proj_weight is not None)
+
+
+def view_fusion(x: torch.Tensor, layer: torch.nn.TransformerEncoderLayer, masks=None) -> torch.Tensor:
+    """One post-norm encoder layer over the views: x [.., V, 64] -> [.., V, 64] on the libafsl kernel.
+
+    ``masks``: optional 4-tuple of keep masks scaled by 1/(1-p) for the dropout sites (attention
+    probabilities [N,V,V], after out_proj [N,V,64], after ReLU [N,V,256], after linear2 [N,V,64]).
+    When omitted they are drawn with torch if the layer is in training mode with p > 0."""
+    lead = x.shape[:-2]
+    v, d = x.shape[-2:]
+    xf = _f32(x.reshape(-1, v, d))
+    n = xf.shape[0]
+    if masks is None:
+        masks = (None, None, None, None)
+        if layer.training:
+            def draw(p, *shape):
+                if p <= 0.0:
+                    return None
+                return (torch.rand(*shape, device=xf.device) >= p).float() / (1.0 - p)
+            masks = (draw(layer.self_attn.dropout, n, v, v), draw(layer.dropout1.p, n, v, d),
+                     draw(layer.dropout.p, n, v, layer.linear1.out_features), draw(layer.dropout2.p, n, v, d))
+    named = dict(layer.named_parameters())
+    params = [named[k] for k in _FUSION_PARAMS]
+    y = _ViewFusion.apply(xf, tuple(masks), *params)
+    return y.view(*lead, v, d)
+
+
 # ---------------------------------------------------------------------------------- grouped BN + ReLU + pool
 class _GbnReluPool(torch.autograd.Function):
     """y = MaxPool3(ReLU(BN(u + conv_bias))) with u the bias-free convolution output.

@@ -176,6 +176,34 @@ int afsl_eval_vote_i32(const int32_t* pred, const int32_t* clip_ids, const int32
                        int32_t* correct_clips, int32_t* n_clips, int E, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * View fusion: one post-norm transformer encoder layer (1 head, ReLU FFN, d_model 64,
+ * dim_feedforward 256) over the V views of every sample; the output [N, V*64] is the
+ * V tokens laid side by side.  Replaces SelfAttention.forward,
+ * models/main_modules.py:222-228 (nn.TransformerEncoderLayer).
+ *   x [N,V,64] -> y [N,V,64]
+ * weights: packed fp32 block of afsl_view_fusion_weight_floats() floats =
+ *   in_proj_weight[192,64] | in_proj_bias | out_proj.weight[64,64] | bias |
+ *   linear1.weight[256,64] | bias | linear2.weight[64,256] | bias | norm1.w | norm1.b |
+ *   norm2.w | norm2.b   (= afsl_view_fusion_param_floats() parameters)
+ *   followed by the transposed copies in_proj^T | out_proj^T | linear1^T | linear2^T.
+ * drop_* [opt]: keep masks already scaled by 1/(1-p) for the four dropout sites
+ *   (attention probabilities [N,V,V], after out_proj [N,V,64], after ReLU [N,V,256],
+ *   after linear2 [N,V,64]); NULL = no dropout (eval mode).
+ * bwd recomputes the forward per tile; d_weights_partial is a ZERO-INITIALISED buffer
+ * [afsl_view_fusion_grid(N,V), param_floats] of per-CTA partial sums (the caller adds
+ * them up: no atomics, reproducible).
+ * ------------------------------------------------------------------------- */
+int afsl_view_fusion_weight_floats(void);
+int afsl_view_fusion_param_floats(void);
+int afsl_view_fusion_grid(int N, int V);
+int afsl_view_fusion_fwd_f32(const float* x, const float* weights, float* y, const float* drop_attn,
+                             const float* drop1, const float* drop_ffn, const float* drop2, int N, int V,
+                             int d, int ffn, void* stream);
+int afsl_view_fusion_bwd_f32(const float* x, const float* weights, const float* d_y, const float* drop_attn,
+                             const float* drop1, const float* drop_ffn, const float* drop2, float* d_x,
+                             float* d_weights_partial, int N, int V, int d, int ffn, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Grouped BatchNorm + ReLU + MaxPool(3, stride 3) over convolution outputs whose
  * batch axis holds G groups of `group` consecutive samples with independent batch
  * statistics - one group = one encoder call of the reference (conv_block,

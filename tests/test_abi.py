@@ -41,7 +41,8 @@ def test_header_symbols_exported(lib):
 
 def test_ctypes_table_matches_header(lib):
     decl = declared_functions()
-    bound = set(lib.SIGNATURES) | {"afsl_version", "afsl_last_error", "afsl_launch_count"}
+    bound = set(lib.SIGNATURES) | {"afsl_version", "afsl_last_error", "afsl_launch_count",
+                                   "afsl_view_fusion_weight_floats", "afsl_view_fusion_param_floats"}
     assert bound == set(decl), (bound ^ set(decl))
     for name, argtypes in lib.SIGNATURES.items():
         args = decl[name]
