@@ -38,6 +38,9 @@ SIGNATURES = {
     "afsl_gbn_stats_f32": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "afsl_gbn_relu_pool_fwd_f32": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "afsl_gbn_relu_pool_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "afsl_stage1_moments_f64": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "afsl_stage1_fwd_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "afsl_stage1_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "afsl_eval_vote_i32": [_P, _P, _P, _P, _P, _I, _P, _P, _I, _P],
 }
 
@@ -62,6 +65,8 @@ def load() -> ctypes.CDLL:
     lib.afsl_launch_count.restype = c_longlong
     lib.afsl_view_fusion_weight_floats.restype = c_int
     lib.afsl_view_fusion_param_floats.restype = c_int
+    lib.afsl_stage1_channels.restype = c_int
+    lib.afsl_stage1_acc_slots.restype = c_int
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

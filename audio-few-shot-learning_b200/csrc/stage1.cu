@@ -1,0 +1,323 @@
+// Encoder stage 1 fused: Conv3x3(1 -> 64, pad 1) + grouped BatchNorm + ReLU + MaxPool(3,3), forward and
+// backward, without ever materialising the full-resolution 64-channel activation.
+//
+// Reference: conv_block(in_channels=1, 64, pool 3) = the first block of conv_encoder,
+// models/main_modules.py:43-81, applied per view per set per episode (:18-23) -> batch statistics per
+// group of `group` consecutive samples.  With one input channel the convolution is 9 multiply-adds per
+// output, while its output is 64x larger than its input (5.1 MB vs 80 KB per spectrogram): the cuDNN path
+// (conv -> stats -> BN/ReLU/pool, and wgrad over the full-resolution gradient) is bound by ~10 passes over
+// that tensor.  Here:
+//   moments : per group the 9 shifted sums S_k = sum x(p+k) and the 45 products R_kl = sum x(p+k) x(p+l)
+//             over all positions p (zero padding).  The conv output u_c = sum_k w_ck x(p+k) has
+//             sum u_c = sum_k w_ck S_k and sum u_c^2 = sum_kl w_ck w_cl R_kl, so mean / variance of all 64
+//             channels follow from 54 numbers per group (host-side, tiny) - exact in real arithmetic.
+//   forward : per pooled position recompute the 3x3 window of conv outputs from a shared-memory input
+//             tile, apply z = a u + b (BatchNorm folded, conv bias folded into the statistics), ReLU, max.
+//   backward: per pooled position recompute the window, route dy to the first argmax (as
+//             at::max_pool2d_with_indices), and accumulate per (group, channel)
+//             s1 = sum dz, s2 = sum dz*xhat, T_k = sum dz * x(p_argmax + k); the weight gradient is
+//             dW_c[k] = sum_g a_gc [ T_gck - m1 S_gk - m2 rstd (sum_l w_cl R_glk - mean S_gk) ] (host, tiny).
+// Compute-bound on the fp32 pipe (~90 FFMA per pooled output per channel), traffic = input + pooled output.
+#include "afsl_common.cuh"
+
+namespace afsl {
+namespace {
+
+constexpr int kThreads = 512;        // 16 warps x 4 channels: keeps the 44 backward accumulators per thread in registers
+constexpr int kWarps = kThreads / kWarp;
+constexpr int kC = 64;              // output channels of stage 1
+constexpr int kCPW = kC / kWarps;   // channels per warp
+constexpr int kBands = 8;           // pooled rows per tile
+constexpr int kAcc = 11;            // s1, s2, T_0..T_8
+
+struct S1Params {
+  const float* x;        // [G*group, H, W]
+  const float* w;        // [kC, 9]
+  const float* a;        // [G,kC] or [kC]  (z = a*u + b)
+  const float* b;
+  const float* mean;     // [G,kC] or [kC]  mean of u   (backward)
+  const float* rstd;
+  const float* dy;       // [G*group, kC, PH, PW]
+  float* y;              // [G*group, kC, PH, PW]
+  double* moments;       // [G, 54]
+  float* partial;        // [G, parts, kC, kAcc]
+  int G, group, H, W, PH, PW, per_group, parts;
+};
+
+// ---------------------------------------------------------------- input moments
+__global__ void __launch_bounds__(kThreads) stage1_moments_kernel(const S1Params p) {
+  __shared__ double red[kWarps];
+  const int H = p.H, W = p.W, hw = H * W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // grid = G * parts_m CTAs; CTA (g, part) strides over the group's elements
+  const int parts = gridDim.x / p.G;
+  const int g = blockIdx.x / parts, part = blockIdx.x - g * parts;
+  const float* x0 = p.x + (size_t)g * p.group * hw;
+  float acc[54];
+#pragma unroll
+  for (int k = 0; k < 54; ++k) acc[k] = 0.f;
+  const int total = p.group * hw;
+  for (int o = part * kThreads + threadIdx.x; o < total; o += parts * kThreads) {
+    const int s = o / hw, rem = o - s * hw;
+    const int i = rem / W, j = rem - i * W;
+    const float* pl = x0 + (size_t)s * hw;
+    float v[9];
+#pragma unroll
+    for (int a = -1; a <= 1; ++a)
+#pragma unroll
+      for (int b = -1; b <= 1; ++b) {
+        const int ii = i + a, jj = j + b;
+        v[(a + 1) * 3 + (b + 1)] = (ii >= 0 && ii < H && jj >= 0 && jj < W) ? __ldg(pl + (size_t)ii * W + jj) : 0.f;
+      }
+    int q = 9;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      acc[k] += v[k];
+#pragma unroll
+      for (int l = k; l < 9; ++l) {
+        acc[q] = fmaf(v[k], v[l], acc[q]);
+        ++q;
+      }
+    }
+  }
+  // block reduction in double, one value at a time (54 values, once per CTA)
+  for (int k = 0; k < 54; ++k) {
+    double v = (double)acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int q = 0; q < kWarps; ++q) t += red[q];
+      p.moments[((size_t)g * parts + part) * 54 + k] = t;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- tile staging shared by fwd / bwd
+// tile = rows [3*ph0 - 1, 3*ph0 + 3*bands + 1) x cols [-1, W + 1) of one sample, zero padded; stride W + 2
+__device__ inline void stage_tile(const float* __restrict__ pl, float* tile, int H, int W, int ph0, int bands) {
+  const int rows = 3 * bands + 2, ld = W + 2;
+  for (int o = threadIdx.x; o < rows * ld; o += kThreads) {
+    const int r = o / ld, c = o - r * ld;
+    const int i = 3 * ph0 - 1 + r, j = c - 1;
+    tile[o] = (i >= 0 && i < H && j >= 0 && j < W) ? __ldg(pl + (size_t)i * W + j) : 0.f;
+  }
+}
+
+// 5x5 input patch of the pooling window at (band bl, column pw) inside the tile
+__device__ __forceinline__ void load_patch(const float* tile, int ld, int bl, int pw, float (&v)[25]) {
+  const float* base = tile + (size_t)(3 * bl) * ld + 3 * pw;
+#pragma unroll
+  for (int r = 0; r < 5; ++r)
+#pragma unroll
+    for (int c = 0; c < 5; ++c) v[r * 5 + c] = base[r * ld + c];
+}
+
+// conv output at window element (r, q) from the patch and the channel's 9 weights
+__device__ __forceinline__ float conv_at(const float (&v)[25], const float (&w)[9], int r, int q) {
+  float u = 0.f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) u = fmaf(w[a * 3 + b], v[(r + a) * 5 + (q + b)], u);
+  return u;
+}
+
+__global__ void __launch_bounds__(kThreads) stage1_fwd_kernel(const S1Params p) {
+  extern __shared__ __align__(16) float smem[];
+  float* tile = smem;                                    // [(3*kBands+2) * (W+2)]
+  float* sw = tile + (3 * kBands + 2) * (p.W + 2);       // [kC*9] weights, [kC] a, [kC] b
+  const int H = p.H, W = p.W, PH = p.PH, PW = p.PW, ld = W + 2, hw = H * W, phw = PH * PW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tiles_per_sample = (PH + kBands - 1) / kBands;
+  const long long total_tiles = (long long)p.G * p.group * tiles_per_sample;
+  for (int i = threadIdx.x; i < kC * 9; i += kThreads) sw[i] = __ldg(p.w + i);
+  int cur_g = -1;
+  for (long long tl = blockIdx.x; tl < total_tiles; tl += gridDim.x) {
+    const int s = (int)(tl / tiles_per_sample), tix = (int)(tl - (long long)s * tiles_per_sample);
+    const int g = s / p.group;
+    const int ph0 = tix * kBands, bands = min(kBands, PH - ph0);
+    __syncthreads();
+    if (g != cur_g) {                                    // per-(group, channel) affine
+      for (int c = threadIdx.x; c < kC; c += kThreads) {
+        const int idx = p.per_group ? g * kC + c : c;
+        sw[kC * 9 + c] = __ldg(p.a + idx);
+        sw[kC * 10 + c] = __ldg(p.b + idx);
+      }
+      cur_g = g;
+    }
+    stage_tile(p.x + (size_t)s * hw, tile, H, W, ph0, bands);
+    __syncthreads();
+    const int npos = bands * PW;
+    for (int pos = lane; pos < npos; pos += 32) {
+      const int bl = pos / PW, pw = pos - bl * PW;
+      float v[25];
+      load_patch(tile, ld, bl, pw, v);
+      float* yout = p.y + ((size_t)s * kC) * phw + (size_t)(ph0 + bl) * PW + pw;
+#pragma unroll 1
+      for (int cc = 0; cc < kCPW; ++cc) {
+        const int c = warp * kCPW + cc;
+        float w[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) w[k] = sw[c * 9 + k];
+        const float a = sw[kC * 9 + c], b = sw[kC * 10 + c];
+        float zmax = -INFINITY;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const float z = fmaf(a, conv_at(v, w, r, q), b);
+            zmax = (z > zmax || z != z) ? ((zmax != zmax) ? zmax : z) : zmax;
+          }
+        yout[(size_t)c * phw] = zmax != zmax ? zmax : fmaxf(zmax, 0.f);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) stage1_bwd_kernel(const S1Params p) {
+  extern __shared__ __align__(16) float smem[];
+  float* tile = smem;
+  float* sw = tile + (3 * kBands + 2) * (p.W + 2);       // [kC*9] w, [kC] a, [kC] b, [kC] mean, [kC] rstd
+  const int H = p.H, W = p.W, PH = p.PH, PW = p.PW, ld = W + 2, hw = H * W, phw = PH * PW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tiles_per_sample = (PH + kBands - 1) / kBands;
+  const int tiles_per_group = p.group * tiles_per_sample;
+  // CTA (g, part) walks the tiles part, part + parts, ... of group g and owns partial[g][part]
+  const int g = blockIdx.x / p.parts, part = blockIdx.x - g * p.parts;
+  for (int i = threadIdx.x; i < kC * 9; i += kThreads) sw[i] = __ldg(p.w + i);
+  for (int c = threadIdx.x; c < kC; c += kThreads) {
+    const int idx = p.per_group ? g * kC + c : c;
+    sw[kC * 9 + c] = __ldg(p.a + idx);
+    sw[kC * 10 + c] = __ldg(p.b + idx);
+    sw[kC * 11 + c] = __ldg(p.mean + idx);
+    sw[kC * 12 + c] = __ldg(p.rstd + idx);
+  }
+  float acc[kCPW][kAcc];
+#pragma unroll
+  for (int cc = 0; cc < kCPW; ++cc)
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) acc[cc][k] = 0.f;
+
+  for (int tl = part; tl < tiles_per_group; tl += p.parts) {
+    const int sl = tl / tiles_per_sample, tix = tl - sl * tiles_per_sample;
+    const int s = g * p.group + sl;
+    const int ph0 = tix * kBands, bands = min(kBands, PH - ph0);
+    __syncthreads();
+    stage_tile(p.x + (size_t)s * hw, tile, H, W, ph0, bands);
+    __syncthreads();
+    const int npos = bands * PW;
+    for (int pos = lane; pos < npos; pos += 32) {
+      const int bl = pos / PW, pw = pos - bl * PW;
+      float v[25];
+      load_patch(tile, ld, bl, pw, v);
+      const float* dyp = p.dy + ((size_t)s * kC) * phw + (size_t)(ph0 + bl) * PW + pw;
+#pragma unroll
+      for (int cc = 0; cc < kCPW; ++cc) {
+        const int c = warp * kCPW + cc;
+        const float dyv = __ldg(dyp + (size_t)c * phw);
+        float w[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) w[k] = sw[c * 9 + k];
+        const float a = sw[kC * 9 + c], b = sw[kC * 10 + c];
+        float zmax = -INFINITY, umax = 0.f;
+        int arg = 0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const float u = conv_at(v, w, r, q);
+            const float z = fmaf(a, u, b);
+            if ((z > zmax || z != z) && !(zmax != zmax)) { zmax = z; umax = u; arg = r * 3 + q; }
+          }
+        if (zmax > 0.f) {                               // ReLU gate; dz = dy routed to the window argmax
+          const float xhat = (umax - sw[kC * 11 + c]) * sw[kC * 12 + c];
+          acc[cc][0] += dyv;
+          acc[cc][1] = fmaf(dyv, xhat, acc[cc][1]);
+          // x(p_argmax + tap): the argmax is a runtime index, so read the 3x3 neighbourhood from the shared tile
+          const int ar = arg / 3, aq = arg - ar * 3;
+          const float* nb = tile + (size_t)(3 * bl + ar) * ld + 3 * pw + aq;
+#pragma unroll
+          for (int ka = 0; ka < 3; ++ka)
+#pragma unroll
+            for (int kb = 0; kb < 3; ++kb)
+              acc[cc][2 + ka * 3 + kb] = fmaf(dyv, nb[ka * ld + kb], acc[cc][2 + ka * 3 + kb]);
+        }
+      }
+    }
+  }
+  // warp reduction of the register accumulators, one (channel, slot) at a time, then one store per value
+  float* out = p.partial + (((size_t)g * p.parts + part) * kC) * kAcc;
+#pragma unroll
+  for (int cc = 0; cc < kCPW; ++cc)
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) {
+      const float t = warp_sum(acc[cc][k]);
+      if (lane == 0) out[(size_t)(warp * kCPW + cc) * kAcc + k] = t;
+    }
+}
+
+size_t smem_bytes(int W, bool bwd) {
+  return ((size_t)(3 * kBands + 2) * (W + 2) + kC * 9 + kC * (bwd ? 4 : 2)) * sizeof(float);
+}
+
+int check(const S1Params& p, const char* name) {
+  AFSL_REQUIRE(p.G > 0 && p.group > 0 && p.H >= 3 && p.W >= 3, "%s: bad sizes G=%d group=%d H=%d W=%d", name, p.G, p.group, p.H,
+               p.W);
+  AFSL_REQUIRE(p.W <= 1024, "%s: W=%d too wide for the shared-memory tile", name, p.W);
+  return AFSL_OK;
+}
+
+}  // namespace
+}  // namespace afsl
+
+extern "C" int afsl_stage1_channels(void) { return afsl::kC; }
+extern "C" int afsl_stage1_acc_slots(void) { return afsl::kAcc; }
+
+extern "C" int afsl_stage1_moments_f64(const float* x, double* moments, int parts, int G, int group, int H, int W,
+                                        void* stream) {
+  using namespace afsl;
+  AFSL_REQUIRE(x && moments && parts > 0, "afsl_stage1_moments_f64: null pointer / parts");
+  S1Params p{};
+  p.x = x; p.moments = moments; p.G = G; p.group = group; p.H = H; p.W = W;
+  if (int rc = check(p, "afsl_stage1_moments_f64")) return rc;
+  stage1_moments_kernel<<<G * parts, kThreads, 0, (cudaStream_t)stream>>>(p);
+  AFSL_CHECK_LAUNCH("afsl_stage1_moments_f64");
+  return AFSL_OK;
+}
+
+extern "C" int afsl_stage1_fwd_f32(const float* x, const float* weight, const float* a, const float* b, float* y, int G,
+                                    int group, int H, int W, int per_group, void* stream) {
+  using namespace afsl;
+  AFSL_REQUIRE(x && weight && a && b && y, "afsl_stage1_fwd_f32: null pointer");
+  S1Params p{};
+  p.x = x; p.w = weight; p.a = a; p.b = b; p.y = y;
+  p.G = G; p.group = group; p.H = H; p.W = W; p.PH = H / 3; p.PW = W / 3; p.per_group = per_group;
+  if (int rc = check(p, "afsl_stage1_fwd_f32")) return rc;
+  const size_t bytes = smem_bytes(W, false);
+  if (int rc = opt_in_smem(stage1_fwd_kernel, bytes, "afsl_stage1_fwd_f32")) return rc;
+  const long long tiles = (long long)G * group * ((p.PH + kBands - 1) / kBands);
+  const int cap = persistent_grid(stage1_fwd_kernel, kThreads, bytes, 1 << 30);
+  stage1_fwd_kernel<<<(int)(tiles < cap ? tiles : cap), kThreads, bytes, (cudaStream_t)stream>>>(p);
+  AFSL_CHECK_LAUNCH("afsl_stage1_fwd_f32");
+  return AFSL_OK;
+}
+
+extern "C" int afsl_stage1_bwd_f32(const float* x, const float* weight, const float* a, const float* b, const float* mean,
+                                    const float* rstd, const float* d_y, float* partial, int parts, int G, int group, int H,
+                                    int W, int per_group, void* stream) {
+  using namespace afsl;
+  AFSL_REQUIRE(x && weight && a && b && mean && rstd && d_y && partial && parts > 0, "afsl_stage1_bwd_f32: null pointer / parts");
+  S1Params p{};
+  p.x = x; p.w = weight; p.a = a; p.b = b; p.mean = mean; p.rstd = rstd; p.dy = d_y; p.partial = partial;
+  p.G = G; p.group = group; p.H = H; p.W = W; p.PH = H / 3; p.PW = W / 3; p.per_group = per_group; p.parts = parts;
+  if (int rc = check(p, "afsl_stage1_bwd_f32")) return rc;
+  const size_t bytes = smem_bytes(W, true);
+  if (int rc = opt_in_smem(stage1_bwd_kernel, bytes, "afsl_stage1_bwd_f32")) return rc;
+  stage1_bwd_kernel<<<G * parts, kThreads, bytes, (cudaStream_t)stream>>>(p);
+  AFSL_CHECK_LAUNCH("afsl_stage1_bwd_f32");
+  return AFSL_OK;
+}

@@ -107,6 +107,9 @@ class ConvBlock(nn.Sequential):
     def forward(self, x):
         conv, bn, relu, pool = self[0], self[1], self[2], self[3]
         is3 = _all_equal(pool.kernel_size, 3) and _all_equal(pool.stride, 3) and _all_equal(pool.padding, 0)
+        if x.is_cuda and is3 and FUSED_STAGE1 and FUSED_STAGES and ops.stage1_supported(conv, x):
+            # 1-channel first block: convolution fused into the BatchNorm/ReLU/pool kernel (no cuDNN call)
+            return ops.stage1_conv_bn_relu_pool(x, conv, bn, getattr(bn, "group_size", None))
         if x.is_cuda and is3 and FUSED_STAGES:
             # bias-free cuDNN convolution; the bias is folded into the BatchNorm statistics by the kernel
             u = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
@@ -123,6 +126,7 @@ def _all_equal(v, k) -> bool:
 
 
 FUSED_VIEW_FUSION = True
+FUSED_STAGE1 = True
 FUSED_STAGES = True     # switch for A/B measurements of the fused BatchNorm-ReLU-MaxPool kernels
 
 

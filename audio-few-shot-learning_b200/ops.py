@@ -514,6 +514,119 @@ def gbn_relu_pool(u: torch.Tensor, bn: torch.nn.BatchNorm2d, group_size: Optiona
     return _GbnReluPool.apply(u, gamma, beta, conv_bias, mean, rstd, 1, n, False)
 
 
+# ---------------------------------------------------------------------------------- fused encoder stage 1
+_TRIU9 = None
+
+
+def _moments_to_sr(moments: torch.Tensor):
+    """[G,54] double -> S [G,9], R [G,9,9] (symmetric)."""
+    global _TRIU9
+    if _TRIU9 is None or _TRIU9.device != moments.device:
+        _TRIU9 = torch.triu_indices(9, 9, device=moments.device)
+    g = moments.shape[0]
+    r = torch.zeros(g, 9, 9, device=moments.device, dtype=torch.float64)
+    r[:, _TRIU9[0], _TRIU9[1]] = moments[:, 9:]
+    r = r + r.transpose(1, 2) - torch.diag_embed(torch.diagonal(r, dim1=1, dim2=2))
+    return moments[:, :9], r
+
+
+class _Stage1(torch.autograd.Function):
+    """y = MaxPool3(ReLU(BN(conv3x3(x) + bias))) for a 1-channel input, batch statistics per group."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, a, b, mean_u, rstd, s_mom, r_mom, groups, group, per_group):
+        n, _, h, w = x.shape
+        c = weight.shape[0]
+        y = torch.empty(n, c, h // 3, w // 3, device=x.device, dtype=torch.float32)
+        w9 = weight.detach().reshape(c, 9).float().contiguous()
+        call("afsl_stage1_fwd_f32", ptr(x), ptr(w9), ptr(a), ptr(b), ptr(y), groups, group, h, w, int(per_group), stream_ptr())
+        ctx.save_for_backward(x, w9, gamma, a, b, mean_u, rstd, s_mom, r_mom)
+        ctx.dims = (groups, group, int(per_group), bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, d_y):
+        x, w9, gamma, a, b, mean_u, rstd, s_mom, r_mom = ctx.saved_tensors
+        groups, group, per_group, has_bias = ctx.dims
+        n, _, h, w = x.shape
+        c = w9.shape[0]
+        d_y = _f32(d_y)
+        sms = torch.cuda.get_device_properties(x.device).multi_processor_count
+        parts = max(1, min(group * ((h // 3 + 7) // 8), (2 * sms + groups - 1) // groups))
+        partial = torch.empty(groups, parts, c, 11, device=x.device, dtype=torch.float32)
+        call("afsl_stage1_bwd_f32", ptr(x), ptr(w9), ptr(a), ptr(b), ptr(mean_u), ptr(rstd), ptr(d_y), ptr(partial), parts,
+             groups, group, h, w, per_group, stream_ptr())
+        acc = partial.double().sum(1)                                   # [G,C,11]
+        s1, s2, t = acc[..., 0], acc[..., 1], acc[..., 2:]               # [G,C], [G,C], [G,C,9]
+        a_gc = (a if per_group else a.unsqueeze(0).expand(groups, c)).double()
+        if per_group:
+            m = float(group * h * w)
+            m1, m2 = s1 / m, s2 / m
+            wr = torch.einsum("cl,glk->gck", w9.double(), r_mom)          # sum_l w_cl R_glk
+            corr = rstd.double().unsqueeze(-1) * (wr - mean_u.double().unsqueeze(-1) * s_mom.unsqueeze(1))
+            d_w = (a_gc.unsqueeze(-1) * (t - m1.unsqueeze(-1) * s_mom.unsqueeze(1) - m2.unsqueeze(-1) * corr)).sum(0)
+            d_bias = torch.zeros(c, device=x.device) if has_bias else None     # exactly zero under batch statistics
+        else:
+            d_w = (a_gc.unsqueeze(-1) * t).sum(0)
+            d_bias = (a_gc * s1).sum(0).float() if has_bias else None
+        d_gamma, d_beta = s2.sum(0).float(), s1.sum(0).float()
+        return (None, d_w.float().view(c, 1, 3, 3), d_bias, d_gamma, d_beta) + (None,) * 9
+
+
+def stage1_supported(conv: torch.nn.Conv2d, x: torch.Tensor) -> bool:
+    return (conv.in_channels == 1 and conv.out_channels == 64 and tuple(conv.kernel_size) == (3, 3)
+            and tuple(conv.padding) == (1, 1) and tuple(conv.stride) == (1, 1) and tuple(conv.dilation) == (1, 1)
+            and conv.groups == 1 and not x.requires_grad and x.shape[-1] >= 3 and x.shape[-2] >= 3 and x.shape[-1] <= 1024)
+
+
+def stage1_conv_bn_relu_pool(x: torch.Tensor, conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d,
+                             group_size: Optional[int] = None) -> torch.Tensor:
+    """First encoder block on a 1-channel spectrogram batch ``x [N,1,H,W]`` in two libafsl launches
+    (input moments, fused conv+BN+ReLU+pool), the 64-channel full-resolution tensor never hits HBM."""
+    x = _f32(x)
+    n, _, h, w = x.shape
+    c = conv.out_channels
+    gamma, beta = _f32(bn.weight), _f32(bn.bias)
+    bias = conv.bias
+    w9d = conv.weight.detach().reshape(c, 9).double()
+    use_batch_stats = bn.training or not bn.track_running_stats
+    if use_batch_stats:
+        group = int(group_size) if group_size else n
+        if n % group:
+            raise ValueError(f"batch of {n} samples is not a whole number of groups of {group}")
+        groups = n // group
+        sms = torch.cuda.get_device_properties(x.device).multi_processor_count
+        parts = max(1, (4 * sms + groups - 1) // groups)
+        mom = torch.empty(groups, parts, 54, device=x.device, dtype=torch.float64)
+        call("afsl_stage1_moments_f64", ptr(x), ptr(mom), parts, groups, group, h, w, stream_ptr())
+        s_mom, r_mom = _moments_to_sr(mom.sum(1))
+        m = float(group * h * w)
+        mean_u = (s_mom @ w9d.t()) / m                                          # [G,C]
+        eu2 = torch.einsum("ck,gkl,cl->gc", w9d, r_mom, w9d) / m
+        var = (eu2 - mean_u * mean_u).clamp_min(0.0)
+        rstd = torch.rsqrt(var + bn.eps)
+        a = (gamma.double() * rstd)
+        b = beta.double() - mean_u * a
+        if bn.training and bn.track_running_stats:
+            with torch.no_grad():
+                mo = bn.momentum
+                bn.num_batches_tracked += groups
+                decay = (1.0 - mo) ** torch.arange(groups - 1, -1, -1, device=x.device, dtype=torch.float64)
+                keep = (1.0 - mo) ** groups
+                true_mean = mean_u if bias is None else mean_u + bias.detach().double()
+                bn.running_mean.mul_(keep).add_(((decay.unsqueeze(1) * true_mean).sum(0) * mo).float())
+                bn.running_var.mul_(keep).add_(((decay.unsqueeze(1) * var).sum(0) * (mo * m / max(m - 1, 1))).float())
+        return _Stage1.apply(x, conv.weight, bias, gamma, beta, a.float().contiguous(), b.float().contiguous(),
+                             mean_u.float().contiguous(), rstd.float().contiguous(), s_mom, r_mom, groups, group, True)
+    rstd = torch.rsqrt(bn.running_var.double() + bn.eps)
+    mean_u = bn.running_mean.double() - (bias.detach().double() if bias is not None else 0.0)
+    a = gamma.double() * rstd
+    b = beta.double() - mean_u * a
+    empty = torch.empty(0, device=x.device, dtype=torch.float64)
+    return _Stage1.apply(x, conv.weight, bias, gamma, beta, a.float().contiguous(), b.float().contiguous(),
+                         mean_u.float().contiguous(), rstd.float().contiguous(), empty, empty, 1, n, False)
+
+
 # ---------------------------------------------------------------------------------- majority vote
 @torch.no_grad()
 def eval_vote(pred, clip_ids, labels, posterior, seg_offsets, tie_strategy: str = "min_label"):

@@ -225,6 +225,31 @@ int afsl_gbn_relu_pool_bwd_f32(const float* x, const float* mean, const float* r
                                const float* beta, const float* d_y, float* d_x, float* sums, int G,
                                int group, int C, int H, int W, int stats_per_group, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Encoder stage 1 fused: Conv3x3(1 -> 64, pad 1) + grouped BatchNorm + ReLU +
+ * MaxPool(3,3) without materialising the full-resolution activation.  Replaces the
+ * first conv_block of conv_encoder (models/main_modules.py:43-81) per group of
+ * `group` consecutive samples (one encoder call of the reference, :18-23).
+ *   x [G*group,1,H,W] -> y [G*group,64,H/3,W/3]
+ * moments: per group and part the 9 shifted sums and 45 shifted products of the input
+ *   (double [G,parts,54]: S_0..S_8, then R_kl for k <= l row by row); mean / variance
+ *   of every conv channel follow from them on the host.
+ * fwd: z = a*u + b with u the bias-free conv output; a, b (and mean, rstd of u in
+ *   bwd) are [G,64] (per_group = 1) or [64].
+ * bwd: partial [G,parts,64,11] = per channel (sum dz, sum dz*xhat, T_0..T_8) with
+ *   T_k = sum dz * x(p_argmax + tap k); weight / BatchNorm gradients are assembled
+ *   from these and the moments on the host.  The input gets no gradient.
+ * ------------------------------------------------------------------------- */
+int afsl_stage1_channels(void);
+int afsl_stage1_acc_slots(void);
+int afsl_stage1_moments_f64(const float* x, double* moments, int parts, int G, int group, int H, int W,
+                            void* stream);
+int afsl_stage1_fwd_f32(const float* x, const float* weight, const float* a, const float* b, float* y, int G,
+                        int group, int H, int W, int per_group, void* stream);
+int afsl_stage1_bwd_f32(const float* x, const float* weight, const float* a, const float* b, const float* mean,
+                        const float* rstd, const float* d_y, float* partial, int parts, int G, int group, int H,
+                        int W, int per_group, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

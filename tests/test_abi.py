@@ -42,7 +42,8 @@ def test_header_symbols_exported(lib):
 def test_ctypes_table_matches_header(lib):
     decl = declared_functions()
     bound = set(lib.SIGNATURES) | {"afsl_version", "afsl_last_error", "afsl_launch_count",
-                                   "afsl_view_fusion_weight_floats", "afsl_view_fusion_param_floats"}
+                                   "afsl_view_fusion_weight_floats", "afsl_view_fusion_param_floats",
+                                   "afsl_stage1_channels", "afsl_stage1_acc_slots"}
     assert bound == set(decl), (bound ^ set(decl))
     for name, argtypes in lib.SIGNATURES.items():
         args = decl[name]
@@ -50,7 +51,7 @@ def test_ctypes_table_matches_header(lib):
         for ct, text in zip(argtypes, args):
             if "*" in text:
                 assert ct is ctypes.c_void_p, (name, text)
-            elif text.startswith("float"):
+            elif text.startswith("float") or text.startswith("double"):
                 assert ct is ctypes.c_float, (name, text)
             else:
                 assert ct is ctypes.c_int, (name, text)

@@ -482,3 +482,45 @@ def test_view_fusion_vs_torch(ops, n, v, with_masks):
     close(xa.grad, xb.grad, rtol=1e-4)
     for (k, a), (_, b) in zip(layer.named_parameters(), ref.named_parameters()):
         close(a.grad, b.grad, rtol=1e-4)
+
+
+# ------------------------------------------------------------------ fused encoder stage 1 (conv1 + BN + ReLU + pool)
+@pytest.mark.parametrize("n,group,h,w", [(10, 5, 128, 157), (6, 3, 128, 126), (4, 4, 33, 40), (50, 25, 128, 157)])
+def test_stage1_fused_vs_torch(ops, n, group, h, w):
+    """Fused stage 1 vs the eager chain conv2d -> per-group BatchNorm2d -> ReLU -> MaxPool2d(3) (fp32, TF32 off)."""
+    gen = torch.Generator().manual_seed(n + h)
+    x = (torch.randn(n, 1, h, w, generator=gen) * 1.3 + 0.2).cuda()
+    conv, bn = torch.nn.Conv2d(1, 64, 3, padding=1).cuda(), torch.nn.BatchNorm2d(64).cuda()
+    conv_r, bn_r = torch.nn.Conv2d(1, 64, 3, padding=1).cuda(), torch.nn.BatchNorm2d(64).cuda()
+    with torch.no_grad():
+        bn.weight.uniform_(-1.5, 1.5); bn.bias.uniform_(-0.5, 0.5)
+    conv_r.load_state_dict(conv.state_dict()); bn_r.load_state_dict(bn.state_dict())
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        y = ops.stage1_conv_bn_relu_pool(x, conv, bn, group)
+        yr = torch.cat([torch.nn.functional.max_pool2d(torch.relu(bn_r(conv_r(x[i:i + group]))), 3, 3) for i in range(0, n, group)])
+        close(y, yr, rtol=2e-5)
+        gy = torch.randn(y.shape, generator=gen).cuda()
+        y.backward(gy); yr.backward(gy)
+        wscale = float(conv_r.weight.grad.abs().max())
+        close(conv.weight.grad, conv_r.weight.grad, rtol=1e-4)
+        close(conv.bias.grad, conv_r.bias.grad, rtol=0, scale=1e-4 * wscale)          # exactly 0 vs round-off
+        close(bn.weight.grad, bn_r.weight.grad, rtol=1e-4)
+        close(bn.bias.grad, bn_r.bias.grad, rtol=1e-4)
+        close(bn.running_mean, bn_r.running_mean, rtol=1e-5)
+        close(bn.running_var, bn_r.running_var, rtol=1e-5)
+        assert int(bn.num_batches_tracked) == int(bn_r.num_batches_tracked)
+        # eval mode (running statistics), gradients included
+        for mod in (conv, bn, conv_r, bn_r):
+            mod.zero_grad(); mod.eval()
+        ye = ops.stage1_conv_bn_relu_pool(x, conv, bn, group)
+        yer = torch.nn.functional.max_pool2d(torch.relu(bn_r(conv_r(x))), 3, 3)
+        close(ye, yer, rtol=2e-5)
+        ye.backward(gy); yer.backward(gy)
+        close(conv.weight.grad, conv_r.weight.grad, rtol=1e-4)
+        close(conv.bias.grad, conv_r.bias.grad, rtol=1e-4)
+        close(bn.weight.grad, bn_r.weight.grad, rtol=1e-4)
+        close(bn.bias.grad, bn_r.bias.grad, rtol=1e-4)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
