@@ -24,7 +24,7 @@ SIGNATURES = {
     "afsl_proto_scores_fwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "afsl_proto_scores_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "afsl_proto_head_fwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "afsl_proto_head_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "afsl_proto_head_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "afsl_l2_normalize_fwd_f32": [_P, _P, _I, _I, _F, _P],
     "afsl_l2_normalize_bwd_f32": [_P, _P, _P, _I, _I, _F, _P],
     "afsl_cpl_fwd_f32": [_P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _P],

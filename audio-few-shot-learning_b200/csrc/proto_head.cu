@@ -13,6 +13,7 @@
 #include <cstdlib>
 
 #include "afsl_common.cuh"
+#include "proto_head.cuh"
 
 namespace afsl {
 namespace {
@@ -21,30 +22,6 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / kWarp;
 constexpr bool kStagedByDefault = false;  // measured on B200: occupancy (8 CTAs/SM) beats staging (2 CTAs/SM) at 5w5s5q
 
-struct HeadParams {
-  // forward inputs
-  const float* support;     // [E,Ns,D] or null (then protos_in is used)
-  const int32_t* s_labels;  // [E,Ns]
-  const float* protos_in;   // [E,W,D] or null
-  const float* queries;     // [rows,D] or null (prototype-only call)
-  const int32_t* q_labels;  // [rows] or null
-  const int32_t* q_offsets; // [E+1] or null
-  // forward outputs (nullable)
-  float* protos_out;
-  float* scores;
-  float* loss;
-  int32_t* pred;
-  float* posterior;
-  int32_t* correct;
-  // backward
-  const float* d_loss;          // [E]
-  const float* d_scores;        // [rows,W] or null
-  const float* d_protos_extra;  // [E,W,D] or null
-  float* d_support;             // [E,Ns,D] or null
-  float* d_protos;              // [E,W,D] or null
-  float* d_queries;             // [rows,D] or null
-  int E, Ns, Nq, W, D;
-};
 
 // shared memory carve-up (floats/ints are both 4 bytes)
 struct Smem {
@@ -377,6 +354,7 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(const HeadParams p) 
       if (p.queries)
         build_prototypes<kStaged>(s, kStaged ? stage : p.support + (size_t)e * p.Ns * p.D, nullptr, p.W, p.D);
     } else if (p.protos_in) {
+      if (p.s_labels) bucket_rows(s, p.s_labels + (size_t)e * p.Ns, p.Ns, p.W);   // saved prototypes + dS scatter
       load_prototypes(s, p.protos_in + (size_t)e * p.W * p.D, p.W, p.D);
       if (kStaged) mbar_wait(&g.bars[st], (it >> 1) & 1);
     } else {
@@ -536,6 +514,13 @@ bool pick_variant(int D, int W, Variant& v) {
 int launch(const HeadParams& p, bool bwd, cudaStream_t stream, const char* name) {
   AFSL_REQUIRE(p.E >= 0 && p.W > 0 && p.D > 0, "%s: bad sizes E=%d W=%d D=%d", name, p.E, p.W, p.D);
   if (p.E == 0) return AFSL_OK;
+  // small W*D: one warp per episode, prototypes in registers (proto_head_warp.cu); AFSL_HEAD_WARP=0 disables it
+  const char* warp_env = getenv("AFSL_HEAD_WARP");     // read per launch so the tests can exercise both paths
+  if (!warp_env || atoi(warp_env) != 0) {
+    bool handled = false;
+    const int rc = launch_head_warp(p, bwd, stream, name, &handled);
+    if (rc != AFSL_OK || handled) return rc;
+  }
   Variant v;
   AFSL_REQUIRE(pick_variant(p.D, p.W, v), "%s: unsupported embedding dim D=%d (supported: 16,32,64,128,256,512,1024)", name, p.D);
   size_t bytes = smem_words(p.Ns, p.Nq, p.W, p.D, v.slots, bwd) * sizeof(float);
@@ -643,15 +628,17 @@ extern "C" int afsl_proto_head_fwd_f32(const float* support, const int32_t* s_la
   return afsl::launch(p, false, (cudaStream_t)stream, "afsl_proto_head_fwd_f32");
 }
 
-extern "C" int afsl_proto_head_bwd_f32(const float* support, const int32_t* s_labels, const float* queries,
-                                        const int32_t* q_labels, const int32_t* q_offsets, const float* d_loss,
-                                        const float* d_protos_extra, float* d_support, float* d_queries, int E, int Ns,
-                                        int Nq, int W, int D, void* stream) {
-  AFSL_REQUIRE(support && s_labels && queries && q_labels && d_loss && d_support && d_queries,
+extern "C" int afsl_proto_head_bwd_f32(const float* support, const float* protos, const int32_t* s_labels,
+                                        const float* queries, const int32_t* q_labels, const int32_t* q_offsets,
+                                        const float* d_loss, const float* d_protos_extra, float* d_support,
+                                        float* d_queries, int E, int Ns, int Nq, int W, int D, void* stream) {
+  AFSL_REQUIRE((support || protos) && s_labels && queries && q_labels && d_loss && d_support && d_queries,
                "afsl_proto_head_bwd_f32: null pointer");
   AFSL_REQUIRE(Ns > 0 && Nq > 0, "afsl_proto_head_bwd_f32: Ns=%d Nq=%d", Ns, Nq);
   HeadParams p{};
-  p.support = support; p.s_labels = s_labels; p.queries = queries; p.q_labels = q_labels; p.q_offsets = q_offsets;
+  // the forward's prototypes, when given, replace the re-read of the support block
+  p.support = protos ? nullptr : support; p.protos_in = protos;
+  p.s_labels = s_labels; p.queries = queries; p.q_labels = q_labels; p.q_offsets = q_offsets;
   p.d_loss = d_loss; p.d_protos_extra = d_protos_extra; p.d_support = d_support; p.d_queries = d_queries;
   p.E = E; p.Ns = Ns; p.Nq = Nq; p.W = W; p.D = D;
   return afsl::launch(p, true, (cudaStream_t)stream, "afsl_proto_head_bwd_f32");

@@ -1,0 +1,37 @@
+// Parameter block shared by the prototype-head kernels (proto_head.cu: one CTA per episode, any shape;
+// proto_head_warp.cu: one warp per episode with the prototypes in registers, small W*D).
+#pragma once
+
+#include "afsl_common.cuh"
+
+namespace afsl {
+
+struct HeadParams {
+  // forward inputs
+  const float* support;     // [E,Ns,D] or null (then protos_in is used)
+  const int32_t* s_labels;  // [E,Ns]
+  const float* protos_in;   // [E,W,D] or null
+  const float* queries;     // [rows,D] or null (prototype-only call)
+  const int32_t* q_labels;  // [rows] or null
+  const int32_t* q_offsets; // [E+1] or null
+  // forward outputs (nullable)
+  float* protos_out;
+  float* scores;
+  float* loss;
+  int32_t* pred;
+  float* posterior;
+  int32_t* correct;
+  // backward
+  const float* d_loss;          // [E]
+  const float* d_scores;        // [rows,W] or null
+  const float* d_protos_extra;  // [E,W,D] or null
+  float* d_support;             // [E,Ns,D] or null
+  float* d_protos;              // [E,W,D] or null
+  float* d_queries;             // [rows,D] or null
+  int E, Ns, Nq, W, D;
+};
+
+// proto_head_warp.cu: launches the warp-per-episode kernels when the shape fits them; *handled says whether it did
+int launch_head_warp(const HeadParams& p, bool bwd, cudaStream_t stream, const char* name, bool* handled);
+
+}  // namespace afsl

@@ -142,21 +142,22 @@ class _ProtoHead(torch.autograd.Function):
         correct = torch.empty(e, device=dev, dtype=torch.int32)
         call("afsl_proto_head_fwd_f32", ptr(support), ptr(s_labels), ptr(queries), ptr(q_labels), None, ptr(protos), None,
              ptr(loss), None, None, ptr(correct), e, ns, nq, n_way, d, stream_ptr())
-        ctx.save_for_backward(support, s_labels, queries, q_labels)
+        ctx.save_for_backward(support, s_labels, queries, q_labels, protos)
         ctx.dims = (e, ns, nq, n_way, d)
         ctx.mark_non_differentiable(correct)
         return loss, protos, correct
 
     @staticmethod
     def backward(ctx, d_loss, d_protos, _d_correct):
-        support, s_labels, queries, q_labels = ctx.saved_tensors
+        support, s_labels, queries, q_labels, protos = ctx.saved_tensors
         e, ns, nq, w, d = ctx.dims
         d_loss = _f32(d_loss) if d_loss is not None else torch.zeros(e, device=support.device)
         d_protos = _f32(d_protos) if d_protos is not None else None
         d_support = torch.empty_like(support)
         d_queries = torch.empty_like(queries)
-        call("afsl_proto_head_bwd_f32", ptr(support), ptr(s_labels), ptr(queries), ptr(q_labels), None, ptr(d_loss),
-             ptr(d_protos), ptr(d_support), ptr(d_queries), e, ns, nq, w, d, stream_ptr())
+        # the saved prototypes stand in for the support block: the backward reads P and Q only
+        call("afsl_proto_head_bwd_f32", ptr(support), ptr(protos), ptr(s_labels), ptr(queries), ptr(q_labels), None,
+             ptr(d_loss), ptr(d_protos), ptr(d_support), ptr(d_queries), e, ns, nq, w, d, stream_ptr())
         return d_support, None, d_queries, None, None
 
 

@@ -167,8 +167,8 @@ def kernel_rooflines(device, peak_gbs, episodes):
     ds, dq = torch.empty_like(s), torch.empty_like(q)
     fwd = lambda: call("afsl_proto_head_fwd_f32", ptr(s), ptr(sl), ptr(q), ptr(ql), None, ptr(protos), None, ptr(loss), None,
                        None, ptr(correct), e, ns, nq, ways, d, st)
-    bwd = lambda: call("afsl_proto_head_bwd_f32", ptr(s), ptr(sl), ptr(q), ptr(ql), None, ptr(dl), None, ptr(ds), ptr(dq), e,
-                       ns, nq, ways, d, st)
+    bwd = lambda: call("afsl_proto_head_bwd_f32", ptr(s), ptr(protos), ptr(sl), ptr(q), ptr(ql), None, ptr(dl), None, ptr(ds),
+                       ptr(dq), e, ns, nq, ways, d, st)       # protos = the forward's output, as ops._ProtoHead passes it
     t_f, t_b = timed(fwd), timed(bwd)
     b_f = (4.0 * d * (ns + nq + ways) + 4 * (ns + nq) + 8) * e            # read S,Q ; write prototypes, loss, correct
     b_b = (4.0 * d * 2 * (ns + nq) + 4 * (ns + nq) + 4) * e                # re-read S,Q ; write dS,dQ

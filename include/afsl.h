@@ -89,16 +89,18 @@ int afsl_proto_scores_bwd_f32(const float* protos, const float* queries, const i
  * Outputs as above plus protos [E,W,D] [opt].
  * bwd: d_support, d_queries of sum_e d_loss[e]*loss[e]; d_protos_extra [E,W,D]
  * [opt] is an additional gradient arriving at the prototypes from another
- * consumer (the CPL / angular branch, loops/loops.py:44-50).
+ * consumer (the CPL / angular branch, loops/loops.py:44-50).  protos [E,W,D]
+ * [opt]: the prototypes the forward wrote; when given, the support block is
+ * not re-read (support may then be NULL), otherwise they are recomputed.
  * ------------------------------------------------------------------------- */
 int afsl_proto_head_fwd_f32(const float* support, const int32_t* s_labels, const float* queries,
                             const int32_t* q_labels, const int32_t* q_offsets, float* protos,
                             float* scores, float* loss, int32_t* pred, float* posterior,
                             int32_t* correct, int E, int Ns, int Nq, int W, int D, void* stream);
-int afsl_proto_head_bwd_f32(const float* support, const int32_t* s_labels, const float* queries,
-                            const int32_t* q_labels, const int32_t* q_offsets, const float* d_loss,
-                            const float* d_protos_extra, float* d_support, float* d_queries,
-                            int E, int Ns, int Nq, int W, int D, void* stream);
+int afsl_proto_head_bwd_f32(const float* support, const float* protos, const int32_t* s_labels,
+                            const float* queries, const int32_t* q_labels, const int32_t* q_offsets,
+                            const float* d_loss, const float* d_protos_extra, float* d_support,
+                            float* d_queries, int E, int Ns, int Nq, int W, int D, void* stream);
 
 /* ---------------------------------------------------------------------------
  * Row L2 normalisation x / max(||x||, eps).  Replaces F.normalize on the

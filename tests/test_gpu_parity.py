@@ -89,9 +89,13 @@ def test_head_scores_gradient_path(ops):
     close(q.grad, qc.grad)
 
 
-@pytest.mark.parametrize("ways,shots,nq,dim", [(5, 5, 5, 64), (5, 5, 5, 256), (20, 5, 5, 256), (5, 1, 15, 128), (3, 2, 4, 32)])
-def test_head_batched_vs_oracle(ops, ways, shots, nq, dim):
-    """E episodes at once == the oracle applied episode by episode (incl. extra prototype gradient)."""
+@pytest.mark.parametrize("path", ["warp", "cta"])
+@pytest.mark.parametrize("ways,shots,nq,dim", [(5, 5, 5, 64), (5, 5, 5, 256), (20, 5, 5, 256), (5, 1, 15, 128), (3, 2, 4, 32),
+                                               (20, 5, 5, 64), (10, 3, 7, 128), (2, 5, 40, 256)])
+def test_head_batched_vs_oracle(ops, monkeypatch, ways, shots, nq, dim, path):
+    """E episodes at once == the oracle applied episode by episode (incl. extra prototype gradient), through
+    both kernel families: one warp per episode (registers; small W*D) and one CTA per episode (any shape)."""
+    monkeypatch.setenv("AFSL_HEAD_WARP", "1" if path == "warp" else "0")
     e = 37
     gen = torch.Generator().manual_seed(ways * 1000 + dim)
     s = torch.randn(e, ways * shots, dim, generator=gen)
