@@ -14,7 +14,10 @@
 // One CTA per episode; prototypes (normalised) and the W x Nq similarity matrix live in shared
 // memory; P and Q are read from HBM once in the forward and twice in the backward (second read of
 // Q hits L2).  fp32, warp-shuffle reductions over the embedding dimension.
+#include <cstdlib>
+
 #include "afsl_common.cuh"
+#include "cpl.cuh"
 
 namespace afsl {
 namespace {
@@ -23,18 +26,6 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / kWarp;
 constexpr float kCosEps = 1e-8f;
 
-struct CplParams {
-  const float* protos;     // [E,W,D]
-  const float* queries;    // [E,Nq,D]
-  const int32_t* labels;   // [E,Nq]
-  const uint32_t* keep;    // [E,Nq,words] or null
-  float temperature;
-  float* loss;             // [E]          (forward)
-  const float* d_loss;     // [E]          (backward)
-  float* d_protos;         // [E,W,D]
-  float* d_queries;        // [E,Nq,D]
-  int E, Nq, W, D;
-};
 
 struct Smem {
   float* phat;   // [W*D]  normalised prototypes
@@ -357,6 +348,12 @@ int launch(const CplParams& p, bool bwd, cudaStream_t stream, const char* name) 
   AFSL_REQUIRE(p.E >= 0 && p.Nq > 0 && p.W > 0, "%s: bad sizes E=%d Nq=%d W=%d", name, p.E, p.Nq, p.W);
   AFSL_REQUIRE(p.temperature != 0.f, "%s: temperature must be non-zero", name);
   if (p.E == 0) return AFSL_OK;
+  const char* warp_env = getenv("AFSL_CPL_WARP");      // read per launch so the tests can exercise both paths
+  if (!warp_env || atoi(warp_env) != 0) {
+    bool handled = false;
+    const int rc = launch_cpl_warp(p, bwd, stream, name, &handled);
+    if (rc != AFSL_OK || handled) return rc;
+  }
   KernelFn f, b;
   AFSL_REQUIRE(pick(p.D, f, b), "%s: unsupported embedding dim D=%d (supported: 16,32,64,128,256,512,1024)", name, p.D);
   KernelFn fn = bwd ? b : f;

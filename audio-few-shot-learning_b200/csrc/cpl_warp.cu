@@ -1,0 +1,309 @@
+// CPL loss, one WARP per episode (same closed form and reference as cpl.cu: CPL_Loss.forward /
+// similarity_sampling, loops/loss.py:118-165), for the shapes whose W normalised prototypes fit a 5 KB
+// shared-memory slice per warp (5-way at Dp <= 256).
+//
+// Lane l owns Dp/32 columns of every row.  Query rows stream through registers kB at a time; the kB*(W+1)
+// per-lane partials of a batch (W dot products with the normalised prototypes + the row's squared norm) are
+// combined by one transposing butterfly, which leaves lane u*(W+1)+w with <p^_w, q_u>, so the division by the
+// norm and the temperature happens once per matrix entry.  The W x Nq similarity matrix lives in the warp's
+// shared-memory slice; the masked log-sum-exp of row i runs on lane i.  The backward builds dL/dC column by
+// column (lane j), then walks the query rows a second time (L2 hits) to store dQ and accumulate dP in registers.
+// No CTA-wide barrier anywhere: warps are independent, 4 per CTA, one episode each.
+#include "cpl.cuh"
+#include "warp_rows.cuh"
+
+namespace afsl {
+namespace {
+
+using namespace warp_rows;
+
+constexpr float kCosEps = 1e-8f;
+
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+__host__ __device__ inline int slice_words(int kWD, int W, int Nq) {
+  const int n = kWD + 2 * W * Nq + 4 * Nq;
+  return (n + 3) & ~3;
+}
+
+__device__ __forceinline__ bool kept_default(const int* lab, int i, int j) { return j == i || lab[j] != lab[i]; }
+
+template <int kW, int kV, int kB, bool kBwd>
+__global__ void __launch_bounds__(kCtaThreads) cpl_warp_kernel(const CplParams p) {
+  extern __shared__ __align__(16) float smem_raw[];
+  constexpr int kH = kV / 2, kD = kV * 32, kC = kW + 1, kVals = kB * kC, kN = pow2_ceil(kVals);
+  static_assert(kVals <= 32, "a batch of rows must fit one value per lane");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = blockIdx.x * kWarpsPerCta + warp;
+  if (e >= p.E) return;
+  const int Nq = p.Nq, words = (Nq + 31) >> 5;
+  float* sp = smem_raw + (size_t)warp * slice_words(kW * kD, kW, Nq);   // [kW*kD] normalised prototypes
+  float* sim = sp + kW * kD;                                            // [kW*Nq] C
+  float* grad = sim + kW * Nq;                                          // [kW*Nq] dL/dC (backward)
+  float* rmax = grad + kW * Nq;                                         // [Nq]
+  float* rsum = rmax + Nq;                                              // [Nq]
+  float* qinv = rsum + Nq;                                              // [Nq] 1/|q_j|, negative flags the eps clamp
+  int* lab = reinterpret_cast<int*>(qinv + Nq);                         // [Nq]
+  const int u_l = lane / kC, c_l = lane - u_l * kC;
+  const bool lane_valid = lane < kVals;
+  const uint32_t* keep_e = p.keep ? p.keep + (size_t)e * Nq * words : nullptr;
+
+  const float* qry = p.queries + (size_t)e * Nq * kD;
+  const int nq_pad = (Nq + kB - 1) / kB * kB;
+  const int total = kBwd ? 2 * nq_pad : nq_pad;          // the backward walks the rows twice
+  auto row_ptr = [&](int t) -> const float* {
+    const int r = t < nq_pad ? t : t - nq_pad;
+    return qry + (size_t)min(r, Nq - 1) * kD;
+  };
+
+  // ------------------------------------------------------------------ normalised prototypes -> shared
+  float pinv[kW];
+  {
+    f32x2 x[kW][kH];
+#pragma unroll
+    for (int w = 0; w < kW; ++w) load_row<kV>(p.protos + ((size_t)e * kW + w) * kD, lane, x[w]);
+    for (int k = lane; k < Nq; k += 32) lab[k] = p.labels[(size_t)e * Nq + k];
+    float ss[pow2_ceil(kW)];
+#pragma unroll
+    for (int w = 0; w < pow2_ceil(kW); ++w) ss[w] = 0.f;
+#pragma unroll
+    for (int w = 0; w < kW; ++w) {
+      f32x2 a = 0ull;
+#pragma unroll
+      for (int j = 0; j < kH; ++j) a = fma2(x[w][j], x[w][j], a);
+      ss[w] = sum2(a);
+    }
+    const float tot = reduce_values<pow2_ceil(kW)>(ss, lane);
+#pragma unroll
+    for (int w = 0; w < kW; ++w) {
+      const float nrm = sqrtf(__shfl_sync(kFull, tot, w));
+      const float r = 1.f / fmaxf(nrm, kCosEps);
+      pinv[w] = nrm > kCosEps ? 1.f / nrm : -1.f / kCosEps;   // negative flags the clamp
+      const f32x2 r2 = pack2(r, r);
+#pragma unroll
+      for (int j = 0; j < kH; ++j) x[w][j] = mul2(x[w][j], r2);
+      sts_row<kV>(sp + w * kD, lane, x[w]);
+    }
+  }
+  f32x2 buf[kB][kH];
+#pragma unroll
+  for (int u = 0; u < kB; ++u) load_row<kV>(row_ptr(u), lane, buf[u]);
+  __syncwarp();
+
+  // ------------------------------------------------------------------ pass 1: C[w,j] = <p^_w, q^_j> / T
+  for (int t0 = 0; t0 < nq_pad; t0 += kB) {
+    float part[kN];
+#pragma unroll
+    for (int u = 0; u < kB; ++u) {
+      f32x2 a = 0ull;
+#pragma unroll
+      for (int j = 0; j < kH; ++j) a = fma2(buf[u][j], buf[u][j], a);
+      part[u * kC + kW] = sum2(a);
+    }
+#pragma unroll
+    for (int w = 0; w < kW; ++w) {
+      f32x2 pw[kH];
+      lds_row<kV>(sp + w * kD, lane, pw);
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        f32x2 a0 = 0ull, a1 = 0ull;
+#pragma unroll
+        for (int j = 0; j < kH; ++j) {
+          if (j & 1) a1 = fma2(pw[j], buf[u][j], a1); else a0 = fma2(pw[j], buf[u][j], a0);
+        }
+        part[u * kC + w] = kH > 1 ? sum2(add2(a0, a1)) : sum2(a0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kB; ++u)
+      if (t0 + u + kB < total) load_row<kV>(row_ptr(t0 + u + kB), lane, buf[u]);
+#pragma unroll
+    for (int k = kVals; k < kN; ++k) part[k] = 0.f;
+    const float tot = reduce_values<kN>(part, lane);
+    const float nrm = sqrtf(__shfl_sync(kFull, tot, u_l * kC + kW));
+    const int j_l = t0 + u_l;
+    if (lane_valid && j_l < Nq) {
+      if (c_l < kW) sim[c_l * Nq + j_l] = __fdiv_rn(__fdiv_rn(tot, fmaxf(nrm, kCosEps)), p.temperature);
+      else qinv[j_l] = nrm > kCosEps ? 1.f / nrm : -1.f / kCosEps;
+    }
+  }
+  __syncwarp();
+
+  // ------------------------------------------------------------------ masked log-sum-exp of row i on lane i
+  float loss_acc = 0.f;
+  for (int i0 = 0; i0 < Nq; i0 += 32) {
+    const int i = i0 + lane;
+    const bool active = i < Nq;
+    const int ic = active ? i : Nq - 1;
+    const int y = lab[ic];
+    const bool valid = active && y >= 0 && y < kW;
+    const float* row = sim + (valid ? y : 0) * Nq;
+    float m = -INFINITY, se = 0.f;
+    for (int j0 = 0; j0 < Nq; j0 += 32) {
+      const uint32_t word = keep_e ? keep_e[(size_t)ic * words + (j0 >> 5)] : 0u;
+      const int jn = min(32, Nq - j0);
+      for (int jj = 0; jj < jn; ++jj) {
+        const int j = j0 + jj;
+        const bool k = keep_e ? ((word >> jj) & 1u) : kept_default(lab, ic, j);
+        if (k) m = fmaxf(m, row[j]);
+      }
+    }
+    for (int j0 = 0; j0 < Nq; j0 += 32) {
+      const uint32_t word = keep_e ? keep_e[(size_t)ic * words + (j0 >> 5)] : 0u;
+      const int jn = min(32, Nq - j0);
+      for (int jj = 0; jj < jn; ++jj) {
+        const int j = j0 + jj;
+        const bool k = keep_e ? ((word >> jj) & 1u) : kept_default(lab, ic, j);
+        if (k) se += expf(row[j] - m);
+      }
+    }
+    if (valid) {
+      loss_acc += -((row[i] - m) - logf(se));
+      if (kBwd) { rmax[i] = m; rsum[i] = se; }
+    } else if (active && kBwd) {   // label without a prototype: row contributes nothing
+      rmax[i] = 0.f; rsum[i] = 1.f;
+    }
+  }
+  if (!kBwd) {
+    const float tot = warp_sum(loss_acc);
+    // (1/Nq) * NLLLoss(mean): loops/loss.py:131
+    if (lane == 0) p.loss[e] = (float)(1.0 / (double)Nq) * (tot / (float)Nq);
+    return;
+  }
+  __syncwarp();
+
+  // ------------------------------------------------------------------ dL/dC, column j on lane j
+  // dL/dC[w,j] = g * sum_{i: y_i = w} ( keep_ij * softmax_i[j] - [j == i] ),  g = d_loss / Nq^2
+  const float g = p.d_loss[e] * (float)(1.0 / (double)Nq) / (float)Nq;
+  for (int j0 = 0; j0 < Nq; j0 += 32) {
+    const int j = j0 + lane;
+    const bool active = j < Nq;
+    const int jc = active ? j : Nq - 1;
+    float cj[kW], acc[kW];
+#pragma unroll
+    for (int w = 0; w < kW; ++w) { cj[w] = sim[w * Nq + jc]; acc[w] = 0.f; }
+    for (int i = 0; i < Nq; ++i) {          // members of every class in ascending order
+      const int w = lab[i];
+      if (w < 0 || w >= kW) continue;       // warp-uniform
+      float c = cj[0];
+#pragma unroll
+      for (int v = 1; v < kW; ++v) c = w == v ? cj[v] : c;
+      const bool k = keep_e ? ((keep_e[(size_t)i * words + (jc >> 5)] >> (jc & 31)) & 1u) : kept_default(lab, i, jc);
+      float t = k ? expf(c - rmax[i]) / rsum[i] : 0.f;
+      if (jc == i) t -= 1.f;
+#pragma unroll
+      for (int v = 0; v < kW; ++v) acc[v] += w == v ? t : 0.f;
+    }
+    if (active) {
+#pragma unroll
+      for (int w = 0; w < kW; ++w) grad[w * Nq + j] = g * acc[w];
+    }
+  }
+  __syncwarp();
+
+  // ------------------------------------------------------------------ pass 2: dQ rows out, dP^ in registers
+  // queries:    dq^ = 1/T sum_w G[w,j] p^_w ;  dq = (dq^ - q^ <q^,dq^>) / |q|
+  // prototypes: dp^ = 1/T sum_j G[w,j] q^_j (ascending j) ;  dp = (dp^ - p^ <p^,dp^>) / |p|
+  const float inv_t = 1.f / p.temperature;
+  f32x2 dPh[kW][kH];
+#pragma unroll
+  for (int w = 0; w < kW; ++w)
+#pragma unroll
+    for (int j = 0; j < kH; ++j) dPh[w][j] = 0ull;
+  float* dq = p.d_queries + (size_t)e * Nq * kD;
+  for (int t0 = nq_pad; t0 < total; t0 += kB) {
+#pragma unroll
+    for (int u = 0; u < kB; ++u) {
+      const int j = t0 - nq_pad + u;
+      const bool live = j < Nq;
+      const int jc = live ? j : Nq - 1;
+      const float qi = qinv[jc];
+      const bool clamped = qi < 0.f;
+      const float inv = fabsf(qi);
+      const f32x2 inv2 = pack2(inv, inv);
+      f32x2 qh[kH], out[kH];
+#pragma unroll
+      for (int k = 0; k < kH; ++k) { qh[k] = mul2(buf[u][k], inv2); out[k] = 0ull; }
+#pragma unroll
+      for (int w = 0; w < kW; ++w) {
+        const float gw = live ? grad[w * Nq + jc] * inv_t : 0.f;    // a replayed slot contributes exactly nothing
+        const float gj = gw * inv;
+        const f32x2 gw2 = pack2(gw, gw), gj2 = pack2(gj, gj);
+        f32x2 pw[kH];
+        lds_row<kV>(sp + w * kD, lane, pw);
+#pragma unroll
+        for (int k = 0; k < kH; ++k) {
+          out[k] = fma2(gw2, pw[k], out[k]);
+          dPh[w][k] = fma2(gj2, buf[u][k], dPh[w][k]);
+        }
+      }
+      f32x2 a = 0ull;
+#pragma unroll
+      for (int k = 0; k < kH; ++k) a = fma2(out[k], qh[k], a);
+      float dot = warp_sum(sum2(a));
+      if (clamped) dot = 0.f;  // norm clamped to eps: the denominator is a constant
+      const f32x2 nd2 = pack2(-dot, -dot);
+#pragma unroll
+      for (int k = 0; k < kH; ++k) out[k] = mul2(fma2(nd2, qh[k], out[k]), inv2);
+      if (live) store_row<kV>(dq + (size_t)j * kD, lane, out);
+      if (t0 + u + kB < total) load_row<kV>(row_ptr(t0 + u + kB), lane, buf[u]);
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < kW; ++w) {
+    f32x2 ph[kH];
+    lds_row<kV>(sp + w * kD, lane, ph);
+    f32x2 a = 0ull;
+#pragma unroll
+    for (int k = 0; k < kH; ++k) a = fma2(dPh[w][k], ph[k], a);
+    float dot = warp_sum(sum2(a));
+    const bool clamped = pinv[w] < 0.f;
+    if (clamped) dot = 0.f;
+    const float inv = fabsf(pinv[w]);
+    const f32x2 nd2 = pack2(-dot, -dot), inv2 = pack2(inv, inv);
+#pragma unroll
+    for (int k = 0; k < kH; ++k) dPh[w][k] = mul2(fma2(nd2, ph[k], dPh[w][k]), inv2);
+    store_row<kV>(p.d_protos + ((size_t)e * kW + w) * kD, lane, dPh[w]);
+  }
+}
+
+using KernelFn = void (*)(const CplParams);
+
+template <int kW, int kV>
+void variant(bool bwd, KernelFn& fn) {
+  constexpr int kB = 32 / (kW + 1) < 6 ? 32 / (kW + 1) : 6;
+  fn = bwd ? cpl_warp_kernel<kW, kV, kB, true> : cpl_warp_kernel<kW, kV, kB, false>;
+}
+
+bool pick_variant(int W, int D, bool bwd, KernelFn& fn) {
+#define AFSL_WV(W_, D_)                  \
+  if (W == W_ && D == D_) {              \
+    variant<W_, D_ / 32>(bwd, fn);       \
+    return true;                         \
+  }
+  AFSL_WV(5, 256) AFSL_WV(5, 128) AFSL_WV(5, 64)
+#undef AFSL_WV
+  return false;
+}
+
+}  // namespace
+
+int launch_cpl_warp(const CplParams& p, bool bwd, cudaStream_t stream, const char* name, bool* handled) {
+  *handled = false;
+  KernelFn fn = nullptr;
+  if (!pick_variant(p.W, p.D, bwd, fn)) return AFSL_OK;
+  const size_t bytes = (size_t)kWarpsPerCta * slice_words(p.W * p.D, p.W, p.Nq) * sizeof(float);
+  if (bytes > 64 * 1024) return AFSL_OK;            // very long query lists: the CTA-per-episode kernel takes them
+  *handled = true;
+  if (int rc = opt_in_smem(fn, bytes, name)) return rc;
+  const int grid = (p.E + kWarpsPerCta - 1) / kWarpsPerCta;
+  fn<<<grid, kCtaThreads, bytes, stream>>>(p);
+  AFSL_CHECK_LAUNCH(name);
+  return AFSL_OK;
+}
+
+}  // namespace afsl

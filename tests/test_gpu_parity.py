@@ -159,8 +159,10 @@ def test_l2_normalize(ops):
 
 
 # ------------------------------------------------------------------ CPL
+@pytest.mark.parametrize("path", ["warp", "cta"])
 @pytest.mark.parametrize("name", golden_names("cpl_"))
-def test_cpl_vs_reference(ops, name):
+def test_cpl_vs_reference(ops, monkeypatch, name, path):
+    monkeypatch.setenv("AFSL_CPL_WARP", "1" if path == "warp" else "0")
     g = load_golden(name)
     p = dev(g["prototypes"]).requires_grad_(True)
     q = dev(g["queries"]).requires_grad_(True)
@@ -181,9 +183,14 @@ def test_cpl_vs_reference(ops, name):
         close(q2.grad, t(g["d_queries"]))
 
 
-def test_cpl_batched_vs_oracle(ops):
-    e, ways, per, dim, m, temp = 19, 5, 6, 256, 3, 2.6981
-    gen = torch.Generator().manual_seed(77)
+@pytest.mark.parametrize("path", ["warp", "cta"])
+@pytest.mark.parametrize("ways,per,dim,m", [(5, 6, 256, 3), (5, 5, 256, 5), (5, 20, 64, 5), (5, 9, 128, 2), (4, 7, 64, 3)])
+def test_cpl_batched_vs_oracle(ops, monkeypatch, ways, per, dim, m, path):
+    """E episodes at once == the closed-form oracle episode by episode, sampled-negative masks included,
+    through both kernel families (one warp per episode for 5-way; one CTA per episode for any shape)."""
+    monkeypatch.setenv("AFSL_CPL_WARP", "1" if path == "warp" else "0")
+    e, temp = 19, 2.6981
+    gen = torch.Generator().manual_seed(77 + ways * per)
     p = torch.randn(e, ways, dim, generator=gen)
     q = torch.randn(e, ways * per, dim, generator=gen)
     labels = torch.stack([torch.arange(ways).repeat_interleave(per)[torch.randperm(ways * per, generator=gen)] for _ in range(e)])
@@ -191,7 +198,7 @@ def test_cpl_batched_vs_oracle(ops):
     keep = torch.stack([ohead.cpl_draw_keep(labels[i], m) for i in range(e)])
     wl = torch.rand(e, generator=gen) + 0.5
     pg, qg = p.cuda().requires_grad_(True), q.cuda().requires_grad_(True)
-    loss = ops.cpl_loss(pg, qg, labels.cuda(), temp, keep=keep)
+    loss = ops.cpl_loss(pg, qg, labels.cuda(), temp, keep=None if m >= per else keep)
     (loss * wl.cuda()).sum().backward()
     for i in range(e):
         pc, qc = p[i].clone().requires_grad_(True), q[i].clone().requires_grad_(True)
