@@ -133,10 +133,12 @@ def kernel_rooflines(device, peak_gbs, episodes):
         torch.cuda.synchronize()
         return start.elapsed_time(end) / reps * 1e-3
 
+    traffic = ncu_traffic()
+
     def entry(name, bytes_per_launch, sec, units, launches=1, **extra):
         out[name] = {"bound": "hbm", "achieved": bytes_per_launch / sec / 1e9, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": bytes_per_launch / sec / 1e9 / peak_gbs, "traffic": None, "ms": sec * 1e3, "units": units,
-                     "bytes_per_launch": bytes_per_launch, "launches": launches, **extra}
+                     "frac": bytes_per_launch / sec / 1e9 / peak_gbs, "traffic": traffic.get(name), "ms": sec * 1e3,
+                     "units": units, "bytes_per_launch": bytes_per_launch, "launches": launches, **extra}
 
     st = stream_ptr()
     # ---- SpecAugment: 4 views written; algorithmic bytes 4*N*F*T*(1+V) per launch (10.05 MB / 25-sample set)
@@ -170,13 +172,17 @@ def kernel_rooflines(device, peak_gbs, episodes):
     bwd = lambda: call("afsl_proto_head_bwd_f32", ptr(s), ptr(protos), ptr(sl), ptr(q), ptr(ql), None, ptr(dl), None, ptr(ds),
                        ptr(dq), e, ns, nq, ways, d, st)       # protos = the forward's output, as ops._ProtoHead passes it
     t_f, t_b = timed(fwd), timed(bwd)
+    # compulsory traffic of the kernels as built: the backward takes the forward's prototypes (W rows) instead of
+    # re-reading the Ns support rows, so it moves 4D(W+Nq) in and 4D(Ns+Nq) out
     b_f = (4.0 * d * (ns + nq + ways) + 4 * (ns + nq) + 8) * e            # read S,Q ; write prototypes, loss, correct
-    b_b = (4.0 * d * 2 * (ns + nq) + 4 * (ns + nq) + 4) * e                # re-read S,Q ; write dS,dQ
+    b_b = (4.0 * d * (ways + nq) + 4.0 * d * (ns + nq) + 4 * (ns + nq) + 4) * e   # read P,Q ; write dS,dQ
     entry("proto_head_fwd", b_f, t_f, f"{e} episodes 5w5s5q D=256")
     entry("proto_head_bwd", b_b, t_b, f"{e} episodes 5w5s5q D=256")
-    # SURVEY 8d unit: 4*D*[3*(Ns+Nq)+W] + 4*(Ns+Nq) + 4 = 158.9 KB per episode for fwd+bwd
-    entry("proto_head_fwd_bwd", (4.0 * d * (3 * (ns + nq) + ways) + 4 * (ns + nq) + 4) * e, t_f + t_b,
-          f"{e} episodes 5w5s5q D=256", launches=2, episodes_per_s=e / (t_f + t_b))
+    entry("proto_head_fwd_bwd", b_f + b_b, t_f + t_b, f"{e} episodes 5w5s5q D=256", launches=2,
+          episodes_per_s=e / (t_f + t_b),
+          # SURVEY 8d's unit counts a re-read of the support block in the backward: 158.9 KB per episode
+          survey_unit_bytes_per_launch=(4.0 * d * (3 * (ns + nq) + ways) + 4 * (ns + nq) + 4) * e,
+          survey_unit_frac=(4.0 * d * (3 * (ns + nq) + ways) + 4 * (ns + nq) + 4) * e / (t_f + t_b) / 1e9 / peak_gbs)
     # ---- evaluation head (prototypes + distances + argmax + accuracy): 4*D*(Ns+Nq) + 4*(Ns+Nq) + 8 B per task
     ev = lambda: call("afsl_proto_head_fwd_f32", ptr(s), ptr(sl), ptr(q), ptr(ql), None, None, None, None, ptr(pred), ptr(post),
                       ptr(correct), e, ns, nq, ways, d, st)
@@ -191,7 +197,38 @@ def kernel_rooflines(device, peak_gbs, episodes):
     entry("cpl_fwd", (4.0 * d * (nq + ways) + 4 * nq + 4) * e, t_cf, f"{e} episodes Nq=25 Dp=256")
     entry("cpl_bwd", (4.0 * d * 2 * (nq + ways) + 4 * nq + 4) * e, t_cb, f"{e} episodes Nq=25 Dp=256")
     entry("cpl_fwd_bwd", (4.0 * d * 3 * (nq + ways) + nq * nq / 8) * e, t_cf + t_cb, f"{e} episodes Nq=25 Dp=256", launches=2)
-    del s, q, ds, dq, p, dp
+    del s, ds, dq, p, dp
+    # ---- angular loss (config 3: prototypes as anchors, miner angle 0, alpha 40 deg), Dp=64, Nq=25:
+    #      4*Dp*3*(Nq+W) B per episode fwd+bwd (23 KB); Gram-matrix / mining arithmetic dominates
+    da = 64
+    pa = torch.nn.functional.normalize(torch.randn(e, ways, da, device=device), dim=-1)
+    qa = torch.nn.functional.normalize(torch.randn(e, nq, da, device=device), dim=-1)
+    dpa, dqa = torch.empty_like(pa), torch.empty_like(qa)
+    af = lambda: call("afsl_angular_fwd_f32", ptr(pa), ptr(qa), ptr(ql), 0.0, 40.0, 1, 0, ptr(loss), e, nq, ways, da, st)
+    ab = lambda: call("afsl_angular_bwd_f32", ptr(pa), ptr(qa), ptr(ql), 0.0, 40.0, 1, 0, ptr(dl), ptr(dpa), ptr(dqa), e, nq,
+                      ways, da, st)
+    t_af, t_ab = timed(af, reps=5), timed(ab, reps=5)
+    entry("angular_fwd", (4.0 * da * (nq + ways) + 4 * nq + 4) * e, t_af, f"{e} episodes Nq=25 Dp=64 anchors angle=0")
+    entry("angular_bwd", (4.0 * da * 2 * (nq + ways) + 4 * nq + 4) * e, t_ab, f"{e} episodes Nq=25 Dp=64 anchors angle=0")
+    entry("angular_fwd_bwd", 4.0 * da * 3 * (nq + ways) * e, t_af + t_ab, f"{e} episodes Nq=25 Dp=64 anchors angle=0", launches=2)
+    del pa, qa, dpa, dqa
+    # ---- evaluation sweep (config 5): (W, K) x D, Q = 5, tasks per launch sized to stay above the 126 MB L2
+    for w_, k_, d_ in ((5, 1, 64), (5, 5, 64), (20, 5, 64), (5, 1, 256), (20, 1, 256), (20, 5, 256)):
+        ns_, nq_ = w_ * k_, w_ * 5
+        e_ = min(65536, max(2048, int(3.0e8 // (4 * d_ * (ns_ + nq_)))))
+        s_ = torch.randn(e_, ns_, d_, device=device)
+        q_ = torch.randn(e_, nq_, d_, device=device)
+        sl_ = torch.arange(w_, device=device, dtype=torch.int32).repeat_interleave(k_).expand(e_, -1).contiguous()
+        ql_ = torch.arange(w_, device=device, dtype=torch.int32).repeat_interleave(5).expand(e_, -1).contiguous()
+        pred_ = torch.empty(e_ * nq_, device=device, dtype=torch.int32)
+        post_ = torch.empty(e_ * nq_, device=device)
+        corr_ = torch.empty(e_, device=device, dtype=torch.int32)
+        t_ = timed(lambda: call("afsl_proto_head_fwd_f32", ptr(s_), ptr(sl_), ptr(q_), ptr(ql_), None, None, None, None,
+                                ptr(pred_), ptr(post_), ptr(corr_), e_, ns_, nq_, w_, d_, st))
+        entry(f"eval_head_{w_}w{k_}s_d{d_}", (4.0 * d_ * (ns_ + nq_) + 4 * (ns_ + nq_) + 8 * nq_ + 4) * e_, t_,
+              f"{e_} tasks {w_}w{k_}s5q D={d_}", tasks_per_s=e_ / t_)
+        del s_, q_
+    del q
     # ---- grouped BN + ReLU + MaxPool, stage-1 shape [G*25, 64, 128, 157]
     g, grp, c, h, wd_ = 16, 25, 64, MELS, T_LEN
     xx = torch.randn(g * grp, c, h, wd_, device=device)
@@ -211,6 +248,16 @@ def kernel_rooflines(device, peak_gbs, episodes):
     entry("gbn_relu_pool_fwd", nx + ny, t_gf, f"{g} groups x 25 x [64,128,157]")
     entry("gbn_relu_pool_bwd", 2 * (nx + ny) + nx, t_gb, f"{g} groups x 25 x [64,128,157]", launches=2)
     return out
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernels above, from the committed
+    `ncu --set full` captures of tools/kernels_bench.py (profiles/ncu_traffic.json; same shapes as timed here)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return {}
+    with open(path) as fh:
+        return {k: v for k, v in json.load(fh).items() if not k.startswith("_")}
 
 
 def cpu_episode_runner(threads):
@@ -359,7 +406,9 @@ def run_b200(args):
                 "d2h_bytes_per_step": int(loss_host.numel() * 4), "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks.summary,
-        "roofline": roofs.get("specaug_views"),
+        # the fused loss-head pair (prototypes + distances + log-softmax/NLL forward, and its backward): the
+        # kernels BASELINE.json's "head HBM GB/s" names; every other libafsl kernel is listed under "kernels"
+        "roofline": roofs.get("proto_head_fwd_bwd"),
         "kernels": roofs,
         "cpu_baseline": cpu,
     }
