@@ -18,29 +18,19 @@
 //     positive or negative (the reference duplicates rows instead of weighting them);
 //   pooled branch (loss.py:84-96): pairs (a,p) in P u Q with equal label weighted by their number
 //     of mined negatives; negatives are all other-label rows with weight 1.
+#include <cstdlib>
+
 #include "afsl_common.cuh"
+#include "angular.cuh"
 
 namespace afsl {
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 64;
 constexpr int kWarps = kThreads / kWarp;
 constexpr float kNormEps = 1e-12f;   // F.normalize
 constexpr float kPairEps = 1e-6f;    // F.pairwise_distance
 
-struct AngParams {
-  const float* protos;    // [E,W,D]
-  const float* queries;   // [E,Nq,D]
-  const int32_t* labels;  // [E,Nq]
-  float miner_angle;      // radians
-  float t2;               // tan^2(alpha)
-  int anchors, normalize_ref;
-  float* loss;            // [E]
-  const float* d_loss;    // [E]      (backward)
-  float* d_protos;        // [E,W,D]
-  float* d_queries;       // [E,Nq,D]
-  int E, Nq, W, D;
-};
 
 struct Smem {
   float* gram;   // [N*N]
@@ -289,6 +279,12 @@ int launch(const AngParams& p, bool bwd, cudaStream_t stream, const char* name) 
   AFSL_REQUIRE(p.protos && p.queries && p.labels, "%s: null pointer", name);
   AFSL_REQUIRE(p.E >= 0 && p.Nq > 0 && p.W > 0 && p.D > 0, "%s: bad sizes E=%d Nq=%d W=%d D=%d", name, p.E, p.Nq, p.W, p.D);
   if (p.E == 0) return AFSL_OK;
+  const char* warp_env = getenv("AFSL_ANGULAR_WARP");   // read per launch so the tests can exercise both paths
+  if (!warp_env || atoi(warp_env) != 0) {
+    bool handled = false;
+    const int rc = launch_angular_warp(p, bwd, stream, name, &handled);
+    if (rc != AFSL_OK || handled) return rc;
+  }
   const size_t bytes = smem_words(p.W + p.Nq, p.D) * sizeof(float);
   auto fn = bwd ? angular_kernel<true> : angular_kernel<false>;
   if (int rc = opt_in_smem(fn, bytes, name)) return rc;

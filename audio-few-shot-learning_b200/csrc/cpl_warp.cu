@@ -22,12 +22,6 @@ using namespace warp_rows;
 
 constexpr float kCosEps = 1e-8f;
 
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
-  f32x2 r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-
 __host__ __device__ inline int round4(int n) { return (n + 3) & ~3; }
 // per-warp slice: p^ [W*D] | C [W*Nq] | G/T pairs [W*Nqp*2] | G/T/|q| pairs [W*Nqp*2] | rmax, rsum [Nq] | 1/|q| [Nqp] | labels [Nq]
 __host__ __device__ inline int slice_words(int kWD, int W, int Nq, int Nqp) {

@@ -27,6 +27,12 @@ __device__ __forceinline__ void stg2(float* p, f32x2 a, f32x2 b) {
 __device__ __forceinline__ void stg1(float* p, f32x2 a) {
   asm volatile("st.global.L1::no_allocate.b64 [%0], %1;" ::"l"(p), "l"(a) : "memory");
 }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
   f32x2 r;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));

@@ -213,8 +213,10 @@ def test_cpl_batched_vs_oracle(ops, monkeypatch, ways, per, dim, m, path):
 @pytest.mark.parametrize("anchors", [True, False])
 @pytest.mark.parametrize("angle", [0.0, 15.0, 30.0])
 @pytest.mark.parametrize("unit_protos", [True, False])
-def test_angular_vs_restated_oracle(ops, anchors, angle, unit_protos):
+@pytest.mark.parametrize("path", ["warp", "cta"])
+def test_angular_vs_restated_oracle(ops, monkeypatch, anchors, angle, unit_protos, path):
     from oracle import angular as oang
+    monkeypatch.setenv("AFSL_ANGULAR_WARP", "1" if path == "warp" else "0")
     e, ways, per, dim = 6, 5, 5, 64
     gen = torch.Generator().manual_seed(int(angle) * 10 + int(anchors) + 100 * int(unit_protos))
     protos = torch.randn(e, ways, dim, generator=gen)
