@@ -24,12 +24,8 @@ constexpr int kLg = kNMax + 1;     // Gram row stride: conflict-free row and col
 constexpr float kNormEps = 1e-12f; // F.normalize
 constexpr float kPairEps = 1e-6f;  // F.pairwise_distance
 
-// per-warp shared-memory slice (floats): rows | gram | dgram | nu | norm | csum | manc (int) | cnt (bytes)
-constexpr int kSliceWords = kNMax * kLd + 2 * kNMax * kLg + 4 * kNMax + kNMax * kNMax / 4;
-
-struct Pair {
-  float base, omega;
-};
+// per-warp shared-memory slice (floats): rows | gram | dgram | nu | norm | csum | gsum | manc (int) | cnt (bytes)
+constexpr int kSliceWords = kNMax * kLd + 2 * kNMax * kLg + 5 * kNMax + kNMax * kNMax / 4;
 
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
@@ -66,7 +62,8 @@ __global__ void __launch_bounds__(kCtaThreads) angular_warp_kernel(const AngPara
   float* nu = dgram + kNMax * kLg;                      // [kNMax] negative weight
   float* norm = nu + kNMax;                             // [kNMax] raw norms
   float* csum = norm + kNMax;                           // [kNMax] component sum of the normalised row
-  int* manc = reinterpret_cast<int*>(csum + kNMax);     // [kNMax] mined triplets per anchor
+  float* gsq = csum + kNMax;                            // [kNMax] sum_k g of the pair whose positive is row q (anchors branch)
+  int* manc = reinterpret_cast<int*>(gsq + kNMax);      // [kNMax] mined triplets per anchor
   unsigned char* cnt = reinterpret_cast<unsigned char*>(manc + kNMax);   // [kNMax][kNMax] mined negatives per (a, q)
   const bool row = lane < N;
 
@@ -219,7 +216,22 @@ __global__ void __launch_bounds__(kCtaThreads) angular_warp_kernel(const AngPara
   for (int k = 0; k < kLg; ++k) dgram[lane * kLg + k] = 0.f;
   __syncwarp();
   const float scale = den > 0.f ? p.d_loss[e] / den : 0.f;
+  gsq[lane] = 0.f;
   for (int pass = 1; pass >= 0; --pass) {
+    if (pass == 0 && p.anchors) {
+      // every query has exactly one pair, so after pass 1 row q of dL/dGram holds 4 t2 rho g of that pair:
+      // the anchor's row is the sum of its positives' rows (ascending q), plus the -2(1+t2) sum_k g terms
+      for (unsigned mm = mask0; mm != 0; mm &= mm - 1) {
+        const int o = __ffs(mm) - 1;
+        for (int k = 0; k < N; ++k) dgram[q * kLg + k] += dgram[o * kLg + k];
+      }
+      for (unsigned mm = mask0; mm != 0; mm &= mm - 1) {
+        const int o = __ffs(mm) - 1;
+        dgram[q * kLg + o] += -2.f * (1.f + p.t2) * gsq[o];
+      }
+      __syncwarp();
+      break;
+    }
     for (unsigned mm = pass ? mask1 : mask0; mm != 0; mm &= mm - 1) {     // no warp-level primitive inside: lanes run free
       const int o = __ffs(mm) - 1;
       const int a = pass ? o : q, qq = pass ? q : o;
@@ -239,6 +251,7 @@ __global__ void __launch_bounds__(kCtaThreads) angular_warp_kernel(const AngPara
         dgram[q * kLg + k] += 4.f * p.t2 * rho * g;
       }
       if (pass == 0) dgram[a * kLg + qq] += -2.f * (1.f + p.t2) * gsum;
+      else gsq[q] = gsum;
     }
     __syncwarp();
   }
