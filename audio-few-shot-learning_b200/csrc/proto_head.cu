@@ -18,7 +18,7 @@
 namespace afsl {
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 64;
 constexpr int kWarps = kThreads / kWarp;
 constexpr bool kStagedByDefault = false;  // measured on B200: occupancy (8 CTAs/SM) beats staging (2 CTAs/SM) at 5w5s5q
 

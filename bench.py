@@ -215,7 +215,7 @@ def kernel_rooflines(device, peak_gbs, episodes):
     # ---- evaluation sweep (config 5): (W, K) x D, Q = 5, tasks per launch sized to stay above the 126 MB L2
     for w_, k_, d_ in ((5, 1, 64), (5, 5, 64), (20, 5, 64), (5, 1, 256), (20, 1, 256), (20, 5, 256)):
         ns_, nq_ = w_ * k_, w_ * 5
-        e_ = min(65536, max(2048, int(3.0e8 // (4 * d_ * (ns_ + nq_)))))
+        e_ = min(65536, max(2048, int(1.5e9 // (4 * d_ * (ns_ + nq_)))))
         s_ = torch.randn(e_, ns_, d_, device=device)
         q_ = torch.randn(e_, nq_, d_, device=device)
         sl_ = torch.arange(w_, device=device, dtype=torch.int32).repeat_interleave(k_).expand(e_, -1).contiguous()
