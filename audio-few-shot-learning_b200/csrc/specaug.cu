@@ -13,6 +13,8 @@
 // instruction, which keeps every 32 B sector fully used.  The tile (+1 halo row each side, needed
 // because grid_sample's y coordinate is f +- 1 ulp for 36 of the 128 rows) is staged in shared
 // memory for the time-warp gather.
+#include <cstdlib>
+
 #include "afsl_common.cuh"
 
 namespace afsl {
@@ -191,6 +193,141 @@ __global__ void __launch_bounds__(kThreads) specaug_kernel(const SpecParams p) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// Vectorised variant (the one that normally runs): a CTA owns kTileRows consecutive mel rows of one sample.
+// A sample is F*T contiguous floats and kTileRows*T is a multiple of 4, so a tile is a 16-byte aligned run
+// of float4s whatever T is: the tile is read ONCE with 128-bit loads (plus two scalar halo rows), parked in
+// shared memory for the time-warp gather, and all four views leave as 128-bit stores (the op is 80 % writes).
+// Per-column warp tables (source column, blend weight) are computed once per CTA into shared memory.
+// Element arithmetic is identical to specaug_kernel above (same rounded operations, same order).
+constexpr int kTileRows = 32;
+constexpr int kMaxMasksSm = 8;
+
+__global__ void __launch_bounds__(kThreads) specaug_tile_kernel(const SpecParams p) {
+  extern __shared__ __align__(16) float sm[];
+  const int T = p.T, F = p.F;
+  const int tiles_per_sample = (F + kTileRows - 1) / kTileRows;
+  const int n = blockIdx.x / tiles_per_sample, tix = blockIdx.x - n * tiles_per_sample;
+  const int f0 = tix * kTileRows, rows = min(kTileRows, F - f0);
+  const int pad = (4 - (T & 3)) & 3;                    // interior starts 16-byte aligned
+  float* tile = sm + pad;                               // [(rows + 2) * T]: row 0 = halo above, interior from tile + T
+  float* col_w = sm + pad + (kTileRows + 2) * T + 4;    // [T]
+  int* col_lo = reinterpret_cast<int*>(col_w + T);      // [T]
+  int* masks = col_lo + T;                              // [2][kMaxMasksSm][2]: time masks then frequency masks
+  const size_t plane = (size_t)p.N * F * T;
+  const bool want_copy = p.views_mask & 1, want_warp = p.views_mask & 2, want_tm = p.views_mask & 4,
+             want_fm = p.views_mask & 8;
+  const int set = n / p.set_size;
+  const float* xs = p.x + (size_t)n * F * T;
+
+  // per-column tables + masks
+  for (int t = threadIdx.x; t < T; t += kThreads) {
+    int lo = 0;
+    float w = 0.f;
+    if (want_warp) {
+      const float gx = p.src_x ? __ldg(p.src_x + (size_t)n * T + t)
+                               : spline_source_x(t, __ldg(p.warp_p + n), __ldg(p.warp_d + n), T);
+      const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), (float)(T - 1));
+      const float fl = floorf(ix);
+      lo = (int)fl;
+      w = __fsub_rn(ix, fl);
+    }
+    col_lo[t] = lo;
+    col_w[t] = w;
+  }
+  if (threadIdx.x < 2 * p.num_mask) {
+    masks[threadIdx.x] = __ldg(p.time_masks + (size_t)set * p.num_mask * 2 + threadIdx.x);
+    masks[2 * kMaxMasksSm + threadIdx.x] = __ldg(p.freq_masks + (size_t)set * p.num_mask * 2 + threadIdx.x);
+  }
+  // halo rows (scalar: rows are not 16-byte aligned) - only the warp view reads them
+  if (want_warp) {
+    for (int t = threadIdx.x; t < 2 * T; t += kThreads) {
+      const bool top = t < T;
+      const int f = top ? f0 - 1 : f0 + rows, tt = top ? t : t - T;
+      tile[(top ? 0 : (rows + 1) * T) + tt] = (f >= 0 && f < F) ? __ldg(xs + (size_t)f * T + tt) : 0.f;
+    }
+  }
+  __syncthreads();
+
+  const unsigned magic = (unsigned)((0x100000000ull + T - 1) / T);    // i / T for i < 2^16 via mulhi, one fix-up
+  const int n4 = rows * T / 4;
+  const float4* src4 = reinterpret_cast<const float4*>(xs + (size_t)f0 * T);
+  float4* out4 = reinterpret_cast<float4*>(p.views + (size_t)n * F * T + (size_t)f0 * T);
+  const size_t plane4 = plane / 4;
+  float4* tile4 = reinterpret_cast<float4*>(tile + T);
+  // pass 1: one 128-bit read of the tile; copy / mask views straight from registers
+  for (int i4 = threadIdx.x; i4 < n4; i4 += kThreads) {
+    const float4 v = ldg_stream(src4 + i4);
+    if (want_warp) tile4[i4] = v;
+    if (want_copy) stg_stream(out4 + i4, v);
+    if (want_tm || want_fm) {
+      const int i = 4 * i4;
+      int r = (int)__umulhi((unsigned)i, magic);
+      if (r * T > i) --r;
+      int t = i - r * T;
+      float e[4] = {v.x, v.y, v.z, v.w}, tmv[4], fmv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        bool tm = false, fm = false;
+        const int f = f0 + r;
+        for (int m = 0; m < p.num_mask; ++m) {
+          const int a = masks[2 * m], la = masks[2 * m + 1];
+          tm |= (t >= a && t < a + la);
+          const int b = masks[2 * kMaxMasksSm + 2 * m], lb = masks[2 * kMaxMasksSm + 2 * m + 1];
+          fm |= (f >= b && f < b + lb);
+        }
+        tmv[k] = tm ? p.mask_value : e[k];
+        fmv[k] = fm ? p.mask_value : e[k];
+        if (++t == T) { t = 0; ++r; }
+      }
+      if (want_tm) stg_stream(out4 + 2 * plane4 + i4, make_float4(tmv[0], tmv[1], tmv[2], tmv[3]));
+      if (want_fm) stg_stream(out4 + 3 * plane4 + i4, make_float4(fmv[0], fmv[1], fmv[2], fmv[3]));
+    }
+  }
+  if (!want_warp) return;
+  __syncthreads();
+  // pass 2: time-warp view, bilinear gather out of the shared tile (tile row = f - f0 + 1)
+  for (int i4 = threadIdx.x; i4 < n4; i4 += kThreads) {
+    const int i = 4 * i4;
+    int r = (int)__umulhi((unsigned)i, magic);
+    if (r * T > i) --r;
+    int t = i - r * T;
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int f = f0 + r;
+      const int yn = __ldg(p.row_lo + f);
+      const float wn = __ldg(p.row_w + f);            // n = iy - floor(iy); s = 1 - n
+      const float ws = __fsub_rn(1.f, wn);
+      const int rr = yn - (f0 - 1);
+      const bool north_in = yn >= 0 && yn < F, south_in = yn + 1 >= 0 && yn + 1 < F;
+      const bool staged = rr >= 0 && rr + 1 < rows + 2;
+      const float* north = tile + rr * T;
+      const float* south = north + T;
+      const int xw = col_lo[t];
+      const float ww = col_w[t], we = __fsub_rn(1.f, ww);
+      const bool west_in = xw >= 0 && xw < T, east_in = xw + 1 >= 0 && xw + 1 < T;
+      float v_nw = 0.f, v_ne = 0.f, v_sw = 0.f, v_se = 0.f;
+      if (staged) {
+        if (north_in) { if (west_in) v_nw = north[xw]; if (east_in) v_ne = north[xw + 1]; }
+        if (south_in && wn != 0.f) { if (west_in) v_sw = south[xw]; if (east_in) v_se = south[xw + 1]; }
+      } else {  // generic row tables: fall back to global memory
+        if (north_in) { if (west_in) v_nw = __ldg(xs + (size_t)yn * T + xw); if (east_in) v_ne = __ldg(xs + (size_t)yn * T + xw + 1); }
+        if (south_in) { if (west_in) v_sw = __ldg(xs + (size_t)(yn + 1) * T + xw); if (east_in) v_se = __ldg(xs + (size_t)(yn + 1) * T + xw + 1); }
+      }
+      // out = nw*(s*e) + ne*(s*w) + sw*(n*e) + se*(n*w), each product and sum rounded (grid_sampler order)
+      float acc = __fmul_rn(v_nw, __fmul_rn(ws, we));
+      acc = __fadd_rn(acc, __fmul_rn(v_ne, __fmul_rn(ws, ww)));
+      acc = __fadd_rn(acc, __fmul_rn(v_sw, __fmul_rn(wn, we)));
+      acc = __fadd_rn(acc, __fmul_rn(v_se, __fmul_rn(wn, ww)));
+      o[k] = acc;
+      if (++t == T) { t = 0; ++r; }
+    }
+    stg_stream(out4 + plane4 + i4, make_float4(o[0], o[1], o[2], o[3]));
+  }
+}
+
 }  // namespace
 }  // namespace afsl
 
@@ -217,6 +354,20 @@ extern "C" int afsl_specaug_views_f32(const float* x, float* views, const int32_
   p.x = x; p.views = views; p.warp_p = warp_p; p.warp_d = warp_d; p.src_x = src_x; p.row_lo = row_lo; p.row_w = row_w;
   p.time_masks = time_masks; p.freq_masks = freq_masks; p.num_mask = num_mask; p.mask_value = mask_value;
   p.N = N; p.set_size = set_size; p.F = F; p.T = T; p.views_mask = views_mask;
+  // vectorised tile kernel whenever samples are whole float4 runs (F*T % 4 == 0: always for the 128-mel inputs)
+  static_assert(kTileRows % 4 == 0, "tiles must start on a float4 boundary for every T");
+  const bool vec_ok = ((size_t)F * T) % 4 == 0 && T >= 4 && num_mask <= kMaxMasksSm && aligned16(x) && aligned16(views) &&
+                      ((size_t)N * F * T) % 4 == 0 && (size_t)kTileRows * T < 65536;
+  const char* vec_env = getenv("AFSL_SPECAUG_TILE");     // read per launch so the tests can exercise both kernels
+  if (vec_ok && (!vec_env || atoi(vec_env) != 0)) {
+    const size_t tb = ((size_t)(kTileRows + 2) * T + 8 + 2 * (size_t)T + 4 * kMaxMasksSm) * sizeof(float);
+    if (int rc = opt_in_smem(specaug_tile_kernel, tb, "afsl_specaug_views_f32")) return rc;
+    const long long ctas = (long long)N * ((F + kTileRows - 1) / kTileRows);
+    AFSL_REQUIRE(ctas < (1ll << 31), "afsl_specaug_views_f32: too many tiles (%lld)", ctas);
+    specaug_tile_kernel<<<(unsigned)ctas, kThreads, tb, (cudaStream_t)stream>>>(p);
+    AFSL_CHECK_LAUNCH("afsl_specaug_views_f32");
+    return AFSL_OK;
+  }
   const size_t bytes = (size_t)(kRows + 2) * T * sizeof(float);
   const int tj = (T + 31) / 32;
   AFSL_REQUIRE(tj <= 16, "afsl_specaug_views_f32: T=%d too long (max 512 columns)", T);

@@ -248,8 +248,10 @@ def warp_atol(x):
     return 2.4e-7 * (t_len - 1) / 2 * 2 * float(x.abs().max())
 
 
+@pytest.mark.parametrize("kernel", ["tile", "rows"])
 @pytest.mark.parametrize("name", golden_names("specaug_"))
-def test_specaug_vs_reference(ops, name):
+def test_specaug_vs_reference(ops, monkeypatch, name, kernel):
+    monkeypatch.setenv("AFSL_SPECAUG_TILE", "1" if kernel == "tile" else "0")
     g = load_golden(name)
     x = dev(g["x"])
     n = x.shape[0]
@@ -268,10 +270,14 @@ def test_specaug_vs_reference(ops, name):
     assert torch.equal(v2[2], v[2]) and torch.equal(v2[3], v[3])
 
 
-def test_specaug_batched_sets_vs_oracle(ops):
-    """Several 25-sample sets in one launch, each with its own masks, vs the oracle set by set."""
+@pytest.mark.parametrize("kernel", ["tile", "rows"])
+@pytest.mark.parametrize("t_len", [157, 126, 64, 101])
+def test_specaug_batched_sets_vs_oracle(ops, monkeypatch, t_len, kernel):
+    """Several 25-sample sets in one launch, each with its own masks, vs the oracle set by set; both kernels
+    (128-bit tile kernel, warp-per-row kernel) and time lengths with every alignment of T modulo 4."""
+    monkeypatch.setenv("AFSL_SPECAUG_TILE", "1" if kernel == "tile" else "0")
     cfg = {"specaug_params": {"mask_param": 16, "W": 22, "num_mask": 2, "mask_value": 0.25, "p": 0.282}}
-    sets, n, t_len = 5, 25, 157
+    sets, n = 5, 25
     gen = torch.Generator().manual_seed(9)
     x = torch.randn(sets * n, 1, 128, t_len, generator=gen)
     torch.manual_seed(123)
