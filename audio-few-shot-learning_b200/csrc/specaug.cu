@@ -204,125 +204,165 @@ __global__ void __launch_bounds__(kThreads) specaug_kernel(const SpecParams p) {
 constexpr int kTileRows = 32;
 constexpr int kMaxMasksSm = 8;
 
+// masks of one set: up to two (start, len) pairs in registers (len 0 = unused), more through shared memory
+struct MaskSet {
+  int a0, l0, a1, l1;
+  const int* more;   // pairs 2.. in shared memory
+  int n_more;
+  __device__ __forceinline__ bool hit(int v) const {
+    bool h = ((unsigned)(v - a0) < (unsigned)l0) | ((unsigned)(v - a1) < (unsigned)l1);
+    for (int k = 0; k < n_more; ++k) h |= (unsigned)(v - more[2 * k]) < (unsigned)more[2 * k + 1];
+    return h;
+  }
+};
+
+__device__ __forceinline__ MaskSet load_masks(const int* m, int num) {
+  MaskSet s;
+  s.a0 = num > 0 ? m[0] : 0; s.l0 = num > 0 ? max(m[1], 0) : 0;
+  s.a1 = num > 1 ? m[2] : 0; s.l1 = num > 1 ? max(m[3], 0) : 0;
+  s.more = m + 4;
+  s.n_more = num > 2 ? num - 2 : 0;
+  return s;
+}
+
 __global__ void __launch_bounds__(kThreads) specaug_tile_kernel(const SpecParams p) {
   extern __shared__ __align__(16) float sm[];
-  const int T = p.T, F = p.F;
+  const int T = p.T, F = p.F, ldT = T + 4;              // tile rows carry two zero columns on either side
   const int tiles_per_sample = (F + kTileRows - 1) / kTileRows;
   const int n = blockIdx.x / tiles_per_sample, tix = blockIdx.x - n * tiles_per_sample;
   const int f0 = tix * kTileRows, rows = min(kTileRows, F - f0);
-  const int pad = (4 - (T & 3)) & 3;                    // interior starts 16-byte aligned
-  float* tile = sm + pad;                               // [(rows + 2) * T]: row 0 = halo above, interior from tile + T
-  float* col_w = sm + pad + (kTileRows + 2) * T + 4;    // [T]
-  int* col_lo = reinterpret_cast<int*>(col_w + T);      // [T]
-  int* masks = col_lo + T;                              // [2][kMaxMasksSm][2]: time masks then frequency masks
+  float* tile = sm;                                     // [(rows + 2) * ldT]: row 0 = halo above
+  float* col_w = sm + (kTileRows + 2) * ldT;            // [T] east weight
+  int* col_lo = reinterpret_cast<int*>(col_w + T);      // [T] west column inside a padded tile row (0 .. T+2)
+  float* row_wn = reinterpret_cast<float*>(col_lo + T); // [kTileRows + 1] south weight of the row
+  int* row_off = reinterpret_cast<int*>(row_wn + kTileRows + 1);   // [kTileRows + 1] tile offset of the north source row
+  int* masks = row_off + kTileRows + 1;                 // [2][kMaxMasksSm][2]: time masks then frequency masks
   const size_t plane = (size_t)p.N * F * T;
   const bool want_copy = p.views_mask & 1, want_warp = p.views_mask & 2, want_tm = p.views_mask & 4,
              want_fm = p.views_mask & 8;
   const int set = n / p.set_size;
   const float* xs = p.x + (size_t)n * F * T;
 
-  // per-column tables + masks
-  for (int t = threadIdx.x; t < T; t += kThreads) {
-    int lo = 0;
-    float w = 0.f;
-    if (want_warp) {
+  // per-column / per-row tables and masks
+  int staged_all = 1;
+  if (want_warp) {
+    for (int t = threadIdx.x; t < T; t += kThreads) {
       const float gx = p.src_x ? __ldg(p.src_x + (size_t)n * T + t)
                                : spline_source_x(t, __ldg(p.warp_p + n), __ldg(p.warp_d + n), T);
+      // grid_sampler_unnormalize, align_corners=True: ((g + 1) / 2) * (size - 1)
       const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), (float)(T - 1));
       const float fl = floorf(ix);
-      lo = (int)fl;
-      w = __fsub_rn(ix, fl);
+      // west neighbour xw, east xw + 1; columns outside [0, T) read the zero padding (zeros padding mode):
+      // padded index = xw + 2, clamped so that fully outside pairs land on (0,1) or (T+2,T+3)
+      const float cl = fminf(fmaxf(fl, -2.f), (float)T);
+      col_lo[t] = (int)cl + 2;
+      col_w[t] = __fsub_rn(ix, fl);
     }
-    col_lo[t] = lo;
-    col_w[t] = w;
+    for (int r = threadIdx.x; r <= rows; r += kThreads) {   // entry `rows` is a dummy for the wrap of the last float4
+      const int f = min(f0 + r, F - 1);
+      const int yn = __ldg(p.row_lo + f);
+      const int rr = yn - (f0 - 1);                    // tile row of the north source row; south = rr + 1
+      const bool ok = rr >= 0 && rr + 1 < rows + 2;
+      row_off[r] = (ok ? rr : 0) * ldT;
+      row_wn[r] = __ldg(p.row_w + f);
+      if (!ok && r < rows) staged_all = 0;
+    }
+    for (int r = threadIdx.x; r < rows + 2; r += kThreads) {
+      float* tr = tile + r * ldT;
+      tr[0] = tr[1] = tr[T + 2] = tr[T + 3] = 0.f;
+    }
+    // halo rows (scalar: rows are not 16-byte aligned); rows outside the image are zeros
+    for (int t = threadIdx.x; t < 2 * T; t += kThreads) {
+      const bool top = t < T;
+      const int f = top ? f0 - 1 : f0 + rows, tt = top ? t : t - T;
+      tile[(top ? 0 : rows + 1) * ldT + 2 + tt] = (f >= 0 && f < F) ? __ldg(xs + (size_t)f * T + tt) : 0.f;
+    }
   }
   if (threadIdx.x < 2 * p.num_mask) {
     masks[threadIdx.x] = __ldg(p.time_masks + (size_t)set * p.num_mask * 2 + threadIdx.x);
     masks[2 * kMaxMasksSm + threadIdx.x] = __ldg(p.freq_masks + (size_t)set * p.num_mask * 2 + threadIdx.x);
   }
-  // halo rows (scalar: rows are not 16-byte aligned) - only the warp view reads them
-  if (want_warp) {
-    for (int t = threadIdx.x; t < 2 * T; t += kThreads) {
-      const bool top = t < T;
-      const int f = top ? f0 - 1 : f0 + rows, tt = top ? t : t - T;
-      tile[(top ? 0 : (rows + 1) * T) + tt] = (f >= 0 && f < F) ? __ldg(xs + (size_t)f * T + tt) : 0.f;
-    }
-  }
-  __syncthreads();
+  staged_all = __syncthreads_and(staged_all);
+  const MaskSet tms = load_masks(masks, want_tm ? p.num_mask : 0);
+  const MaskSet fms = load_masks(masks + 2 * kMaxMasksSm, want_fm ? p.num_mask : 0);
 
   const unsigned magic = (unsigned)((0x100000000ull + T - 1) / T);    // i / T for i < 2^16 via mulhi, one fix-up
   const int n4 = rows * T / 4;
   const float4* src4 = reinterpret_cast<const float4*>(xs + (size_t)f0 * T);
   float4* out4 = reinterpret_cast<float4*>(p.views + (size_t)n * F * T + (size_t)f0 * T);
   const size_t plane4 = plane / 4;
-  float4* tile4 = reinterpret_cast<float4*>(tile + T);
-  // pass 1: one 128-bit read of the tile; copy / mask views straight from registers
+  // pass 1: one 128-bit read of the tile; copy / mask views straight from registers.
+  // Element k of a float4 sits at (r + wrap_k, t + k - wrap_k * T) with wrap_k = (t + k >= T): branch-free.
   for (int i4 = threadIdx.x; i4 < n4; i4 += kThreads) {
     const float4 v = ldg_stream(src4 + i4);
-    if (want_warp) tile4[i4] = v;
     if (want_copy) stg_stream(out4 + i4, v);
-    if (want_tm || want_fm) {
-      const int i = 4 * i4;
-      int r = (int)__umulhi((unsigned)i, magic);
-      if (r * T > i) --r;
-      int t = i - r * T;
-      float e[4] = {v.x, v.y, v.z, v.w}, tmv[4], fmv[4];
+    const int i = 4 * i4;
+    int r = (int)__umulhi((unsigned)i, magic);
+    r -= (r * T > i);
+    const int t = i - r * T;
+    const float e[4] = {v.x, v.y, v.z, v.w};
+    float tmv[4], fmv[4];
+    const bool f_lo = fms.hit(f0 + r), f_hi = fms.hit(f0 + r + 1);
+    float* trow = tile + (r + 1) * ldT + 2 + t;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        bool tm = false, fm = false;
-        const int f = f0 + r;
-        for (int m = 0; m < p.num_mask; ++m) {
-          const int a = masks[2 * m], la = masks[2 * m + 1];
-          tm |= (t >= a && t < a + la);
-          const int b = masks[2 * kMaxMasksSm + 2 * m], lb = masks[2 * kMaxMasksSm + 2 * m + 1];
-          fm |= (f >= b && f < b + lb);
-        }
-        tmv[k] = tm ? p.mask_value : e[k];
-        fmv[k] = fm ? p.mask_value : e[k];
-        if (++t == T) { t = 0; ++r; }
-      }
-      if (want_tm) stg_stream(out4 + 2 * plane4 + i4, make_float4(tmv[0], tmv[1], tmv[2], tmv[3]));
-      if (want_fm) stg_stream(out4 + 3 * plane4 + i4, make_float4(fmv[0], fmv[1], fmv[2], fmv[3]));
+    for (int k = 0; k < 4; ++k) {
+      const bool wrap = t + k >= T;
+      const int tk = wrap ? t + k - T : t + k;
+      if (want_warp) trow[wrap ? k + 4 : k] = e[k];         // next tile row starts ldT = T + 4 further on
+      tmv[k] = tms.hit(tk) ? p.mask_value : e[k];
+      fmv[k] = (wrap ? f_hi : f_lo) ? p.mask_value : e[k];
     }
+    if (want_tm) stg_stream(out4 + 2 * plane4 + i4, make_float4(tmv[0], tmv[1], tmv[2], tmv[3]));
+    if (want_fm) stg_stream(out4 + 3 * plane4 + i4, make_float4(fmv[0], fmv[1], fmv[2], fmv[3]));
   }
   if (!want_warp) return;
   __syncthreads();
-  // pass 2: time-warp view, bilinear gather out of the shared tile (tile row = f - f0 + 1)
+  // pass 2: time-warp view, bilinear gather out of the shared tile
+  //   out = nw*(s*e) + ne*(s*w) + sw*(n*e) + se*(n*w), each product and sum rounded (grid_sampler order)
   for (int i4 = threadIdx.x; i4 < n4; i4 += kThreads) {
     const int i = 4 * i4;
     int r = (int)__umulhi((unsigned)i, magic);
-    if (r * T > i) --r;
-    int t = i - r * T;
+    r -= (r * T > i);
+    const int t = i - r * T;
     float o[4];
+    if (staged_all) {
+      const float wn_lo = row_wn[r], wn_hi = row_wn[r + 1];
+      const int off_lo = row_off[r], off_hi = row_off[r + 1];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int f = f0 + r;
-      const int yn = __ldg(p.row_lo + f);
-      const float wn = __ldg(p.row_w + f);            // n = iy - floor(iy); s = 1 - n
-      const float ws = __fsub_rn(1.f, wn);
-      const int rr = yn - (f0 - 1);
-      const bool north_in = yn >= 0 && yn < F, south_in = yn + 1 >= 0 && yn + 1 < F;
-      const bool staged = rr >= 0 && rr + 1 < rows + 2;
-      const float* north = tile + rr * T;
-      const float* south = north + T;
-      const int xw = col_lo[t];
-      const float ww = col_w[t], we = __fsub_rn(1.f, ww);
-      const bool west_in = xw >= 0 && xw < T, east_in = xw + 1 >= 0 && xw + 1 < T;
-      float v_nw = 0.f, v_ne = 0.f, v_sw = 0.f, v_se = 0.f;
-      if (staged) {
-        if (north_in) { if (west_in) v_nw = north[xw]; if (east_in) v_ne = north[xw + 1]; }
-        if (south_in && wn != 0.f) { if (west_in) v_sw = south[xw]; if (east_in) v_se = south[xw + 1]; }
-      } else {  // generic row tables: fall back to global memory
+      for (int k = 0; k < 4; ++k) {
+        const bool wrap = t + k >= T;
+        const int tk = wrap ? t + k - T : t + k;
+        const float wn = wrap ? wn_hi : wn_lo, ws = __fsub_rn(1.f, wn);
+        const float ww = col_w[tk], we = __fsub_rn(1.f, ww);
+        const float* nw = tile + (wrap ? off_hi : off_lo) + col_lo[tk];
+        float acc = __fmul_rn(nw[0], __fmul_rn(ws, we));
+        acc = __fadd_rn(acc, __fmul_rn(nw[1], __fmul_rn(ws, ww)));
+        acc = __fadd_rn(acc, __fmul_rn(nw[ldT], __fmul_rn(wn, we)));
+        acc = __fadd_rn(acc, __fmul_rn(nw[ldT + 1], __fmul_rn(wn, ww)));
+        o[k] = acc;
+      }
+    } else {
+      // generic row tables (source rows outside the tile + halo): gather from global memory
+      int rk = r, tk = t;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int f = f0 + rk;
+        const int yn = __ldg(p.row_lo + f);
+        const float wn = __ldg(p.row_w + f), ws = __fsub_rn(1.f, wn);
+        const bool north_in = yn >= 0 && yn < F, south_in = yn + 1 >= 0 && yn + 1 < F;
+        const int xw = col_lo[tk] - 2;
+        const float ww = col_w[tk], we = __fsub_rn(1.f, ww);
+        const bool west_in = xw >= 0 && xw < T, east_in = xw + 1 >= 0 && xw + 1 < T;
+        float v_nw = 0.f, v_ne = 0.f, v_sw = 0.f, v_se = 0.f;
         if (north_in) { if (west_in) v_nw = __ldg(xs + (size_t)yn * T + xw); if (east_in) v_ne = __ldg(xs + (size_t)yn * T + xw + 1); }
         if (south_in) { if (west_in) v_sw = __ldg(xs + (size_t)(yn + 1) * T + xw); if (east_in) v_se = __ldg(xs + (size_t)(yn + 1) * T + xw + 1); }
+        float acc = __fmul_rn(v_nw, __fmul_rn(ws, we));
+        acc = __fadd_rn(acc, __fmul_rn(v_ne, __fmul_rn(ws, ww)));
+        acc = __fadd_rn(acc, __fmul_rn(v_sw, __fmul_rn(wn, we)));
+        acc = __fadd_rn(acc, __fmul_rn(v_se, __fmul_rn(wn, ww)));
+        o[k] = acc;
+        if (++tk == T) { tk = 0; ++rk; }
       }
-      // out = nw*(s*e) + ne*(s*w) + sw*(n*e) + se*(n*w), each product and sum rounded (grid_sampler order)
-      float acc = __fmul_rn(v_nw, __fmul_rn(ws, we));
-      acc = __fadd_rn(acc, __fmul_rn(v_ne, __fmul_rn(ws, ww)));
-      acc = __fadd_rn(acc, __fmul_rn(v_sw, __fmul_rn(wn, we)));
-      acc = __fadd_rn(acc, __fmul_rn(v_se, __fmul_rn(wn, ww)));
-      o[k] = acc;
-      if (++t == T) { t = 0; ++r; }
     }
     stg_stream(out4 + plane4 + i4, make_float4(o[0], o[1], o[2], o[3]));
   }
@@ -360,7 +400,7 @@ extern "C" int afsl_specaug_views_f32(const float* x, float* views, const int32_
                       ((size_t)N * F * T) % 4 == 0 && (size_t)kTileRows * T < 65536;
   const char* vec_env = getenv("AFSL_SPECAUG_TILE");     // read per launch so the tests can exercise both kernels
   if (vec_ok && (!vec_env || atoi(vec_env) != 0)) {
-    const size_t tb = ((size_t)(kTileRows + 2) * T + 8 + 2 * (size_t)T + 4 * kMaxMasksSm) * sizeof(float);
+    const size_t tb = ((size_t)(kTileRows + 2) * (T + 4) + 2 * (size_t)T + 2 * (kTileRows + 1) + 4 * kMaxMasksSm) * sizeof(float);
     if (int rc = opt_in_smem(specaug_tile_kernel, tb, "afsl_specaug_views_f32")) return rc;
     const long long ctas = (long long)N * ((F + kTileRows - 1) / kTileRows);
     AFSL_REQUIRE(ctas < (1ll << 31), "afsl_specaug_views_f32: too many tiles (%lld)", ctas);
