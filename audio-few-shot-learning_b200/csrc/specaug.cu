@@ -225,12 +225,13 @@ __device__ __forceinline__ MaskSet load_masks(const int* m, int num) {
   return s;
 }
 
-__global__ void __launch_bounds__(kThreads) specaug_tile_kernel(const SpecParams p) {
+__global__ void __launch_bounds__(kThreads, 6) specaug_tile_kernel(const SpecParams p) {
   extern __shared__ __align__(16) float sm[];
   const int T = p.T, F = p.F, ldT = T + 4;              // tile rows carry two zero columns on either side
+  // a CTA walks p.split consecutive tiles of ONE sample: the column tables and masks are set up once
   const int tiles_per_sample = (F + kTileRows - 1) / kTileRows;
-  const int n = blockIdx.x / tiles_per_sample, tix = blockIdx.x - n * tiles_per_sample;
-  const int f0 = tix * kTileRows, rows = min(kTileRows, F - f0);
+  const int ctas_per_sample = (tiles_per_sample + p.split - 1) / p.split;
+  const int n = blockIdx.x / ctas_per_sample, part = blockIdx.x - n * ctas_per_sample;
   float* tile = sm;                                     // [(rows + 2) * ldT]: row 0 = halo above
   float* col_w = sm + (kTileRows + 2) * ldT;            // [T] east weight
   int* col_lo = reinterpret_cast<int*>(col_w + T);      // [T] west column inside a padded tile row (0 .. T+2)
@@ -243,8 +244,7 @@ __global__ void __launch_bounds__(kThreads) specaug_tile_kernel(const SpecParams
   const int set = n / p.set_size;
   const float* xs = p.x + (size_t)n * F * T;
 
-  // per-column / per-row tables and masks
-  int staged_all = 1;
+  // per-column tables and masks (once per CTA)
   if (want_warp) {
     for (int t = threadIdx.x; t < T; t += kThreads) {
       const float gx = p.src_x ? __ldg(p.src_x + (size_t)n * T + t)
@@ -258,6 +258,22 @@ __global__ void __launch_bounds__(kThreads) specaug_tile_kernel(const SpecParams
       col_lo[t] = (int)cl + 2;
       col_w[t] = __fsub_rn(ix, fl);
     }
+  }
+  if (threadIdx.x < 2 * p.num_mask) {
+    masks[threadIdx.x] = __ldg(p.time_masks + (size_t)set * p.num_mask * 2 + threadIdx.x);
+    masks[2 * kMaxMasksSm + threadIdx.x] = __ldg(p.freq_masks + (size_t)set * p.num_mask * 2 + threadIdx.x);
+  }
+  __syncthreads();
+  const MaskSet tms = load_masks(masks, want_tm ? p.num_mask : 0);
+  const MaskSet fms = load_masks(masks + 2 * kMaxMasksSm, want_fm ? p.num_mask : 0);
+  const unsigned magic = (unsigned)((0x100000000ull + T - 1) / T);    // i / T for i < 2^16 via mulhi, one fix-up
+  const size_t plane4 = plane / 4;
+
+  for (int tix = part * p.split; tix < min((part + 1) * p.split, tiles_per_sample); ++tix) {
+  const int f0 = tix * kTileRows, rows = min(kTileRows, F - f0);
+  // per-row tables, zero padding columns and halo rows of this tile
+  int staged_all = 1;
+  if (want_warp) {
     for (int r = threadIdx.x; r <= rows; r += kThreads) {   // entry `rows` is a dummy for the wrap of the last float4
       const int f = min(f0 + r, F - 1);
       const int yn = __ldg(p.row_lo + f);
@@ -278,19 +294,10 @@ __global__ void __launch_bounds__(kThreads) specaug_tile_kernel(const SpecParams
       tile[(top ? 0 : rows + 1) * ldT + 2 + tt] = (f >= 0 && f < F) ? __ldg(xs + (size_t)f * T + tt) : 0.f;
     }
   }
-  if (threadIdx.x < 2 * p.num_mask) {
-    masks[threadIdx.x] = __ldg(p.time_masks + (size_t)set * p.num_mask * 2 + threadIdx.x);
-    masks[2 * kMaxMasksSm + threadIdx.x] = __ldg(p.freq_masks + (size_t)set * p.num_mask * 2 + threadIdx.x);
-  }
   staged_all = __syncthreads_and(staged_all);
-  const MaskSet tms = load_masks(masks, want_tm ? p.num_mask : 0);
-  const MaskSet fms = load_masks(masks + 2 * kMaxMasksSm, want_fm ? p.num_mask : 0);
-
-  const unsigned magic = (unsigned)((0x100000000ull + T - 1) / T);    // i / T for i < 2^16 via mulhi, one fix-up
   const int n4 = rows * T / 4;
   const float4* src4 = reinterpret_cast<const float4*>(xs + (size_t)f0 * T);
   float4* out4 = reinterpret_cast<float4*>(p.views + (size_t)n * F * T + (size_t)f0 * T);
-  const size_t plane4 = plane / 4;
   // pass 1: one 128-bit read of the tile; copy / mask views straight from registers.
   // Element k of a float4 sits at (r + wrap_k, t + k - wrap_k * T) with wrap_k = (t + k >= T): branch-free.
   for (int i4 = threadIdx.x; i4 < n4; i4 += kThreads) {
@@ -315,7 +322,7 @@ __global__ void __launch_bounds__(kThreads) specaug_tile_kernel(const SpecParams
     if (want_tm) stg_stream(out4 + 2 * plane4 + i4, make_float4(tmv[0], tmv[1], tmv[2], tmv[3]));
     if (want_fm) stg_stream(out4 + 3 * plane4 + i4, make_float4(fmv[0], fmv[1], fmv[2], fmv[3]));
   }
-  if (!want_warp) return;
+  if (!want_warp) continue;
   __syncthreads();
   // pass 2: time-warp view, bilinear gather out of the shared tile
   //   out = nw*(s*e) + ne*(s*w) + sw*(n*e) + se*(n*w), each product and sum rounded (grid_sampler order)
@@ -366,6 +373,8 @@ __global__ void __launch_bounds__(kThreads) specaug_tile_kernel(const SpecParams
     }
     stg_stream(out4 + plane4 + i4, make_float4(o[0], o[1], o[2], o[3]));
   }
+  __syncthreads();          // the next tile overwrites the shared tile and row tables
+  }  // tiles of this CTA
 }
 
 }  // namespace
@@ -402,7 +411,12 @@ extern "C" int afsl_specaug_views_f32(const float* x, float* views, const int32_
   if (vec_ok && (!vec_env || atoi(vec_env) != 0)) {
     const size_t tb = ((size_t)(kTileRows + 2) * (T + 4) + 2 * (size_t)T + 2 * (kTileRows + 1) + 4 * kMaxMasksSm) * sizeof(float);
     if (int rc = opt_in_smem(specaug_tile_kernel, tb, "afsl_specaug_views_f32")) return rc;
-    const long long ctas = (long long)N * ((F + kTileRows - 1) / kTileRows);
+    // whole samples per CTA (column tables computed once per sample) when that still fills the machine several
+    // times over, otherwise one tile per CTA
+    const int tps = (F + kTileRows - 1) / kTileRows;
+    const int cap = persistent_grid(specaug_tile_kernel, kThreads, tb, 1 << 30);
+    p.split = (long long)N >= 4LL * cap ? tps : 1;
+    const long long ctas = (long long)N * ((tps + p.split - 1) / p.split);
     AFSL_REQUIRE(ctas < (1ll << 31), "afsl_specaug_views_f32: too many tiles (%lld)", ctas);
     specaug_tile_kernel<<<(unsigned)ctas, kThreads, tb, (cudaStream_t)stream>>>(p);
     AFSL_CHECK_LAUNCH("afsl_specaug_views_f32");

@@ -297,6 +297,23 @@ def test_specaug_batched_sets_vs_oracle(ops, monkeypatch, t_len, kernel):
         close(v[1, sl], ref[1], rtol=0, scale=warp_atol(x))
 
 
+def test_specaug_whole_sample_ctas_match_row_kernel(ops, monkeypatch):
+    """Large launches switch the tile kernel to one CTA per sample (column tables set up once per sample);
+    its four views must equal, bit for bit, those of the warp-per-row kernel that the oracle tests pin."""
+    sets, n, t_len = 240, 25, 44
+    gen = torch.Generator().manual_seed(21)
+    x = torch.randn(sets * n, 1, 128, t_len, generator=gen).cuda()
+    wp = torch.randint(8, t_len - 8, (sets * n,), generator=gen)
+    wd = torch.randint(-8, 8, (sets * n,), generator=gen)
+    tm = torch.stack([torch.randint(0, t_len - 12, (sets, 2), generator=gen), torch.randint(1, 12, (sets, 2), generator=gen)], -1)
+    fm = torch.stack([torch.randint(0, 110, (sets, 2), generator=gen), torch.randint(1, 16, (sets, 2), generator=gen)], -1)
+    monkeypatch.setenv("AFSL_SPECAUG_TILE", "1")
+    a = ops.specaug_views(x, wp, wd, tm, fm, -1.5, set_size=n)
+    monkeypatch.setenv("AFSL_SPECAUG_TILE", "0")
+    b = ops.specaug_views(x, wp, wd, tm, fm, -1.5, set_size=n)
+    assert torch.equal(a, b)
+
+
 # ------------------------------------------------------------------ majority vote
 def test_vote_vs_reference(ops):
     g = load_golden("vote_cases")
