@@ -39,8 +39,8 @@ SIGNATURES = {
     "afsl_gbn_relu_pool_fwd_f32": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "afsl_gbn_relu_pool_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "afsl_stage1_moments_f64": [_P, _P, _I, _I, _I, _I, _I, _P],
-    "afsl_stage1_fwd_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "afsl_stage1_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "afsl_stage1_fwd_f32": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "afsl_stage1_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "afsl_eval_vote_i32": [_P, _P, _P, _P, _P, _I, _P, _P, _I, _P],
 }
 

@@ -29,6 +29,7 @@ constexpr int kC = 64;              // output channels of stage 1
 constexpr int kCPW = kC / kWarps;   // channels per warp
 constexpr int kBands = 8;           // pooled rows per tile
 constexpr int kAcc = 11;            // s1, s2, T_0..T_8
+constexpr unsigned char kInactive = 15;   // argmax code of an output zeroed by the ReLU (or NaN): no gradient
 
 struct S1Params {
   const float* x;        // [G*group, H, W]
@@ -39,6 +40,8 @@ struct S1Params {
   const float* rstd;
   const float* dy;       // [G*group, kC, PH, PW]
   float* y;              // [G*group, kC, PH, PW]
+  unsigned char* arg_out;      // [G*group, kC, PH, PW] or null: window argmax 0..8 of each pooled output, kInactive if ReLU cut it
+  const unsigned char* arg_in; // backward: the forward's codes (null = recompute the windows)
   double* moments;       // [G, 54]
   float* partial;        // [G, parts, kC, kAcc]
   int G, group, H, W, PH, PW, per_group, parts;
@@ -135,17 +138,29 @@ __global__ void __launch_bounds__(kThreads) stage1_fwd_kernel(const S1Params p) 
   const int tiles_per_sample = (PH + kBands - 1) / kBands;
   const long long total_tiles = (long long)p.G * p.group * tiles_per_sample;
   for (int i = threadIdx.x; i < kC * 9; i += kThreads) sw[i] = __ldg(p.w + i);
+  __syncthreads();
+  // this warp's kCPW channels: weights live in registers for the whole kernel
+  float w[kCPW][9];
+#pragma unroll
+  for (int cc = 0; cc < kCPW; ++cc)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) w[cc][k] = sw[(warp * kCPW + cc) * 9 + k];
+  // per group: z = fma(a, u, b) on the bias-free convolution output u.  The affine is NOT folded into the taps:
+  // when |a| is small the window's z values collide in fp32 and the winner is the first of the collided set,
+  // which only matches at::max_pool2d_with_indices if z is a monotone function of u as it is in the eager chain
+  float ca[kCPW], cb[kCPW];
   int cur_g = -1;
   for (long long tl = blockIdx.x; tl < total_tiles; tl += gridDim.x) {
     const int s = (int)(tl / tiles_per_sample), tix = (int)(tl - (long long)s * tiles_per_sample);
     const int g = s / p.group;
     const int ph0 = tix * kBands, bands = min(kBands, PH - ph0);
     __syncthreads();
-    if (g != cur_g) {                                    // per-(group, channel) affine
-      for (int c = threadIdx.x; c < kC; c += kThreads) {
-        const int idx = p.per_group ? g * kC + c : c;
-        sw[kC * 9 + c] = __ldg(p.a + idx);
-        sw[kC * 10 + c] = __ldg(p.b + idx);
+    if (g != cur_g) {                                    // per-(group, channel) affine z = a u + b
+#pragma unroll
+      for (int cc = 0; cc < kCPW; ++cc) {
+        const int idx = (p.per_group ? g * kC : 0) + warp * kCPW + cc;
+        ca[cc] = __ldg(p.a + idx);
+        cb[cc] = __ldg(p.b + idx);
       }
       cur_g = g;
     }
@@ -156,23 +171,25 @@ __global__ void __launch_bounds__(kThreads) stage1_fwd_kernel(const S1Params p) 
       const int bl = pos / PW, pw = pos - bl * PW;
       float v[25];
       load_patch(tile, ld, bl, pw, v);
-      float* yout = p.y + ((size_t)s * kC) * phw + (size_t)(ph0 + bl) * PW + pw;
-#pragma unroll 1
+      const size_t o0 = ((size_t)s * kC) * phw + (size_t)(ph0 + bl) * PW + pw;
+#pragma unroll
       for (int cc = 0; cc < kCPW; ++cc) {
         const int c = warp * kCPW + cc;
-        float w[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) w[k] = sw[c * 9 + k];
-        const float a = sw[kC * 9 + c], b = sw[kC * 10 + c];
-        float zmax = -INFINITY;
+        float z[9];
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            const float z = fmaf(a, conv_at(v, w, r, q), b);
-            zmax = (z > zmax || z != z) ? ((zmax != zmax) ? zmax : z) : zmax;
-          }
-        yout[(size_t)c * phw] = zmax != zmax ? zmax : fmaxf(zmax, 0.f);
+          for (int q = 0; q < 3; ++q) z[r * 3 + q] = fmaf(ca[cc], conv_at(v, w[cc], r, q), cb[cc]);
+        // NaN / inf inputs poison the batch statistics, hence a and b, hence every z of the group: a window is
+        // either NaN-free or all NaN, and fmaxf of all-NaN operands is NaN - same output as a NaN-sticky scan
+        const float zmax = fmaxf(fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3])), fmaxf(fmaxf(z[4], z[5]), fmaxf(fmaxf(z[6], z[7]), z[8])));
+        p.y[o0 + (size_t)c * phw] = zmax != zmax ? zmax : fmaxf(zmax, 0.f);
+        if (p.arg_out) {
+          int arg = 8;                                    // first maximum in window order (at::max_pool2d_with_indices)
+#pragma unroll
+          for (int k = 7; k >= 0; --k) arg = z[k] == zmax ? k : arg;
+          p.arg_out[o0 + (size_t)c * phw] = zmax > 0.f ? (unsigned char)arg : kInactive;
+        }
       }
     }
   }
@@ -210,6 +227,44 @@ __global__ void __launch_bounds__(kThreads) stage1_bwd_kernel(const S1Params p) 
     stage_tile(p.x + (size_t)s * hw, tile, H, W, ph0, bands);
     __syncthreads();
     const int npos = bands * PW;
+    if (p.arg_in) {
+      // the forward recorded which window element won (and whether the ReLU let it through): only that
+      // element's convolution output (for xhat) and its 3x3 input neighbourhood are needed
+      for (int pos = lane; pos < npos; pos += 32) {
+        const int bl = pos / PW, pw = pos - bl * PW;
+        const size_t o0 = ((size_t)s * kC + warp * kCPW) * phw + (size_t)(ph0 + bl) * PW + pw;
+        int codes[kCPW];
+        float dys[kCPW];
+#pragma unroll
+        for (int cc = 0; cc < kCPW; ++cc) {              // all loads of the position first: kCPW x 2 in flight
+          codes[cc] = __ldg(p.arg_in + o0 + (size_t)cc * phw);
+          dys[cc] = __ldg(p.dy + o0 + (size_t)cc * phw);
+        }
+#pragma unroll
+        for (int cc = 0; cc < kCPW; ++cc) {
+          const int c = warp * kCPW + cc;
+          const int code = codes[cc];
+          if (code >= 9) continue;
+          const float dyv = dys[cc];
+          const int ar = code / 3, aq = code - ar * 3;
+          const float* nb = tile + (size_t)(3 * bl + ar) * ld + 3 * pw + aq;
+          float xs[9], u = 0.f;
+#pragma unroll
+          for (int ka = 0; ka < 3; ++ka)
+#pragma unroll
+            for (int kb = 0; kb < 3; ++kb) {
+              xs[ka * 3 + kb] = nb[ka * ld + kb];
+              u = fmaf(sw[c * 9 + ka * 3 + kb], xs[ka * 3 + kb], u);
+            }
+          const float xhat = (u - sw[kC * 11 + c]) * sw[kC * 12 + c];
+          acc[cc][0] += dyv;
+          acc[cc][1] = fmaf(dyv, xhat, acc[cc][1]);
+#pragma unroll
+          for (int k = 0; k < 9; ++k) acc[cc][2 + k] = fmaf(dyv, xs[k], acc[cc][2 + k]);
+        }
+      }
+      continue;
+    }
     for (int pos = lane; pos < npos; pos += 32) {
       const int bl = pos / PW, pw = pos - bl * PW;
       float v[25];
@@ -289,12 +344,12 @@ extern "C" int afsl_stage1_moments_f64(const float* x, double* moments, int part
   return AFSL_OK;
 }
 
-extern "C" int afsl_stage1_fwd_f32(const float* x, const float* weight, const float* a, const float* b, float* y, int G,
-                                    int group, int H, int W, int per_group, void* stream) {
+extern "C" int afsl_stage1_fwd_f32(const float* x, const float* weight, const float* a, const float* b, float* y,
+                                    unsigned char* argmax, int G, int group, int H, int W, int per_group, void* stream) {
   using namespace afsl;
   AFSL_REQUIRE(x && weight && a && b && y, "afsl_stage1_fwd_f32: null pointer");
   S1Params p{};
-  p.x = x; p.w = weight; p.a = a; p.b = b; p.y = y;
+  p.x = x; p.w = weight; p.a = a; p.b = b; p.y = y; p.arg_out = argmax;
   p.G = G; p.group = group; p.H = H; p.W = W; p.PH = H / 3; p.PW = W / 3; p.per_group = per_group;
   if (int rc = check(p, "afsl_stage1_fwd_f32")) return rc;
   const size_t bytes = smem_bytes(W, false);
@@ -307,12 +362,12 @@ extern "C" int afsl_stage1_fwd_f32(const float* x, const float* weight, const fl
 }
 
 extern "C" int afsl_stage1_bwd_f32(const float* x, const float* weight, const float* a, const float* b, const float* mean,
-                                    const float* rstd, const float* d_y, float* partial, int parts, int G, int group, int H,
-                                    int W, int per_group, void* stream) {
+                                    const float* rstd, const float* d_y, const unsigned char* argmax, float* partial, int parts,
+                                    int G, int group, int H, int W, int per_group, void* stream) {
   using namespace afsl;
   AFSL_REQUIRE(x && weight && a && b && mean && rstd && d_y && partial && parts > 0, "afsl_stage1_bwd_f32: null pointer / parts");
   S1Params p{};
-  p.x = x; p.w = weight; p.a = a; p.b = b; p.mean = mean; p.rstd = rstd; p.dy = d_y; p.partial = partial;
+  p.x = x; p.w = weight; p.a = a; p.b = b; p.mean = mean; p.rstd = rstd; p.dy = d_y; p.partial = partial; p.arg_in = argmax;
   p.G = G; p.group = group; p.H = H; p.W = W; p.PH = H / 3; p.PW = W / 3; p.per_group = per_group; p.parts = parts;
   if (int rc = check(p, "afsl_stage1_bwd_f32")) return rc;
   const size_t bytes = smem_bytes(W, true);

@@ -540,14 +540,18 @@ class _Stage1(torch.autograd.Function):
         c = weight.shape[0]
         y = torch.empty(n, c, h // 3, w // 3, device=x.device, dtype=torch.float32)
         w9 = weight.detach().reshape(c, 9).float().contiguous()
-        call("afsl_stage1_fwd_f32", ptr(x), ptr(w9), ptr(a), ptr(b), ptr(y), groups, group, h, w, int(per_group), stream_ptr())
-        ctx.save_for_backward(x, w9, gamma, a, b, mean_u, rstd, s_mom, r_mom)
+        # window argmax codes (1 byte per pooled output) let the backward skip recomputing the 3x3 windows
+        need_grad = any(ctx.needs_input_grad)
+        arg = torch.empty(n, c, h // 3, w // 3, device=x.device, dtype=torch.uint8) if need_grad else None
+        call("afsl_stage1_fwd_f32", ptr(x), ptr(w9), ptr(a), ptr(b), ptr(y), ptr(arg), groups, group, h, w, int(per_group),
+             stream_ptr())
+        ctx.save_for_backward(x, w9, gamma, a, b, mean_u, rstd, s_mom, r_mom, arg)
         ctx.dims = (groups, group, int(per_group), bias is not None)
         return y
 
     @staticmethod
     def backward(ctx, d_y):
-        x, w9, gamma, a, b, mean_u, rstd, s_mom, r_mom = ctx.saved_tensors
+        x, w9, gamma, a, b, mean_u, rstd, s_mom, r_mom, arg = ctx.saved_tensors
         groups, group, per_group, has_bias = ctx.dims
         n, _, h, w = x.shape
         c = w9.shape[0]
@@ -555,8 +559,8 @@ class _Stage1(torch.autograd.Function):
         sms = torch.cuda.get_device_properties(x.device).multi_processor_count
         parts = max(1, min(group * ((h // 3 + 7) // 8), (2 * sms + groups - 1) // groups))
         partial = torch.empty(groups, parts, c, 11, device=x.device, dtype=torch.float32)
-        call("afsl_stage1_bwd_f32", ptr(x), ptr(w9), ptr(a), ptr(b), ptr(mean_u), ptr(rstd), ptr(d_y), ptr(partial), parts,
-             groups, group, h, w, per_group, stream_ptr())
+        call("afsl_stage1_bwd_f32", ptr(x), ptr(w9), ptr(a), ptr(b), ptr(mean_u), ptr(rstd), ptr(d_y), ptr(arg), ptr(partial),
+             parts, groups, group, h, w, per_group, stream_ptr())
         acc = partial.double().sum(1)                                   # [G,C,11]
         s1, s2, t = acc[..., 0], acc[..., 1], acc[..., 2:]               # [G,C], [G,C], [G,C,9]
         a_gc = (a if per_group else a.unsqueeze(0).expand(groups, c)).double()

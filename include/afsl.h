@@ -241,16 +241,19 @@ int afsl_gbn_relu_pool_bwd_f32(const float* x, const float* mean, const float* r
  * bwd: partial [G,parts,64,11] = per channel (sum dz, sum dz*xhat, T_0..T_8) with
  *   T_k = sum dz * x(p_argmax + tap k); weight / BatchNorm gradients are assembled
  *   from these and the moments on the host.  The input gets no gradient.
+ * argmax [G*group,64,H/3,W/3] bytes [opt]: written by fwd (window element 0..8 that won the
+ *   max, 15 where the ReLU zeroed the output); when passed to bwd only that element is
+ *   recomputed instead of the whole 3x3 window of convolution outputs.
  * ------------------------------------------------------------------------- */
 int afsl_stage1_channels(void);
 int afsl_stage1_acc_slots(void);
 int afsl_stage1_moments_f64(const float* x, double* moments, int parts, int G, int group, int H, int W,
                             void* stream);
-int afsl_stage1_fwd_f32(const float* x, const float* weight, const float* a, const float* b, float* y, int G,
-                        int group, int H, int W, int per_group, void* stream);
+int afsl_stage1_fwd_f32(const float* x, const float* weight, const float* a, const float* b, float* y,
+                        unsigned char* argmax, int G, int group, int H, int W, int per_group, void* stream);
 int afsl_stage1_bwd_f32(const float* x, const float* weight, const float* a, const float* b, const float* mean,
-                        const float* rstd, const float* d_y, float* partial, int parts, int G, int group, int H,
-                        int W, int per_group, void* stream);
+                        const float* rstd, const float* d_y, const unsigned char* argmax, float* partial, int parts,
+                        int G, int group, int H, int W, int per_group, void* stream);
 
 #ifdef __cplusplus
 }
