@@ -39,8 +39,11 @@ SIGNATURES = {
     "afsl_gbn_relu_pool_fwd_f32": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "afsl_gbn_relu_pool_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "afsl_stage1_moments_f64": [_P, _P, _I, _I, _I, _I, _I, _P],
-    "afsl_stage1_fwd_f32": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "afsl_stage1_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "afsl_stage1_fwd_f32": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "afsl_stage1_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "afsl_gbn_stats_nhwc_f32": [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "afsl_gbn_relu_pool_nhwc_fwd_f32": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "afsl_gbn_relu_pool_nhwc_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P],
     "afsl_eval_vote_i32": [_P, _P, _P, _P, _P, _I, _P, _P, _I, _P],
 }
 
@@ -67,6 +70,8 @@ def load() -> ctypes.CDLL:
     lib.afsl_view_fusion_param_floats.restype = c_int
     lib.afsl_stage1_channels.restype = c_int
     lib.afsl_stage1_acc_slots.restype = c_int
+    lib.afsl_gbn_nhwc_parts.restype = c_int
+    lib.afsl_gbn_nhwc_parts.argtypes = [c_int]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
@@ -80,13 +85,17 @@ def launch_count() -> int:
     return int(load().afsl_launch_count())
 
 
-def ptr(t):
-    """Device pointer of a tensor or None; enforces the ABI's layout rules."""
+def ptr(t, channels_last: bool = False):
+    """Device pointer of a tensor or None; enforces the ABI's layout rules (``channels_last``: the tensor must be
+    dense in NHWC order - the entry points that take it say so)."""
     if t is None:
         return None
     if not t.is_cuda:
         raise AfslError("libafsl operates on CUDA tensors only (no CPU path); got a %s tensor" % t.device)
-    if not t.is_contiguous():
+    if channels_last:
+        if not t.is_contiguous(memory_format=torch.channels_last):
+            raise AfslError("this libafsl entry point needs a channels-last (NHWC) tensor")
+    elif not t.is_contiguous():
         raise AfslError("libafsl needs contiguous tensors")
     p = t.data_ptr()
     if p % 16 and t.numel():

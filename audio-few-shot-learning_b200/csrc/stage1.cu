@@ -45,6 +45,7 @@ struct S1Params {
   double* moments;       // [G, 54]
   float* partial;        // [G, parts, kC, kAcc]
   int G, group, H, W, PH, PW, per_group, parts;
+  int nhwc;              // y / argmax / dy are channels-last [G*group, PH, PW, kC] instead of [G*group, kC, PH, PW]
 };
 
 // ---------------------------------------------------------------- input moments
@@ -172,9 +173,10 @@ __global__ void __launch_bounds__(kThreads) stage1_fwd_kernel(const S1Params p) 
       float v[25];
       load_patch(tile, ld, bl, pw, v);
       const size_t o0 = ((size_t)s * kC) * phw + (size_t)(ph0 + bl) * PW + pw;
+      float outv[kCPW];
+      unsigned char outc[kCPW];
 #pragma unroll
       for (int cc = 0; cc < kCPW; ++cc) {
-        const int c = warp * kCPW + cc;
         float z[9];
 #pragma unroll
         for (int r = 0; r < 3; ++r)
@@ -183,12 +185,24 @@ __global__ void __launch_bounds__(kThreads) stage1_fwd_kernel(const S1Params p) 
         // NaN / inf inputs poison the batch statistics, hence a and b, hence every z of the group: a window is
         // either NaN-free or all NaN, and fmaxf of all-NaN operands is NaN - same output as a NaN-sticky scan
         const float zmax = fmaxf(fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3])), fmaxf(fmaxf(z[4], z[5]), fmaxf(fmaxf(z[6], z[7]), z[8])));
-        p.y[o0 + (size_t)c * phw] = zmax != zmax ? zmax : fmaxf(zmax, 0.f);
+        outv[cc] = zmax != zmax ? zmax : fmaxf(zmax, 0.f);
+        int arg = 8;                                      // first maximum in window order (at::max_pool2d_with_indices)
         if (p.arg_out) {
-          int arg = 8;                                    // first maximum in window order (at::max_pool2d_with_indices)
 #pragma unroll
           for (int k = 7; k >= 0; --k) arg = z[k] == zmax ? k : arg;
-          p.arg_out[o0 + (size_t)c * phw] = zmax > 0.f ? (unsigned char)arg : kInactive;
+        }
+        outc[cc] = zmax > 0.f ? (unsigned char)arg : kInactive;
+      }
+      if (p.nhwc) {      // the warp's kCPW = 4 channels of this pooled pixel are one float4 / one 32-bit word of codes
+        const size_t px = ((size_t)s * phw + (size_t)(ph0 + bl) * PW + pw) * kC + warp * kCPW;
+        *reinterpret_cast<float4*>(p.y + px) = make_float4(outv[0], outv[1], outv[2], outv[3]);
+        if (p.arg_out) *reinterpret_cast<uchar4*>(p.arg_out + px) = make_uchar4(outc[0], outc[1], outc[2], outc[3]);
+      } else {
+#pragma unroll
+        for (int cc = 0; cc < kCPW; ++cc) {
+          const size_t o = o0 + (size_t)(warp * kCPW + cc) * phw;
+          p.y[o] = outv[cc];
+          if (p.arg_out) p.arg_out[o] = outc[cc];
         }
       }
     }
@@ -235,10 +249,18 @@ __global__ void __launch_bounds__(kThreads) stage1_bwd_kernel(const S1Params p) 
         const size_t o0 = ((size_t)s * kC + warp * kCPW) * phw + (size_t)(ph0 + bl) * PW + pw;
         int codes[kCPW];
         float dys[kCPW];
+        if (p.nhwc) {
+          const size_t px = ((size_t)s * phw + (size_t)(ph0 + bl) * PW + pw) * kC + warp * kCPW;
+          const uchar4 c4 = __ldg(reinterpret_cast<const uchar4*>(p.arg_in + px));
+          const float4 d4 = __ldg(reinterpret_cast<const float4*>(p.dy + px));
+          codes[0] = c4.x; codes[1] = c4.y; codes[2] = c4.z; codes[3] = c4.w;
+          dys[0] = d4.x; dys[1] = d4.y; dys[2] = d4.z; dys[3] = d4.w;
+        } else {
 #pragma unroll
-        for (int cc = 0; cc < kCPW; ++cc) {              // all loads of the position first: kCPW x 2 in flight
-          codes[cc] = __ldg(p.arg_in + o0 + (size_t)cc * phw);
-          dys[cc] = __ldg(p.dy + o0 + (size_t)cc * phw);
+          for (int cc = 0; cc < kCPW; ++cc) {            // all loads of the position first: kCPW x 2 in flight
+            codes[cc] = __ldg(p.arg_in + o0 + (size_t)cc * phw);
+            dys[cc] = __ldg(p.dy + o0 + (size_t)cc * phw);
+          }
         }
 #pragma unroll
         for (int cc = 0; cc < kCPW; ++cc) {
@@ -345,11 +367,13 @@ extern "C" int afsl_stage1_moments_f64(const float* x, double* moments, int part
 }
 
 extern "C" int afsl_stage1_fwd_f32(const float* x, const float* weight, const float* a, const float* b, float* y,
-                                    unsigned char* argmax, int G, int group, int H, int W, int per_group, void* stream) {
+                                    unsigned char* argmax, int G, int group, int H, int W, int per_group,
+                                    int channels_last, void* stream) {
   using namespace afsl;
   AFSL_REQUIRE(x && weight && a && b && y, "afsl_stage1_fwd_f32: null pointer");
+  static_assert(kCPW == 4, "the channels-last stores move one float4 / uchar4 per lane");
   S1Params p{};
-  p.x = x; p.w = weight; p.a = a; p.b = b; p.y = y; p.arg_out = argmax;
+  p.x = x; p.w = weight; p.a = a; p.b = b; p.y = y; p.arg_out = argmax; p.nhwc = channels_last;
   p.G = G; p.group = group; p.H = H; p.W = W; p.PH = H / 3; p.PW = W / 3; p.per_group = per_group;
   if (int rc = check(p, "afsl_stage1_fwd_f32")) return rc;
   const size_t bytes = smem_bytes(W, false);
@@ -363,10 +387,12 @@ extern "C" int afsl_stage1_fwd_f32(const float* x, const float* weight, const fl
 
 extern "C" int afsl_stage1_bwd_f32(const float* x, const float* weight, const float* a, const float* b, const float* mean,
                                     const float* rstd, const float* d_y, const unsigned char* argmax, float* partial, int parts,
-                                    int G, int group, int H, int W, int per_group, void* stream) {
+                                    int G, int group, int H, int W, int per_group, int channels_last, void* stream) {
   using namespace afsl;
   AFSL_REQUIRE(x && weight && a && b && mean && rstd && d_y && partial && parts > 0, "afsl_stage1_bwd_f32: null pointer / parts");
+  AFSL_REQUIRE(!channels_last || argmax, "afsl_stage1_bwd_f32: the channels-last backward needs the forward's argmax codes");
   S1Params p{};
+  p.nhwc = channels_last;
   p.x = x; p.w = weight; p.a = a; p.b = b; p.mean = mean; p.rstd = rstd; p.dy = d_y; p.partial = partial; p.arg_in = argmax;
   p.G = G; p.group = group; p.H = H; p.W = W; p.PH = H / 3; p.PW = W / 3; p.per_group = per_group; p.parts = parts;
   if (int rc = check(p, "afsl_stage1_bwd_f32")) return rc;

@@ -111,8 +111,12 @@ class ConvBlock(nn.Sequential):
             # 1-channel first block: convolution fused into the BatchNorm/ReLU/pool kernel (no cuDNN call)
             return ops.stage1_conv_bn_relu_pool(x, conv, bn, getattr(bn, "group_size", None))
         if x.is_cuda and is3 and FUSED_STAGES:
-            # bias-free cuDNN convolution; the bias is folded into the BatchNorm statistics by the kernel
-            u = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+            # bias-free cuDNN convolution; the bias is folded into the BatchNorm statistics by the kernel.
+            # A channels-last input (stage 1 emits one) gives a channels-last output without conversion kernels.
+            weight = conv.weight
+            if ops._is_nhwc(x):
+                weight = weight.contiguous(memory_format=torch.channels_last)
+            u = F.conv2d(x, weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
             if u.shape[-1] >= 3 and u.shape[-2] >= 3:
                 return ops.gbn_relu_pool(u, bn, getattr(bn, "group_size", None), conv_bias=conv.bias)
             x = u if conv.bias is None else u + conv.bias.view(1, -1, 1, 1)
@@ -168,7 +172,7 @@ class StandardCNN(nn.Module):
 
     def forward(self, x):
         x = self.conv_encoder(x)
-        return self.logits(x.view(x.size(0), -1))
+        return self.logits(x.reshape(x.size(0), -1))      # logical NCHW order whatever the memory format
 
 
 class StandardHybrid(nn.Module):

@@ -441,6 +441,12 @@ def view_fusion(x: torch.Tensor, layer: torch.nn.TransformerEncoderLayer, masks=
 
 
 # ---------------------------------------------------------------------------------- grouped BN + ReLU + pool
+def _is_nhwc(t: torch.Tensor) -> bool:
+    """Dense channels-last 4-d tensor that is not also NCHW-contiguous (1x1 planes count as NCHW)."""
+    return (t.dim() == 4 and t.shape[1] % 4 == 0 and not t.is_contiguous()
+            and t.is_contiguous(memory_format=torch.channels_last))
+
+
 class _GbnReluPool(torch.autograd.Function):
     """y = MaxPool3(ReLU(BN(u + conv_bias))) with u the bias-free convolution output.
 
@@ -450,12 +456,19 @@ class _GbnReluPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, u, gamma, beta, conv_bias, mean, rstd, groups, group, per_group):
         n, c, h, w = u.shape
-        y = torch.empty(n, c, h // 3, w // 3, device=u.device, dtype=torch.float32)
-        call("afsl_gbn_relu_pool_fwd_f32", ptr(u), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(y), groups, group, c, h, w,
-             int(per_group), stream_ptr())
+        nhwc = _is_nhwc(u)
+        if nhwc:
+            y = torch.empty(n, c, h // 3, w // 3, device=u.device, dtype=torch.float32, memory_format=torch.channels_last)
+            call("afsl_gbn_relu_pool_nhwc_fwd_f32", ptr(u, True), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(y, True),
+                 groups, group, c, h, w, int(per_group), stream_ptr())
+        else:
+            y = torch.empty(n, c, h // 3, w // 3, device=u.device, dtype=torch.float32)
+            call("afsl_gbn_relu_pool_fwd_f32", ptr(u), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(y), groups, group, c,
+                 h, w, int(per_group), stream_ptr())
         ctx.save_for_backward(u, gamma, beta, mean, rstd)
         ctx.dims = (groups, group, int(per_group))
         ctx.has_bias = conv_bias is not None
+        ctx.nhwc = nhwc
         return y
 
     @staticmethod
@@ -463,11 +476,19 @@ class _GbnReluPool(torch.autograd.Function):
         u, gamma, beta, mean, rstd = ctx.saved_tensors
         groups, group, per_group = ctx.dims
         n, c, h, w = u.shape
-        d_y = _f32(d_y)
-        d_u = torch.empty_like(u)
         sums = torch.empty(groups, c, 2, device=u.device, dtype=torch.float32)
-        call("afsl_gbn_relu_pool_bwd_f32", ptr(u), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(d_y), ptr(d_u), ptr(sums),
-             groups, group, c, h, w, per_group, stream_ptr())
+        if ctx.nhwc:
+            d_y = d_y.float().contiguous(memory_format=torch.channels_last)
+            d_u = torch.empty_like(u, memory_format=torch.channels_last)
+            parts = int(_lib.load().afsl_gbn_nhwc_parts(groups))
+            ws = torch.empty(groups, parts, c, 2, device=u.device, dtype=torch.float64)
+            call("afsl_gbn_relu_pool_nhwc_bwd_f32", ptr(u, True), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(d_y, True),
+                 ptr(d_u, True), ptr(ws), parts, ptr(sums), groups, group, c, h, w, per_group, stream_ptr())
+        else:
+            d_y = _f32(d_y)
+            d_u = torch.empty_like(u)
+            call("afsl_gbn_relu_pool_bwd_f32", ptr(u), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(d_y), ptr(d_u),
+                 ptr(sums), groups, group, c, h, w, per_group, stream_ptr())
         totals = sums.sum(0)
         d_gamma, d_beta = totals[:, 1].contiguous(), totals[:, 0].contiguous()
         d_bias = None
@@ -487,7 +508,8 @@ def gbn_relu_pool(u: torch.Tensor, bn: torch.nn.BatchNorm2d, group_size: Optiona
     Eval mode: running statistics.  ``conv_bias`` (per channel) is folded into the statistics instead
     of being added to the tensor.  One libafsl launch per pass instead of the eager chain.
     """
-    u = _f32(u)
+    nhwc = _is_nhwc(u)
+    u = u.float() if nhwc else _f32(u)                   # channels-last activations stay channels-last
     n, c, h, w = u.shape
     gamma, beta = _f32(bn.weight), _f32(bn.bias)
     use_batch_stats = bn.training or not bn.track_running_stats
@@ -498,7 +520,14 @@ def gbn_relu_pool(u: torch.Tensor, bn: torch.nn.BatchNorm2d, group_size: Optiona
         groups = n // group
         mean = torch.empty(groups, c, device=u.device, dtype=torch.float32)
         rstd, var = torch.empty_like(mean), torch.empty_like(mean)
-        call("afsl_gbn_stats_f32", ptr(u), ptr(mean), ptr(rstd), ptr(var), groups, group, c, h, w, float(bn.eps), stream_ptr())
+        if nhwc:
+            parts = int(_lib.load().afsl_gbn_nhwc_parts(groups))
+            ws = torch.empty(groups, parts, c, 2, device=u.device, dtype=torch.float64)
+            call("afsl_gbn_stats_nhwc_f32", ptr(u, True), ptr(ws), parts, ptr(mean), ptr(rstd), ptr(var), groups, group, c, h, w,
+                 float(bn.eps), stream_ptr())
+        else:
+            call("afsl_gbn_stats_f32", ptr(u), ptr(mean), ptr(rstd), ptr(var), groups, group, c, h, w, float(bn.eps),
+                 stream_ptr())
         if bn.training and bn.track_running_stats:
             with torch.no_grad():
                 count = group * h * w
@@ -517,6 +546,9 @@ def gbn_relu_pool(u: torch.Tensor, bn: torch.nn.BatchNorm2d, group_size: Optiona
 
 # ---------------------------------------------------------------------------------- fused encoder stage 1
 _TRIU9 = None
+# stage 1 writes its pooled output channels-last, which keeps stages 2-4 (cuDNN's NHWC-native sm_100 convolutions +
+# the channels-last BatchNorm/ReLU/pool kernels) free of layout-conversion kernels; False = NCHW everywhere (A/B switch)
+STAGE1_CHANNELS_LAST = True
 
 
 def _moments_to_sr(moments: torch.Tensor):
@@ -538,15 +570,18 @@ class _Stage1(torch.autograd.Function):
     def forward(ctx, x, weight, bias, gamma, beta, a, b, mean_u, rstd, s_mom, r_mom, groups, group, per_group):
         n, _, h, w = x.shape
         c = weight.shape[0]
-        y = torch.empty(n, c, h // 3, w // 3, device=x.device, dtype=torch.float32)
+        nhwc = STAGE1_CHANNELS_LAST and h // 3 > 1 and w // 3 > 1
+        fmt = torch.channels_last if nhwc else torch.contiguous_format
+        y = torch.empty(n, c, h // 3, w // 3, device=x.device, dtype=torch.float32, memory_format=fmt)
         w9 = weight.detach().reshape(c, 9).float().contiguous()
         # window argmax codes (1 byte per pooled output) let the backward skip recomputing the 3x3 windows
         need_grad = any(ctx.needs_input_grad)
-        arg = torch.empty(n, c, h // 3, w // 3, device=x.device, dtype=torch.uint8) if need_grad else None
-        call("afsl_stage1_fwd_f32", ptr(x), ptr(w9), ptr(a), ptr(b), ptr(y), ptr(arg), groups, group, h, w, int(per_group),
-             stream_ptr())
+        arg = torch.empty(n, c, h // 3, w // 3, device=x.device, dtype=torch.uint8, memory_format=fmt) if need_grad else None
+        call("afsl_stage1_fwd_f32", ptr(x), ptr(w9), ptr(a), ptr(b), ptr(y, nhwc), ptr(arg, nhwc), groups, group, h, w,
+             int(per_group), int(nhwc), stream_ptr())
         ctx.save_for_backward(x, w9, gamma, a, b, mean_u, rstd, s_mom, r_mom, arg)
         ctx.dims = (groups, group, int(per_group), bias is not None)
+        ctx.nhwc = nhwc
         return y
 
     @staticmethod
@@ -555,12 +590,13 @@ class _Stage1(torch.autograd.Function):
         groups, group, per_group, has_bias = ctx.dims
         n, _, h, w = x.shape
         c = w9.shape[0]
-        d_y = _f32(d_y)
+        nhwc = ctx.nhwc
+        d_y = d_y.float().contiguous(memory_format=torch.channels_last) if nhwc else _f32(d_y)
         sms = torch.cuda.get_device_properties(x.device).multi_processor_count
         parts = max(1, min(group * ((h // 3 + 7) // 8), (2 * sms + groups - 1) // groups))
         partial = torch.empty(groups, parts, c, 11, device=x.device, dtype=torch.float32)
-        call("afsl_stage1_bwd_f32", ptr(x), ptr(w9), ptr(a), ptr(b), ptr(mean_u), ptr(rstd), ptr(d_y), ptr(arg), ptr(partial),
-             parts, groups, group, h, w, per_group, stream_ptr())
+        call("afsl_stage1_bwd_f32", ptr(x), ptr(w9), ptr(a), ptr(b), ptr(mean_u), ptr(rstd), ptr(d_y, nhwc), ptr(arg, nhwc),
+             ptr(partial), parts, groups, group, h, w, per_group, int(nhwc), stream_ptr())
         acc = partial.double().sum(1)                                   # [G,C,11]
         s1, s2, t = acc[..., 0], acc[..., 1], acc[..., 2:]               # [G,C], [G,C], [G,C,9]
         a_gc = (a if per_group else a.unsqueeze(0).expand(groups, c)).double()

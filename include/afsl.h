@@ -241,6 +241,7 @@ int afsl_gbn_relu_pool_bwd_f32(const float* x, const float* mean, const float* r
  * bwd: partial [G,parts,64,11] = per channel (sum dz, sum dz*xhat, T_0..T_8) with
  *   T_k = sum dz * x(p_argmax + tap k); weight / BatchNorm gradients are assembled
  *   from these and the moments on the host.  The input gets no gradient.
+ * channels_last: y, argmax and d_y are [G*group,H/3,W/3,64] instead of [G*group,64,H/3,W/3].
  * argmax [G*group,64,H/3,W/3] bytes [opt]: written by fwd (window element 0..8 that won the
  *   max, 15 where the ReLU zeroed the output); when passed to bwd only that element is
  *   recomputed instead of the whole 3x3 window of convolution outputs.
@@ -250,10 +251,31 @@ int afsl_stage1_acc_slots(void);
 int afsl_stage1_moments_f64(const float* x, double* moments, int parts, int G, int group, int H, int W,
                             void* stream);
 int afsl_stage1_fwd_f32(const float* x, const float* weight, const float* a, const float* b, float* y,
-                        unsigned char* argmax, int G, int group, int H, int W, int per_group, void* stream);
+                        unsigned char* argmax, int G, int group, int H, int W, int per_group, int channels_last,
+                        void* stream);
 int afsl_stage1_bwd_f32(const float* x, const float* weight, const float* a, const float* b, const float* mean,
                         const float* rstd, const float* d_y, const unsigned char* argmax, float* partial, int parts,
-                        int G, int group, int H, int W, int per_group, void* stream);
+                        int G, int group, int H, int W, int per_group, int channels_last, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Channels-last (NHWC) variants of the grouped BatchNorm + ReLU + MaxPool kernels:
+ * x physically [G*group,H,W,C], y / d_y [G*group,H/3,W/3,C], C a multiple of 4.
+ * cuDNN's sm_100 convolutions are NHWC-native; with channels-last activations no
+ * layout-conversion kernels run around them.  The per-(group, channel) reductions are
+ * two-stage: partial is caller-provided workspace, double [G,parts,C,2], with
+ * parts = afsl_gbn_nhwc_parts(G).  channels_last = 1 in afsl_stage1_{fwd,bwd}_f32
+ * makes stage 1 write y / argmax (and read d_y) in this layout.
+ * ------------------------------------------------------------------------- */
+int afsl_gbn_nhwc_parts(int G);
+int afsl_gbn_stats_nhwc_f32(const float* x, double* partial, int parts, float* mean, float* rstd,
+                            float* var_biased, int G, int group, int C, int H, int W, float eps, void* stream);
+int afsl_gbn_relu_pool_nhwc_fwd_f32(const float* x, const float* mean, const float* rstd, const float* gamma,
+                                    const float* beta, float* y, int G, int group, int C, int H, int W,
+                                    int stats_per_group, void* stream);
+int afsl_gbn_relu_pool_nhwc_bwd_f32(const float* x, const float* mean, const float* rstd, const float* gamma,
+                                    const float* beta, const float* d_y, float* d_x, double* partial, int parts,
+                                    float* sums, int G, int group, int C, int H, int W, int stats_per_group,
+                                    void* stream);
 
 #ifdef __cplusplus
 }

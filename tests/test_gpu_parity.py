@@ -375,13 +375,17 @@ def test_full_size_properties(ops):
 
 
 # ------------------------------------------------------------------ grouped BatchNorm + ReLU + MaxPool
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
 @pytest.mark.parametrize("shape,group", [((50, 8, 20, 25), 25), ((12, 64, 42, 52), 4), ((6, 16, 14, 17), 3),
                                           ((10, 64, 4, 5), 5), ((4, 4, 128, 157), 2)])
-def test_gbn_relu_pool_vs_torch(ops, shape, group):
-    """Fused kernels vs the eager fp32 chain (per-group nn.BatchNorm2d -> ReLU -> MaxPool2d(3)) on the GPU."""
+def test_gbn_relu_pool_vs_torch(ops, shape, group, layout):
+    """Fused kernels vs the eager fp32 chain (per-group nn.BatchNorm2d -> ReLU -> MaxPool2d(3)) on the GPU, for
+    NCHW activations and for channels-last ones (the layout the encoder runs in)."""
     n, c, h, w = shape
     gen = torch.Generator().manual_seed(n * c + h)
     x = (torch.randn(shape, generator=gen) * 2 + 0.7).cuda()
+    if layout == "nhwc":
+        x = x.contiguous(memory_format=torch.channels_last)
     bn = torch.nn.BatchNorm2d(c).cuda()
     ref = torch.nn.BatchNorm2d(c).cuda()
     with torch.no_grad():
@@ -391,6 +395,7 @@ def test_gbn_relu_pool_vs_torch(ops, shape, group):
     cb = (torch.randn(c, generator=gen) * 0.3).cuda().requires_grad_(True)       # convolution bias, folded by the kernel
     cbr = cb.detach().clone().requires_grad_(True)
     y = ops.gbn_relu_pool(xa, bn, group, conv_bias=cb)
+    assert ops._is_nhwc(y) == (layout == "nhwc" and h // 3 > 1 or layout == "nhwc" and w // 3 > 1) or y.shape[2] * y.shape[3] == 1
     yr = torch.cat([torch.nn.functional.max_pool2d(torch.relu(ref(xb[i:i + group] + cbr.view(1, -1, 1, 1))), 3, 3)
                     for i in range(0, n, group)])
     close(y, yr, rtol=1e-5)
