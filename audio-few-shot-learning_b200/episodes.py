@@ -71,11 +71,15 @@ class EpisodeRunner:
     ``normalize_prototypes``), ``train_query_augmentations``, ``specaug_params.*``.
     ``replay_reference_rng`` makes every host-side draw (SpecAugment parameters, view shuffle, CPL
     negatives) follow the reference's generators and order episode by episode.
+    ``use_cuda_graph`` replays the device part of ``train_step`` from a CUDA graph (one capture per batch shape).
     """
 
     def __init__(self, model, experiment_config: dict, optimizer: Optional[torch.optim.Optimizer] = None,
-                 replay_reference_rng: bool = False):
+                 replay_reference_rng: bool = False, use_cuda_graph: bool = False):
         self.model = model
+        self.use_cuda_graph = use_cuda_graph      # capture / replay the device part of train_step per batch shape
+        self._graphs: Dict[tuple, tuple] = {}
+        self.launches_per_replay = 0
         self.cfg = experiment_config
         self.optimizer = optimizer
         self.replay = replay_reference_rng
@@ -84,29 +88,73 @@ class EpisodeRunner:
         self.grad_sync = None          # set by parallel.EpisodeDataParallel: all-reduce of the flat gradient
 
     # ------------------------------------------------------------------ views
-    def _views(self, spec: torch.Tensor, augment: bool) -> List[torch.Tensor]:
-        """[E,N,1,F,T] -> list of V tensors [E,N,1,F,T] (datasets/batch_creation.py:111-121)."""
+    def _draw_views(self, e: int, n: int, t_len: int, augment: bool):
+        """Host-side SpecAugment parameters of E sets (datasets/batch_creation.py:111-121), or None."""
         if self.specaug is None or not augment:
+            return None
+        return self.specaug.draw_batch(e, n, t_len, replay_reference_rng=self.replay)
+
+    def _views(self, spec: torch.Tensor, params) -> List[torch.Tensor]:
+        """[E,N,1,F,T] -> list of V tensors [E,N,1,F,T]; ``params``: SpecAugParams (host or device tensors) or None."""
+        if params is None:
             return [spec]
         e, n = spec.shape[:2]
-        params = self.specaug.draw_batch(e, n, spec.shape[-1], replay_reference_rng=self.replay)
         views = self.specaug.apply_batch(spec.reshape(e * n, *spec.shape[2:]), params, exact_spline=self.replay)
         return [views[v].view(e, n, *spec.shape[2:]) for v in range(4)]
 
     # ------------------------------------------------------------------ training
-    def train_step(self, batch: EpisodeBatch) -> Dict[str, torch.Tensor]:
-        """One optimizer step on E episodes.  Returns per-episode losses (device tensors)."""
+    def _draw_step_randomness(self, batch: EpisodeBatch) -> Dict[str, object]:
+        """Everything the step draws on the HOST, in the reference's order per step: SpecAugment parameters
+        (support then query, batch_creation.py:113-115), the view shuffle of contrastive_forward
+        (prototypical.py:66-70) and the CPL negatives (loss.py:149).  Returned as host tensors; the device part
+        of the step (``_train_compute``) is a pure function of the batch and of these."""
+        cfg = self.cfg
+        e, ns = batch.support.shape[:2]
+        nq, t_len = batch.query.shape[1], batch.support.shape[-1]
+        rnd: Dict[str, object] = {"sup": self._draw_views(e, ns, t_len, True),
+                                  "qry": self._draw_views(e, nq, t_len, cfg["train_query_augmentations"])}
+        views = 4 if rnd["qry"] is not None else 1
+        if cfg["use_contrastive"] and hasattr(self.model, "attention_model"):
+            perms = []
+            for _ in range(e):
+                rest = list(range(1, views))
+                random.shuffle(rest)
+                perms.append([0] + rest)
+            rnd["perm"] = torch.tensor(perms, dtype=torch.int64)
+        if cfg["use_contrastive"] and cfg["loss"]["cpl"]["use"]:
+            m = int(cfg["loss"]["cpl"]["m_param"])
+            ql = batch.query_labels
+            if self.concat_views:
+                ql = ql.repeat(1, views)
+            if self.replay:
+                rnd["keep"] = ops.pack_keep(torch.stack([draw_keep_reference(row, m) for row in ql.cpu()]))
+            elif m < ql.shape[1] // batch.n_way:               # balanced synthetic / sampled episodes
+                rnd["keep"] = ops.pack_keep(draw_keep_vectorised(ql.cpu(), m, batch.n_way))
+        return rnd
+
+    @staticmethod
+    def _rnd_to(rnd: Dict[str, object], device) -> Dict[str, object]:
+        out = {}
+        for k, v in rnd.items():
+            if isinstance(v, torch.Tensor):
+                out[k] = v.to(device, non_blocking=True)
+            elif v is None:
+                out[k] = None
+            else:                                              # SpecAugParams
+                out[k] = type(v)(v.warp_p.to(device=device, dtype=torch.int32), v.warp_d.to(device=device, dtype=torch.int32),
+                                 v.time_masks.to(device=device, dtype=torch.int32),
+                                 v.freq_masks.to(device=device, dtype=torch.int32), v.set_size)
+        return out
+
+    def _train_compute(self, batch: EpisodeBatch, rnd: Dict[str, object]) -> Dict[str, torch.Tensor]:
+        """Device part of one step: views -> encoder -> fusion -> fused head (+ CPL / angular) -> backward."""
         cfg, model = self.cfg, self.model
-        model.train()
-        batch = batch.to(next(model.parameters()).device)
         model.n_way = batch.n_way
-        s_views = self._views(batch.support, True)
-        q_views = self._views(batch.query, cfg["train_query_augmentations"])
+        s_views = self._views(batch.support, rnd["sup"])
+        q_views = self._views(batch.query, rnd["qry"])
         sl, ql = batch.support_labels, batch.query_labels
         if self.concat_views:                                   # loops/loops.py:33-37
             sl, ql = sl.repeat(1, len(s_views)), ql.repeat(1, len(q_views))
-        if self.optimizer is not None:
-            self.optimizer.zero_grad(set_to_none=True)
         # support + query features, then the fused head: prototypes + FSL loss in one kernel
         support_features = model.compute_features(s_views)
         query_features = model(q_views)
@@ -116,52 +164,116 @@ class EpisodeRunner:
         total = fsl
         if cfg["use_contrastive"]:
             project = cfg["project_prototypes"]
-            cfeats, cprotos = self._contrastive_forward_batched(project)
+            cfeats, cprotos = self._contrastive_forward_batched(project, rnd.get("perm"))
             if not project and cfg["normalize_prototypes"]:     # loops/loops.py:45-48
                 cprotos = ops.l2_normalize(cprotos, eps=1e-12)
-            extra = self._extra_loss(cprotos, cfeats, ql, batch.n_way)
+            extra = self._extra_loss(cprotos, cfeats, ql, rnd.get("keep"))
             total = fsl + cfg["loss"]["l_param"] * extra
             out["cpl_loss"] = extra
         out["loss"] = total
         total.mean().backward()
+        return {k: v.detach() for k, v in out.items()}
+
+    def train_step(self, batch: EpisodeBatch) -> Dict[str, torch.Tensor]:
+        """One optimizer step on E episodes.  Returns per-episode losses (device tensors).
+
+        With ``use_cuda_graph`` the device part (views, encoder, head, losses, backward) is captured once per batch
+        shape and replayed: the host only draws the step's randomness, refreshes the static input buffers and
+        launches one graph, then the (eager) gradient all-reduce and optimizer step."""
+        model = self.model
+        model.train()
+        device = next(model.parameters()).device
+        rnd = self._draw_step_randomness(batch)
+        if self.use_cuda_graph:
+            if self.replay:
+                raise ValueError("use_cuda_graph needs replay_reference_rng=False: the reference-exact warp spline is "
+                                 "evaluated on the host from the drawn control points")
+            out = self._graph_step(batch, rnd, device)
+        else:
+            if self.optimizer is not None:
+                self.optimizer.zero_grad(set_to_none=True)
+            out = self._train_compute(batch.to(device), self._rnd_to(rnd, device))
         if self.grad_sync is not None:
             self.grad_sync()
         if self.optimizer is not None:
             self.optimizer.step()
-        return {k: v.detach() for k, v in out.items()}
+        return out
 
-    def _contrastive_forward_batched(self, project: bool):
+    # ------------------------------------------------------------------ CUDA-graph replay of the device part
+    def _graph_step(self, batch: EpisodeBatch, rnd: Dict[str, object], device) -> Dict[str, torch.Tensor]:
+        key = (tuple(batch.support.shape), tuple(batch.query.shape), batch.n_way,
+               tuple(sorted(k for k, v in rnd.items() if v is not None)))
+        state = self._graphs.get(key)
+        if state is None:
+            state = self._capture(batch, rnd, device)
+            self._graphs[key] = state
+        s_batch, s_rnd, graph, s_out = state
+        for dst, src in ((s_batch.support, batch.support), (s_batch.support_labels, batch.support_labels),
+                         (s_batch.query, batch.query), (s_batch.query_labels, batch.query_labels)):
+            dst.copy_(src, non_blocking=True)
+        self._copy_rnd(s_rnd, rnd)
+        graph.replay()
+        return s_out
+
+    @staticmethod
+    def _copy_rnd(dst: Dict[str, object], src: Dict[str, object]) -> None:
+        for k, v in src.items():
+            if isinstance(v, torch.Tensor):
+                dst[k].copy_(v, non_blocking=True)
+            elif v is not None:
+                dst[k].warp_p.copy_(v.warp_p, non_blocking=True)
+                dst[k].warp_d.copy_(v.warp_d, non_blocking=True)
+                dst[k].time_masks.copy_(v.time_masks, non_blocking=True)
+                dst[k].freq_masks.copy_(v.freq_masks, non_blocking=True)
+
+    def _capture(self, batch: EpisodeBatch, rnd: Dict[str, object], device):
+        """Static buffers + three eager warm-up steps on a side stream (cuDNN autotuning, lazy initialisation),
+        then the capture.  Gradients are (re)created inside the capture so that every replay rewrites them."""
+        s_batch = EpisodeBatch(*(torch.empty_like(t, device=device) for t in (batch.support, batch.support_labels, batch.query,
+                                                                               batch.query_labels)), batch.n_way)
+        for dst, src in ((s_batch.support, batch.support), (s_batch.support_labels, batch.support_labels),
+                         (s_batch.query, batch.query), (s_batch.query_labels, batch.query_labels)):
+            dst.copy_(src)
+        s_rnd = self._rnd_to(rnd, device)
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                for prm in self.model.parameters():
+                    prm.grad = None
+                self._train_compute(s_batch, s_rnd)
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        for prm in self.model.parameters():
+            prm.grad = None
+        graph = torch.cuda.CUDAGraph()
+        launches = ops.launch_count()
+        with torch.cuda.graph(graph):
+            s_out = self._train_compute(s_batch, s_rnd)
+        self.launches_per_replay = ops.launch_count() - launches     # libafsl kernels inside one replay
+        return s_batch, s_rnd, graph, s_out
+
+    def _contrastive_forward_batched(self, project: bool, perm: Optional[torch.Tensor] = None):
         """contrastive_forward for E episodes with an independent view permutation per episode.
 
         The reference shuffles views 1..V-1 with ``random.shuffle`` once per episode
-        (prototypical.py:66-70).  Here the E permutations are drawn up front (same Python ``random``
-        stream, one ``shuffle`` of a (V-1)-list per episode) and applied with one gather."""
+        (prototypical.py:66-70).  The E permutations are drawn up front by ``_draw_step_randomness`` (same Python
+        ``random`` stream, one ``shuffle`` of a (V-1)-list per episode) and applied with one gather."""
         model = self.model
         if not hasattr(model, "attention_model"):
             return model.contrastive_forward(project)
         feats = torch.stack(model.query_feature_list, dim=-2)            # [E, N, V, D]
         e, n, v, d = feats.shape
-        perms = []
-        for _ in range(e):
-            rest = list(range(1, v))
-            random.shuffle(rest)
-            perms.append([0] + rest)
-        idx = torch.tensor(perms, device=feats.device).view(e, 1, v, 1).expand(e, n, v, d)
+        idx = perm.to(feats.device).view(e, 1, v, 1).expand(e, n, v, d)
         shuffled = model.attention_model(torch.gather(feats, 2, idx))
         projected = model.projection_head(shuffled)
         protos = model.projection_head(model.prototypes) if project else model.prototypes
         return projected, protos
 
-    def _extra_loss(self, protos, feats, labels, n_way):
+    def _extra_loss(self, protos, feats, labels, keep=None):
         lc = self.cfg["loss"]
         if lc["cpl"]["use"]:
-            m, temp = int(lc["cpl"]["m_param"]), float(lc["cpl"]["t_param"])
-            if self.replay:
-                keep = torch.stack([draw_keep_reference(row, m) for row in labels.cpu()])
-            else:
-                per_class = labels.shape[1] // n_way          # balanced synthetic / sampled episodes
-                keep = None if m >= per_class else draw_keep_vectorised(labels, m, n_way)
-            return ops.cpl_loss(protos, feats, labels, temp, keep=keep)
+            return ops.cpl_loss(protos, feats, labels, float(lc["cpl"]["t_param"]), keep=keep)
         if lc["angular"]["use"]:
             return ops.angular_loss(protos, feats, labels, float(lc["angular"]["angle"]), 40.0,
                                     bool(lc["angular"]["prototypes_as_anchors"]), False)
@@ -179,18 +291,19 @@ class EpisodeRunner:
         model.eval()
         batch = batch.to(next(model.parameters()).device)
         model.n_way = batch.n_way
-        s_views = self._views(batch.support, True)
+        t_len = batch.support.shape[-1]
+        s_views = self._views(batch.support, self._draw_views(*batch.support.shape[:2], t_len, True))
         sl = batch.support_labels
         if self.concat_views:
             sl = sl.repeat(1, len(s_views))
         support_features = model.compute_features(s_views)
         if seg_offsets is None:
-            q_views = self._views(batch.query, augment_query)
+            q_views = self._views(batch.query, self._draw_views(*batch.query.shape[:2], t_len, augment_query))
             ql = batch.query_labels.repeat(1, len(q_views)) if self.concat_views else batch.query_labels
             feats = model(q_views)
             _, _, correct, _ = ops.proto_eval(support_features, sl, feats, ql, n_way=batch.n_way)
             return correct.cpu().numpy().astype(np.float64) / ql.shape[1]
-        q_views = self._views(batch.query, augment_query)
+        q_views = self._views(batch.query, self._draw_views(*batch.query.shape[:2], t_len, augment_query))
         feats = model(q_views)[0]                                # packed rows
         ql = batch.query_labels[0]
         max_rows = int((seg_offsets[1:] - seg_offsets[:-1]).max())

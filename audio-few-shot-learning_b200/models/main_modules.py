@@ -193,7 +193,9 @@ class StandardHybrid(nn.Module):
         print(f'Num Layers: {seq_layers} -> Trainable Params: {self.params}')
 
     def many_to_one(self, t, lengths):
-        return t[torch.arange(t.size(0)), lengths - 1]
+        if isinstance(lengths, int):                   # the only call site passes skip.shape[-2]
+            return t[:, lengths - 1]
+        return t[torch.arange(t.size(0), device=t.device), lengths - 1]
 
     def forward(self, x):
         x = self.conv_encoder(x)

@@ -320,7 +320,7 @@ def run_b200(args):
 
     model = build_model(device)
     opt = torch.optim.Adam(model.parameters(), lr=EXPERIMENT_CONFIG["lr"])
-    runner = EpisodeRunner(model, EXPERIMENT_CONFIG, opt, replay_reference_rng=False)
+    runner = EpisodeRunner(model, EXPERIMENT_CONFIG, opt, replay_reference_rng=False, use_cuda_graph=not args.no_graph)
     dp = parallel.EpisodeDataParallel(model)
     runner.grad_sync = dp.sync_gradients if world > 1 else None
 
@@ -348,7 +348,8 @@ def run_b200(args):
         end.record()
         barrier()
     ms = start.elapsed_time(end)
-    launches = ops.launch_count() - launches0
+    # kernels launched eagerly + those inside the replayed CUDA graph (counted once, at capture)
+    launches = ops.launch_count() - launches0 + (runner.launches_per_replay * args.steps if runner.use_cuda_graph else 0)
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -400,6 +401,7 @@ def run_b200(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "episodes_per_step_per_gpu": E, "global_episodes_per_step": world * E,
                    "parallelism": f"episode-sharded dp{world}", "cudnn_conv_tf32": torch.backends.cudnn.allow_tf32,
+                   "cuda_graph": runner.use_cuda_graph,
                    "l2": f"inputs rotate over {n_rot} batches; per-step activations exceed the 126 MB L2",
                    "peaks": pk_src},
         "e2e": {"value": e2e_value, "unit": "episodes/s", "h2d_bytes_per_step": host[0].nbytes(),
@@ -425,6 +427,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--episodes", type=int, default=32, help="episodes per step per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-kernels", action="store_true")
     args = ap.parse_args()

@@ -23,7 +23,7 @@ dev = torch.device("cuda", 0)
 torch.backends.cudnn.benchmark = True
 model = bench.build_model(dev)
 opt = torch.optim.Adam(model.parameters(), lr=7e-4)
-runner = EpisodeRunner(model, bench.EXPERIMENT_CONFIG, opt)
+runner = EpisodeRunner(model, bench.EXPERIMENT_CONFIG, opt)      # eager launches: the profiler attributes time per op
 batch = synthetic_batch(args.episodes, 5, 5, 5, 157).to(dev)
 for _ in range(3):
     runner.train_step(batch)
