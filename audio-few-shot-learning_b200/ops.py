@@ -27,6 +27,13 @@ def _i32(t: torch.Tensor) -> torch.Tensor:
     return t.to(dtype=torch.int32).contiguous()
 
 
+def _same_dim(what: str, a: torch.Tensor, b: torch.Tensor) -> None:
+    """The kernels take ONE embedding dimension D for both operands; a mismatch (e.g. fused 4-view support
+    features against single-view query features) would read out of bounds, so it is refused here."""
+    if a.shape[-1] != b.shape[-1]:
+        raise ValueError(f"{what}: embedding dimensions differ ({tuple(a.shape)} vs {tuple(b.shape)})")
+
+
 def _batched(feats: torch.Tensor, labels: Optional[torch.Tensor]):
     """-> (feats [E,N,D], labels [E,N] or None, had_batch_dim)."""
     if feats.dim() == 2:
@@ -118,6 +125,7 @@ def l2_scores(queries: torch.Tensor, protos: torch.Tensor) -> torch.Tensor:
     """-cdist(queries, protos): [Nq,D],[W,D] -> [Nq,W] (or with a leading E)."""
     q, _, had = _batched(queries, None)
     p = protos if protos.dim() == 3 else protos.unsqueeze(0)
+    _same_dim("l2_scores", q, p)
     scores, _ = _ProtoScores.apply(_f32(p), _f32(q), None, None, True, False)
     return scores if had else scores[0]
 
@@ -126,6 +134,7 @@ def proto_loss(protos: torch.Tensor, queries: torch.Tensor, labels: torch.Tensor
     """FSL loss per episode: mean NLL of log_softmax(-cdist).  Returns a 0-dim tensor without E."""
     q, l, had = _batched(queries, labels)
     p = protos if protos.dim() == 3 else protos.unsqueeze(0)
+    _same_dim("proto_loss", q, p)
     _, loss = _ProtoScores.apply(_f32(p), _f32(q), _i32(l), None, False, True)
     return loss if had else loss[0]
 
@@ -165,6 +174,9 @@ def proto_head(support, s_labels, queries, q_labels, n_way: Optional[int] = None
     """Fused prototypes + FSL loss (+ #correct): returns (loss [E], protos [E,W,D], correct [E])."""
     s, sl, had = _batched(support, s_labels)
     q, ql, _ = _batched(queries, q_labels)
+    _same_dim("proto_head", s, q)
+    if q.shape[0] != s.shape[0]:
+        raise ValueError(f"proto_head: {s.shape[0]} support episodes vs {q.shape[0]} query episodes")
     if n_way is None:
         n_way = infer_n_way(sl[0])
     loss, protos, correct = _ProtoHead.apply(_f32(s), _i32(sl), _f32(q), _i32(ql), int(n_way))
@@ -181,6 +193,7 @@ def proto_eval(support, s_labels, queries, q_labels=None, n_way: Optional[int] =
     """
     s, sl, _ = _batched(support, s_labels)
     e, ns, d = s.shape
+    _same_dim("proto_eval", s, queries)
     if n_way is None:
         n_way = infer_n_way(sl[0])
     dev = s.device
@@ -272,6 +285,7 @@ def cpl_loss(protos, queries, labels, temperature: float, keep: Optional[torch.T
     "all queries of the other classes" (M >= per-class count)."""
     q, l, had = _batched(queries, labels)
     p = protos if protos.dim() == 3 else protos.unsqueeze(0)
+    _same_dim("cpl_loss", q, p)
     kp = None
     if keep is not None:
         kp = keep if keep.dim() == 3 else keep.unsqueeze(0)
@@ -312,6 +326,7 @@ def angular_loss(protos, queries, labels, miner_angle_deg: float, alpha_deg: flo
     """Angular loss with angular mining per episode (AngularLossClass, loops/loss.py:39-97)."""
     q, l, had = _batched(queries, labels)
     p = protos if protos.dim() == 3 else protos.unsqueeze(0)
+    _same_dim("angular_loss", q, p)
     loss = _Angular.apply(_f32(p), _f32(q), _i32(l), miner_angle_deg, alpha_deg, prototypes_as_anchors, normalize_ref)
     return loss if had else loss[0]
 

@@ -305,6 +305,65 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def eval_throughput(runner, device, world, rank, tasks_per_step, steps):
+    """Test tasks / s through EpisodeRunner.eval_step (BASELINE metric's second half), device-resident inputs:
+    (a) single-segment 5-way 5-shot 5-query tasks (loops/loops.py:84-121), (b) multi-segment tasks with
+    S ~ U{1..8} segments per query clip and the majority vote (loops/loops.py:250-279).  Ranks own contiguous task
+    blocks; the per-task accuracies are all-gathered at the end (inside the timed region)."""
+    import numpy as np
+    import torch.distributed as dist
+    from afsl_b200 import parallel
+    from afsl_b200.episodes import EpisodeBatch, synthetic_batch
+    out = {}
+    e = tasks_per_step
+    single = [synthetic_batch(e, N_WAY, K_SHOT, K_QUERY, T_LEN, seed=7000 + 10 * rank + i, device=str(device)) for i in range(2)]
+    # multi-segment: 25 query clips per task, 1..8 segments each, packed rows + CSR offsets
+    rng = np.random.RandomState(4321 + rank)
+    seg = rng.randint(1, 9, size=(e, N_WAY * K_QUERY))
+    rows_per_task = seg.sum(1)
+    offsets = torch.from_numpy(np.concatenate([[0], np.cumsum(rows_per_task)]).astype(np.int64))
+    rows = int(offsets[-1])
+    clip_ids = torch.from_numpy(np.concatenate([np.repeat(np.arange(N_WAY * K_QUERY), s) for s in seg]).astype(np.int64))
+    clip_label = np.arange(N_WAY).repeat(K_QUERY)
+    row_labels = torch.from_numpy(np.concatenate([np.repeat(clip_label, s) for s in seg]).astype(np.int64))
+    gen = torch.Generator(device=device).manual_seed(99 + rank)
+    multi = EpisodeBatch(single[0].support, single[0].support_labels,
+                         torch.randn(1, rows, 1, MELS, T_LEN, generator=gen, device=device), row_labels.view(1, -1).to(device), N_WAY)
+    clip_ids, offsets_dev = clip_ids.to(device), offsets.to(device)
+
+    def timed(fn, units):
+        for _ in range(2):
+            fn(0)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        accs = [fn(i) for i in range(steps)]
+        acc = parallel.gather_accuracies(np.concatenate(accs), world * steps * e)
+        b.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        return {"value": world * steps * units / (ms * 1e-3), "ms_per_step": ms / steps, "tasks_per_step_per_gpu": e,
+                "mean_accuracy": float(acc.mean())}
+
+    # test_query_augmentations = true (README.md:92): the view-fusion model needs the four query views at test time too
+    out["test_tasks_per_s"] = dict(timed(lambda i: runner.eval_step(single[i % 2], augment_query=True), e), unit="tasks/s",
+                                   workload="5-way 5-shot 5-query single-segment tasks, SpecAugment support + query views, "
+                                            "eval-mode encoder")
+    out["multiseg_tasks_per_s"] = dict(timed(lambda i: runner.eval_step(multi, augment_query=True, clip_ids=clip_ids,
+                                                                        seg_offsets=offsets_dev, tie_strategy="min_label"), e),
+                                       unit="tasks/s",
+                                       rows_per_step_per_gpu=rows,
+                                       workload="5-way 5-shot, 25 query clips x U{1..8} segments per task, majority vote (min_label)")
+    return out
+
+
 def run_b200(args):
     import torch.distributed as dist
     import afsl_b200.ops as ops
@@ -374,6 +433,10 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
     e2e_value = world * E * args.steps / (e2e_ms * 1e-3)
+    h2d_bytes = host[0].nbytes() * world            # whole job, like `value`
+
+    del host
+    evals = eval_throughput(runner, device, world, rank, args.eval_tasks, max(2, args.steps // 2)) if not args.skip_eval else {}
 
     if rank != 0:
         if world > 1:
@@ -404,8 +467,8 @@ def run_b200(args):
                    "cuda_graph": runner.use_cuda_graph,
                    "l2": f"inputs rotate over {n_rot} batches; per-step activations exceed the 126 MB L2",
                    "peaks": pk_src},
-        "e2e": {"value": e2e_value, "unit": "episodes/s", "h2d_bytes_per_step": host[0].nbytes(),
-                "d2h_bytes_per_step": int(loss_host.numel() * 4), "ms_per_step": e2e_ms / args.steps},
+        "e2e": {"value": e2e_value, "unit": "episodes/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": int(loss_host.numel() * 4) * world, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks.summary,
         # the fused loss-head pair (prototypes + distances + log-softmax/NLL forward, and its backward): the
@@ -413,6 +476,7 @@ def run_b200(args):
         "roofline": roofs.get("proto_head_fwd_bwd"),
         "kernels": roofs,
         "cpu_baseline": cpu,
+        "extra_metrics": evals,
     }
     print(json.dumps(line))
     if world > 1:
@@ -428,6 +492,8 @@ def main():
     ap.add_argument("--episodes", type=int, default=32, help="episodes per step per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--eval-tasks", type=int, default=64, help="test tasks per eval step per GPU")
+    ap.add_argument("--skip-eval", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-kernels", action="store_true")
     args = ap.parse_args()

@@ -72,3 +72,17 @@ def test_no_cpu_fallback(lib):
     y = torch.arange(5).repeat_interleave(5)
     with pytest.raises(lib.AfslError):
         ops.prototypes(x, y)
+
+
+def test_embedding_dimension_mismatch_is_refused(lib):
+    """Fused 4-view support features (D=256) against single-view query features (D=64) must raise, not read
+    out of bounds (the kernels take one D for both operands)."""
+    import afsl_b200.ops as ops
+    s, q = torch.randn(2, 25, 256), torch.randn(2, 25, 64)
+    y = torch.arange(5).repeat_interleave(5).expand(2, -1)
+    with pytest.raises(ValueError, match="embedding dimensions differ"):
+        ops.proto_head(s, y, q, y, n_way=5)
+    with pytest.raises(ValueError, match="embedding dimensions differ"):
+        ops.proto_eval(s, y, q, y, n_way=5)
+    with pytest.raises(ValueError, match="embedding dimensions differ"):
+        ops.cpl_loss(torch.randn(2, 5, 256), q, y, 1.0)
