@@ -337,6 +337,116 @@ __global__ void __launch_bounds__(kThreads) stage1_bwd_kernel(const S1Params p) 
     }
 }
 
+// ---------------------------------------------------------------- backward, channels-last: lanes = channels
+// With y / argmax / dy channels-last, a WARP takes one pooled pixel at a time and each lane two of its 64
+// channels: dy (256 B) and the codes (64 B) of a pixel are one coalesced load per warp, the per-channel
+// accumulators (s1, s2, T_0..T_8) are 22 registers per lane, and the 3x3 neighbourhoods of all lanes fall inside
+// the pixel's 5x5 input patch (tile row stride = 8 mod 32 banks: the 25 words sit in 25 different banks).
+// The 16 warps' accumulators are added in warp order through shared memory (deterministic).
+constexpr int kLanesCh = 2;   // channels per lane
+
+__device__ __forceinline__ int bwd_tile_ld(int W) { return ((W + 2 + 23) / 32) * 32 + 8; }   // >= W + 2, = 8 (mod 32)
+
+__global__ void __launch_bounds__(kThreads, 2) stage1_bwd_nhwc_kernel(const S1Params p) {
+  extern __shared__ __align__(16) float smem[];
+  const int H = p.H, W = p.W, PH = p.PH, PW = p.PW, hw = H * W, phw = PH * PW;
+  const int ld = bwd_tile_ld(W);
+  float* tile = smem;                                   // [(3*kBands+2) * ld]
+  float* red = tile + (3 * kBands + 2) * ld;            // [kWarps][kC][kAcc] cross-warp reduction
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tiles_per_sample = (PH + kBands - 1) / kBands;
+  const int tiles_per_group = p.group * tiles_per_sample;
+  const int g = blockIdx.x / p.parts, part = blockIdx.x - g * p.parts;
+  const int c0 = kLanesCh * lane;
+  float w[kLanesCh][9], mean[kLanesCh], rstd[kLanesCh];
+#pragma unroll
+  for (int cc = 0; cc < kLanesCh; ++cc) {
+    const int idx = (p.per_group ? g * kC : 0) + c0 + cc;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) w[cc][k] = __ldg(p.w + (c0 + cc) * 9 + k);
+    mean[cc] = __ldg(p.mean + idx);
+    rstd[cc] = __ldg(p.rstd + idx);
+  }
+  float acc[kLanesCh][kAcc];
+#pragma unroll
+  for (int cc = 0; cc < kLanesCh; ++cc)
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) acc[cc][k] = 0.f;
+
+  for (int tl = part; tl < tiles_per_group; tl += p.parts) {
+    const int sl = tl / tiles_per_sample, tix = tl - sl * tiles_per_sample;
+    const int s = g * p.group + sl;
+    const int ph0 = tix * kBands, bands = min(kBands, PH - ph0);
+    __syncthreads();
+    {   // stage rows [3*ph0 - 1, 3*ph0 + 3*bands + 1) x cols [-1, W + 1), zero padded, row stride ld
+      const float* pl = p.x + (size_t)s * hw;
+      const int rows = 3 * bands + 2, wp = W + 2;
+      for (int o = threadIdx.x; o < rows * wp; o += kThreads) {
+        const int r = o / wp, c = o - r * wp;
+        const int i = 3 * ph0 - 1 + r, j = c - 1;
+        tile[r * ld + c] = (i >= 0 && i < H && j >= 0 && j < W) ? __ldg(pl + (size_t)i * W + j) : 0.f;
+      }
+    }
+    __syncthreads();
+    const int npos = bands * PW;
+    const size_t px0 = ((size_t)s * phw + (size_t)ph0 * PW) * kC + c0;    // this lane's channels of the tile's first pixel
+    // software pipeline: the next pixel's dy / codes are in flight while this one is processed
+    int pos = warp;
+    float2 dyv = make_float2(0.f, 0.f);
+    uchar2 cd = make_uchar2(kInactive, kInactive);
+    if (pos < npos) {
+      dyv = __ldg(reinterpret_cast<const float2*>(p.dy + px0 + (size_t)pos * kC));
+      cd = __ldg(reinterpret_cast<const uchar2*>(p.arg_in + px0 + (size_t)pos * kC));
+    }
+    for (; pos < npos; pos += kWarps) {
+      const float2 dy_cur = dyv;
+      const uchar2 cd_cur = cd;
+      const int nxt = pos + kWarps;
+      if (nxt < npos) {
+        dyv = __ldg(reinterpret_cast<const float2*>(p.dy + px0 + (size_t)nxt * kC));
+        cd = __ldg(reinterpret_cast<const uchar2*>(p.arg_in + px0 + (size_t)nxt * kC));
+      }
+      const int bl = pos / PW, pw = pos - bl * PW;
+      const float* patch = tile + (size_t)(3 * bl) * ld + 3 * pw;
+      const float dys[kLanesCh] = {dy_cur.x, dy_cur.y};
+      const int codes[kLanesCh] = {cd_cur.x, cd_cur.y};
+#pragma unroll
+      for (int cc = 0; cc < kLanesCh; ++cc) {
+        const int code = codes[cc];
+        if (code >= 9) continue;                          // ReLU cut this output: no gradient
+        const int ar = code / 3, aq = code - ar * 3;
+        const float* nb = patch + ar * ld + aq;
+        float xs[9], u = 0.f;
+#pragma unroll
+        for (int ka = 0; ka < 3; ++ka)
+#pragma unroll
+          for (int kb = 0; kb < 3; ++kb) {
+            xs[ka * 3 + kb] = nb[ka * ld + kb];
+            u = fmaf(w[cc][ka * 3 + kb], xs[ka * 3 + kb], u);
+          }
+        const float xhat = (u - mean[cc]) * rstd[cc];
+        acc[cc][0] += dys[cc];
+        acc[cc][1] = fmaf(dys[cc], xhat, acc[cc][1]);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[cc][2 + k] = fmaf(dys[cc], xs[k], acc[cc][2 + k]);
+      }
+    }
+  }
+  // add the warps' accumulators in warp order
+  __syncthreads();
+#pragma unroll
+  for (int cc = 0; cc < kLanesCh; ++cc)
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) red[(warp * kC + c0 + cc) * kAcc + k] = acc[cc][k];
+  __syncthreads();
+  float* out = p.partial + (((size_t)g * p.parts + part) * kC) * kAcc;
+  for (int o = threadIdx.x; o < kC * kAcc; o += kThreads) {
+    float t = 0.f;
+    for (int wq = 0; wq < kWarps; ++wq) t += red[wq * kC * kAcc + o];
+    out[o] = t;
+  }
+}
+
 size_t smem_bytes(int W, bool bwd) {
   return ((size_t)(3 * kBands + 2) * (W + 2) + kC * 9 + kC * (bwd ? 4 : 2)) * sizeof(float);
 }
@@ -396,6 +506,14 @@ extern "C" int afsl_stage1_bwd_f32(const float* x, const float* weight, const fl
   p.x = x; p.w = weight; p.a = a; p.b = b; p.mean = mean; p.rstd = rstd; p.dy = d_y; p.partial = partial; p.arg_in = argmax;
   p.G = G; p.group = group; p.H = H; p.W = W; p.PH = H / 3; p.PW = W / 3; p.per_group = per_group; p.parts = parts;
   if (int rc = check(p, "afsl_stage1_bwd_f32")) return rc;
+  if (channels_last) {
+    const int ld = ((W + 2 + 23) / 32) * 32 + 8;
+    const size_t nb = ((size_t)(3 * kBands + 2) * ld + (size_t)kWarps * kC * kAcc) * sizeof(float);
+    if (int rc = opt_in_smem(stage1_bwd_nhwc_kernel, nb, "afsl_stage1_bwd_f32")) return rc;
+    stage1_bwd_nhwc_kernel<<<G * parts, kThreads, nb, (cudaStream_t)stream>>>(p);
+    AFSL_CHECK_LAUNCH("afsl_stage1_bwd_f32");
+    return AFSL_OK;
+  }
   const size_t bytes = smem_bytes(W, true);
   if (int rc = opt_in_smem(stage1_bwd_kernel, bytes, "afsl_stage1_bwd_f32")) return rc;
   stage1_bwd_kernel<<<G * parts, kThreads, bytes, (cudaStream_t)stream>>>(p);

@@ -80,6 +80,12 @@ class EpisodeRunner:
         self.use_cuda_graph = use_cuda_graph      # capture / replay the device part of train_step per batch shape
         self._graphs: Dict[tuple, tuple] = {}
         self.launches_per_replay = 0
+        self._stage: Optional[EpisodeBatch] = None     # device staging buffers of the prefetched next batch
+        self._prefetched: Optional[EpisodeBatch] = None
+        self._copy_stream = None
+        if use_cuda_graph:
+            self._prefetch_done = torch.cuda.Event()
+            self._inputs_consumed = torch.cuda.Event()
         self.cfg = experiment_config
         self.optimizer = optimizer
         self.replay = replay_reference_rng
@@ -174,8 +180,11 @@ class EpisodeRunner:
         total.mean().backward()
         return {k: v.detach() for k, v in out.items()}
 
-    def train_step(self, batch: EpisodeBatch) -> Dict[str, torch.Tensor]:
+    def train_step(self, batch: EpisodeBatch, next_batch: Optional[EpisodeBatch] = None) -> Dict[str, torch.Tensor]:
         """One optimizer step on E episodes.  Returns per-episode losses (device tensors).
+
+        ``next_batch`` (optional, CUDA-graph mode): the batch of the following call; its host->device copy is started
+        on a side stream while this step computes, so the next call finds its inputs already on the device.
 
         With ``use_cuda_graph`` the device part (views, encoder, head, losses, backward) is captured once per batch
         shape and replayed: the host only draws the step's randomness, refreshes the static input buffers and
@@ -189,6 +198,8 @@ class EpisodeRunner:
                 raise ValueError("use_cuda_graph needs replay_reference_rng=False: the reference-exact warp spline is "
                                  "evaluated on the host from the drawn control points")
             out = self._graph_step(batch, rnd, device)
+            if next_batch is not None:
+                self._prefetch(next_batch, device)
         else:
             if self.optimizer is not None:
                 self.optimizer.zero_grad(set_to_none=True)
@@ -208,12 +219,33 @@ class EpisodeRunner:
             state = self._capture(batch, rnd, device)
             self._graphs[key] = state
         s_batch, s_rnd, graph, s_out = state
-        for dst, src in ((s_batch.support, batch.support), (s_batch.support_labels, batch.support_labels),
-                         (s_batch.query, batch.query), (s_batch.query_labels, batch.query_labels)):
+        src_batch = batch
+        if self._prefetched is batch:                       # already on the device (staged by the previous call)
+            torch.cuda.current_stream(device).wait_event(self._prefetch_done)
+            src_batch = self._stage
+        for dst, src in ((s_batch.support, src_batch.support), (s_batch.support_labels, src_batch.support_labels),
+                         (s_batch.query, src_batch.query), (s_batch.query_labels, src_batch.query_labels)):
             dst.copy_(src, non_blocking=True)
+        self._inputs_consumed.record(torch.cuda.current_stream(device))
+        self._prefetched = None
         self._copy_rnd(s_rnd, rnd)
         graph.replay()
         return s_out
+
+    def _prefetch(self, batch: EpisodeBatch, device) -> None:
+        """Start the host->device copy of ``batch`` into the staging buffers on the copy stream; it overlaps the
+        graph replay that was just launched and only waits for the previous staging buffers to have been consumed."""
+        if self._stage is None or self._stage.support.shape != batch.support.shape or self._stage.query.shape != batch.query.shape:
+            self._stage = EpisodeBatch(*(torch.empty_like(t, device=device) for t in (batch.support, batch.support_labels,
+                                                                                      batch.query, batch.query_labels)), batch.n_way)
+            self._copy_stream = torch.cuda.Stream(device=device)
+        self._copy_stream.wait_event(self._inputs_consumed)
+        with torch.cuda.stream(self._copy_stream):
+            for dst, src in ((self._stage.support, batch.support), (self._stage.support_labels, batch.support_labels),
+                             (self._stage.query, batch.query), (self._stage.query_labels, batch.query_labels)):
+                dst.copy_(src, non_blocking=True)
+            self._prefetch_done.record(self._copy_stream)
+        self._prefetched = batch
 
     @staticmethod
     def _copy_rnd(dst: Dict[str, object], src: Dict[str, object]) -> None:

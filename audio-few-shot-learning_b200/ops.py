@@ -608,7 +608,15 @@ class _Stage1(torch.autograd.Function):
         nhwc = ctx.nhwc
         d_y = d_y.float().contiguous(memory_format=torch.channels_last) if nhwc else _f32(d_y)
         sms = torch.cuda.get_device_properties(x.device).multi_processor_count
-        parts = max(1, min(group * ((h // 3 + 7) // 8), (2 * sms + groups - 1) // groups))
+        tiles = group * ((h // 3 + 7) // 8)
+        if nhwc:
+            # two 512-thread CTAs per SM: pick the split whose G*parts CTAs fill whole waves of 2*SMs best
+            slots = 2 * sms
+            eff = lambda pr: groups * pr / (-(-groups * pr // slots) * slots)
+            cand = range(1, min(tiles, 32) + 1)
+            parts = next((pr for pr in cand if pr * groups >= slots and eff(pr) >= 0.95), max(cand, key=eff))
+        else:
+            parts = max(1, min(tiles, (2 * sms + groups - 1) // groups))
         partial = torch.empty(groups, parts, c, 11, device=x.device, dtype=torch.float32)
         call("afsl_stage1_bwd_f32", ptr(x), ptr(w9), ptr(a), ptr(b), ptr(mean_u), ptr(rstd), ptr(d_y, nhwc), ptr(arg, nhwc),
              ptr(partial), parts, groups, group, h, w, per_group, int(nhwc), stream_ptr())
