@@ -31,7 +31,7 @@ SIGNATURES = {
     "afsl_cpl_bwd_f32": [_P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _I, _P],
     "afsl_angular_fwd_f32": [_P, _P, _P, _F, _F, _I, _I, _P, _I, _I, _I, _I, _P],
     "afsl_angular_bwd_f32": [_P, _P, _P, _F, _F, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P],
-    "afsl_specaug_views_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _I, _I, _I, _I, _I, _P],
+    "afsl_specaug_views_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _I, _I, _I, _I, _I, _P],
     "afsl_view_fusion_grid": [_I, _I],
     "afsl_view_fusion_fwd_f32": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "afsl_view_fusion_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],

@@ -31,6 +31,7 @@ struct SpecParams {
   const float* src_x;       // [N,T] or null
   const int32_t* row_lo;    // [F]
   const float* row_w;       // [F]
+  const int32_t* set_ids;     // [N] set of each sample, or null: sample n belongs to set n / set_size
   const int32_t* time_masks;  // [sets,num_mask,2] (start,len)
   const int32_t* freq_masks;  // [sets,num_mask,2]
   int num_mask;
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(kThreads) specaug_kernel(const SpecParams p) {
   for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
     const int n = (int)(item / p.split);
     const int part = (int)(item - (long long)n * p.split);
-    const int set = n / p.set_size;
+    const int set = p.set_ids ? __ldg(p.set_ids + n) : n / p.set_size;
     const float* xs = p.x + (size_t)n * F * T;
     const int32_t* tmk = p.time_masks + (size_t)set * p.num_mask * 2;
     const int32_t* fmk = p.freq_masks + (size_t)set * p.num_mask * 2;
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 6) specaug_tile_kernel(const SpecPar
   const size_t plane = (size_t)p.N * F * T;
   const bool want_copy = p.views_mask & 1, want_warp = p.views_mask & 2, want_tm = p.views_mask & 4,
              want_fm = p.views_mask & 8;
-  const int set = n / p.set_size;
+  const int set = p.set_ids ? __ldg(p.set_ids + n) : n / p.set_size;
   const float* xs = p.x + (size_t)n * F * T;
 
   // per-column tables and masks (once per CTA)
@@ -382,8 +383,8 @@ __global__ void __launch_bounds__(kThreads, 6) specaug_tile_kernel(const SpecPar
 
 extern "C" int afsl_specaug_views_f32(const float* x, float* views, const int32_t* warp_p, const int32_t* warp_d,
                                        const float* src_x, const int32_t* row_lo, const float* row_w,
-                                       const int32_t* time_masks, const int32_t* freq_masks, int num_mask,
-                                       float mask_value, int N, int set_size, int F, int T, int views_mask,
+                                       const int32_t* set_ids, const int32_t* time_masks, const int32_t* freq_masks,
+                                       int num_mask, float mask_value, int N, int set_size, int F, int T, int views_mask,
                                        void* stream) {
   using namespace afsl;
   AFSL_REQUIRE(x && views, "afsl_specaug_views_f32: null pointer");
@@ -401,7 +402,7 @@ extern "C" int afsl_specaug_views_f32(const float* x, float* views, const int32_
   if (N == 0) return AFSL_OK;
   SpecParams p{};
   p.x = x; p.views = views; p.warp_p = warp_p; p.warp_d = warp_d; p.src_x = src_x; p.row_lo = row_lo; p.row_w = row_w;
-  p.time_masks = time_masks; p.freq_masks = freq_masks; p.num_mask = num_mask; p.mask_value = mask_value;
+  p.set_ids = set_ids; p.time_masks = time_masks; p.freq_masks = freq_masks; p.num_mask = num_mask; p.mask_value = mask_value;
   p.N = N; p.set_size = set_size; p.F = F; p.T = T; p.views_mask = views_mask;
   // vectorised tile kernel whenever samples are whole float4 runs (F*T % 4 == 0: always for the 128-mel inputs)
   static_assert(kTileRows % 4 == 0, "tiles must start on a float4 boundary for every T");

@@ -335,10 +335,14 @@ class EpisodeRunner:
             feats = model(q_views)
             _, _, correct, _ = ops.proto_eval(support_features, sl, feats, ql, n_way=batch.n_way)
             return correct.cpu().numpy().astype(np.float64) / ql.shape[1]
-        q_views = self._views(batch.query, self._draw_views(*batch.query.shape[:2], t_len, augment_query))
+        # one SpecAugment draw per task, shared by all its query segments (batch_creation.py:113-115)
+        counts = (seg_offsets[1:] - seg_offsets[:-1]).tolist()
+        q_params = (self.specaug.draw_ragged(counts, t_len, replay_reference_rng=self.replay)
+                    if self.specaug is not None and augment_query else None)
+        q_views = self._views(batch.query, q_params)
         feats = model(q_views)[0]                                # packed rows
         ql = batch.query_labels[0]
-        max_rows = int((seg_offsets[1:] - seg_offsets[:-1]).max())
+        max_rows = int(max(counts))
         pred, post, _, _ = ops.proto_eval(support_features, sl, feats, ql, n_way=batch.n_way,
                                           q_offsets=seg_offsets.to(feats.device), max_rows=max_rows)
         correct, clips = ops.eval_vote(pred, clip_ids, ql, post, seg_offsets, tie_strategy)

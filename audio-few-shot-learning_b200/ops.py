@@ -350,11 +350,13 @@ def _row_tables(rows: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
 @torch.no_grad()
 def specaug_views(x: torch.Tensor, warp_p: torch.Tensor, warp_d: torch.Tensor, time_masks: torch.Tensor,
                   freq_masks: torch.Tensor, mask_value: float, set_size: int, src_x: Optional[torch.Tensor] = None,
-                  views_mask: int = 0b1111, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  views_mask: int = 0b1111, out: Optional[torch.Tensor] = None,
+                  set_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x [N,1,F,T] -> views [4,N,1,F,T] (copy, time-warp, time-mask, freq-mask).
 
     warp_p/warp_d: int [N]; time_masks/freq_masks: int [sets,num_mask,2] = (start, length) with
-    sets = N / set_size.  Views whose bit is clear in ``views_mask`` are left untouched.
+    sets = N / set_size, or ``set_ids`` int [N] naming each sample's set (ragged sets).  Views whose bit is clear
+    in ``views_mask`` are left untouched.
     """
     n, c, f, t = x.shape
     if c != 1:
@@ -368,7 +370,10 @@ def specaug_views(x: torch.Tensor, warp_p: torch.Tensor, warp_d: torch.Tensor, t
     # converted temporaries must stay referenced until the launch has been issued
     wp, wd = _i32(warp_p.to(dev)), _i32(warp_d.to(dev))
     sx = _f32(src_x.to(dev)) if src_x is not None else None
-    call("afsl_specaug_views_f32", ptr(x), ptr(views), ptr(wp), ptr(wd), ptr(sx), ptr(lo), ptr(w), ptr(tm), ptr(fm),
+    sid = _i32(set_ids.to(dev)) if set_ids is not None else None
+    if sid is not None and sid.numel() != n:
+        raise ValueError(f"set_ids has {sid.numel()} entries for {n} samples")
+    call("afsl_specaug_views_f32", ptr(x), ptr(views), ptr(wp), ptr(wd), ptr(sx), ptr(lo), ptr(w), ptr(sid), ptr(tm), ptr(fm),
          int(num_mask), float(mask_value), n, int(set_size), f, t, int(views_mask), stream_ptr())
     return views
 

@@ -30,6 +30,7 @@ class SpecAugParams:
     time_masks: torch.Tensor   # int64 [sets, num_mask, 2]  (start, length)
     freq_masks: torch.Tensor   # int64 [sets, num_mask, 2]
     set_size: int
+    set_ids: Optional[torch.Tensor] = None   # int64 [samples]: ragged sets (then set_size is unused)
 
 
 class SpecAugment():
@@ -97,13 +98,33 @@ class SpecAugment():
         fm = torch.from_numpy(np.stack([f0, f], axis=-1).astype(np.int64))
         return SpecAugParams(warp_p, warp_d, tm, fm, set_size)
 
+    def draw_ragged(self, set_sizes, time: int, replay_reference_rng: bool = True) -> SpecAugParams:
+        """Parameters for one ``apply_augmentations`` call per entry of ``set_sizes`` (sets of different sizes packed
+        back to back, e.g. the query segments of multi-segment tasks, datasets/batch_creation.py:113-115)."""
+        sizes = [int(v) for v in set_sizes]
+        ids = torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes))
+        if replay_reference_rng:
+            wp, wd, tm, fm = [], [], [], []
+            for n in sizes:
+                p, d = self._draw_warp(n, time, self.W)
+                wp.append(p); wd.append(d)
+                tm.append(self._draw_time_masks(time))
+                fm.append(self._draw_freq_masks())
+            return SpecAugParams(torch.cat(wp), torch.cat(wd), torch.tensor(tm, dtype=torch.int64).view(len(sizes), -1, 2),
+                                 torch.tensor(fm, dtype=torch.int64).view(len(sizes), -1, 2), 1, ids)
+        rows = int(sum(sizes))
+        base = self.draw_batch(len(sizes), 1, time, replay_reference_rng=False)
+        return SpecAugParams(torch.randint(self.W, time - self.W, (rows,)), torch.randint(-self.W, self.W, (rows,)),
+                             base.time_masks, base.freq_masks, 1, ids)
+
     # ------------------------------------------------------------------ kernel launches
     def apply_batch(self, spec: torch.Tensor, params: SpecAugParams, views_mask: int = 0b1111,
                     exact_spline: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """spec [N,1,F,T] on the GPU -> [4,N,1,F,T] = (copy, time-warp, time-mask, freq-mask)."""
         src_x = warp_source_x(params.warp_p, params.warp_d, spec.shape[-1]) if exact_spline else None
         return ops.specaug_views(spec, params.warp_p, params.warp_d, params.time_masks, params.freq_masks,
-                                 float(self.mask_value), params.set_size, src_x=src_x, views_mask=views_mask, out=out)
+                                 float(self.mask_value), params.set_size, src_x=src_x, views_mask=views_mask, out=out,
+                                 set_ids=params.set_ids)
 
     def _single(self, spec, view, warp=None, tmasks=None, fmasks=None):
         n, t = spec.shape[0], spec.shape[-1]

@@ -150,8 +150,8 @@ def kernel_rooflines(device, peak_gbs, episodes):
     tm = torch.tensor([[[40, 12]]], device=device, dtype=torch.int32).repeat(sets, 1, 1).contiguous()
     fm = torch.tensor([[[60, 9]]], device=device, dtype=torch.int32).repeat(sets, 1, 1).contiguous()
     lo, w = _row_tables(MELS, device)
-    sec = timed(lambda: call("afsl_specaug_views_f32", ptr(x), ptr(views), ptr(wp), ptr(wd), None, ptr(lo), ptr(w), ptr(tm),
-                             ptr(fm), 1, 0.0, n, 25, MELS, T_LEN, 15, st))
+    sec = timed(lambda: call("afsl_specaug_views_f32", ptr(x), ptr(views), ptr(wp), ptr(wd), None, ptr(lo), ptr(w), None,
+                             ptr(tm), ptr(fm), 1, 0.0, n, 25, MELS, T_LEN, 15, st))
     entry("specaug_views", 4.0 * n * MELS * T_LEN * 5, sec, f"{sets} sets x 25 samples [1,128,157]")
     del x, views
     # ---- fused head, D=256, 5w5s5q

@@ -152,6 +152,8 @@ int afsl_angular_bwd_f32(const float* protos, const float* queries, const int32_
  * Samples are grouped in sets of `set_size` consecutive samples (one
  * apply_augmentations call of the reference = one set); masks are shared by a
  * set: time_masks/freq_masks [n_sets,num_mask,2] = (start, length) int32.
+ * set_ids [N] int32 [opt] names the set of every sample instead (ragged sets: the
+ * packed query segments of multi-segment tasks, one set per task).
  * warp_p, warp_d [N] int32 are the per-sample control point and displacement;
  * src_x [N,T] [opt] overrides the in-kernel Hermite spline with host-computed
  * normalised source coordinates.  row_lo [F] int32 / row_w [F] fp32 are the
@@ -161,8 +163,8 @@ int afsl_angular_bwd_f32(const float* protos, const float* queries, const int32_
  * ------------------------------------------------------------------------- */
 int afsl_specaug_views_f32(const float* x, float* views, const int32_t* warp_p, const int32_t* warp_d,
                            const float* src_x, const int32_t* row_lo, const float* row_w,
-                           const int32_t* time_masks, const int32_t* freq_masks, int num_mask,
-                           float mask_value, int N, int set_size, int F, int T, int views_mask,
+                           const int32_t* set_ids, const int32_t* time_masks, const int32_t* freq_masks,
+                           int num_mask, float mask_value, int N, int set_size, int F, int T, int views_mask,
                            void* stream);
 
 /* ---------------------------------------------------------------------------

@@ -297,6 +297,32 @@ def test_specaug_batched_sets_vs_oracle(ops, monkeypatch, t_len, kernel):
         close(v[1, sl], ref[1], rtol=0, scale=warp_atol(x))
 
 
+@pytest.mark.parametrize("kernel", ["tile", "rows"])
+def test_specaug_ragged_sets_vs_oracle(ops, monkeypatch, kernel):
+    """Sets of different sizes packed back to back (the query segments of multi-segment tasks: one
+    apply_augmentations call per task), named by set_ids, vs the oracle set by set."""
+    from afsl_b200.utils.augmentations import SpecAugment
+    monkeypatch.setenv("AFSL_SPECAUG_TILE", "1" if kernel == "tile" else "0")
+    cfg = {"specaug_params": {"use": True, "mask_param": 16, "W": 22, "num_mask": 1, "mask_value": 0.0, "p": 0.282}}
+    sizes, t_len = [3, 7, 1, 12, 5], 157
+    gen = torch.Generator().manual_seed(17)
+    x = torch.randn(sum(sizes), 1, 128, t_len, generator=gen)
+    torch.manual_seed(5); np.random.seed(5)
+    params = SpecAugment(cfg).draw_ragged(sizes, t_len, replay_reference_rng=True)
+    torch.manual_seed(5); np.random.seed(5)
+    ref_params = [ospec.draw_params(n, t_len, cfg) for n in sizes]          # the same draws, one oracle call per set
+    v = SpecAugment(cfg).apply_batch(x.cuda(), params)
+    a = 0
+    for n, rp in zip(sizes, ref_params):
+        ref = ospec.apply(x[a:a + n], rp, 0.0)
+        sl = slice(a, a + n)
+        assert torch.equal(v[0, sl].cpu(), ref[0])
+        assert torch.equal(v[2, sl].cpu(), ref[2])
+        assert torch.equal(v[3, sl].cpu(), ref[3])
+        close(v[1, sl], ref[1], rtol=0, scale=warp_atol(x))
+        a += n
+
+
 def test_specaug_whole_sample_ctas_match_row_kernel(ops, monkeypatch):
     """Large launches switch the tile kernel to one CTA per sample (column tables set up once per sample);
     its four views must equal, bit for bit, those of the warp-per-row kernel that the oracle tests pin."""
