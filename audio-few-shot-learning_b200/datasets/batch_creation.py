@@ -1,0 +1,126 @@
+"""Episode sampling (host-side mirror of datasets/batch_creation.py:21-170) and its batched form.
+
+``sample_episode`` keeps the reference's signature, return value and - draw for draw - its use of Python's
+``random`` (class sample, per-class shuffle, segment pick) and of the SpecAugment generators, so that with the same
+seeds it selects the same clips and draws the same masks as the reference.  The dataset protocol is the reference's:
+``class_to_label``, ``data_df`` (columns ``label`` / ``index_column``), ``multi_segm``, ``input_type``,
+``specaug_use``, ``experiment_config`` and ``__getitem__ -> (spectrogram [S,1,128,T], label)``.
+SpecAugment runs on the GPU kernel, so the views are produced after the move to ``device``.
+
+``sample_episode_batch`` draws E episodes (same per-episode draw order) and returns an ``EpisodeBatch`` for
+``EpisodeRunner``: index selection is one pass over a per-class index table built once per dataset instead of
+one pandas filter per class per episode.
+
+The waveform front end (``input_type == 'wav'``: MelSpectrogram + global normalisation on the GPU) is out of scope
+of this build and raises.
+"""
+from __future__ import annotations
+
+import random
+from typing import Dict, List, Tuple
+
+import torch
+
+from ..episodes import EpisodeBatch
+from ..utils.augmentations import SpecAugment
+
+
+def augment_spectrogram(item, experiment_config):
+    """Four SpecAugment views of a set (datasets/batch_creation.py:10-13)."""
+    return SpecAugment(experiment_config).apply_augmentations(item)
+
+
+def _class_index_table(dataset) -> Dict[int, List[int]]:
+    """label id -> dataset indices in ``data_df`` order, cached on the dataset (replaces the per-episode pandas
+    filter of batch_creation.py:37-38; the lists are copied before they are shuffled)."""
+    table = getattr(dataset, "_afsl_class_index_table", None)
+    if table is None:
+        name_to_label = dataset.class_to_label
+        table = {label: [] for label in name_to_label.values()}
+        for name, idx in zip(dataset.data_df["label"].tolist(), dataset.data_df["index_column"].tolist()):
+            table[name_to_label[name]].append(idx)
+        try:
+            dataset._afsl_class_index_table = table
+        except AttributeError:
+            pass
+    return table
+
+
+def _episode_classes(dataset, n_classes: int, k_support: int, k_query: int):
+    """The reference's draws of one episode, class by class: the sorted class sample up front, then - lazily, so that
+    the caller's segment picks for class c happen before class c+1's shuffle exactly as in the reference
+    (batch_creation.py:25,36-48) - one shuffle of each sampled class's index list.
+    Yields (new label, support indices, query indices)."""
+    class_labels = list(dataset.class_to_label.values())
+    sampled = sorted(random.sample(class_labels, n_classes))
+    table = _class_index_table(dataset)
+    label_to_name = {v: k for k, v in dataset.class_to_label.items()}
+    for new_label, label in enumerate(sampled):
+        indices = list(table[label])
+        random.shuffle(indices)
+        if len(indices) < k_support + k_query:
+            raise ValueError(f"Not enough samples for class {label_to_name[label]}. "
+                             f"Available: {len(indices)}, required: {k_support + k_query}")
+        yield new_label, indices[:k_support], indices[k_support:k_support + k_query]
+
+
+def sample_episode(dataset, n_classes, k_support, k_query, is_test, device, feat_extractor, augment_query):
+    """One episode: (support view list, support labels, query view list, query labels, audio ids)."""
+    if dataset.input_type != "spec":
+        raise NotImplementedError("input_type 'wav' (GPU MelSpectrogram front end) is outside this build's scope")
+    support_set, support_labels, query_set, query_labels, audio_ids = [], [], [], [], []
+    query_counter = 0
+    for new_label, s_idx, q_idx in _episode_classes(dataset, n_classes, k_support, k_query):
+        for idx in s_idx:
+            spectrogram, _ = dataset[idx]
+            if spectrogram.shape[0] != 1:                                  # multi-segment clip: one random segment
+                spectrogram = spectrogram[random.randint(0, spectrogram.shape[0] - 1)].unsqueeze(0)
+            support_set.append(spectrogram)
+            support_labels.append(new_label)
+        for idx in q_idx:
+            spectrogram, _ = dataset[idx]
+            if is_test == False and spectrogram.shape[0] != 1:             # noqa: E712 - test keeps every segment
+                spectrogram = spectrogram[random.randint(0, spectrogram.shape[0] - 1)].unsqueeze(0)
+            query_set.append(spectrogram)
+            query_labels.extend([new_label] * spectrogram.shape[0])
+            audio_ids.extend([query_counter] * spectrogram.shape[0])
+            query_counter += 1
+    support_set = torch.cat(support_set, dim=0).to(device)
+    query_set = torch.cat(query_set, dim=0).to(device)
+    if dataset.specaug_use == True:                                         # noqa: E712
+        support_list = augment_spectrogram(support_set, dataset.experiment_config)
+        query_list = augment_spectrogram(query_set, dataset.experiment_config) if augment_query == True else [query_set]  # noqa: E712
+    else:
+        support_list, query_list = [support_set], [query_set]
+    return (support_list, torch.tensor(support_labels), query_list, torch.tensor(query_labels), torch.tensor(audio_ids))
+
+
+def sample_episode_batch(dataset, episodes: int, n_classes: int, k_support: int, k_query: int,
+                         pin_memory: bool = False) -> EpisodeBatch:
+    """E single-segment training episodes as one host ``EpisodeBatch`` ([E,Ns,1,F,T] / [E,Nq,1,F,T], labels
+    0..W-1 block-sorted as the reference builds them).  Draw order per episode = ``sample_episode``'s; the
+    SpecAugment views are NOT taken here - ``EpisodeRunner`` draws and applies them on the device."""
+    if dataset.input_type != "spec":
+        raise NotImplementedError("input_type 'wav' (GPU MelSpectrogram front end) is outside this build's scope")
+    def fetch(idxs):
+        rows = []
+        for idx in idxs:
+            spectrogram, _ = dataset[idx]
+            if spectrogram.shape[0] != 1:                                  # multi-segment clip: one random segment
+                spectrogram = spectrogram[random.randint(0, spectrogram.shape[0] - 1)].unsqueeze(0)
+            rows.append(spectrogram)
+        return rows
+
+    sup, qry = [], []
+    for _ in range(episodes):
+        s_rows, q_rows = [], []
+        for _, s_idx, q_idx in _episode_classes(dataset, n_classes, k_support, k_query):
+            s_rows += fetch(s_idx)                                         # support picks before query picks, per class
+            q_rows += fetch(q_idx)
+        sup.append(torch.cat(s_rows))
+        qry.append(torch.cat(q_rows))
+    support, query = torch.stack(sup), torch.stack(qry)
+    sl = torch.arange(n_classes).repeat_interleave(k_support).expand(episodes, -1).contiguous()
+    ql = torch.arange(n_classes).repeat_interleave(k_query).expand(episodes, -1).contiguous()
+    batch = EpisodeBatch(support, sl, query, ql, n_classes)
+    return batch.pin() if pin_memory else batch

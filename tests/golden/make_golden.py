@@ -355,9 +355,78 @@ def gen_epoch():
          **{"init_" + k: v for k, v in init.items()}, **{"after_" + k: v for k, v in after.items()})
 
 
+def gen_epoch_first():
+    """First episode of gen_epoch alone (same seeds, same initial weights): its loss does not go through Adam,
+    so it pins the forward of the whole loop (sampler -> encoder -> prototypes -> FSL loss) tightly."""
+    from loops.loops import training_epoch
+    from loops.loss import FSL_Loss
+    from models.main_modules import StandardCNN, ProjectionHead
+    from models.prototypical import ContrastivePrototypicalNetworksWithoutAttention
+    cfg = {"specaug_params": {"use": False, "mask_param": 16, "W": 22, "num_mask": 1, "mask_value": 0, "p": 0.282}}
+    mc = {"Projection": {"input_dim": 64, "hidden_dim": 32, "output_dim": 64}}
+    ds = FakeDataset(cfg, t_len=157, seed=5)
+
+    class Enc(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.encoder = StandardCNN(1, (1, 1, 128, 157), 64, [3, 3], 64)
+        def forward(self, views):
+            return [self.encoder(v) for v in views]
+    torch.manual_seed(500)
+    net = ContrastivePrototypicalNetworksWithoutAttention(Enc(), ProjectionHead(mc))
+    for m in net.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    random.seed(1234); np.random.seed(1234); torch.manual_seed(1234)
+    msg = training_epoch(net, ds, opt, 1, "cpu", FSL_Loss(), None, 0.0, False, False, 5, 5, 5, None, False, False)
+    save("epoch_cnn_first", loss=msg["loss"], fsl_loss=msg["fsl_loss"])
+
+
+class FakeMultiSegDataset(FakeDataset):
+    """Clips with 1..4 segments each (multi_segm datasets return [S,1,128,T] per item)."""
+
+    def __init__(self, cfg, classes=7, per_class=9, t_len=32, seed=0):
+        import pandas as pd
+        g = torch.Generator().manual_seed(seed)
+        n = classes * per_class
+        self.segments = torch.randint(1, 5, (n,), generator=g).tolist()
+        self.clips = [torch.randn(sg, 1, 128, t_len, generator=g) for sg in self.segments]
+        names = [f"c{i}" for i in range(classes)]
+        self.class_to_label = {nm: i for i, nm in enumerate(names)}
+        order = torch.randperm(n, generator=g).tolist()            # rows of data_df are not grouped by class
+        self.data_df = pd.DataFrame({"label": [names[i % classes] for i in order], "index_column": order})
+        self.multi_segm = True
+        self.input_type = "spec"
+        self.specaug_use = False
+        self.waveaug_use = False
+        self.experiment_config = cfg
+
+    def __getitem__(self, i):
+        return self.clips[i], 0
+
+
+def gen_sampler():
+    """The reference's sample_episode on a multi-segment fake dataset: which clips / segments it selects, in which
+    order, with which labels and audio ids, for train (is_test=False) and test (is_test=True) episodes."""
+    from datasets.batch_creation import sample_episode
+    cfg = {"specaug_params": {"use": False}}
+    ds = FakeMultiSegDataset(cfg, seed=11)
+    out = {}
+    for name, is_test, seed in (("train", False, 21), ("test", True, 22), ("train2", False, 23)):
+        random.seed(seed)
+        s_list, s_lab, q_list, q_lab, ids = sample_episode(ds, 5, 3, 4, is_test, "cpu", None, False)
+        assert len(s_list) == 1 and len(q_list) == 1
+        fp = lambda x: x[:, 0, :2, :4].reshape(x.shape[0], -1).clone()     # 8 values identify a segment
+        out.update({f"{name}_support": fp(s_list[0]), f"{name}_support_labels": s_lab, f"{name}_query": fp(q_list[0]),
+                    f"{name}_query_labels": q_lab, f"{name}_audio_ids": ids, f"{name}_seed": seed,
+                    f"{name}_state_after": random.random()})
+    save("sampler_multiseg", dataset_seed=11, **out)
+
+
 if __name__ == "__main__":
     import_reference()
     torch.set_num_threads(1)            # fixed reduction order for the fixtures
-    which = sys.argv[1:] or ["head", "cpl", "specaug", "vote", "modules", "epoch"]
+    which = sys.argv[1:] or ["head", "cpl", "specaug", "vote", "modules", "epoch", "epoch_first", "sampler"]
     for name in which:
         globals()["gen_" + name]()

@@ -638,3 +638,73 @@ def test_runner_cuda_graph_matches_eager(ops):
             close(a, b, rtol=0, scale=3 * 2 * cfg["lr"] + 1e-6)
     finally:
         torch.backends.cudnn.allow_tf32 = tf32
+
+
+# ------------------------------------------------------------------ training / validation loops vs the reference's own loops
+class _FakeDataset:
+    """Same construction as tests/golden/make_golden.py::FakeDataset (single-segment clips)."""
+
+    def __init__(self, seed, classes=6, per_class=12, t_len=157):
+        import pandas as pd
+        g = torch.Generator().manual_seed(seed)
+        self.items = torch.randn(classes * per_class, 1, 1, 128, t_len, generator=g)
+        names = [f"c{i}" for i in range(classes)]
+        self.class_to_label = {n: i for i, n in enumerate(names)}
+        self.data_df = pd.DataFrame({"label": [names[i // per_class] for i in range(classes * per_class)],
+                                     "index_column": list(range(classes * per_class))})
+        self.multi_segm, self.input_type, self.specaug_use, self.waveaug_use = False, "spec", False, False
+        self.experiment_config = {"specaug_params": {"use": False}}
+
+    def __getitem__(self, i):
+        return self.items[i], 0
+
+
+def test_training_epoch_and_validation_vs_reference_loops(ops):
+    """loops.training_epoch (two episodes, one optimizer step each) and loops.evaluate_single_segment on the GPU
+    reproduce what the REFERENCE's loops/loops.py produced on the same fake dataset, seeds and initial weights
+    (tests/golden/epoch_cnn_plain.npz: Conv4 ProtoNet, no views - BASELINE config 1)."""
+    import random
+    from afsl_b200.loops.loops import evaluate_single_segment, training_epoch
+    from afsl_b200.loops.loss import FSL_Loss
+    from afsl_b200.models.main_modules import EncoderModule, ProjectionHead, StandardCNN
+    from afsl_b200.models.prototypical import ContrastivePrototypicalNetworksWithoutAttention
+    g = load_golden("epoch_cnn_plain")
+    ds = _FakeDataset(int(g["items_seed"]))
+    assert abs(float(ds.items.double().sum()) - float(g["items_checksum"])) < 1e-6
+    mc = {"Projection": {"input_dim": 64, "hidden_dim": 32, "output_dim": 64}}
+    backbone = EncoderModule({"encoder_name": "CNN"}, {}, encoder=StandardCNN(1, (1, 1, 128, 157), 64, [3, 3], 64))
+    net = ContrastivePrototypicalNetworksWithoutAttention(backbone, ProjectionHead(mc))
+    net.load_state_dict({k[len("init_"):]: t(v) for k, v in g.items() if k.startswith("init_")})
+    for m in net.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    net = net.cuda()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    init = {k[len("init_"):]: t(v) for k, v in g.items() if k.startswith("init_")}
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        random.seed(1234); np.random.seed(1234); torch.manual_seed(1234)
+        first = training_epoch(net, ds, opt, 1, "cuda", FSL_Loss(), None, 0.0, False, False, 5, 5, 5, None, False, False)
+        # restart from the initial weights for the two-episode epoch of the fixture
+        net.load_state_dict(init)
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+        random.seed(1234); np.random.seed(1234); torch.manual_seed(1234)
+        msg = training_epoch(net, ds, opt, 2, "cuda", FSL_Loss(), None, 0.0, False, False, 5, 5, 5, None, False, False)
+        random.seed(99)
+        val_mean, val_std = evaluate_single_segment(net, ds, 3, "cuda", 5, 5, 5, None, False)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    # the first episode does not go through the optimizer: tight.  The second one follows an Adam step, whose
+    # normalised update turns last-bit differences of near-zero gradients into +-lr parameter differences.
+    g1 = load_golden("epoch_cnn_first")
+    assert abs(first["loss"] - float(g1["loss"])) <= 1e-5 * abs(float(g1["loss"]))
+    assert abs(msg["loss"] - float(g["loss"])) <= 1e-3 * abs(float(g["loss"]))
+    assert abs(msg["fsl_loss"] - float(g["fsl_loss"])) <= 1e-3 * abs(float(g["fsl_loss"]))
+    assert np.isnan(msg["cpl_loss"])
+    assert abs(val_mean - float(g["val_mean"])) < 1e-9 and abs(val_std - float(g["val_std"])) < 1e-9
+    after = net.state_dict()
+    for k, v in g.items():
+        if k.startswith("after_") and "num_batches_tracked" not in k:
+            # two Adam steps: +-lr per step where a near-zero gradient's sign differs in the last bit
+            close(after[k[len("after_"):]], t(v), rtol=0, scale=2 * 2 * 1e-3 + 1e-6)

@@ -198,3 +198,64 @@ def test_gloo_two_ranks_match_single_process(tmp_path):
     want = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
     torch.testing.assert_close(got["grad"], want, rtol=1e-5, atol=1e-7)
     assert np.array_equal(got["acc"], np.arange(7, dtype=np.float64) / 10.0)
+
+
+# ------------------------------------------------------------------ episode sampler vs the reference's sample_episode
+class _FakeMultiSegDataset:
+    """Same construction as tests/golden/make_golden.py::FakeMultiSegDataset (clips of 1..4 segments)."""
+
+    def __init__(self, seed, classes=7, per_class=9, t_len=32):
+        import pandas as pd
+        g = torch.Generator().manual_seed(seed)
+        n = classes * per_class
+        self.segments = torch.randint(1, 5, (n,), generator=g).tolist()
+        self.clips = [torch.randn(sg, 1, 128, t_len, generator=g) for sg in self.segments]
+        names = [f"c{i}" for i in range(classes)]
+        self.class_to_label = {nm: i for i, nm in enumerate(names)}
+        order = torch.randperm(n, generator=g).tolist()
+        self.data_df = pd.DataFrame({"label": [names[i % classes] for i in order], "index_column": order})
+        self.multi_segm, self.input_type, self.specaug_use, self.waveaug_use = True, "spec", False, False
+        self.experiment_config = {"specaug_params": {"use": False}}
+
+    def __getitem__(self, i):
+        return self.clips[i], 0
+
+
+def test_sample_episode_matches_reference_draws():
+    """sample_episode picks the clips / segments, labels and audio ids of the reference's sample_episode
+    (datasets/batch_creation.py:21-170) draw for draw, and leaves Python's RNG in the same state."""
+    import random
+    from conftest import load_golden
+    from afsl_b200.datasets.batch_creation import sample_episode, sample_episode_batch
+    g = load_golden("sampler_multiseg")
+    ds = _FakeMultiSegDataset(int(g["dataset_seed"]))
+    fp = lambda x: x[:, 0, :2, :4].reshape(x.shape[0], -1)
+    for name, is_test in (("train", False), ("test", True), ("train2", False)):
+        random.seed(int(g[f"{name}_seed"]))
+        s_list, s_lab, q_list, q_lab, ids = sample_episode(ds, 5, 3, 4, is_test, "cpu", None, False)
+        assert len(s_list) == 1 and len(q_list) == 1
+        assert torch.equal(fp(s_list[0]), torch.from_numpy(g[f"{name}_support"]))
+        assert torch.equal(fp(q_list[0]), torch.from_numpy(g[f"{name}_query"]))
+        assert torch.equal(s_lab, torch.from_numpy(g[f"{name}_support_labels"]))
+        assert torch.equal(q_lab, torch.from_numpy(g[f"{name}_query_labels"]))
+        assert torch.equal(ids, torch.from_numpy(g[f"{name}_audio_ids"]))
+        assert random.random() == float(g[f"{name}_state_after"])
+    # batched sampler: episode e of the batch == the e-th sample_episode call of the same stream
+    random.seed(int(g["train_seed"]))
+    batch = sample_episode_batch(ds, 1, 5, 3, 4)
+    assert torch.equal(fp(batch.support[0]), torch.from_numpy(g["train_support"]))
+    assert torch.equal(fp(batch.query[0]), torch.from_numpy(g["train_query"]))
+    assert torch.equal(batch.support_labels[0], torch.from_numpy(g["train_support_labels"]))
+    with pytest.raises(ValueError, match="Not enough samples"):
+        sample_episode(ds, 5, 8, 4, False, "cpu", None, False)
+
+
+def test_early_stopping_protocol(tmp_path):
+    from afsl_b200.callbacks.early_stopping import EarlyStopping
+    model = torch.nn.Linear(2, 2)
+    msgs = []
+    stop = EarlyStopping(patience=3, verbose=True, path=str(tmp_path / "model.pt"), trace_func=msgs.append)
+    for epoch, acc in enumerate([0.5, 0.6, 0.55, 0.58, 0.59], 1):
+        stop(acc, model, epoch)
+    assert stop.early_stop and stop.counter == 3 and stop.best_score == 0.6
+    assert (tmp_path / "model.pt").exists() and any("EarlyStopping counter: 2 out of 3" in m for m in msgs)
