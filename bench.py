@@ -247,6 +247,27 @@ def kernel_rooflines(device, peak_gbs, episodes):
     entry("gbn_stats", nx, t_s, f"{g} groups x 25 x [64,128,157]")
     entry("gbn_relu_pool_fwd", nx + ny, t_gf, f"{g} groups x 25 x [64,128,157]")
     entry("gbn_relu_pool_bwd", 2 * (nx + ny) + nx, t_gb, f"{g} groups x 25 x [64,128,157]", launches=2)
+    del xx, yy, dyy, dxx
+    # ---- the same three passes channels-last, stage-2 shape [G*25, 42, 52, 64] (the layout the encoder runs in)
+    g, grp, c, h, wd_ = 32, 25, 64, 42, 52
+    xc = torch.randn(g * grp, c, h, wd_, device=device).contiguous(memory_format=torch.channels_last)
+    yc = torch.empty(g * grp, c, h // 3, wd_ // 3, device=device).contiguous(memory_format=torch.channels_last)
+    dyc, dxc = torch.randn_like(yc), torch.empty_like(xc)
+    mean, rstd, var = (torch.empty(g, c, device=device) for _ in range(3))
+    sums = torch.empty(g, c, 2, device=device)
+    from afsl_b200 import _lib
+    parts = int(_lib.load().afsl_gbn_nhwc_parts(g))
+    ws = torch.empty(g, parts, c, 2, device=device, dtype=torch.float64)
+    t_s = timed(lambda: call("afsl_gbn_stats_nhwc_f32", ptr(xc, True), ptr(ws), parts, ptr(mean), ptr(rstd), ptr(var), g, grp, c, h,
+                             wd_, 1e-5, st), reps=10)
+    t_gf = timed(lambda: call("afsl_gbn_relu_pool_nhwc_fwd_f32", ptr(xc, True), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta),
+                              ptr(yc, True), g, grp, c, h, wd_, 1, st), reps=10)
+    t_gb = timed(lambda: call("afsl_gbn_relu_pool_nhwc_bwd_f32", ptr(xc, True), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta),
+                              ptr(dyc, True), ptr(dxc, True), ptr(ws), parts, ptr(sums), g, grp, c, h, wd_, 1, st), reps=10)
+    nx, ny = xc.numel() * 4.0, yc.numel() * 4.0
+    entry("nhwc_gbn_stats", nx, t_s, f"{g} groups x 25 x [42,52,64] channels-last", launches=2)
+    entry("nhwc_gbn_relu_pool_fwd", nx + ny, t_gf, f"{g} groups x 25 x [42,52,64] channels-last")
+    entry("nhwc_gbn_relu_pool_bwd", 2 * (nx + ny) + nx, t_gb, f"{g} groups x 25 x [42,52,64] channels-last", launches=3)
     return out
 
 

@@ -708,3 +708,61 @@ def test_training_epoch_and_validation_vs_reference_loops(ops):
         if k.startswith("after_") and "num_batches_tracked" not in k:
             # two Adam steps: +-lr per step where a near-zero gradient's sign differs in the last bit
             close(after[k[len("after_"):]], t(v), rtol=0, scale=2 * 2 * 1e-3 + 1e-6)
+
+
+# ------------------------------------------------------------------ one whole training episode vs the CPU oracle
+@pytest.mark.parametrize("loss_kind", ["cpl", "angular"])
+def test_runner_episode_vs_oracle_episode(ops, loss_kind):
+    """EpisodeRunner.train_step on ONE episode with replay_reference_rng=True == oracle/episode.py::train_step (the
+    restatement of loops/loops.py:26-61 pinned to the reference) on the same seeds: SpecAugment draws, view shuffle,
+    CPL negatives, losses and the parameter update.  Config 2 (CPL) and config 3 (angular, NSynth-shaped)."""
+    import copy
+    import random
+    import bench
+    from afsl_b200.episodes import EpisodeRunner, synthetic_batch
+    from afsl_b200.models.main_modules import EncoderModule, ProjectionHead, SelfAttention
+    from afsl_b200.models.prototypical import ContrastivePrototypicalNetworks
+    from oracle import episode as oep
+    from oracle import modules as om
+    cfg = copy.deepcopy(bench.EXPERIMENT_CONFIG)
+    mcfg = copy.deepcopy(bench.MODEL_CONFIG)
+    mcfg["Attention"]["dropout"] = 0.0
+    t_len = 157
+    if loss_kind == "angular":
+        cfg["loss"]["cpl"]["use"] = False
+        cfg["loss"]["angular"] = {"use": True, "angle": 0, "prototypes_as_anchors": True}
+        cfg["loss"]["l_param"] = 1.0
+        cfg["specaug_params"] = {"use": True, "mask_param": 9, "W": 36, "num_mask": 1, "mask_value": 0, "p": 0.42157}
+        mcfg["Projection"] = {"input_dim": 256, "hidden_dim": 64, "output_dim": 64}
+        t_len = 126
+    else:
+        cfg["loss"]["cpl"]["m_param"] = 3          # sampled negatives: exercises the host-drawn keep mask
+    pc = mcfg["Projection"]
+    torch.manual_seed(42)
+    ref = om.FusedViewsNet(om.ViewEncoder(om.build_encoder("Hybrid", t_len)), om.ViewFusion(64, 1, 256, 0.0),
+                           om.Projection(pc["input_dim"], pc["hidden_dim"], pc["output_dim"]))
+    net = ContrastivePrototypicalNetworks(EncoderModule(cfg, mcfg), SelfAttention(mcfg), ProjectionHead(mcfg))
+    net.load_state_dict(ref.state_dict())
+    for m in list(ref.modules()) + list(net.modules()):
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    net = net.cuda()
+    lr = 1e-3
+    ropt, nopt = torch.optim.Adam(ref.parameters(), lr=lr), torch.optim.Adam(net.parameters(), lr=lr)
+    batch = synthetic_batch(1, 5, 5, 5, t_len, seed=321)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(9); np.random.seed(9); random.seed(9)
+        r_total, r_fsl, r_extra = oep.train_step(ref, ropt, batch.support[0], batch.support_labels[0], batch.query[0],
+                                                 batch.query_labels[0], cfg)
+        torch.manual_seed(9); np.random.seed(9); random.seed(9)
+        out = EpisodeRunner(net, cfg, nopt, replay_reference_rng=True).train_step(batch)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert abs(float(out["fsl_loss"][0]) - r_fsl) <= 2e-5 * abs(r_fsl)
+    assert abs(float(out["cpl_loss"][0]) - r_extra) <= 1e-4 * abs(r_extra) + 1e-7
+    assert abs(float(out["loss"][0]) - r_total) <= 5e-5 * abs(r_total)
+    for (name, a), b in zip(net.state_dict().items(), ref.state_dict().values()):
+        if "num_batches_tracked" not in name:
+            close(a, b, rtol=0, scale=2 * lr + 1e-6)         # one Adam step: +-lr where a ~0 gradient flips sign

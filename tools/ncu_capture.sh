@@ -6,17 +6,25 @@
 set -u
 tag=${1:-r1}; shift || true
 kernels=("$@")
-[ ${#kernels[@]} -eq 0 ] && kernels=(head_fwd_kernel head_bwd_kernel cpl_fwd_kernel cpl_bwd_kernel specaug_kernel)
+[ ${#kernels[@]} -eq 0 ] && kernels=(head_warp_kernel:4:head_fwd head_warp_kernel:27:head_bwd cpl_warp_kernel:4:cpl_fwd cpl_warp_kernel:27:cpl_bwd specaug_tile_kernel:4:specaug_tile angular_warp_kernel:2:angular_fwd angular_warp_kernel:10:angular_bwd)
 out=gpurun_out
 mkdir -p $out
-BENCH="python bench.py --steps 2 --warmup 3 --episodes 32 --skip-cpu --skip-kernels"
+BENCH="python bench.py --steps 2 --warmup 3 --episodes 32 --skip-cpu --skip-kernels --skip-eval"
 $BENCH > $out/${tag}_bench_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $out/${tag}_launches.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none --graph-profiling node -c 8000 --csv --log-file $out/${tag}_launches.csv \
     $BENCH > $out/${tag}_launches.log 2>&1
 echo "launch list rc=$?"
 KB="python tools/kernels_bench.py"
 $KB > $out/${tag}_kb_plain.log 2>&1 || { echo "kernels_bench failed"; exit 1; }
-for k in "${kernels[@]}"; do
-  ncu --set full --clock-control none --import-source on -k regex:$k -s 4 -c 1 -f -o $out/${tag}_$k $KB > $out/${tag}_ncu_$k.log 2>&1
+for spec in "${kernels[@]}"; do
+  IFS=: read -r k skip label <<< "$spec"
+  skip=${skip:-4}; label=${label:-$k}
+  ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -f -o $out/${tag}_$label $KB > $out/${tag}_ncu_$label.log 2>&1
+  echo "$label rc=$?"
+done
+# fused encoder stage 1 at the training shape
+S1="python tools/stage1_bench.py"
+$S1 > $out/${tag}_s1_plain.log 2>&1 && for k in stage1_fwd_kernel stage1_bwd_nhwc_kernel; do
+  ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o $out/${tag}_$k $S1 > $out/${tag}_ncu_$k.log 2>&1
   echo "$k rc=$?"
 done
