@@ -711,7 +711,7 @@ def test_training_epoch_and_validation_vs_reference_loops(ops):
 
 
 # ------------------------------------------------------------------ one whole training episode vs the CPU oracle
-@pytest.mark.parametrize("loss_kind", ["cpl", "angular"])
+@pytest.mark.parametrize("loss_kind", ["cpl", "angular", "concat_cpl"])
 def test_runner_episode_vs_oracle_episode(ops, loss_kind):
     """EpisodeRunner.train_step on ONE episode with replay_reference_rng=True == oracle/episode.py::train_step (the
     restatement of loops/loops.py:26-61 pinned to the reference) on the same seeds: SpecAugment draws, view shuffle,
@@ -721,7 +721,7 @@ def test_runner_episode_vs_oracle_episode(ops, loss_kind):
     import bench
     from afsl_b200.episodes import EpisodeRunner, synthetic_batch
     from afsl_b200.models.main_modules import EncoderModule, ProjectionHead, SelfAttention
-    from afsl_b200.models.prototypical import ContrastivePrototypicalNetworks
+    from afsl_b200.models.prototypical import ContrastivePrototypicalNetworks, ContrastivePrototypicalNetworksWithoutAttention
     from oracle import episode as oep
     from oracle import modules as om
     cfg = copy.deepcopy(bench.EXPERIMENT_CONFIG)
@@ -737,11 +737,19 @@ def test_runner_episode_vs_oracle_episode(ops, loss_kind):
         t_len = 126
     else:
         cfg["loss"]["cpl"]["m_param"] = 3          # sampled negatives: exercises the host-drawn keep mask
+    if loss_kind == "concat_cpl":                  # no view fusion: views stacked along the sample axis, labels repeated
+        cfg["use_attention"] = False
+        mcfg["Projection"] = {"input_dim": 64, "hidden_dim": 128, "output_dim": 64}
     pc = mcfg["Projection"]
     torch.manual_seed(42)
-    ref = om.FusedViewsNet(om.ViewEncoder(om.build_encoder("Hybrid", t_len)), om.ViewFusion(64, 1, 256, 0.0),
-                           om.Projection(pc["input_dim"], pc["hidden_dim"], pc["output_dim"]))
-    net = ContrastivePrototypicalNetworks(EncoderModule(cfg, mcfg), SelfAttention(mcfg), ProjectionHead(mcfg))
+    if loss_kind == "concat_cpl":
+        ref = om.ConcatViewsNet(om.ViewEncoder(om.build_encoder("Hybrid", t_len)),
+                                om.Projection(pc["input_dim"], pc["hidden_dim"], pc["output_dim"]))
+        net = ContrastivePrototypicalNetworksWithoutAttention(EncoderModule(cfg, mcfg), ProjectionHead(mcfg))
+    else:
+        ref = om.FusedViewsNet(om.ViewEncoder(om.build_encoder("Hybrid", t_len)), om.ViewFusion(64, 1, 256, 0.0),
+                               om.Projection(pc["input_dim"], pc["hidden_dim"], pc["output_dim"]))
+        net = ContrastivePrototypicalNetworks(EncoderModule(cfg, mcfg), SelfAttention(mcfg), ProjectionHead(mcfg))
     net.load_state_dict(ref.state_dict())
     for m in list(ref.modules()) + list(net.modules()):
         if isinstance(m, torch.nn.Dropout):
