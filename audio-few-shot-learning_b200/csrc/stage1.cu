@@ -49,54 +49,71 @@ struct S1Params {
 };
 
 // ---------------------------------------------------------------- input moments
+// CTA (g, part) walks 16-row bands of the group's samples: the band (+ halo, zero padded) is staged in shared
+// memory once, then every thread takes pixels of the band and reads its 3x3 neighbourhood from the tile
+// (the first version fetched the nine neighbours of every pixel from global memory with a bounds test each).
+constexpr int kMomRows = 64;
+
 __global__ void __launch_bounds__(kThreads) stage1_moments_kernel(const S1Params p) {
-  __shared__ double red[kWarps];
-  const int H = p.H, W = p.W, hw = H * W;
+  extern __shared__ __align__(16) float mtile[];         // [(kMomRows + 2) * (W + 2)]
+  const int H = p.H, W = p.W, hw = H * W, ld = W + 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // grid = G * parts_m CTAs; CTA (g, part) strides over the group's elements
+  // grid = G * parts_m CTAs; CTA (g, part) strides over the group's bands
   const int parts = gridDim.x / p.G;
   const int g = blockIdx.x / parts, part = blockIdx.x - g * parts;
   const float* x0 = p.x + (size_t)g * p.group * hw;
   float acc[54];
 #pragma unroll
   for (int k = 0; k < 54; ++k) acc[k] = 0.f;
-  const int total = p.group * hw;
-  for (int o = part * kThreads + threadIdx.x; o < total; o += parts * kThreads) {
-    const int s = o / hw, rem = o - s * hw;
-    const int i = rem / W, j = rem - i * W;
+  const int bands_per_sample = (H + kMomRows - 1) / kMomRows;
+  const int total_bands = p.group * bands_per_sample;
+  for (int bd = part; bd < total_bands; bd += parts) {
+    const int s = bd / bands_per_sample, i0 = (bd - s * bands_per_sample) * kMomRows;
+    const int rows = min(kMomRows, H - i0);
     const float* pl = x0 + (size_t)s * hw;
-    float v[9];
+    __syncthreads();
+    // a warp per tile row, lanes across the columns: no index division anywhere in the loops
+    for (int r = warp; r < rows + 2; r += kWarps) {
+      const int i = i0 - 1 + r;
+      const bool row_in = i >= 0 && i < H;
+      const float* src = pl + (size_t)i * W - 1;
+#pragma unroll 6
+      for (int c = lane; c < ld; c += 32) mtile[r * ld + c] = (row_in && c >= 1 && c <= W) ? __ldg(src + c) : 0.f;
+    }
+    __syncthreads();
+    for (int r = warp; r < rows; r += kWarps)
+    for (int c = lane; c < W; c += 32) {
+      const float* nb = mtile + r * ld + c;            // top-left of the pixel's 3x3 neighbourhood
+      float v[9];
 #pragma unroll
-    for (int a = -1; a <= 1; ++a)
+      for (int a = 0; a < 3; ++a)
 #pragma unroll
-      for (int b = -1; b <= 1; ++b) {
-        const int ii = i + a, jj = j + b;
-        v[(a + 1) * 3 + (b + 1)] = (ii >= 0 && ii < H && jj >= 0 && jj < W) ? __ldg(pl + (size_t)ii * W + jj) : 0.f;
-      }
-    int q = 9;
+        for (int b = 0; b < 3; ++b) v[a * 3 + b] = nb[a * ld + b];
+      int q = 9;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      acc[k] += v[k];
+      for (int k = 0; k < 9; ++k) {
+        acc[k] += v[k];
 #pragma unroll
-      for (int l = k; l < 9; ++l) {
-        acc[q] = fmaf(v[k], v[l], acc[q]);
-        ++q;
+        for (int l = k; l < 9; ++l) {
+          acc[q] = fmaf(v[k], v[l], acc[q]);
+          ++q;
+        }
       }
     }
   }
-  // block reduction in double, one value at a time (54 values, once per CTA)
-  for (int k = 0; k < 54; ++k) {
-    double v = (double)acc[k];
+  // CTA reduction: every warp folds its 54 sums with shuffles (fp32 partials of one band set), then the 16 warp
+  // results of each moment are added in double, in warp order
+  __shared__ float wsum[kWarps][54];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
-    if (lane == 0) red[warp] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double t = 0.0;
-      for (int q = 0; q < kWarps; ++q) t += red[q];
-      p.moments[((size_t)g * parts + part) * 54 + k] = t;
-    }
+  for (int k = 0; k < 54; ++k) {
+    const float t = warp_sum(acc[k]);
+    if (lane == 0) wsum[warp][k] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 54) {
+    double t = 0.0;
+    for (int q = 0; q < kWarps; ++q) t += (double)wsum[q][threadIdx.x];
+    p.moments[((size_t)g * parts + part) * 54 + threadIdx.x] = t;
   }
 }
 
@@ -471,7 +488,9 @@ extern "C" int afsl_stage1_moments_f64(const float* x, double* moments, int part
   S1Params p{};
   p.x = x; p.moments = moments; p.G = G; p.group = group; p.H = H; p.W = W;
   if (int rc = check(p, "afsl_stage1_moments_f64")) return rc;
-  stage1_moments_kernel<<<G * parts, kThreads, 0, (cudaStream_t)stream>>>(p);
+  const size_t mb = (size_t)(kMomRows + 2) * (W + 2) * sizeof(float);
+  if (int rc = opt_in_smem(stage1_moments_kernel, mb, "afsl_stage1_moments_f64")) return rc;
+  stage1_moments_kernel<<<G * parts, kThreads, mb, (cudaStream_t)stream>>>(p);
   AFSL_CHECK_LAUNCH("afsl_stage1_moments_f64");
   return AFSL_OK;
 }
