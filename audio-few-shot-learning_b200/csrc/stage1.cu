@@ -167,6 +167,11 @@ __global__ void __launch_bounds__(kThreads) stage1_fwd_kernel(const S1Params p) 
   // when |a| is small the window's z values collide in fp32 and the winner is the first of the collided set,
   // which only matches at::max_pool2d_with_indices if z is a monotone function of u as it is in the eager chain
   float ca[kCPW], cb[kCPW];
+  f32x2 w2[kCPW / 2][9], ca2[kCPW / 2], cb2[kCPW / 2];     // channel pairs packed for FFMA2
+#pragma unroll
+  for (int cp = 0; cp < kCPW / 2; ++cp)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) w2[cp][k] = pack2(w[2 * cp][k], w[2 * cp + 1][k]);
   int cur_g = -1;
   for (long long tl = blockIdx.x; tl < total_tiles; tl += gridDim.x) {
     const int s = (int)(tl / tiles_per_sample), tix = (int)(tl - (long long)s * tiles_per_sample);
@@ -180,6 +185,11 @@ __global__ void __launch_bounds__(kThreads) stage1_fwd_kernel(const S1Params p) 
         ca[cc] = __ldg(p.a + idx);
         cb[cc] = __ldg(p.b + idx);
       }
+#pragma unroll
+      for (int cp = 0; cp < kCPW / 2; ++cp) {
+        ca2[cp] = pack2(ca[2 * cp], ca[2 * cp + 1]);
+        cb2[cp] = pack2(cb[2 * cp], cb[2 * cp + 1]);
+      }
       cur_g = g;
     }
     stage_tile(p.x + (size_t)s * hw, tile, H, W, ph0, bands);
@@ -192,13 +202,29 @@ __global__ void __launch_bounds__(kThreads) stage1_fwd_kernel(const S1Params p) 
       const size_t o0 = ((size_t)s * kC) * phw + (size_t)(ph0 + bl) * PW + pw;
       float outv[kCPW];
       unsigned char outc[kCPW];
+      // packed fp32x2: two channels per FFMA2 (same fma as the scalar chain, tap order a, b ascending)
+      f32x2 v2[25];
 #pragma unroll
-      for (int cc = 0; cc < kCPW; ++cc) {
-        float z[9];
+      for (int k = 0; k < 25; ++k) v2[k] = pack2(v[k], v[k]);
+      float zz[kCPW][9];
+#pragma unroll
+      for (int cp = 0; cp < kCPW / 2; ++cp) {
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
-          for (int q = 0; q < 3; ++q) z[r * 3 + q] = fmaf(ca[cc], conv_at(v, w[cc], r, q), cb[cc]);
+          for (int q = 0; q < 3; ++q) {
+            f32x2 u = 0ull;
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+              for (int b = 0; b < 3; ++b) u = fma2(w2[cp][a * 3 + b], v2[(r + a) * 5 + (q + b)], u);
+            const f32x2 z2 = fma2(ca2[cp], u, cb2[cp]);
+            unpack2(z2, zz[2 * cp][r * 3 + q], zz[2 * cp + 1][r * 3 + q]);
+          }
+      }
+#pragma unroll
+      for (int cc = 0; cc < kCPW; ++cc) {
+        const float (&z)[9] = zz[cc];
         // NaN / inf inputs poison the batch statistics, hence a and b, hence every z of the group: a window is
         // either NaN-free or all NaN, and fmaxf of all-NaN operands is NaN - same output as a NaN-sticky scan
         const float zmax = fmaxf(fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3])), fmaxf(fmaxf(z[4], z[5]), fmaxf(fmaxf(z[6], z[7]), z[8])));
