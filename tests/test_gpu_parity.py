@@ -774,3 +774,37 @@ def test_runner_episode_vs_oracle_episode(ops, loss_kind):
     for (name, a), b in zip(net.state_dict().items(), ref.state_dict().values()):
         if "num_batches_tracked" not in name:
             close(a, b, rtol=0, scale=2 * lr + 1e-6)         # one Adam step: +-lr where a ~0 gradient flips sign
+
+
+# ------------------------------------------------------------------ plain ProtoNet class (M3) and the cosine logits (P3)
+@pytest.mark.parametrize("use_softmax,norm", [(False, None), (True, 2.0)])
+def test_prototypical_networks_vs_torch(ops, use_softmax, norm):
+    """PrototypicalNetworks (models/prototypical.py:16-43 + few_shot_classifier.py:82-126): feature centering /
+    normalisation, prototypes, -cdist scores, optional softmax, and cosine_distance_to_prototypes, vs plain torch."""
+    from afsl_b200.models.prototypical import PrototypicalNetworks
+    gen = torch.Generator().manual_seed(3)
+    ways, shots, nq, din, d = 5, 4, 7, 40, 64
+    backbone = torch.nn.Linear(din, d).cuda()
+    center = torch.randn(d, generator=gen).cuda() * 0.1
+    model = PrototypicalNetworks(backbone=backbone, use_softmax=use_softmax, feature_centering=center, feature_normalization=norm)
+    xs = torch.randn(ways * shots, din, generator=gen).cuda()
+    xq = torch.randn(ways * nq, din, generator=gen).cuda()
+    ys = torch.arange(ways).repeat_interleave(shots)[torch.randperm(ways * shots, generator=gen)].cuda()
+    with torch.no_grad():
+        model.process_support_set(xs, ys)
+        scores = model(xq)
+        cos = model.cosine_distance_to_prototypes(model.compute_features(xq))
+        fs, fq = backbone(xs) - center, backbone(xq) - center
+        if norm is not None:
+            fs, fq = torch.nn.functional.normalize(fs, p=norm, dim=1), torch.nn.functional.normalize(fq, p=norm, dim=1)
+        protos = torch.stack([fs[ys == w].mean(0) for w in range(ways)])
+        ref = -torch.cdist(fq, protos)
+        if use_softmax:
+            ref = ref.softmax(-1)
+        ref_cos = torch.nn.functional.normalize(fq, dim=1) @ torch.nn.functional.normalize(protos, dim=1).T
+    close(model.prototypes, protos)
+    close(scores, ref)
+    close(cos, ref_cos)
+    assert not model.is_transductive()
+    with pytest.raises(ValueError, match="Illegal backbone or feature shape"):
+        model._raise_error_if_features_are_multi_dimensional(torch.zeros(2, 3, 4, 5))
