@@ -11,14 +11,17 @@ SpecAugment runs on the GPU kernel, so the views are produced after the move to 
 ``EpisodeRunner``: index selection is one pass over a per-class index table built once per dataset instead of
 one pandas filter per class per episode.
 
-The waveform front end (``input_type == 'wav'``: MelSpectrogram + global normalisation on the GPU) is out of scope
-of this build and raises.
+``input_type == 'wav'`` follows the reference too: 5-second splits of the waveform (``variable_wav_splits``), the
+caller's ``feat_extractor`` (torchaudio ``MelSpectrogram``, a library op) on the device, ``10*log10(x + eps)`` and the
+dataset's global normalisation.  Waveform augmentation (``waveaug_use``) needs torch_audiomentations, which is not
+part of this build, and raises.
 """
 from __future__ import annotations
 
 import random
 from typing import Dict, List, Tuple
 
+import numpy as np
 import torch
 
 from ..episodes import EpisodeBatch
@@ -64,10 +67,78 @@ def _episode_classes(dataset, n_classes: int, k_support: int, k_query: int):
         yield new_label, indices[:k_support], indices[k_support:k_support + k_query]
 
 
+def variable_wav_splits(sample):
+    """5-second (80 000-sample) pieces of a 16 kHz waveform (datasets/batch_creation.py:172-213): shorter clips are
+    tiled up to one piece; longer ones are cut, and - as in the reference, which tiles the WHOLE clip there - the
+    remainder piece is the first 5 seconds of the clip repeated."""
+    expected_size = 5 * 16000
+    raw_splits = []
+    if sample.shape[0] < expected_size:
+        multiply_up = int(np.ceil(expected_size / sample.shape[0]))
+        raw_splits.append(sample.repeat((multiply_up,))[:expected_size])
+    else:
+        start = 0
+        while start < sample.shape[0]:
+            to_end = sample.shape[0] - start
+            if to_end >= expected_size:
+                raw_splits.append(sample[start:start + expected_size])
+                start += expected_size
+            else:
+                multiply_up = int(np.ceil(expected_size / to_end))
+                raw_splits.append(sample.repeat((multiply_up,))[:expected_size])
+                start = sample.shape[0]
+    return raw_splits
+
+
+def mel_spec_function_gpu(x, mel_transform):
+    """Log-mel spectrogram in dB of a waveform batch (datasets/batch_creation.py:215-218)."""
+    mel_spec = mel_transform(x)
+    return 20.0 / 2 * torch.log10(mel_spec + torch.finfo(mel_spec.dtype).eps)
+
+
+def _sample_wav_episode(dataset, n_classes, k_support, k_query, is_test, device, feat_extractor, augment_query):
+    """``input_type == 'wav'`` branch of sample_episode (datasets/batch_creation.py:77-101,138-143)."""
+    if dataset.waveaug_use == True:                                         # noqa: E712
+        raise NotImplementedError("waveform augmentation needs torch_audiomentations, which is outside this build")
+    multi_segm = dataset.multi_segm
+    support_set, support_labels, query_set, query_labels, audio_ids = [], [], [], [], []
+    query_counter = 0
+    for new_label, s_idx, q_idx in _episode_classes(dataset, n_classes, k_support, k_query):
+        for idx in s_idx:
+            wav, _ = dataset[idx]
+            if multi_segm == True:                                          # noqa: E712
+                pieces = variable_wav_splits(wav)
+                picked = torch.from_numpy(pieces[random.randint(0, len(pieces) - 1)]).reshape(1, -1)
+            else:
+                picked = torch.from_numpy(wav).reshape(1, -1)
+            support_set.append(picked)
+            support_labels.append(new_label)
+        for idx in q_idx:
+            wav, _ = dataset[idx]
+            if multi_segm == True:                                          # noqa: E712
+                pieces = variable_wav_splits(wav)
+                if is_test == False:                                        # noqa: E712
+                    picked = torch.from_numpy(pieces[random.randint(0, len(pieces) - 1)].reshape(1, -1))
+                else:
+                    picked = torch.cat([torch.from_numpy(piece.reshape(1, -1)) for piece in pieces], dim=0)
+            else:
+                picked = torch.from_numpy(wav.reshape(1, -1))
+            query_set.append(picked)
+            query_labels.extend([new_label] * picked.shape[0])
+            audio_ids.extend([query_counter] * picked.shape[0])
+            query_counter += 1
+    mean, std = dataset.get_normalization_stats()
+    stacked = torch.cat(support_set + query_set, dim=0).to(device)
+    spectrograms = ((mel_spec_function_gpu(stacked, mel_transform=feat_extractor) - mean) / std).unsqueeze(1)
+    n_support = n_classes * k_support
+    return ([spectrograms[:n_support]], torch.tensor(support_labels), [spectrograms[n_support:]], torch.tensor(query_labels),
+            torch.tensor(audio_ids))
+
+
 def sample_episode(dataset, n_classes, k_support, k_query, is_test, device, feat_extractor, augment_query):
     """One episode: (support view list, support labels, query view list, query labels, audio ids)."""
-    if dataset.input_type != "spec":
-        raise NotImplementedError("input_type 'wav' (GPU MelSpectrogram front end) is outside this build's scope")
+    if dataset.input_type == "wav":
+        return _sample_wav_episode(dataset, n_classes, k_support, k_query, is_test, device, feat_extractor, augment_query)
     support_set, support_labels, query_set, query_labels, audio_ids = [], [], [], [], []
     query_counter = 0
     for new_label, s_idx, q_idx in _episode_classes(dataset, n_classes, k_support, k_query):

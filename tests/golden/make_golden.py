@@ -424,9 +424,48 @@ def gen_sampler():
     save("sampler_multiseg", dataset_seed=11, **out)
 
 
+class FakeWavDataset:
+    """16 kHz waveforms of 1.5 .. 12 s as numpy arrays (input_type 'wav', multi-segment)."""
+
+    def __init__(self, cfg, classes=6, per_class=8, seed=0):
+        import pandas as pd
+        rng = np.random.RandomState(seed)
+        n = classes * per_class
+        lengths = rng.randint(24000, 192000, size=n)
+        self.wavs = [(rng.randn(int(length)) * 0.1).astype(np.float32) for length in lengths]
+        names = [f"c{i}" for i in range(classes)]
+        self.class_to_label = {nm: i for i, nm in enumerate(names)}
+        self.data_df = pd.DataFrame({"label": [names[i // per_class] for i in range(n)], "index_column": list(range(n))})
+        self.multi_segm, self.input_type, self.specaug_use, self.waveaug_use = True, "wav", False, False
+        self.experiment_config = cfg
+
+    def __getitem__(self, i):
+        return self.wavs[i], 0
+
+    def get_normalization_stats(self):
+        return -21.5, 13.25
+
+
+def gen_sampler_wav():
+    """The reference's sample_episode on waveform input: 5-second splits, MelSpectrogram, dB, global normalisation."""
+    import torchaudio
+    from datasets.batch_creation import sample_episode
+    ds = FakeWavDataset({"specaug_params": {"use": False}}, seed=3)
+    mel = torchaudio.transforms.MelSpectrogram(sample_rate=16000, n_mels=128, n_fft=1024, hop_length=512, power=2.0)
+    out = {}
+    for name, is_test, seed in (("train", False, 31), ("test", True, 32)):
+        random.seed(seed)
+        s_list, s_lab, q_list, q_lab, ids = sample_episode(ds, 4, 2, 3, is_test, "cpu", mel, False)
+        fp = lambda x: x[:, 0, ::16, ::20].reshape(x.shape[0], -1).clone()
+        out.update({f"{name}_support": fp(s_list[0]), f"{name}_support_labels": s_lab, f"{name}_query": fp(q_list[0]),
+                    f"{name}_query_labels": q_lab, f"{name}_audio_ids": ids, f"{name}_seed": seed,
+                    f"{name}_shape": np.array(q_list[0].shape)})
+    save("sampler_wav", dataset_seed=3, **out)
+
+
 if __name__ == "__main__":
     import_reference()
     torch.set_num_threads(1)            # fixed reduction order for the fixtures
-    which = sys.argv[1:] or ["head", "cpl", "specaug", "vote", "modules", "epoch", "epoch_first", "sampler"]
+    which = sys.argv[1:] or ["head", "cpl", "specaug", "vote", "modules", "epoch", "epoch_first", "sampler", "sampler_wav"]
     for name in which:
         globals()["gen_" + name]()

@@ -259,3 +259,53 @@ def test_early_stopping_protocol(tmp_path):
         stop(acc, model, epoch)
     assert stop.early_stop and stop.counter == 3 and stop.best_score == 0.6
     assert (tmp_path / "model.pt").exists() and any("EarlyStopping counter: 2 out of 3" in m for m in msgs)
+
+
+class _FakeWavDataset:
+    """Same construction as tests/golden/make_golden.py::FakeWavDataset (16 kHz waveforms of 1.5 .. 12 s)."""
+
+    def __init__(self, seed, classes=6, per_class=8):
+        import pandas as pd
+        rng = np.random.RandomState(seed)
+        n = classes * per_class
+        lengths = rng.randint(24000, 192000, size=n)
+        self.wavs = [(rng.randn(int(length)) * 0.1).astype(np.float32) for length in lengths]
+        names = [f"c{i}" for i in range(classes)]
+        self.class_to_label = {nm: i for i, nm in enumerate(names)}
+        self.data_df = pd.DataFrame({"label": [names[i // per_class] for i in range(n)], "index_column": list(range(n))})
+        self.multi_segm, self.input_type, self.specaug_use, self.waveaug_use = True, "wav", False, False
+        self.experiment_config = {"specaug_params": {"use": False}}
+
+    def __getitem__(self, i):
+        return self.wavs[i], 0
+
+    def get_normalization_stats(self):
+        return -21.5, 13.25
+
+
+def test_sample_episode_waveform_input_matches_reference():
+    """input_type 'wav': 5-second splits, the caller's MelSpectrogram, 10*log10, global normalisation - the episode
+    tensors, labels and audio ids of the reference's sample_episode on the same fake dataset and seeds."""
+    import random
+    torchaudio = pytest.importorskip("torchaudio")
+    from conftest import load_golden
+    from afsl_b200.datasets.batch_creation import sample_episode, variable_wav_splits
+    g = load_golden("sampler_wav")
+    ds = _FakeWavDataset(int(g["dataset_seed"]))
+    mel = torchaudio.transforms.MelSpectrogram(sample_rate=16000, n_mels=128, n_fft=1024, hop_length=512, power=2.0)
+    fp = lambda x: x[:, 0, ::16, ::20].reshape(x.shape[0], -1)
+    for name, is_test in (("train", False), ("test", True)):
+        random.seed(int(g[f"{name}_seed"]))
+        s_list, s_lab, q_list, q_lab, ids = sample_episode(ds, 4, 2, 3, is_test, "cpu", mel, False)
+        assert list(q_list[0].shape) == g[f"{name}_shape"].tolist()
+        torch.testing.assert_close(fp(s_list[0]), torch.from_numpy(g[f"{name}_support"]), rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(fp(q_list[0]), torch.from_numpy(g[f"{name}_query"]), rtol=1e-5, atol=1e-5)
+        assert torch.equal(s_lab, torch.from_numpy(g[f"{name}_support_labels"]))
+        assert torch.equal(q_lab, torch.from_numpy(g[f"{name}_query_labels"]))
+        assert torch.equal(ids, torch.from_numpy(g[f"{name}_audio_ids"]))
+    # splits: short clips are tiled to 5 s, long clips are cut and the remainder piece is tiled
+    assert [p.shape[0] for p in variable_wav_splits(np.ones(30000, np.float32))] == [80000]
+    assert [p.shape[0] for p in variable_wav_splits(np.ones(170000, np.float32))] == [80000, 80000, 80000]
+    ds.waveaug_use = True
+    with pytest.raises(NotImplementedError):
+        sample_episode(ds, 4, 2, 3, False, "cpu", mel, False)
