@@ -298,7 +298,10 @@ AngParams make(const float* protos, const float* queries, const int32_t* labels,
                int anchors, int normalize_ref, int E, int Nq, int W, int D) {
   AngParams p{};
   p.protos = protos; p.queries = queries; p.labels = labels;
-  p.miner_angle = (float)((double)miner_angle_deg * 3.14159265358979323846 / 180.0);
+  const double ang = (double)miner_angle_deg * 3.14159265358979323846 / 180.0;
+  p.miner_angle = (float)ang;
+  p.miner_never = ang >= 1.5707963267948966 ? 1 : 0;
+  p.miner_tan = ang <= -1.5707963267948966 ? -INFINITY : (float)tan(ang);
   const double t = tan((double)alpha_deg * 3.14159265358979323846 / 180.0);
   p.t2 = (float)(t * t);
   p.anchors = anchors; p.normalize_ref = normalize_ref;

@@ -11,6 +11,8 @@ struct AngParams {
   const float* queries;   // [E,Nq,D]
   const int32_t* labels;  // [E,Nq]
   float miner_angle;      // radians
+  float miner_tan;        // tan(miner_angle): atan(r) > angle  <=>  r > tan(angle) for angle in (-pi/2, pi/2)
+  int miner_never;        // angle >= pi/2: atan never exceeds it, nothing is mined
   float t2;               // tan^2(alpha)
   int anchors, normalize_ref;
   float* loss;            // [E]

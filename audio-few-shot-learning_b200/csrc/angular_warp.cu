@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(kCtaThreads) angular_warp_kernel(const AngPara
       const float dot = (ra * gram[k * kLg + a] + rq * gram[k * kLg + q]) * inv;
       const float nc2 = gkk + cc - 2.f * dot + 2.f * kPairEps * (csk - csum_c) + deps;
       const float nc = sqrtf(fmaxf(nc2, 0.f));
-      const bool pass = act && ((negmask >> k) & 1u) && atanf(ap / (2.f * nc)) > p.miner_angle;
+      // atan(ap / (2 nc)) > angle without the arctangent and the division: ap > 2 nc tan(angle)
+      const bool pass = act && ((negmask >> k) & 1u) && !p.miner_never && ap > 2.f * nc * p.miner_tan;
       count += pass;
       const unsigned b = __ballot_sync(kFull, pass);
       if (lane == k) wneg += __popc(b);

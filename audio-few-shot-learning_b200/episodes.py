@@ -312,6 +312,51 @@ class EpisodeRunner:
         raise ValueError("use_contrastive is set but neither loss.cpl.use nor loss.angular.use")
 
     # ------------------------------------------------------------------ evaluation
+    def _eval_compute(self, batch: EpisodeBatch, rnd: Dict[str, object]):
+        """Device part of a single-segment evaluation step -> (#correct per task [E] int32, queries per task)."""
+        model = self.model
+        s_views = self._views(batch.support, rnd["sup"])
+        q_views = self._views(batch.query, rnd["qry"])
+        sl, ql = batch.support_labels, batch.query_labels
+        if self.concat_views:
+            sl, ql = sl.repeat(1, len(s_views)), ql.repeat(1, len(q_views))
+        support_features = model.compute_features(s_views)
+        feats = model(q_views)
+        _, _, correct, _ = ops.proto_eval(support_features, sl, feats, ql, n_way=batch.n_way)
+        return correct, ql.shape[1]
+
+    def _eval_graph_step(self, batch: EpisodeBatch, rnd: Dict[str, object], device):
+        """Single-segment evaluation replayed from a CUDA graph (one capture per batch shape), like _graph_step."""
+        key = ("eval", tuple(batch.support.shape), tuple(batch.query.shape), batch.n_way,
+               tuple(sorted(k for k, v in rnd.items() if v is not None)))
+        state = self._graphs.get(key)
+        if state is None:
+            s_batch = EpisodeBatch(*(torch.empty_like(t, device=device) for t in (batch.support, batch.support_labels,
+                                                                                   batch.query, batch.query_labels)), batch.n_way)
+            for dst, src in ((s_batch.support, batch.support), (s_batch.support_labels, batch.support_labels),
+                             (s_batch.query, batch.query), (s_batch.query_labels, batch.query_labels)):
+                dst.copy_(src)
+            s_rnd = self._rnd_to(rnd, device)
+            side = torch.cuda.Stream(device=device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._eval_compute(s_batch, s_rnd)
+            torch.cuda.current_stream(device).wait_stream(side)
+            torch.cuda.synchronize(device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                s_out = self._eval_compute(s_batch, s_rnd)
+            state = (s_batch, s_rnd, graph, s_out)
+            self._graphs[key] = state
+        s_batch, s_rnd, graph, s_out = state
+        for dst, src in ((s_batch.support, batch.support), (s_batch.support_labels, batch.support_labels),
+                         (s_batch.query, batch.query), (s_batch.query_labels, batch.query_labels)):
+            dst.copy_(src, non_blocking=True)
+        self._copy_rnd(s_rnd, rnd)
+        graph.replay()
+        return s_out
+
     @torch.no_grad()
     def eval_step(self, batch: EpisodeBatch, augment_query: bool = False, clip_ids: Optional[torch.Tensor] = None,
                   seg_offsets: Optional[torch.Tensor] = None, tie_strategy: str = "") -> np.ndarray:
@@ -321,20 +366,23 @@ class EpisodeRunner:
         [1,rows,...] packed over tasks, with ``seg_offsets`` [E+1] and ``clip_ids`` [rows]."""
         model = self.model
         model.eval()
-        batch = batch.to(next(model.parameters()).device)
+        device = next(model.parameters()).device
         model.n_way = batch.n_way
         t_len = batch.support.shape[-1]
+        if seg_offsets is None:
+            rnd = {"sup": self._draw_views(*batch.support.shape[:2], t_len, True),
+                   "qry": self._draw_views(*batch.query.shape[:2], t_len, augment_query)}
+            if self.use_cuda_graph and not self.replay:
+                correct, per_task = self._eval_graph_step(batch, rnd, device)
+            else:
+                correct, per_task = self._eval_compute(batch.to(device), self._rnd_to(rnd, device))
+            return correct.cpu().numpy().astype(np.float64) / per_task
+        batch = batch.to(device)
         s_views = self._views(batch.support, self._draw_views(*batch.support.shape[:2], t_len, True))
         sl = batch.support_labels
         if self.concat_views:
             sl = sl.repeat(1, len(s_views))
         support_features = model.compute_features(s_views)
-        if seg_offsets is None:
-            q_views = self._views(batch.query, self._draw_views(*batch.query.shape[:2], t_len, augment_query))
-            ql = batch.query_labels.repeat(1, len(q_views)) if self.concat_views else batch.query_labels
-            feats = model(q_views)
-            _, _, correct, _ = ops.proto_eval(support_features, sl, feats, ql, n_way=batch.n_way)
-            return correct.cpu().numpy().astype(np.float64) / ql.shape[1]
         # one SpecAugment draw per task, shared by all its query segments (batch_creation.py:113-115)
         counts = (seg_offsets[1:] - seg_offsets[:-1]).tolist()
         q_params = (self.specaug.draw_ragged(counts, t_len, replay_reference_rng=self.replay)

@@ -808,3 +808,19 @@ def test_prototypical_networks_vs_torch(ops, use_softmax, norm):
     assert not model.is_transductive()
     with pytest.raises(ValueError, match="Illegal backbone or feature shape"):
         model._raise_error_if_features_are_multi_dimensional(torch.zeros(2, 3, 4, 5))
+
+
+def test_runner_eval_cuda_graph_matches_eager(ops):
+    """Single-segment eval_step replayed from a CUDA graph returns the eager step's per-task accuracies."""
+    import random
+    import bench
+    from afsl_b200.episodes import EpisodeRunner, synthetic_batch
+    dev = torch.device("cuda", 0)
+    model = bench.build_model(dev)
+    accs = []
+    for graph in (False, True):
+        runner = EpisodeRunner(model, bench.EXPERIMENT_CONFIG, None, replay_reference_rng=False, use_cuda_graph=graph)
+        torch.manual_seed(5); np.random.seed(5); random.seed(5)
+        accs.append(np.concatenate([runner.eval_step(synthetic_batch(6, 5, 5, 5, 157, seed=40 + i), augment_query=True)
+                                    for i in range(3)]))
+    assert accs[0].shape == (18,) and np.array_equal(accs[0], accs[1])
