@@ -824,3 +824,37 @@ def test_runner_eval_cuda_graph_matches_eager(ops):
         accs.append(np.concatenate([runner.eval_step(synthetic_batch(6, 5, 5, 5, 157, seed=40 + i), augment_query=True)
                                     for i in range(3)]))
     assert accs[0].shape == (18,) and np.array_equal(accs[0], accs[1])
+
+
+@pytest.mark.parametrize("path", ["warp", "cta"])
+def test_head_edge_cases(ops, monkeypatch, path):
+    """One episode, one query per class, a class without support rows (NaN prototype, as the reference's empty mean),
+    and a single query row: same outputs as the oracle, NaNs included."""
+    monkeypatch.setenv("AFSL_HEAD_WARP", "1" if path == "warp" else "0")
+    gen = torch.Generator().manual_seed(8)
+    ways, dim = 5, 256
+    # (a) a class with no support rows -> its prototype is NaN, every score against it is NaN
+    s = torch.randn(1, 8, dim, generator=gen)
+    sl = torch.tensor([[0, 1, 1, 2, 4, 4, 0, 2]])                 # class 3 is empty
+    q = torch.randn(1, 6, dim, generator=gen)
+    ql = torch.tensor([[0, 1, 2, 3, 4, 0]])
+    protos = ops.prototypes(s.cuda(), sl.cuda(), n_way=ways)[0].cpu()
+    ref = torch.stack([s[0][sl[0] == w].mean(0) for w in range(ways)])
+    assert torch.isnan(protos[3]).all() and torch.isnan(ref[3]).all()
+    torch.testing.assert_close(protos, ref, rtol=1e-6, atol=1e-6, equal_nan=True)
+    loss, _, _ = ops.proto_head(s.cuda(), sl.cuda(), q.cuda(), ql.cuda(), n_way=ways)
+    assert torch.isnan(loss).all() and torch.isnan(ohead.fsl_loss(ref, q[0], ql[0]))
+    # (b) a single query row, single episode, 1-shot
+    s1 = torch.randn(1, ways, dim, generator=gen)
+    q1 = torch.randn(1, 1, dim, generator=gen)
+    sl1, ql1 = torch.arange(ways).view(1, -1), torch.tensor([[2]])
+    sg, qg = s1.cuda().requires_grad_(True), q1.cuda().requires_grad_(True)
+    loss1, protos1, correct1 = ops.proto_head(sg, sl1.cuda(), qg, ql1.cuda(), n_way=ways)
+    loss1.sum().backward()
+    sc, qc = s1[0].clone().requires_grad_(True), q1[0].clone().requires_grad_(True)
+    lo = ohead.fsl_loss(ohead.prototypes(sc, sl1[0]), qc, ql1[0])
+    lo.backward()
+    close(loss1[0], lo)
+    close(sg.grad[0], sc.grad)
+    close(qg.grad[0], qc.grad)
+    assert int(correct1[0]) == ohead.evaluate_task(ohead.l2_scores(qc, ohead.prototypes(sc, sl1[0])), ql1[0])[0]
