@@ -8,14 +8,14 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_void_p
 
 import torch
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libafsl.so")
 
-_P, _I, _F = c_void_p, c_int, c_float
+_P, _I, _F, _D = c_void_p, c_int, c_float, c_double
 
 # name -> argument ctypes, mirroring include/afsl.h exactly
 SIGNATURES = {
@@ -44,6 +44,9 @@ SIGNATURES = {
     "afsl_gbn_stats_nhwc_f32": [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "afsl_gbn_relu_pool_nhwc_fwd_f32": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "afsl_gbn_relu_pool_nhwc_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P],
+    "afsl_bn_running_update_f32": [_P, _P, _P, _P, _P, _P, _F, _F, _I, _I, _P],
+    "afsl_stage1_finalize_f64": [_P, _I, _P, _P, _P, _F, _D, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "afsl_stage1_dw_f32": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _D, _I, _P, _P, _P, _P, _P],
     "afsl_eval_vote_i32": [_P, _P, _P, _P, _P, _I, _P, _P, _I, _P],
 }
 

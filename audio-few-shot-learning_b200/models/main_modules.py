@@ -83,6 +83,9 @@ class GroupedBatchNorm1d(nn.BatchNorm1d):
 
 def _update_running(bn, mean: torch.Tensor, var_biased: torch.Tensor, count: int) -> None:
     """Apply ``g`` sequential momentum updates in one shot (groups in batch order)."""
+    if mean.is_cuda:
+        ops.bn_running_update(bn, mean, var_biased, float(count))
+        return
     g = mean.shape[0]
     m = bn.momentum
     bn.num_batches_tracked += g

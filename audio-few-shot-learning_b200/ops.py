@@ -549,38 +549,33 @@ def gbn_relu_pool(u: torch.Tensor, bn: torch.nn.BatchNorm2d, group_size: Optiona
             call("afsl_gbn_stats_f32", ptr(u), ptr(mean), ptr(rstd), ptr(var), groups, group, c, h, w, float(bn.eps),
                  stream_ptr())
         if bn.training and bn.track_running_stats:
-            with torch.no_grad():
-                count = group * h * w
-                m = bn.momentum
-                bn.num_batches_tracked += groups
-                decay = (1.0 - m) ** torch.arange(groups - 1, -1, -1, device=u.device, dtype=torch.float32)
-                keep = (1.0 - m) ** groups
-                true_mean = mean if conv_bias is None else mean + conv_bias
-                bn.running_mean.mul_(keep).add_((decay.unsqueeze(1) * true_mean).sum(0), alpha=m)
-                bn.running_var.mul_(keep).add_((decay.unsqueeze(1) * var).sum(0), alpha=m * count / max(count - 1, 1))
+            bn_running_update(bn, mean, var, float(group * h * w), shift=conv_bias)
         return _GbnReluPool.apply(u, gamma, beta, conv_bias, mean, rstd, groups, group, True)
     mean = _f32(bn.running_mean) if conv_bias is None else _f32(bn.running_mean - conv_bias)
     rstd = torch.rsqrt(bn.running_var.float() + bn.eps)
     return _GbnReluPool.apply(u, gamma, beta, conv_bias, mean, rstd, 1, n, False)
 
 
+# ---------------------------------------------------------------------------------- BatchNorm running statistics
+@torch.no_grad()
+def bn_running_update(bn, mean: torch.Tensor, var_biased: torch.Tensor, count: float, shift: Optional[torch.Tensor] = None) -> None:
+    """The momentum updates that one module call per group would make, in group order (one launch).
+    ``mean`` / ``var_biased`` [G,C] batch statistics, ``count`` elements per (group, channel), ``shift`` [C] an optional
+    convolution bias that was folded out of ``mean``."""
+    if bn.momentum is None:
+        raise NotImplementedError("momentum=None (cumulative average) is not used by the reference encoders")
+    groups, c = mean.shape
+    sh = _f32(shift.detach()) if shift is not None else None
+    call("afsl_bn_running_update_f32", ptr(_f32(mean)), ptr(_f32(var_biased)), ptr(sh), ptr(bn.running_mean), ptr(bn.running_var),
+         ptr(bn.num_batches_tracked), float(bn.momentum), float(count / max(count - 1, 1)), groups, c, stream_ptr())
+
+
 # ---------------------------------------------------------------------------------- fused encoder stage 1
-_TRIU9 = None
 # stage 1 writes its pooled output channels-last, which keeps stages 2-4 (cuDNN's NHWC-native sm_100 convolutions +
 # the channels-last BatchNorm/ReLU/pool kernels) free of layout-conversion kernels; False = NCHW everywhere (A/B switch)
 STAGE1_CHANNELS_LAST = True
 
 
-def _moments_to_sr(moments: torch.Tensor):
-    """[G,54] double -> S [G,9], R [G,9,9] (symmetric)."""
-    global _TRIU9
-    if _TRIU9 is None or _TRIU9.device != moments.device:
-        _TRIU9 = torch.triu_indices(9, 9, device=moments.device)
-    g = moments.shape[0]
-    r = torch.zeros(g, 9, 9, device=moments.device, dtype=torch.float64)
-    r[:, _TRIU9[0], _TRIU9[1]] = moments[:, 9:]
-    r = r + r.transpose(1, 2) - torch.diag_embed(torch.diagonal(r, dim1=1, dim2=2))
-    return moments[:, :9], r
 
 
 class _Stage1(torch.autograd.Function):
@@ -625,21 +620,15 @@ class _Stage1(torch.autograd.Function):
         partial = torch.empty(groups, parts, c, 11, device=x.device, dtype=torch.float32)
         call("afsl_stage1_bwd_f32", ptr(x), ptr(w9), ptr(a), ptr(b), ptr(mean_u), ptr(rstd), ptr(d_y, nhwc), ptr(arg, nhwc),
              ptr(partial), parts, groups, group, h, w, per_group, int(nhwc), stream_ptr())
-        acc = partial.double().sum(1)                                   # [G,C,11]
-        s1, s2, t = acc[..., 0], acc[..., 1], acc[..., 2:]               # [G,C], [G,C], [G,C,9]
-        a_gc = (a if per_group else a.unsqueeze(0).expand(groups, c)).double()
-        if per_group:
-            m = float(group * h * w)
-            m1, m2 = s1 / m, s2 / m
-            wr = torch.einsum("cl,glk->gck", w9.double(), r_mom)          # sum_l w_cl R_glk
-            corr = rstd.double().unsqueeze(-1) * (wr - mean_u.double().unsqueeze(-1) * s_mom.unsqueeze(1))
-            d_w = (a_gc.unsqueeze(-1) * (t - m1.unsqueeze(-1) * s_mom.unsqueeze(1) - m2.unsqueeze(-1) * corr)).sum(0)
-            d_bias = torch.zeros(c, device=x.device) if has_bias else None     # exactly zero under batch statistics
-        else:
-            d_w = (a_gc.unsqueeze(-1) * t).sum(0)
-            d_bias = (a_gc * s1).sum(0).float() if has_bias else None
-        d_gamma, d_beta = s2.sum(0).float(), s1.sum(0).float()
-        return (None, d_w.float().view(c, 1, 3, 3), d_bias, d_gamma, d_beta) + (None,) * 9
+        # dW_c[k] = sum_g a_gc [ T_gck - m1 S_gk - m2 rstd (sum_l w_cl R_glk - mean S_gk) ], d_gamma = sum s2, d_beta = sum s1
+        # (one glue kernel; d_bias is exactly zero under batch statistics, gamma*rstd*sum(dz) under running ones)
+        d_w = torch.empty(c, 9, device=x.device, dtype=torch.float32)
+        d_gamma, d_beta = torch.empty(c, device=x.device), torch.empty(c, device=x.device)
+        d_bias = torch.empty(c, device=x.device) if has_bias else None
+        call("afsl_stage1_dw_f32", ptr(partial), parts, groups, ptr(s_mom) if per_group else None, ptr(r_mom) if per_group else None,
+             ptr(w9), ptr(a), ptr(mean_u), ptr(rstd), float(group * h * w), per_group, ptr(d_w), ptr(d_gamma), ptr(d_beta),
+             ptr(d_bias), stream_ptr())
+        return (None, d_w.view(c, 1, 3, 3), d_bias, d_gamma, d_beta) + (None,) * 9
 
 
 def stage1_supported(conv: torch.nn.Conv2d, x: torch.Tensor) -> bool:
@@ -657,7 +646,6 @@ def stage1_conv_bn_relu_pool(x: torch.Tensor, conv: torch.nn.Conv2d, bn: torch.n
     c = conv.out_channels
     gamma, beta = _f32(bn.weight), _f32(bn.bias)
     bias = conv.bias
-    w9d = conv.weight.detach().reshape(c, 9).double()
     use_batch_stats = bn.training or not bn.track_running_stats
     if use_batch_stats:
         group = int(group_size) if group_size else n
@@ -668,25 +656,17 @@ def stage1_conv_bn_relu_pool(x: torch.Tensor, conv: torch.nn.Conv2d, bn: torch.n
         parts = max(1, (4 * sms + groups - 1) // groups)
         mom = torch.empty(groups, parts, 54, device=x.device, dtype=torch.float64)
         call("afsl_stage1_moments_f64", ptr(x), ptr(mom), parts, groups, group, h, w, stream_ptr())
-        s_mom, r_mom = _moments_to_sr(mom.sum(1))
+        # mean_c = w_c.S / m, E[u_c^2] = w_c^T R w_c / m -> mean, variance, rstd and the folded affine, one glue kernel
         m = float(group * h * w)
-        mean_u = (s_mom @ w9d.t()) / m                                          # [G,C]
-        eu2 = torch.einsum("ck,gkl,cl->gc", w9d, r_mom, w9d) / m
-        var = (eu2 - mean_u * mean_u).clamp_min(0.0)
-        rstd = torch.rsqrt(var + bn.eps)
-        a = (gamma.double() * rstd)
-        b = beta.double() - mean_u * a
+        w9 = conv.weight.detach().reshape(c, 9).float().contiguous()
+        s_mom = torch.empty(groups, 9, device=x.device, dtype=torch.float64)
+        r_mom = torch.empty(groups, 9, 9, device=x.device, dtype=torch.float64)
+        mean_u, var, rstd, a, b = (torch.empty(groups, c, device=x.device, dtype=torch.float32) for _ in range(5))
+        call("afsl_stage1_finalize_f64", ptr(mom), parts, ptr(w9), ptr(gamma), ptr(beta), float(bn.eps), m, ptr(s_mom),
+             ptr(r_mom), ptr(mean_u), ptr(var), ptr(rstd), ptr(a), ptr(b), groups, stream_ptr())
         if bn.training and bn.track_running_stats:
-            with torch.no_grad():
-                mo = bn.momentum
-                bn.num_batches_tracked += groups
-                decay = (1.0 - mo) ** torch.arange(groups - 1, -1, -1, device=x.device, dtype=torch.float64)
-                keep = (1.0 - mo) ** groups
-                true_mean = mean_u if bias is None else mean_u + bias.detach().double()
-                bn.running_mean.mul_(keep).add_(((decay.unsqueeze(1) * true_mean).sum(0) * mo).float())
-                bn.running_var.mul_(keep).add_(((decay.unsqueeze(1) * var).sum(0) * (mo * m / max(m - 1, 1))).float())
-        return _Stage1.apply(x, conv.weight, bias, gamma, beta, a.float().contiguous(), b.float().contiguous(),
-                             mean_u.float().contiguous(), rstd.float().contiguous(), s_mom, r_mom, groups, group, True)
+            bn_running_update(bn, mean_u, var, m, shift=bias)
+        return _Stage1.apply(x, conv.weight, bias, gamma, beta, a, b, mean_u, rstd, s_mom, r_mom, groups, group, True)
     rstd = torch.rsqrt(bn.running_var.double() + bn.eps)
     mean_u = bn.running_mean.double() - (bias.detach().double() if bias is not None else 0.0)
     a = gamma.double() * rstd

@@ -279,6 +279,28 @@ int afsl_gbn_relu_pool_nhwc_bwd_f32(const float* x, const float* mean, const flo
                                     float* sums, int G, int group, int C, int H, int W, int stats_per_group,
                                     void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Glue kernels around the encoder stages (each replaces a chain of tiny eager ops).
+ * bn_running_update: the G momentum updates of BatchNorm's running statistics that G
+ *   separate module calls would make, in group order: running_mean <- (1-m) rm + m (mean_g + shift),
+ *   running_var <- (1-m) rv + m var_g * unbias; mean, var_biased [G,C]; shift [C] [opt] (a
+ *   convolution bias folded out of the statistics); num_batches_tracked [opt] += G.
+ * stage1_finalize: moments [G,parts,54] (afsl_stage1_moments_f64) -> S [G,9], R [G,9,9] (double)
+ *   and per (group, conv-1 channel) mean_u, var (biased), rstd, a = gamma*rstd, b = beta - mean_u*a.
+ * stage1_dw: partial [G,parts,64,11] (afsl_stage1_bwd_f32) + S, R -> d_w [64,9], d_gamma, d_beta [64]
+ *   and d_bias [64] [opt] (zero under batch statistics).
+ * ------------------------------------------------------------------------- */
+int afsl_bn_running_update_f32(const float* mean, const float* var_biased, const float* shift,
+                               float* running_mean, float* running_var, long long* num_batches_tracked,
+                               float momentum, float unbias, int G, int C, void* stream);
+int afsl_stage1_finalize_f64(const double* moments, int parts, const float* weight, const float* gamma,
+                             const float* beta, float eps, double count, double* S, double* R, float* mean_u,
+                             float* var, float* rstd, float* a, float* b, int G, void* stream);
+int afsl_stage1_dw_f32(const float* partial, int parts, int G, const double* S, const double* R,
+                       const float* weight, const float* a, const float* mean_u, const float* rstd,
+                       double count, int per_group, float* d_w, float* d_gamma, float* d_beta, float* d_bias,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

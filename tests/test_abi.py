@@ -51,7 +51,9 @@ def test_ctypes_table_matches_header(lib):
         for ct, text in zip(argtypes, args):
             if "*" in text:
                 assert ct is ctypes.c_void_p, (name, text)
-            elif text.startswith("float") or text.startswith("double"):
+            elif text.startswith("double"):
+                assert ct is ctypes.c_double, (name, text)
+            elif text.startswith("float"):
                 assert ct is ctypes.c_float, (name, text)
             else:
                 assert ct is ctypes.c_int, (name, text)
