@@ -85,16 +85,20 @@ __global__ void stage1_finalize_kernel(const double* __restrict__ moments, int p
   }
 }
 
-// grid = 64 channels, block = 32: partial [G, parts, 64, 11] -> d_w [64,9], d_gamma [64], d_beta [64] (+ d_bias when the
-// statistics are running ones).  per_group: batch statistics (a, mean_u, rstd are [G,64]); else eval ([64]).
-__global__ void stage1_dw_kernel(const float* __restrict__ partial, int parts, int G, const double* __restrict__ S,
-                                 const double* __restrict__ R, const float* __restrict__ w9, const float* __restrict__ a,
-                                 const float* __restrict__ mean_u, const float* __restrict__ rstd, double m, int per_group,
-                                 float* d_w, float* d_gamma, float* d_beta, float* d_bias) {
-  const int c = blockIdx.x, k = threadIdx.x;     // k < 9: tap; k == 9: gamma; k == 10: beta / bias
-  if (k > 10) return;
+// grid = 64 channels, block = (11, 32): partial [G, parts, 64, 11] -> d_w [64,9], d_gamma [64], d_beta [64] (+ d_bias when
+// the statistics are running ones).  threadIdx.x = k (k < 9: tap; 9: gamma; 10: beta / bias), threadIdx.y = slice of the
+// groups (g = slice, slice + 32, ...); the 32 slice sums are added in slice order (deterministic).
+// per_group: batch statistics (a, mean_u, rstd are [G,64]); else eval ([64]).
+constexpr int kDwSlices = 32;
+
+__global__ void __launch_bounds__(11 * kDwSlices) stage1_dw_kernel(
+    const float* __restrict__ partial, int parts, int G, const double* __restrict__ S, const double* __restrict__ R,
+    const float* __restrict__ w9, const float* __restrict__ a, const float* __restrict__ mean_u,
+    const float* __restrict__ rstd, double m, int per_group, float* d_w, float* d_gamma, float* d_beta, float* d_bias) {
+  __shared__ double red[kDwSlices][11], red_bias[kDwSlices];
+  const int c = blockIdx.x, k = threadIdx.x, slice = threadIdx.y;
   double acc = 0.0, acc_bias = 0.0;
-  for (int g = 0; g < G; ++g) {
+  for (int g = slice; g < G; g += kDwSlices) {
     double s1 = 0.0, s2 = 0.0, t = 0.0;
     for (int p = 0; p < parts; ++p) {
       const float* src = partial + (((size_t)g * parts + p) * kC1 + c) * 11;
@@ -123,11 +127,18 @@ __global__ void stage1_dw_kernel(const float* __restrict__ partial, int parts, i
       acc_bias += ag * s1;
     }
   }
-  if (k < 9) d_w[c * 9 + k] = (float)acc;
-  else if (k == 9) d_gamma[c] = (float)acc;
+  red[slice][k] = acc;
+  if (k == 10) red_bias[slice] = acc_bias;
+  __syncthreads();
+  if (slice != 0) return;
+  double tot = 0.0, tot_bias = 0.0;
+  for (int q = 0; q < kDwSlices; ++q) tot += red[q][k];
+  if (k < 9) d_w[c * 9 + k] = (float)tot;
+  else if (k == 9) d_gamma[c] = (float)tot;
   else {
-    d_beta[c] = (float)acc;
-    if (d_bias) d_bias[c] = per_group ? 0.f : (float)acc_bias;   // batch statistics remove any per-channel constant
+    for (int q = 0; q < kDwSlices; ++q) tot_bias += red_bias[q];
+    d_beta[c] = (float)tot;
+    if (d_bias) d_bias[c] = per_group ? 0.f : (float)tot_bias;   // batch statistics remove any per-channel constant
   }
 }
 
@@ -164,7 +175,7 @@ extern "C" int afsl_stage1_dw_f32(const float* partial, int parts, int G, const 
   using namespace afsl;
   AFSL_REQUIRE(partial && weight && a && d_w && d_gamma && d_beta && parts > 0 && G > 0, "afsl_stage1_dw_f32: null pointer / sizes");
   AFSL_REQUIRE(!per_group || (S && R && mean_u && rstd), "afsl_stage1_dw_f32: batch statistics need S, R, mean_u, rstd");
-  stage1_dw_kernel<<<kC1, 32, 0, (cudaStream_t)stream>>>(partial, parts, G, S, R, weight, a, mean_u, rstd, count, per_group, d_w,
+  stage1_dw_kernel<<<kC1, dim3(11, kDwSlices), 0, (cudaStream_t)stream>>>(partial, parts, G, S, R, weight, a, mean_u, rstd, count, per_group, d_w,
                                                         d_gamma, d_beta, d_bias);
   AFSL_CHECK_LAUNCH("afsl_stage1_dw_f32");
   return AFSL_OK;

@@ -252,6 +252,120 @@ __global__ void __launch_bounds__(kThreads) stage1_fwd_kernel(const S1Params p) 
   }
 }
 
+// ---------------------------------------------------------------- forward, channels-last: lane = channel pair
+// One warp per pooled pixel, lane l owns channels (2l, 2l+1): the pair's 9 taps, a and b are per-lane constants that
+// stay in registers for the whole kernel (18 + 4 registers instead of 36 weights + 25 patch values + 36 window
+// values per lane in the lane-per-pixel kernel above), the 5x5 input patch is read as warp-uniform shared-memory
+// broadcasts and enters FFMA2 as its scalar operand, and a pooled pixel is stored as one 256-byte row of y plus
+// 64 code bytes.  ~175 issued instructions per (pixel, 64 channels) against ~420 per (32 pixels, 4 channels) x ...
+// = 208 before, 85 registers -> 24 warps per SM (was 16), three independent CTAs per SM hide each other's staging.
+constexpr int kFwdThreads = 256;
+constexpr int kFwdWarps = kFwdThreads / kWarp;
+
+// 4-byte async copy global -> shared; `valid` = false writes a zero (padding) without touching global memory
+__device__ __forceinline__ void cp_async_f32_zfill(float* dst, const float* src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int n = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+
+__global__ void __launch_bounds__(kFwdThreads, 3) stage1_fwd_nhwc_kernel(const S1Params p) {
+  extern __shared__ __align__(16) float tiles[];         // two buffers of [(3*kBands+2) * (W+2)]
+  const int H = p.H, W = p.W, PH = p.PH, PW = p.PW, ld = W + 2, hw = H * W, phw = PH * PW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tiles_per_sample = (PH + kBands - 1) / kBands;
+  const int bands_per_tile = (PH + tiles_per_sample - 1) / tiles_per_sample;      // even split: 42 rows -> 6 x 7
+  const long long total_tiles = (long long)p.G * p.group * tiles_per_sample;
+  const int tile_floats = (3 * kBands + 2) * ld;
+  f32x2 w2[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) w2[k] = pack2(__ldg(p.w + (2 * lane) * 9 + k), __ldg(p.w + (2 * lane + 1) * 9 + k));
+  f32x2 a2 = 0ull, b2 = 0ull;
+  int cur_g = -1, buf = 0;
+  // asynchronous staging of tile `t` (LDGSTS, zero fill outside the image): a warp per tile row, lanes across columns
+  auto prefetch = [&](long long t, float* dst) {
+    const int s = (int)(t / tiles_per_sample), tix = (int)(t - (long long)s * tiles_per_sample);
+    const int ph0 = tix * bands_per_tile, rows = 3 * min(bands_per_tile, PH - ph0) + 2;
+    const float* pl = p.x + (size_t)s * hw;
+    for (int r = warp; r < rows; r += kFwdWarps) {
+      const int i = 3 * ph0 - 1 + r;
+      const bool row_in = i >= 0 && i < H;
+      const float* src = pl + (size_t)(row_in ? i : 0) * W - 1;
+      for (int c = lane; c < ld; c += 32) {
+        const bool in = row_in && c >= 1 && c <= W;
+        cp_async_f32_zfill(dst + r * ld + c, in ? src + c : pl, in);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (blockIdx.x < total_tiles) prefetch(blockIdx.x, tiles);
+  for (long long tl = blockIdx.x; tl < total_tiles; tl += gridDim.x) {
+    const int s = (int)(tl / tiles_per_sample), tix = (int)(tl - (long long)s * tiles_per_sample);
+    const int g = s / p.group;
+    const int ph0 = tix * bands_per_tile, bands = min(bands_per_tile, PH - ph0);
+    const float* tile = tiles + buf * tile_floats;
+    if (g != cur_g) {                                    // z = fma(a, u, b) on the bias-free convolution output u
+      const int idx = (p.per_group ? g * kC : 0) + 2 * lane;
+      a2 = pack2(__ldg(p.a + idx), __ldg(p.a + idx + 1));
+      b2 = pack2(__ldg(p.b + idx), __ldg(p.b + idx + 1));
+      cur_g = g;
+    }
+    // the other buffer was released by the barrier that ended the previous iteration: refill it while this tile is computed
+    if (tl + gridDim.x < total_tiles) {
+      prefetch(tl + gridDim.x, tiles + (buf ^ 1) * tile_floats);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    int bl = 0, pw = warp;
+    while (pw >= PW) { pw -= PW; ++bl; }
+    while (bl < bands) {
+      const float* base = tile + (3 * bl) * ld + 3 * pw;
+      float v[25];
+#pragma unroll
+      for (int r = 0; r < 5; ++r)
+#pragma unroll
+        for (int c = 0; c < 5; ++c) v[r * 5 + c] = base[r * ld + c];
+      float zl[9], zh[9];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          f32x2 u = 0ull;
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+              const float t = v[(r + a) * 5 + (q + b)];
+              u = fma2(w2[a * 3 + b], pack2(t, t), u);       // same fma chain as the scalar kernel, taps ascending
+            }
+          unpack2(fma2(a2, u, b2), zl[r * 3 + q], zh[r * 3 + q]);
+        }
+      float outv[2];
+      unsigned int outc[2];
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const float (&z)[9] = cc ? zh : zl;
+        // NaN handling as in stage1_fwd_kernel: a window is NaN-free or all NaN
+        const float zmax = fmaxf(fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3])), fmaxf(fmaxf(z[4], z[5]), fmaxf(fmaxf(z[6], z[7]), z[8])));
+        outv[cc] = zmax != zmax ? zmax : fmaxf(zmax, 0.f);
+        int arg = 8;                                      // first maximum in window order (at::max_pool2d_with_indices)
+#pragma unroll
+        for (int k = 7; k >= 0; --k) arg = z[k] == zmax ? k : arg;
+        outc[cc] = zmax > 0.f ? (unsigned int)arg : (unsigned int)kInactive;
+      }
+      const size_t px = ((size_t)s * phw + (size_t)(ph0 + bl) * PW + pw) * kC + 2 * lane;
+      *reinterpret_cast<float2*>(p.y + px) = make_float2(outv[0], outv[1]);
+      if (p.arg_out) *reinterpret_cast<unsigned short*>(p.arg_out + px) = (unsigned short)(outc[0] | (outc[1] << 8));
+      pw += kFwdWarps;
+      if (pw >= PW) { pw -= PW; ++bl; }
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) stage1_bwd_kernel(const S1Params p) {
   extern __shared__ __align__(16) float smem[];
   float* tile = smem;
@@ -531,6 +645,16 @@ extern "C" int afsl_stage1_fwd_f32(const float* x, const float* weight, const fl
   p.x = x; p.w = weight; p.a = a; p.b = b; p.y = y; p.arg_out = argmax; p.nhwc = channels_last;
   p.G = G; p.group = group; p.H = H; p.W = W; p.PH = H / 3; p.PW = W / 3; p.per_group = per_group;
   if (int rc = check(p, "afsl_stage1_fwd_f32")) return rc;
+  if (channels_last) {        // lane = channel pair, warp = pooled pixel
+    AFSL_REQUIRE(p.PW >= kFwdWarps, "afsl_stage1_fwd_f32: W=%d too narrow for the channels-last kernel", W);
+    const size_t nb = 2 * (size_t)(3 * kBands + 2) * (W + 2) * sizeof(float);      // double-buffered tile
+    if (int rc = opt_in_smem(stage1_fwd_nhwc_kernel, nb, "afsl_stage1_fwd_f32")) return rc;
+    const long long tiles = (long long)G * group * ((p.PH + kBands - 1) / kBands);
+    const int cap = persistent_grid(stage1_fwd_nhwc_kernel, kFwdThreads, nb, 1 << 30);
+    stage1_fwd_nhwc_kernel<<<(int)(tiles < cap ? tiles : cap), kFwdThreads, nb, (cudaStream_t)stream>>>(p);
+    AFSL_CHECK_LAUNCH("afsl_stage1_fwd_f32");
+    return AFSL_OK;
+  }
   const size_t bytes = smem_bytes(W, false);
   if (int rc = opt_in_smem(stage1_fwd_kernel, bytes, "afsl_stage1_fwd_f32")) return rc;
   const long long tiles = (long long)G * group * ((p.PH + kBands - 1) / kBands);
