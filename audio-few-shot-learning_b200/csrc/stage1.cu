@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kFwdThreads, 3) stage1_fwd_nhwc_kernel(const S
       *reinterpret_cast<float2*>(p.y + px) = make_float2(outv[0], outv[1]);
       if (p.arg_out) *reinterpret_cast<unsigned short*>(p.arg_out + px) = (unsigned short)(outc[0] | (outc[1] << 8));
       pw += kFwdWarps;
-      if (pw >= PW) { pw -= PW; ++bl; }
+      while (pw >= PW) { pw -= PW; ++bl; }
     }
     __syncthreads();
     buf ^= 1;
@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(kThreads, 2) stage1_bwd_nhwc_kernel(const S1Pa
   const int H = p.H, W = p.W, PH = p.PH, PW = p.PW, hw = H * W, phw = PH * PW;
   const int ld = bwd_tile_ld(W);
   float* tile = smem;                                   // [(3*kBands+2) * ld]
-  float* red = tile + (3 * kBands + 2) * ld;            // [kWarps][kC][kAcc] cross-warp reduction
+  float* red = tile + 2 * (3 * kBands + 2) * ld;        // [kWarps][kC][kAcc] cross-warp reduction (after the two tile buffers)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tiles_per_sample = (PH + kBands - 1) / kBands;
   const int tiles_per_group = p.group * tiles_per_sample;
@@ -530,41 +530,67 @@ __global__ void __launch_bounds__(kThreads, 2) stage1_bwd_nhwc_kernel(const S1Pa
 #pragma unroll
     for (int k = 0; k < kAcc; ++k) acc[cc][k] = 0.f;
 
+  // asynchronous staging (LDGSTS, zero fill outside the image) of tile `t` of this group: rows [3*ph0 - 1, 3*ph0 + 3*bands + 1)
+  // x cols [-1, W + 1), row stride ld; a warp per tile row.  Two buffers: the next tile lands while this one is processed.
+  const int tile_floats = (3 * kBands + 2) * ld;
+  auto prefetch = [&](int t, float* dst) {
+    const int sl = t / tiles_per_sample, tix = t - sl * tiles_per_sample;
+    const int ph0 = tix * kBands, rows = 3 * min(kBands, PH - ph0) + 2;
+    const float* pl = p.x + (size_t)(g * p.group + sl) * hw;
+    for (int r = warp; r < rows; r += kWarps) {
+      const int i = 3 * ph0 - 1 + r;
+      const bool row_in = i >= 0 && i < H;
+      const float* src = pl + (size_t)(row_in ? i : 0) * W - 1;
+      for (int c = lane; c < W + 2; c += 32) {
+        const bool in = row_in && c >= 1 && c <= W;
+        cp_async_f32_zfill(dst + r * ld + c, in ? src + c : pl, in);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int buf = 0;
+  if (part < tiles_per_group) prefetch(part, tile);
   for (int tl = part; tl < tiles_per_group; tl += p.parts) {
     const int sl = tl / tiles_per_sample, tix = tl - sl * tiles_per_sample;
     const int s = g * p.group + sl;
     const int ph0 = tix * kBands, bands = min(kBands, PH - ph0);
-    __syncthreads();
-    {   // stage rows [3*ph0 - 1, 3*ph0 + 3*bands + 1) x cols [-1, W + 1), zero padded, row stride ld
-      const float* pl = p.x + (size_t)s * hw;
-      const int rows = 3 * bands + 2, wp = W + 2;
-      for (int o = threadIdx.x; o < rows * wp; o += kThreads) {
-        const int r = o / wp, c = o - r * wp;
-        const int i = 3 * ph0 - 1 + r, j = c - 1;
-        tile[r * ld + c] = (i >= 0 && i < H && j >= 0 && j < W) ? __ldg(pl + (size_t)i * W + j) : 0.f;
-      }
+    const float* cur_tile = tile + buf * tile_floats;
+    if (tl + p.parts < tiles_per_group) {
+      prefetch(tl + p.parts, tile + (buf ^ 1) * tile_floats);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     const int npos = bands * PW;
     const size_t px0 = ((size_t)s * phw + (size_t)ph0 * PW) * kC + c0;    // this lane's channels of the tile's first pixel
-    // software pipeline: the next pixel's dy / codes are in flight while this one is processed
+    // software pipeline: the dy / codes of the next TWO pixels of this warp are in flight while one is processed
     int pos = warp;
-    float2 dyv = make_float2(0.f, 0.f);
-    uchar2 cd = make_uchar2(kInactive, kInactive);
+    float2 dyv = make_float2(0.f, 0.f), dyv2 = dyv;
+    uchar2 cd = make_uchar2(kInactive, kInactive), cd2 = cd;
     if (pos < npos) {
       dyv = __ldg(reinterpret_cast<const float2*>(p.dy + px0 + (size_t)pos * kC));
       cd = __ldg(reinterpret_cast<const uchar2*>(p.arg_in + px0 + (size_t)pos * kC));
     }
+    if (pos + kWarps < npos) {
+      dyv2 = __ldg(reinterpret_cast<const float2*>(p.dy + px0 + (size_t)(pos + kWarps) * kC));
+      cd2 = __ldg(reinterpret_cast<const uchar2*>(p.arg_in + px0 + (size_t)(pos + kWarps) * kC));
+    }
+    int bl = 0, pw = warp;                                 // pos = bl * PW + pw, kept incrementally (no division)
+    while (pw >= PW) { pw -= PW; ++bl; }
     for (; pos < npos; pos += kWarps) {
       const float2 dy_cur = dyv;
       const uchar2 cd_cur = cd;
-      const int nxt = pos + kWarps;
+      dyv = dyv2;
+      cd = cd2;
+      const int nxt = pos + 2 * kWarps;
       if (nxt < npos) {
-        dyv = __ldg(reinterpret_cast<const float2*>(p.dy + px0 + (size_t)nxt * kC));
-        cd = __ldg(reinterpret_cast<const uchar2*>(p.arg_in + px0 + (size_t)nxt * kC));
+        dyv2 = __ldg(reinterpret_cast<const float2*>(p.dy + px0 + (size_t)nxt * kC));
+        cd2 = __ldg(reinterpret_cast<const uchar2*>(p.arg_in + px0 + (size_t)nxt * kC));
       }
-      const int bl = pos / PW, pw = pos - bl * PW;
-      const float* patch = tile + (size_t)(3 * bl) * ld + 3 * pw;
+      const float* patch = cur_tile + (size_t)(3 * bl) * ld + 3 * pw;
+      pw += kWarps;
+      while (pw >= PW) { pw -= PW; ++bl; }
       const float dys[kLanesCh] = {dy_cur.x, dy_cur.y};
       const int codes[kLanesCh] = {cd_cur.x, cd_cur.y};
 #pragma unroll
@@ -588,9 +614,10 @@ __global__ void __launch_bounds__(kThreads, 2) stage1_bwd_nhwc_kernel(const S1Pa
         for (int k = 0; k < 9; ++k) acc[cc][2 + k] = fmaf(dys[cc], xs[k], acc[cc][2 + k]);
       }
     }
+    __syncthreads();                                       // this buffer is refilled during the next iteration
+    buf ^= 1;
   }
   // add the warps' accumulators in warp order
-  __syncthreads();
 #pragma unroll
   for (int cc = 0; cc < kLanesCh; ++cc)
 #pragma unroll
@@ -646,7 +673,6 @@ extern "C" int afsl_stage1_fwd_f32(const float* x, const float* weight, const fl
   p.G = G; p.group = group; p.H = H; p.W = W; p.PH = H / 3; p.PW = W / 3; p.per_group = per_group;
   if (int rc = check(p, "afsl_stage1_fwd_f32")) return rc;
   if (channels_last) {        // lane = channel pair, warp = pooled pixel
-    AFSL_REQUIRE(p.PW >= kFwdWarps, "afsl_stage1_fwd_f32: W=%d too narrow for the channels-last kernel", W);
     const size_t nb = 2 * (size_t)(3 * kBands + 2) * (W + 2) * sizeof(float);      // double-buffered tile
     if (int rc = opt_in_smem(stage1_fwd_nhwc_kernel, nb, "afsl_stage1_fwd_f32")) return rc;
     const long long tiles = (long long)G * group * ((p.PH + kBands - 1) / kBands);
@@ -677,7 +703,7 @@ extern "C" int afsl_stage1_bwd_f32(const float* x, const float* weight, const fl
   if (int rc = check(p, "afsl_stage1_bwd_f32")) return rc;
   if (channels_last) {
     const int ld = ((W + 2 + 23) / 32) * 32 + 8;
-    const size_t nb = ((size_t)(3 * kBands + 2) * ld + (size_t)kWarps * kC * kAcc) * sizeof(float);
+    const size_t nb = (2 * (size_t)(3 * kBands + 2) * ld + (size_t)kWarps * kC * kAcc) * sizeof(float);
     if (int rc = opt_in_smem(stage1_bwd_nhwc_kernel, nb, "afsl_stage1_bwd_f32")) return rc;
     stage1_bwd_nhwc_kernel<<<G * parts, kThreads, nb, (cudaStream_t)stream>>>(p);
     AFSL_CHECK_LAUNCH("afsl_stage1_bwd_f32");

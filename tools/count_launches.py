@@ -26,3 +26,9 @@ for e in small:
     c[e.name[:60]] += 1
 for k, v in c.most_common(12):
     print(v, k)
+big = Counter()
+for e in ev:
+    big[e.name[:90]] += e.device_time
+print("--- top kernels by device time (us) ---")
+for k, v in big.most_common(28):
+    print(f"{v:9.0f}  {k}")
