@@ -502,7 +502,9 @@ bool pick_variant(int D, int W, Variant& v) {
   switch (D) {
     case 16: fill_variant<4, 1>(W, v); return true;
     case 32: fill_variant<8, 1>(W, v); return true;
-    case 64: fill_variant<8, 2>(W, v); return true;
+    case 64:      // many-way: 4 lanes per row (8 rows per warp, two shuffle steps per distance instead of three)
+      if (W >= 8) fill_variant<4, 4>(W, v); else fill_variant<8, 2>(W, v);
+      return true;
     case 128: fill_variant<8, 4>(W, v); return true;
     case 256: fill_variant<8, 8>(W, v); return true;
     case 512: fill_variant<16, 8>(W, v); return true;
@@ -519,6 +521,11 @@ int launch(const HeadParams& p, bool bwd, cudaStream_t stream, const char* name)
   if (!warp_env || atoi(warp_env) != 0) {
     bool handled = false;
     const int rc = launch_head_warp(p, bwd, stream, name, &handled);
+    if (rc != AFSL_OK || handled) return rc;
+  }
+  {   // many-way forward: register batches of query rows against shared-memory prototypes (proto_head_wide.cu)
+    bool handled = false;
+    const int rc = launch_head_wide(p, bwd, stream, name, &handled);
     if (rc != AFSL_OK || handled) return rc;
   }
   Variant v;

@@ -33,5 +33,7 @@ struct HeadParams {
 
 // proto_head_warp.cu: launches the warp-per-episode kernels when the shape fits them; *handled says whether it did
 int launch_head_warp(const HeadParams& p, bool bwd, cudaStream_t stream, const char* name, bool* handled);
+// proto_head_wide.cu: forward launches of many-way episodes (W >= 8, D in {128,256}); same contract
+int launch_head_wide(const HeadParams& p, bool bwd, cudaStream_t stream, const char* name, bool* handled);
 
 }  // namespace afsl

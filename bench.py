@@ -114,6 +114,15 @@ def build_model(device):
     return model
 
 
+def peaks_clock_mhz():
+    """Maximum SM clock (MEASURED_PEAKS.json, else 1965 MHz) for the nominal fp32 FFMA peak."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh).get("sm_max_mhz", 1965.0))
+    except (OSError, ValueError):
+        return 1965.0
+
+
 def kernel_rooflines(device, peak_gbs, episodes):
     """CUDA-event timing of each libafsl kernel alone (direct C-ABI launches on preallocated buffers larger
     than the 126 MB L2, current stream) against its algorithmic bytes (SURVEY 8d / DESIGN.md)."""
@@ -268,6 +277,42 @@ def kernel_rooflines(device, peak_gbs, episodes):
     entry("nhwc_gbn_stats", nx, t_s, f"{g} groups x 25 x [42,52,64] channels-last", launches=2)
     entry("nhwc_gbn_relu_pool_fwd", nx + ny, t_gf, f"{g} groups x 25 x [42,52,64] channels-last")
     entry("nhwc_gbn_relu_pool_bwd", 2 * (nx + ny) + nx, t_gb, f"{g} groups x 25 x [42,52,64] channels-last", launches=3)
+    del xc, yc, dyc, dxc
+    # ---- fused encoder stage 1 (conv1 + grouped BN + ReLU + MaxPool 3) at the training shape, channels-last output.
+    # forward / moments are fp32-FMA bound (90 / 54 multiply-adds per pooled output per channel / per input pixel), so
+    # they are reported against the nominal FFMA peak 148 SMs x 128 lanes x 2 flop x max SM clock; the backward
+    # (dy + argmax codes + input, winners only recomputed) against HBM.
+    g, grp, h, wd_ = 64, 25, MELS, T_LEN
+    ph, pw = h // 3, wd_ // 3
+    n1 = g * grp
+    x1 = torch.randn(n1, 1, h, wd_, device=device)
+    w9 = torch.randn(64, 9, device=device) * 0.3
+    a1, b1 = torch.rand(g, 64, device=device) + 0.5, torch.randn(g, 64, device=device) * 0.1
+    m1, r1 = torch.zeros(g, 64, device=device), torch.ones(g, 64, device=device)
+    y1 = torch.empty(n1, ph, pw, 64, device=device)
+    arg1 = torch.empty(n1, ph, pw, 64, device=device, dtype=torch.uint8)
+    dy1 = torch.randn_like(y1)
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    parts1 = max(1, (4 * sms + g - 1) // g)
+    mom = torch.empty(g, parts1, 54, device=device, dtype=torch.float64)
+    parts_b = max(1, (4 * sms + g - 1) // g)
+    partial = torch.empty(g, parts_b, 64, 11, device=device)
+    t_m = timed(lambda: call("afsl_stage1_moments_f64", ptr(x1), ptr(mom), parts1, g, grp, h, wd_, st), reps=10)
+    t_f = timed(lambda: call("afsl_stage1_fwd_f32", ptr(x1), ptr(w9), ptr(a1), ptr(b1), ptr(y1), ptr(arg1), g, grp, h, wd_, 1, 1,
+                             st), reps=10)
+    t_b = timed(lambda: call("afsl_stage1_bwd_f32", ptr(x1), ptr(w9), ptr(a1), ptr(b1), ptr(m1), ptr(r1), ptr(dy1), ptr(arg1),
+                             ptr(partial), parts_b, g, grp, h, wd_, 1, 1, st), reps=10)
+    fp32_peak = sms * 128 * 2 * peaks_clock_mhz() * 1e6 / 1e12
+
+    def entry_fp32(name, flops, sec, units):
+        out[name] = {"bound": "fp32", "achieved": flops / sec / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                     "frac": flops / sec / 1e12 / fp32_peak, "traffic": traffic.get(name), "ms": sec * 1e3, "units": units,
+                     "flops_per_launch": flops, "launches": 1}
+
+    shape1 = f"{g} groups x 25 x [1,128,157] -> [42,52,64] channels-last"
+    entry_fp32("stage1_fwd", 2.0 * 90 * n1 * ph * pw * 64, t_f, shape1)
+    entry_fp32("stage1_moments", 2.0 * 54 * n1 * h * wd_, t_m, shape1)
+    entry("stage1_bwd", 4.0 * dy1.numel() + arg1.numel() + 4.0 * x1.numel(), t_b, shape1)
     return out
 
 

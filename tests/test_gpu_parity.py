@@ -96,6 +96,7 @@ def test_head_batched_vs_oracle(ops, monkeypatch, ways, shots, nq, dim, path):
     """E episodes at once == the oracle applied episode by episode (incl. extra prototype gradient), through
     both kernel families: one warp per episode (registers; small W*D) and one CTA per episode (any shape)."""
     monkeypatch.setenv("AFSL_HEAD_WARP", "1" if path == "warp" else "0")
+    monkeypatch.setenv("AFSL_HEAD_WIDE", "1" if path == "warp" else "0")     # many-way forward: register-batch kernel / lane groups
     e = 37
     gen = torch.Generator().manual_seed(ways * 1000 + dim)
     s = torch.randn(e, ways * shots, dim, generator=gen)
@@ -119,10 +120,14 @@ def test_head_batched_vs_oracle(ops, monkeypatch, ways, shots, nq, dim, path):
         assert int(correct[i]) == ohead.evaluate_task(ohead.l2_scores(qc, pr), ql[i])[0]
 
 
-def test_head_ragged_tasks(ops):
-    """Packed multi-segment tasks with CSR offsets: labels/posteriors/#correct per task."""
+@pytest.mark.parametrize("ways,shots,dim,wide", [(5, 5, 64, 1), (20, 5, 256, 1), (20, 5, 256, 0), (20, 1, 64, 1), (20, 1, 64, 0),
+                                                 (13, 3, 128, 1)])
+def test_head_ragged_tasks(ops, monkeypatch, ways, shots, dim, wide):
+    """Packed multi-segment tasks with CSR offsets: labels/posteriors/#correct per task (5-way: warp kernel; many-way:
+    the register-batch kernel of proto_head_wide.cu and the lane-group kernel of proto_head.cu)."""
+    monkeypatch.setenv("AFSL_HEAD_WIDE", str(wide))
     gen = torch.Generator().manual_seed(5)
-    ways, shots, dim, tasks = 5, 5, 64, 11
+    tasks = 11
     counts = torch.randint(1, 60, (tasks,), generator=gen)
     off = torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)])
     s = torch.randn(tasks, ways * shots, dim, generator=gen)
