@@ -49,71 +49,204 @@ struct S1Params {
 };
 
 // ---------------------------------------------------------------- input moments
-// CTA (g, part) walks 16-row bands of the group's samples: the band (+ halo, zero padded) is staged in shared
-// memory once, then every thread takes pixels of the band and reads its 3x3 neighbourhood from the tile
-// (the first version fetched the nine neighbours of every pixel from global memory with a bounds test each).
-constexpr int kMomRows = 64;
+// The 54 moments are not accumulated tap pair by tap pair (45 multiply-adds per pixel): with zero padding
+//   R_kl = sum_p x(p+k) x(p+l) = A(l-k) - [edge row left out by k] - [edge column left out by k] + [corner],
+// where A(d) = sum_q x(q) x(q+d) is the image autocorrelation at displacement d = l - k (13 distinct values for
+// d in [-2,2]^2 up to sign), the edge terms are 1-D autocorrelations (lags 0..2) of the first / last row and
+// column, and likewise S_k = sum x - edge row sum - edge column sum + corner (derivation: substitute q = p + k;
+// the pixels q whose p falls outside the image are one edge row and/or one edge column).  Exact in real arithmetic,
+// 14 multiply-adds per pixel.  A warp walks a 32-column strip down a row band with a sliding 3-row window in
+// registers (5 shared-memory loads + 14 FMA per pixel); bands are staged with cp.async, double buffered.
+constexpr int kMomRows = 32;              // rows per band
+constexpr int kMomThreads = 320;          // 10 warps: 5 column strips x 2 half bands at W = 157
+constexpr int kMomWarps = kMomThreads / kWarp;
+constexpr int kMomAcc = 14;               // sum x, A(0,0..2), A(1,-2..2), A(2,-2..2)
 
-__global__ void __launch_bounds__(kThreads) stage1_moments_kernel(const S1Params p) {
-  extern __shared__ __align__(16) float mtile[];         // [(kMomRows + 2) * (W + 2)]
-  const int H = p.H, W = p.W, hw = H * W, ld = W + 2;
+__host__ __device__ inline int mom_ld(int W) { return ((W + 31) / 32) * 32 + 4; }   // cols -2 .. 32*strips+1, zero outside
+
+// 4-byte async copy global -> shared; `valid` = false writes a zero (padding) without touching global memory
+__device__ __forceinline__ void cp_async_f32_zfill(float* dst, const float* src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int n = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+
+// one window step: A = row y (cols x-2..x+2, centre A[2]), B = row y+1, C = row y+2
+__device__ __forceinline__ void mom_step(const float (&A)[5], const float (&B)[5], const float (&C)[5], float (&acc)[kMomAcc]) {
+  const float c = A[2];
+  acc[0] += c;
+  acc[1] = fmaf(c, c, acc[1]);
+  acc[2] = fmaf(c, A[3], acc[2]);
+  acc[3] = fmaf(c, A[4], acc[3]);
+#pragma unroll
+  for (int j = 0; j < 5; ++j) acc[4 + j] = fmaf(c, B[j], acc[4 + j]);
+#pragma unroll
+  for (int j = 0; j < 5; ++j) acc[9 + j] = fmaf(c, C[j], acc[9 + j]);
+}
+__device__ __forceinline__ void mom_load(const float* row, float (&A)[5]) {
+#pragma unroll
+  for (int j = 0; j < 5; ++j) A[j] = row[j];
+}
+
+__global__ void __launch_bounds__(kMomThreads) stage1_moments_kernel(const S1Params p) {
+  extern __shared__ __align__(16) float mtile[];         // two buffers of [(kMomRows + 2) * ld]
+  const int H = p.H, W = p.W, hw = H * W, ld = mom_ld(W);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // grid = G * parts_m CTAs; CTA (g, part) strides over the group's bands
+  // grid = G * parts CTAs; CTA (g, part) strides over the group's (sample, band) units
   const int parts = gridDim.x / p.G;
   const int g = blockIdx.x / parts, part = blockIdx.x - g * parts;
   const float* x0 = p.x + (size_t)g * p.group * hw;
-  float acc[54];
-#pragma unroll
-  for (int k = 0; k < 54; ++k) acc[k] = 0.f;
   const int bands_per_sample = (H + kMomRows - 1) / kMomRows;
   const int total_bands = p.group * bands_per_sample;
-  for (int bd = part; bd < total_bands; bd += parts) {
-    const int s = bd / bands_per_sample, i0 = (bd - s * bands_per_sample) * kMomRows;
-    const int rows = min(kMomRows, H - i0);
-    const float* pl = x0 + (size_t)s * hw;
-    __syncthreads();
-    // a warp per tile row, lanes across the columns: no index division anywhere in the loops
-    for (int r = warp; r < rows + 2; r += kWarps) {
-      const int i = i0 - 1 + r;
-      const bool row_in = i >= 0 && i < H;
-      const float* src = pl + (size_t)i * W - 1;
-#pragma unroll 6
-      for (int c = lane; c < ld; c += 32) mtile[r * ld + c] = (row_in && c >= 1 && c <= W) ? __ldg(src + c) : 0.f;
-    }
-    __syncthreads();
-    for (int r = warp; r < rows; r += kWarps)
-    for (int c = lane; c < W; c += 32) {
-      const float* nb = mtile + r * ld + c;            // top-left of the pixel's 3x3 neighbourhood
-      float v[9];
+  const int strips = (W + 31) / 32;
+  const int tile_floats = (kMomRows + 2) * ld;
+  float acc[kMomAcc];
 #pragma unroll
-      for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int b = 0; b < 3; ++b) v[a * 3 + b] = nb[a * ld + b];
-      int q = 9;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        acc[k] += v[k];
-#pragma unroll
-        for (int l = k; l < 9; ++l) {
-          acc[q] = fmaf(v[k], v[l], acc[q]);
-          ++q;
-        }
+  for (int k = 0; k < kMomAcc; ++k) acc[k] = 0.f;
+  // edge accumulators, role by warp: 0 first row, 1 last row, 2 first column, 3 last column: sum, lag 0, lag 1, lag 2;
+  // lane 0 of warps 4..7: the four corners (value, square)
+  float edge[4] = {0.f, 0.f, 0.f, 0.f};
+
+  auto prefetch = [&](int bd, float* dst) {               // rows [i0, i0 + kMomRows + 2) x cols [-2, ld - 2), zero outside
+    const int sm = bd / bands_per_sample, i0 = (bd - sm * bands_per_sample) * kMomRows;
+    const float* pl = x0 + (size_t)sm * hw;
+    for (int r = warp; r < kMomRows + 2; r += kMomWarps) {
+      const int i = i0 + r;
+      const bool row_in = i < H;
+      const float* src = pl + (size_t)(row_in ? i : 0) * W - 2;
+      for (int c = lane; c < ld; c += 32) {
+        const bool in = row_in && c >= 2 && c < W + 2;
+        cp_async_f32_zfill(dst + r * ld + c, in ? src + c : pl, in);
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int buf = 0;
+  if (part < total_bands) prefetch(part, mtile);
+  for (int bd = part; bd < total_bands; bd += parts) {
+    const int sm = bd / bands_per_sample, i0 = (bd - sm * bands_per_sample) * kMomRows;
+    const int rows = min(kMomRows, H - i0);
+    const float* tile = mtile + buf * tile_floats;
+    if (bd + parts < total_bands) {
+      prefetch(bd + parts, mtile + (buf ^ 1) * tile_floats);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    // ---- autocorrelations: items = column strips x two half bands
+    const int half = (rows + 1) / 2;
+    for (int item = warp; item < 2 * strips; item += kMomWarps) {
+      const int strip = item >> 1, ya = (item & 1) ? half : 0, yb = (item & 1) ? rows : half;
+      if (ya >= yb) continue;
+      const float* col = tile + 32 * strip + lane;        // window column x-2 of pixel x = 32*strip + lane
+      float ra[5], rb[5], rc[5];
+      mom_load(col + ya * ld, ra);
+      mom_load(col + (ya + 1) * ld, rb);
+      mom_load(col + (ya + 2) * ld, rc);
+      int y = ya;
+      for (; y + 3 <= yb; y += 3) {                        // window rows rotate through the three register sets
+        mom_step(ra, rb, rc, acc);
+        mom_load(col + (y + 3) * ld, ra);
+        mom_step(rb, rc, ra, acc);
+        mom_load(col + (y + 4) * ld, rb);
+        mom_step(rc, ra, rb, acc);
+        mom_load(col + min(y + 5, kMomRows + 1) * ld, rc);      // past the halo only when never used
+      }
+      if (y < yb) { mom_step(ra, rb, rc, acc); ++y; }
+      if (y < yb) {                                        // rows past the band's halo are never used: the loads above
+        mom_load(col + min(y + 2, kMomRows + 1) * ld, ra); // stay inside the tile by clamping
+        mom_step(rb, rc, ra, acc);
+      }
+    }
+    // ---- edge rows / columns / corners of the sample inside this band
+    const bool has_top = i0 == 0, has_bot = i0 + rows == H;
+    if (warp == 0 && has_top) {
+      const float* r = tile + 2;
+      for (int xx = lane; xx < W; xx += 32) {
+        const float v = r[xx];
+        edge[0] += v; edge[1] = fmaf(v, v, edge[1]); edge[2] = fmaf(v, r[xx + 1], edge[2]); edge[3] = fmaf(v, r[xx + 2], edge[3]);
+      }
+    } else if (warp == 1 && has_bot) {
+      const float* r = tile + (rows - 1) * ld + 2;
+      for (int xx = lane; xx < W; xx += 32) {
+        const float v = r[xx];
+        edge[0] += v; edge[1] = fmaf(v, v, edge[1]); edge[2] = fmaf(v, r[xx + 1], edge[2]); edge[3] = fmaf(v, r[xx + 2], edge[3]);
+      }
+    } else if (warp == 2 || warp == 3) {
+      const float* c = tile + (warp == 2 ? 2 : W + 1);
+      for (int yy = lane; yy < rows; yy += 32) {
+        const float v = c[yy * ld];
+        edge[0] += v; edge[1] = fmaf(v, v, edge[1]); edge[2] = fmaf(v, c[(yy + 1) * ld], edge[2]);
+        edge[3] = fmaf(v, c[(yy + 2) * ld], edge[3]);
+      }
+    } else if (warp >= 4 && warp < 8 && lane == 0) {
+      const bool bottom = warp >= 6, right = (warp & 1) != 0;
+      if (bottom ? has_bot : has_top) {
+        const float v = tile[(bottom ? rows - 1 : 0) * ld + (right ? W + 1 : 2)];
+        edge[0] += v; edge[1] = fmaf(v, v, edge[1]);
+      }
+    }
+    __syncthreads();                                       // this buffer is refilled during the next iteration
+    buf ^= 1;
   }
-  // CTA reduction: every warp folds its 54 sums with shuffles (fp32 partials of one band set), then the 16 warp
-  // results of each moment are added in double, in warp order
-  __shared__ float wsum[kWarps][54];
+  // ---- CTA reduction (fp32 partials of one band set -> double, warps added in order), then the 54 moments
+  __shared__ float wsum[kMomWarps][kMomAcc];
+  __shared__ float esum[8][4];
+  __shared__ double tot[kMomAcc + 32];
 #pragma unroll
-  for (int k = 0; k < 54; ++k) {
+  for (int k = 0; k < kMomAcc; ++k) {
     const float t = warp_sum(acc[k]);
     if (lane == 0) wsum[warp][k] = t;
   }
+  if (warp < 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float t = warp_sum(edge[k]);
+      if (lane == 0) esum[warp][k] = t;
+    }
+  } else if (warp < 8 && lane == 0) {
+    esum[warp][0] = edge[0]; esum[warp][1] = edge[1]; esum[warp][2] = 0.f; esum[warp][3] = 0.f;
+  }
+  __syncthreads();
+  if (threadIdx.x < kMomAcc) {
+    double t = 0.0;
+    for (int q = 0; q < kMomWarps; ++q) t += (double)wsum[q][threadIdx.x];
+    tot[threadIdx.x] = t;
+  } else if (threadIdx.x >= 32 && threadIdx.x < 64) {
+    const int i = threadIdx.x - 32;
+    tot[kMomAcc + i] = (double)esum[i >> 2][i & 3];
+  }
   __syncthreads();
   if (threadIdx.x < 54) {
-    double t = 0.0;
-    for (int q = 0; q < kWarps; ++q) t += (double)wsum[q][threadIdx.x];
-    p.moments[((size_t)g * parts + part) * 54 + threadIdx.x] = t;
+    // tap k = (ky, kx) in {-1,0,1}^2, row-major; edge row left out by k: first row if ky = +1, last row if ky = -1
+    const double* A = tot + 1;                             // A[0..2]: (0,0..2); A[3..7]: (1,-2..2); A[8..12]: (2,-2..2)
+    const double* E = tot + kMomAcc;                       // E[4*e + j]: e = 0 top, 1 bottom, 2 left, 3 right; corners 4..7 (tl,tr,bl,br)
+    int k, l;
+    if (threadIdx.x < 9) { k = l = threadIdx.x; }
+    else {                                                 // upper triangle row by row after the 9 sums
+      int o = threadIdx.x - 9; k = 0;
+      while (o >= 9 - k) { o -= 9 - k; ++k; }
+      l = k + o;
+    }
+    const int ky = k / 3 - 1, kx = k % 3 - 1, ly = l / 3 - 1, lx = l % 3 - 1;
+    const int erow = ky == 1 ? 0 : 1, ecol = kx == 1 ? 2 : 3;
+    const int corner = 4 + (ky == 1 ? 0 : 2) + (kx == 1 ? 0 : 1);
+    double r;
+    if (threadIdx.x < 9) {
+      r = tot[0];
+      if (ky) r -= E[4 * erow];
+      if (kx) r -= E[4 * ecol];
+      if (ky && kx) r += E[4 * corner];
+    } else {
+      int dy = ly - ky, dx = lx - kx;
+      if (dy < 0 || (dy == 0 && dx < 0)) { dy = -dy; dx = -dx; }
+      r = dy == 0 ? A[dx] : A[3 + 5 * (dy - 1) + dx + 2];
+      if (ky && ly == ky) r -= E[4 * erow + 1 + abs(lx - kx)];
+      if (kx && lx == kx) r -= E[4 * ecol + 1 + abs(ly - ky)];
+      if (ky && kx && l == k) r += E[4 * corner + 1];
+    }
+    p.moments[((size_t)g * parts + part) * 54 + threadIdx.x] = r;
   }
 }
 
@@ -261,13 +394,6 @@ __global__ void __launch_bounds__(kThreads) stage1_fwd_kernel(const S1Params p) 
 // = 208 before, 85 registers -> 24 warps per SM (was 16), three independent CTAs per SM hide each other's staging.
 constexpr int kFwdThreads = 256;
 constexpr int kFwdWarps = kFwdThreads / kWarp;
-
-// 4-byte async copy global -> shared; `valid` = false writes a zero (padding) without touching global memory
-__device__ __forceinline__ void cp_async_f32_zfill(float* dst, const float* src, bool valid) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-  const int n = valid ? 4 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
-}
 
 __global__ void __launch_bounds__(kFwdThreads, 3) stage1_fwd_nhwc_kernel(const S1Params p) {
   extern __shared__ __align__(16) float tiles[];         // two buffers of [(3*kBands+2) * (W+2)]
@@ -655,9 +781,9 @@ extern "C" int afsl_stage1_moments_f64(const float* x, double* moments, int part
   S1Params p{};
   p.x = x; p.moments = moments; p.G = G; p.group = group; p.H = H; p.W = W;
   if (int rc = check(p, "afsl_stage1_moments_f64")) return rc;
-  const size_t mb = (size_t)(kMomRows + 2) * (W + 2) * sizeof(float);
+  const size_t mb = 2 * (size_t)(kMomRows + 2) * mom_ld(W) * sizeof(float);
   if (int rc = opt_in_smem(stage1_moments_kernel, mb, "afsl_stage1_moments_f64")) return rc;
-  stage1_moments_kernel<<<G * parts, kThreads, mb, (cudaStream_t)stream>>>(p);
+  stage1_moments_kernel<<<G * parts, kMomThreads, mb, (cudaStream_t)stream>>>(p);
   AFSL_CHECK_LAUNCH("afsl_stage1_moments_f64");
   return AFSL_OK;
 }

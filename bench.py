@@ -279,8 +279,7 @@ def kernel_rooflines(device, peak_gbs, episodes):
     entry("nhwc_gbn_relu_pool_bwd", 2 * (nx + ny) + nx, t_gb, f"{g} groups x 25 x [42,52,64] channels-last", launches=3)
     del xc, yc, dyc, dxc
     # ---- fused encoder stage 1 (conv1 + grouped BN + ReLU + MaxPool 3) at the training shape, channels-last output.
-    # forward / moments are fp32-FMA bound (90 / 54 multiply-adds per pooled output per channel / per input pixel), so
-    # they are reported against the nominal FFMA peak 148 SMs x 128 lanes x 2 flop x max SM clock; the backward
+    # the forward is fp32-FMA bound (90 multiply-adds per pooled output per channel), so it is reported against the nominal FFMA peak 148 SMs x 128 lanes x 2 flop x max SM clock; the backward
     # (dy + argmax codes + input, winners only recomputed) against HBM.
     g, grp, h, wd_ = 64, 25, MELS, T_LEN
     ph, pw = h // 3, wd_ // 3
@@ -311,7 +310,7 @@ def kernel_rooflines(device, peak_gbs, episodes):
 
     shape1 = f"{g} groups x 25 x [1,128,157] -> [42,52,64] channels-last"
     entry_fp32("stage1_fwd", 2.0 * 90 * n1 * ph * pw * 64, t_f, shape1)
-    entry_fp32("stage1_moments", 2.0 * 54 * n1 * h * wd_, t_m, shape1)
+    entry("stage1_moments", 4.0 * x1.numel(), t_m, shape1)       # one pass over the 1-channel input, 14 FMA per pixel
     entry("stage1_bwd", 4.0 * dy1.numel() + arg1.numel() + 4.0 * x1.numel(), t_b, shape1)
     return out
 

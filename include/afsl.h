@@ -236,7 +236,8 @@ int afsl_gbn_relu_pool_bwd_f32(const float* x, const float* mean, const float* r
  * `group` consecutive samples (one encoder call of the reference, :18-23).
  *   x [G*group,1,H,W] -> y [G*group,64,H/3,W/3]
  * moments: per group and part the 9 shifted sums and 45 shifted products of the input
- *   (double [G,parts,54]: S_0..S_8, then R_kl for k <= l row by row); mean / variance
+ *   (double [G,parts,54]: S_0..S_8, then R_kl for k <= l row by row), obtained from the 13
+ *   image autocorrelations at displacements in [-2,2]^2 plus edge-row / edge-column terms; mean / variance
  *   of every conv channel follow from them on the host.
  * fwd: z = a*u + b with u the bias-free conv output; a, b (and mean, rstd of u in
  *   bwd) are [G,64] (per_group = 1) or [64].

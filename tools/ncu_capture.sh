@@ -6,7 +6,7 @@
 set -u
 tag=${1:-r1}; shift || true
 kernels=("$@")
-[ ${#kernels[@]} -eq 0 ] && kernels=(head_warp_kernel:4:head_fwd head_warp_kernel:27:head_bwd cpl_warp_kernel:4:cpl_fwd cpl_warp_kernel:27:cpl_bwd specaug_tile_kernel:4:specaug_tile angular_warp_kernel:2:angular_fwd angular_warp_kernel:10:angular_bwd)
+[ ${#kernels[@]} -eq 0 ] && kernels=(head_warp_kernel:4:head_fwd head_warp_kernel:27:head_bwd cpl_warp_kernel:4:cpl_fwd cpl_warp_kernel:27:cpl_bwd specaug_tile_kernel:4:specaug_tile angular_warp_kernel:2:angular_fwd angular_warp_kernel:10:angular_bwd head_wide_fwd_kernel:27:head_wide_20w5s_d256)
 out=gpurun_out
 mkdir -p $out
 BENCH="python bench.py --steps 2 --warmup 3 --episodes 32 --skip-cpu --skip-kernels --skip-eval"
@@ -24,7 +24,7 @@ for spec in "${kernels[@]}"; do
 done
 # fused encoder stage 1 at the training shape
 S1="python tools/stage1_bench.py"
-$S1 > $out/${tag}_s1_plain.log 2>&1 && for k in stage1_fwd_kernel stage1_bwd_nhwc_kernel; do
+$S1 > $out/${tag}_s1_plain.log 2>&1 && for k in stage1_fwd_nhwc_kernel stage1_bwd_nhwc_kernel stage1_moments_kernel; do
   ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o $out/${tag}_$k $S1 > $out/${tag}_ncu_$k.log 2>&1
   echo "$k rc=$?"
 done
