@@ -279,8 +279,9 @@ def kernel_rooflines(device, peak_gbs, episodes):
     entry("nhwc_gbn_relu_pool_bwd", 2 * (nx + ny) + nx, t_gb, f"{g} groups x 25 x [42,52,64] channels-last", launches=3)
     del xc, yc, dyc, dxc
     # ---- fused encoder stage 1 (conv1 + grouped BN + ReLU + MaxPool 3) at the training shape, channels-last output.
-    # the forward is fp32-FMA bound (90 multiply-adds per pooled output per channel), so it is reported against the nominal FFMA peak 148 SMs x 128 lanes x 2 flop x max SM clock; the backward
-    # (dy + argmax codes + input, winners only recomputed) against HBM.
+    # The forward is fp32-FMA bound (90 multiply-adds per pooled output per channel): reported against the nominal FFMA
+    # peak 148 SMs x 128 lanes x 2 flop x max SM clock.  The moments pass (one read of the 1-channel input) and the
+    # backward (dy + argmax codes + input, winners only recomputed) are reported against HBM.
     g, grp, h, wd_ = 64, 25, MELS, T_LEN
     ph, pw = h // 3, wd_ // 3
     n1 = g * grp
