@@ -21,7 +21,8 @@ __global__ void bn_running_update_kernel(const float* __restrict__ mean, const f
   if (c < C) {
     float rm = running_mean[c], rv = running_var[c];
     const float sh = shift ? shift[c] : 0.f;
-    for (int g = 0; g < G; ++g) {          // exactly the sequence of updates of G separate calls
+#pragma unroll 8
+    for (int g = 0; g < G; ++g) {          // exactly the sequence of updates of G separate calls (loads batched by the unroll)
       rm = (1.f - momentum) * rm + momentum * (mean[(size_t)g * C + c] + sh);
       rv = (1.f - momentum) * rv + momentum * (var_biased[(size_t)g * C + c] * unbias);
     }
