@@ -552,6 +552,8 @@ def run_b200(args):
 
 
 def main():
+    # stdout carries exactly one JSON line: NCCL's own log lines (e.g. the version banner under NCCL_DEBUG=VERSION) go to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
