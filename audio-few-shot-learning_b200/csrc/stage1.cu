@@ -395,6 +395,11 @@ __global__ void __launch_bounds__(kThreads) stage1_fwd_kernel(const S1Params p) 
 constexpr int kFwdThreads = 256;
 constexpr int kFwdWarps = kFwdThreads / kWarp;
 
+// kCodes = false (no gradient wanted: evaluation sweeps): no argmax codes, and since z = fma(a, u, b) is monotone in u the
+// affine is applied once per pooled pixel to the window's extreme u instead of to its nine elements: the taps are
+// negated where a < 0 (u' = sign(a) u exactly, fma(a, u, b) = fma(|a|, u', b) bit for bit), so max_k z_k =
+// fma(|a|, max_k u'_k, b) - 82 instead of 90 FFMA2 and no compare / select chain per pixel.
+template <bool kCodes>
 __global__ void __launch_bounds__(kFwdThreads, 3) stage1_fwd_nhwc_kernel(const S1Params p) {
   extern __shared__ __align__(16) float tiles[];         // two buffers of [(3*kBands+2) * (W+2)]
   const int H = p.H, W = p.W, PH = p.PH, PW = p.PW, ld = W + 2, hw = H * W, phw = PH * PW;
@@ -432,7 +437,15 @@ __global__ void __launch_bounds__(kFwdThreads, 3) stage1_fwd_nhwc_kernel(const S
     const float* tile = tiles + buf * tile_floats;
     if (g != cur_g) {                                    // z = fma(a, u, b) on the bias-free convolution output u
       const int idx = (p.per_group ? g * kC : 0) + 2 * lane;
-      a2 = pack2(__ldg(p.a + idx), __ldg(p.a + idx + 1));
+      float a_lo = __ldg(p.a + idx), a_hi = __ldg(p.a + idx + 1);
+      if (!kCodes) {                                     // taps carry the sign of a, a its magnitude
+        const float s_lo = a_lo < 0.f ? -1.f : 1.f, s_hi = a_hi < 0.f ? -1.f : 1.f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+          w2[k] = pack2(s_lo * __ldg(p.w + (2 * lane) * 9 + k), s_hi * __ldg(p.w + (2 * lane + 1) * 9 + k));
+        a_lo = fabsf(a_lo); a_hi = fabsf(a_hi);
+      }
+      a2 = pack2(a_lo, a_hi);
       b2 = pack2(__ldg(p.b + idx), __ldg(p.b + idx + 1));
       cur_g = g;
     }
@@ -466,12 +479,25 @@ __global__ void __launch_bounds__(kFwdThreads, 3) stage1_fwd_nhwc_kernel(const S
               const float t = v[(r + a) * 5 + (q + b)];
               u = fma2(w2[a * 3 + b], pack2(t, t), u);       // same fma chain as the scalar kernel, taps ascending
             }
-          unpack2(fma2(a2, u, b2), zl[r * 3 + q], zh[r * 3 + q]);
+          if (kCodes) unpack2(fma2(a2, u, b2), zl[r * 3 + q], zh[r * 3 + q]);
+          else unpack2(u, zl[r * 3 + q], zh[r * 3 + q]);
         }
       float outv[2];
-      unsigned int outc[2];
+      unsigned int outc[2] = {0u, 0u};
+      if (!kCodes) {
+        float um[2];
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
+        for (int cc = 0; cc < 2; ++cc) {
+          const float (&z)[9] = cc ? zh : zl;
+          um[cc] = fmaxf(fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3])), fmaxf(fmaxf(z[4], z[5]), fmaxf(fmaxf(z[6], z[7]), z[8])));
+        }
+        float z0, z1;
+        unpack2(fma2(a2, pack2(um[0], um[1]), b2), z0, z1);
+        outv[0] = z0 != z0 ? z0 : fmaxf(z0, 0.f);
+        outv[1] = z1 != z1 ? z1 : fmaxf(z1, 0.f);
+      }
+#pragma unroll
+      for (int cc = 0; cc < 2 && kCodes; ++cc) {
         const float (&z)[9] = cc ? zh : zl;
         // NaN handling as in stage1_fwd_kernel: a window is NaN-free or all NaN
         const float zmax = fmaxf(fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3])), fmaxf(fmaxf(z[4], z[5]), fmaxf(fmaxf(z[6], z[7]), z[8])));
@@ -483,7 +509,7 @@ __global__ void __launch_bounds__(kFwdThreads, 3) stage1_fwd_nhwc_kernel(const S
       }
       const size_t px = ((size_t)s * phw + (size_t)(ph0 + bl) * PW + pw) * kC + 2 * lane;
       *reinterpret_cast<float2*>(p.y + px) = make_float2(outv[0], outv[1]);
-      if (p.arg_out) *reinterpret_cast<unsigned short*>(p.arg_out + px) = (unsigned short)(outc[0] | (outc[1] << 8));
+      if (kCodes) *reinterpret_cast<unsigned short*>(p.arg_out + px) = (unsigned short)(outc[0] | (outc[1] << 8));
       pw += kFwdWarps;
       while (pw >= PW) { pw -= PW; ++bl; }
     }
@@ -800,10 +826,11 @@ extern "C" int afsl_stage1_fwd_f32(const float* x, const float* weight, const fl
   if (int rc = check(p, "afsl_stage1_fwd_f32")) return rc;
   if (channels_last) {        // lane = channel pair, warp = pooled pixel
     const size_t nb = 2 * (size_t)(3 * kBands + 2) * (W + 2) * sizeof(float);      // double-buffered tile
-    if (int rc = opt_in_smem(stage1_fwd_nhwc_kernel, nb, "afsl_stage1_fwd_f32")) return rc;
+    void (*fn)(const S1Params) = argmax ? stage1_fwd_nhwc_kernel<true> : stage1_fwd_nhwc_kernel<false>;
+    if (int rc = opt_in_smem(fn, nb, "afsl_stage1_fwd_f32")) return rc;
     const long long tiles = (long long)G * group * ((p.PH + kBands - 1) / kBands);
-    const int cap = persistent_grid(stage1_fwd_nhwc_kernel, kFwdThreads, nb, 1 << 30);
-    stage1_fwd_nhwc_kernel<<<(int)(tiles < cap ? tiles : cap), kFwdThreads, nb, (cudaStream_t)stream>>>(p);
+    const int cap = persistent_grid(fn, kFwdThreads, nb, 1 << 30);
+    fn<<<(int)(tiles < cap ? tiles : cap), kFwdThreads, nb, (cudaStream_t)stream>>>(p);
     AFSL_CHECK_LAUNCH("afsl_stage1_fwd_f32");
     return AFSL_OK;
   }

@@ -571,7 +571,11 @@ def test_stage1_fused_vs_torch(ops, n, group, h, w):
     tf32 = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
     try:
+        import copy
+        with torch.no_grad():       # no-gradient variant (no argmax codes, affine applied to the window's extreme u): same bits
+            y_ng = ops.stage1_conv_bn_relu_pool(x, conv, copy.deepcopy(bn), group)
         y = ops.stage1_conv_bn_relu_pool(x, conv, bn, group)
+        assert torch.equal(y_ng, y)
         yr = torch.cat([torch.nn.functional.max_pool2d(torch.relu(bn_r(conv_r(x[i:i + group]))), 3, 3) for i in range(0, n, group)])
         close(y, yr, rtol=2e-5)
         gy = torch.randn(y.shape, generator=gen).cuda()
@@ -588,6 +592,8 @@ def test_stage1_fused_vs_torch(ops, n, group, h, w):
         for mod in (conv, bn, conv_r, bn_r):
             mod.zero_grad(); mod.eval()
         ye = ops.stage1_conv_bn_relu_pool(x, conv, bn, group)
+        with torch.no_grad():
+            assert torch.equal(ops.stage1_conv_bn_relu_pool(x, conv, bn, group), ye)
         yer = torch.nn.functional.max_pool2d(torch.relu(bn_r(conv_r(x))), 3, 3)
         close(ye, yer, rtol=2e-5)
         ye.backward(gy); yer.backward(gy)
