@@ -719,32 +719,34 @@ __global__ void __launch_bounds__(kThreads, 2) stage1_bwd_nhwc_kernel(const S1Pa
     // software pipeline: the dy / codes of the next TWO pixels of this warp are in flight while one is processed
     int pos = warp;
     float2 dyv = make_float2(0.f, 0.f), dyv2 = dyv;
-    uchar2 cd = make_uchar2(kInactive, kInactive), cd2 = cd;
+    // the two code bytes travel as ONE 16-bit register until they are used: a uchar2 is split into its bytes right after the
+    // load, which made every prefetch wait for its own data (44 % of the kernel's stall samples, long scoreboard)
+    unsigned int cd = kInactive | (kInactive << 8), cd2 = cd;                // (32-bit variables: no half-register packing)
     if (pos < npos) {
       dyv = __ldg(reinterpret_cast<const float2*>(p.dy + px0 + (size_t)pos * kC));
-      cd = __ldg(reinterpret_cast<const uchar2*>(p.arg_in + px0 + (size_t)pos * kC));
+      cd = __ldg(reinterpret_cast<const unsigned short*>(p.arg_in + px0 + (size_t)pos * kC));
     }
     if (pos + kWarps < npos) {
       dyv2 = __ldg(reinterpret_cast<const float2*>(p.dy + px0 + (size_t)(pos + kWarps) * kC));
-      cd2 = __ldg(reinterpret_cast<const uchar2*>(p.arg_in + px0 + (size_t)(pos + kWarps) * kC));
+      cd2 = __ldg(reinterpret_cast<const unsigned short*>(p.arg_in + px0 + (size_t)(pos + kWarps) * kC));
     }
     int bl = 0, pw = warp;                                 // pos = bl * PW + pw, kept incrementally (no division)
     while (pw >= PW) { pw -= PW; ++bl; }
     for (; pos < npos; pos += kWarps) {
       const float2 dy_cur = dyv;
-      const uchar2 cd_cur = cd;
+      const unsigned int cd_cur = cd;
       dyv = dyv2;
       cd = cd2;
       const int nxt = pos + 2 * kWarps;
       if (nxt < npos) {
         dyv2 = __ldg(reinterpret_cast<const float2*>(p.dy + px0 + (size_t)nxt * kC));
-        cd2 = __ldg(reinterpret_cast<const uchar2*>(p.arg_in + px0 + (size_t)nxt * kC));
+        cd2 = __ldg(reinterpret_cast<const unsigned short*>(p.arg_in + px0 + (size_t)nxt * kC));
       }
       const float* patch = cur_tile + (size_t)(3 * bl) * ld + 3 * pw;
       pw += kWarps;
       while (pw >= PW) { pw -= PW; ++bl; }
       const float dys[kLanesCh] = {dy_cur.x, dy_cur.y};
-      const int codes[kLanesCh] = {cd_cur.x, cd_cur.y};
+      const int codes[kLanesCh] = {cd_cur & 0xff, cd_cur >> 8};
 #pragma unroll
       for (int cc = 0; cc < kLanesCh; ++cc) {
         const int code = codes[cc];
