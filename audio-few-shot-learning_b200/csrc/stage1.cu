@@ -393,6 +393,7 @@ __global__ void __launch_bounds__(kThreads) stage1_fwd_kernel(const S1Params p) 
 // 64 code bytes.  ~175 issued instructions per (pixel, 64 channels) against ~420 per (32 pixels, 4 channels) x ...
 // = 208 before, 85 registers -> 24 warps per SM (was 16), three independent CTAs per SM hide each other's staging.
 constexpr int kFwdThreads = 256;
+constexpr int kFwdBands = 14;       // pooled rows per tile: fewer, longer tiles = fewer CTA barriers per pixel
 constexpr int kFwdWarps = kFwdThreads / kWarp;
 
 // kCodes = false (no gradient wanted: evaluation sweeps): no argmax codes, and since z = fma(a, u, b) is monotone in u the
@@ -401,13 +402,13 @@ constexpr int kFwdWarps = kFwdThreads / kWarp;
 // fma(|a|, max_k u'_k, b) - 82 instead of 90 FFMA2 and no compare / select chain per pixel.
 template <bool kCodes>
 __global__ void __launch_bounds__(kFwdThreads, 3) stage1_fwd_nhwc_kernel(const S1Params p) {
-  extern __shared__ __align__(16) float tiles[];         // two buffers of [(3*kBands+2) * (W+2)]
+  extern __shared__ __align__(16) float tiles[];         // two buffers of [(3*kFwdBands+2) * (W+2)]
   const int H = p.H, W = p.W, PH = p.PH, PW = p.PW, ld = W + 2, hw = H * W, phw = PH * PW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int tiles_per_sample = (PH + kBands - 1) / kBands;
+  const int tiles_per_sample = (PH + kFwdBands - 1) / kFwdBands;
   const int bands_per_tile = (PH + tiles_per_sample - 1) / tiles_per_sample;      // even split: 42 rows -> 6 x 7
   const long long total_tiles = (long long)p.G * p.group * tiles_per_sample;
-  const int tile_floats = (3 * kBands + 2) * ld;
+  const int tile_floats = (3 * kFwdBands + 2) * ld;
   f32x2 w2[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) w2[k] = pack2(__ldg(p.w + (2 * lane) * 9 + k), __ldg(p.w + (2 * lane + 1) * 9 + k));
@@ -827,10 +828,10 @@ extern "C" int afsl_stage1_fwd_f32(const float* x, const float* weight, const fl
   p.G = G; p.group = group; p.H = H; p.W = W; p.PH = H / 3; p.PW = W / 3; p.per_group = per_group;
   if (int rc = check(p, "afsl_stage1_fwd_f32")) return rc;
   if (channels_last) {        // lane = channel pair, warp = pooled pixel
-    const size_t nb = 2 * (size_t)(3 * kBands + 2) * (W + 2) * sizeof(float);      // double-buffered tile
+    const size_t nb = 2 * (size_t)(3 * kFwdBands + 2) * (W + 2) * sizeof(float);   // double-buffered tile
     void (*fn)(const S1Params) = argmax ? stage1_fwd_nhwc_kernel<true> : stage1_fwd_nhwc_kernel<false>;
     if (int rc = opt_in_smem(fn, nb, "afsl_stage1_fwd_f32")) return rc;
-    const long long tiles = (long long)G * group * ((p.PH + kBands - 1) / kBands);
+    const long long tiles = (long long)G * group * ((p.PH + kFwdBands - 1) / kFwdBands);
     const int cap = persistent_grid(fn, kFwdThreads, nb, 1 << 30);
     fn<<<(int)(tiles < cap ? tiles : cap), kFwdThreads, nb, (cudaStream_t)stream>>>(p);
     AFSL_CHECK_LAUNCH("afsl_stage1_fwd_f32");
