@@ -24,6 +24,19 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+@pytest.fixture(autouse=True)
+def _reproducible_rng(request):
+    """Every test starts from global generators seeded by its own name: module initialisations and random draws that do not
+    pass an explicit generator are the same on every run (a failure is then a property of the code, not of the draw)."""
+    import random
+    import zlib
+    seed = zlib.crc32(request.node.name.encode()) % (2 ** 31)
+    torch.manual_seed(seed)
+    np.random.seed(seed % (2 ** 32))
+    random.seed(seed)
+    yield
+
+
 def load_golden(name):
     """Committed fixture produced by tests/golden/make_golden.py from the real reference."""
     with np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False) as z:
