@@ -166,6 +166,17 @@ __global__ void __launch_bounds__(kCtaThreads) angular_warp_kernel(const AngPara
     const float cc = sum_norm > kNormEps ? 1.f : (sum_norm * inv) * (sum_norm * inv);
     const float csum_c = (ra * csum[a] + rq * cs) * inv;
     int count = 0;
+    if (p.miner_tan == 0.f) {
+      // angle 0: atan(ap / (2 nc)) > 0 iff ap > 0 for any finite nc (ap > 2 nc * 0): the distance to the pair centre is
+      // not needed, every negative of a pair with distinct anchor / positive passes
+      const bool on = act && !p.miner_never && ap > 0.f;
+      for (int k = 0; k < N; ++k) {
+        const bool pass = on && ((negmask >> k) & 1u);
+        count += pass;
+        const unsigned b = __ballot_sync(kFull, pass);
+        if (lane == k) wneg += __popc(b);
+      }
+    } else
     for (int k = 0; k < N; ++k) {
       const float gkk = __shfl_sync(kFull, gdiag, k), csk = __shfl_sync(kFull, cs, k);
       const float dot = (ra * gram[k * kLg + a] + rq * gram[k * kLg + q]) * inv;
