@@ -108,6 +108,23 @@ class EpisodeRunner:
         views = self.specaug.apply_batch(spec.reshape(e * n, *spec.shape[2:]), params, exact_spline=self.replay)
         return [views[v].view(e, n, *spec.shape[2:]) for v in range(4)]
 
+    def _features(self, s_views: List[torch.Tensor], q_views: List[torch.Tensor]):
+        """Support and query features.  When both sets have the same shape and view count, ONE encoder call and one
+        fusion call serve both: the encoder sees the 2V view tensors in the order support v0..v(V-1), query v0..v(V-1) -
+        the group order (BatchNorm statistics per 25-sample group, running-statistics updates) of two separate calls -
+        so nothing changes numerically except that every encoder parameter receives one gradient instead of two
+        (no accumulation kernels) and every encoder kernel launches once with twice the work."""
+        model = self.model
+        if (hasattr(model, "attention_model") and len(s_views) == len(q_views) and s_views[0].dim() == 5
+                and s_views[0].shape == q_views[0].shape):
+            nv, e = len(s_views), s_views[0].shape[0]
+            feats = model.backbone(list(s_views) + list(q_views))
+            s_list, q_list = feats[:nv], feats[nv:]
+            model.query_feature_list = q_list
+            fused = model.attention_model(torch.cat([torch.stack(s_list, dim=-2), torch.stack(q_list, dim=-2)], dim=0))
+            return fused[:e], fused[e:]
+        return model.compute_features(s_views), model(q_views)
+
     # ------------------------------------------------------------------ training
     def _draw_step_randomness(self, batch: EpisodeBatch) -> Dict[str, object]:
         """Everything the step draws on the HOST, in the reference's order per step: SpecAugment parameters
@@ -162,8 +179,7 @@ class EpisodeRunner:
         if self.concat_views:                                   # loops/loops.py:33-37
             sl, ql = sl.repeat(1, len(s_views)), ql.repeat(1, len(q_views))
         # support + query features, then the fused head: prototypes + FSL loss in one kernel
-        support_features = model.compute_features(s_views)
-        query_features = model(q_views)
+        support_features, query_features = self._features(s_views, q_views)
         fsl, protos, _ = ops.proto_head(support_features, sl, query_features, ql, n_way=batch.n_way)
         model.prototypes, model.support_features, model.support_labels = protos, support_features, sl
         out = {"fsl_loss": fsl}
@@ -320,8 +336,7 @@ class EpisodeRunner:
         sl, ql = batch.support_labels, batch.query_labels
         if self.concat_views:
             sl, ql = sl.repeat(1, len(s_views)), ql.repeat(1, len(q_views))
-        support_features = model.compute_features(s_views)
-        feats = model(q_views)
+        support_features, feats = self._features(s_views, q_views)
         _, _, correct, _ = ops.proto_eval(support_features, sl, feats, ql, n_way=batch.n_way)
         return correct, ql.shape[1]
 

@@ -23,8 +23,8 @@ print("kernels:", len(ev), "total us:", round(tot), "| kernels < 20 us:", len(sm
 from collections import Counter
 c = Counter()
 for e in small:
-    c[e.name[:60]] += 1
-for k, v in c.most_common(12):
+    c[e.name[:170]] += 1
+for k, v in c.most_common(40):
     print(v, k)
 big = Counter()
 for e in ev:
