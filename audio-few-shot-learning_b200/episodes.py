@@ -100,13 +100,25 @@ class EpisodeRunner:
             return None
         return self.specaug.draw_batch(e, n, t_len, replay_reference_rng=self.replay)
 
-    def _views(self, spec: torch.Tensor, params) -> List[torch.Tensor]:
-        """[E,N,1,F,T] -> list of V tensors [E,N,1,F,T]; ``params``: SpecAugParams (host or device tensors) or None."""
+    def _views(self, spec: torch.Tensor, params, out: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+        """[E,N,1,F,T] -> list of V tensors [E,N,1,F,T]; ``params``: SpecAugParams (host or device tensors) or None.
+        ``out`` [4, E*N, 1, F, T]: where the kernel writes the views (a slice of a buffer shared with the other set)."""
         if params is None:
             return [spec]
         e, n = spec.shape[:2]
-        views = self.specaug.apply_batch(spec.reshape(e * n, *spec.shape[2:]), params, exact_spline=self.replay)
+        views = self.specaug.apply_batch(spec.reshape(e * n, *spec.shape[2:]), params, exact_spline=self.replay, out=out)
         return [views[v].view(e, n, *spec.shape[2:]) for v in range(4)]
+
+    def _both_views(self, batch: EpisodeBatch, rnd: Dict[str, object]):
+        """Views of the support and the query set.  When both are augmented and have one shape, the two SpecAugment launches
+        write into ONE buffer [8, E*N, 1, F, T] (support views, then query views): the encoder batch of ``_features`` is then
+        that buffer as it stands, no concatenation copy."""
+        sup, qry = batch.support, batch.query
+        if rnd["sup"] is not None and rnd["qry"] is not None and sup.shape == qry.shape and sup.is_cuda:
+            e, n = sup.shape[:2]
+            buf = torch.empty(8, e * n, *sup.shape[2:], device=sup.device, dtype=torch.float32)
+            return self._views(sup, rnd["sup"], out=buf[:4]), self._views(qry, rnd["qry"], out=buf[4:])
+        return self._views(sup, rnd["sup"]), self._views(qry, rnd["qry"])
 
     def _features(self, s_views: List[torch.Tensor], q_views: List[torch.Tensor]):
         """Support and query features.  When both sets have the same shape and view count, ONE encoder call and one
@@ -173,8 +185,7 @@ class EpisodeRunner:
         """Device part of one step: views -> encoder -> fusion -> fused head (+ CPL / angular) -> backward."""
         cfg, model = self.cfg, self.model
         model.n_way = batch.n_way
-        s_views = self._views(batch.support, rnd["sup"])
-        q_views = self._views(batch.query, rnd["qry"])
+        s_views, q_views = self._both_views(batch, rnd)
         sl, ql = batch.support_labels, batch.query_labels
         if self.concat_views:                                   # loops/loops.py:33-37
             sl, ql = sl.repeat(1, len(s_views)), ql.repeat(1, len(q_views))
@@ -331,8 +342,7 @@ class EpisodeRunner:
     def _eval_compute(self, batch: EpisodeBatch, rnd: Dict[str, object]):
         """Device part of a single-segment evaluation step -> (#correct per task [E] int32, queries per task)."""
         model = self.model
-        s_views = self._views(batch.support, rnd["sup"])
-        q_views = self._views(batch.query, rnd["qry"])
+        s_views, q_views = self._both_views(batch, rnd)
         sl, ql = batch.support_labels, batch.query_labels
         if self.concat_views:
             sl, ql = sl.repeat(1, len(s_views)), ql.repeat(1, len(q_views))

@@ -240,6 +240,23 @@ def set_group_size(module: nn.Module, group_size: Optional[int]) -> None:
             m.group_size = group_size
 
 
+def _stack_views(spec_list: Sequence[torch.Tensor], e: int, n: int) -> torch.Tensor:
+    """The V view tensors [E,N,1,F,T] as one encoder batch [V*E*N,1,F,T].  Views that already are consecutive slices of one
+    buffer (what the SpecAugment kernel writes: [V, E*N, 1, F, T]) are re-viewed in place; anything else is concatenated."""
+    first = spec_list[0]
+    if not first.requires_grad and all(
+            x.is_contiguous() and x.shape == first.shape and not x.requires_grad
+            and x.untyped_storage().data_ptr() == first.untyped_storage().data_ptr()
+            and x.storage_offset() == first.storage_offset() + i * first.numel() for i, x in enumerate(spec_list)):
+        shape = (len(spec_list) * e * n, *first.shape[2:])
+        strides, acc = [], 1
+        for d in reversed(shape):
+            strides.append(acc)
+            acc *= d
+        return torch.as_strided(first, shape, tuple(reversed(strides)), first.storage_offset())
+    return torch.cat([x.reshape(e * n, *x.shape[2:]) for x in spec_list], dim=0)
+
+
 class EncoderModule(nn.Module):
     """Applies the encoder to every view (models/main_modules.py:10-23).
 
@@ -260,7 +277,7 @@ class EncoderModule(nn.Module):
             set_group_size(self.encoder, None)
             return [self.encoder(x) for x in spec_list]
         e, n = first.shape[:2]
-        stacked = torch.cat([x.reshape(e * n, *x.shape[2:]) for x in spec_list], dim=0)
+        stacked = _stack_views(spec_list, e, n)
         set_group_size(self.encoder, n)
         try:
             feats = self.encoder(stacked)
