@@ -119,6 +119,24 @@ def test_batched_encoder_equals_per_episode_calls():
             torch.testing.assert_close(got[v][e], want, rtol=1e-4, atol=1e-5)
 
 
+def test_stack_views_reuses_a_shared_buffer():
+    """Views that are consecutive slices of one buffer (what the SpecAugment kernel writes) become the encoder batch
+    without a copy; anything else (separate tensors, gaps, a different order) is concatenated - same values either way."""
+    from afsl_b200.models.main_modules import _stack_views
+    e, n, f, tl = 3, 4, 8, 10
+    buf = torch.randn(6, e * n, 1, f, tl)
+    views = [buf[v].view(e, n, 1, f, tl) for v in range(6)]
+    want = torch.cat([v.reshape(e * n, 1, f, tl) for v in views], 0)
+    got = _stack_views(views, e, n)
+    assert got.data_ptr() == buf.data_ptr() and torch.equal(got, want)                    # in place
+    tail = _stack_views(views[2:5], e, n)                                                 # a run that starts inside the buffer
+    assert tail.data_ptr() == buf[2].data_ptr() and torch.equal(tail, want[2 * e * n:5 * e * n])
+    for other in ([views[1], views[0]], [views[0], views[2]], [v.clone() for v in views[:2]]):
+        out = _stack_views(other, e, n)
+        assert out.data_ptr() != other[0].data_ptr()                                      # copied
+        assert torch.equal(out, torch.cat([v.reshape(e * n, 1, f, tl) for v in other], 0))
+
+
 def test_state_dict_keys_match_reference():
     from afsl_b200.models.main_modules import EncoderModule, ProjectionHead, SelfAttention
     from afsl_b200.models.prototypical import (ContrastivePrototypicalNetworks,
