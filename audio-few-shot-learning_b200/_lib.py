@@ -88,30 +88,61 @@ def launch_count() -> int:
     return int(load().afsl_launch_count())
 
 
+# devices of the tensors whose pointers were taken for the launch being assembled (ptr() ... then call())
+_pending_devices = []
+
+
+class _CurrentStream:
+    """Placeholder returned by stream_ptr(): call() replaces it with the current stream OF THE TENSORS' DEVICE."""
+
+
+_STREAM = _CurrentStream()
+
+
 def ptr(t, channels_last: bool = False):
     """Device pointer of a tensor or None; enforces the ABI's layout rules (``channels_last``: the tensor must be
-    dense in NHWC order - the entry points that take it say so)."""
+    dense in NHWC order - the entry points that take it say so) and records the tensor's device for call()."""
     if t is None:
         return None
-    if not t.is_cuda:
-        raise AfslError("libafsl operates on CUDA tensors only (no CPU path); got a %s tensor" % t.device)
-    if channels_last:
-        if not t.is_contiguous(memory_format=torch.channels_last):
-            raise AfslError("this libafsl entry point needs a channels-last (NHWC) tensor")
-    elif not t.is_contiguous():
-        raise AfslError("libafsl needs contiguous tensors")
-    p = t.data_ptr()
-    if p % 16 and t.numel():
-        raise AfslError("libafsl needs 16-byte aligned tensors")
+    try:
+        if not t.is_cuda:
+            raise AfslError("libafsl operates on CUDA tensors only (no CPU path); got a %s tensor" % t.device)
+        if channels_last:
+            if not t.is_contiguous(memory_format=torch.channels_last):
+                raise AfslError("this libafsl entry point needs a channels-last (NHWC) tensor")
+        elif not t.is_contiguous():
+            raise AfslError("libafsl needs contiguous tensors")
+        p = t.data_ptr()
+        if p % 16 and t.numel():
+            raise AfslError("libafsl needs 16-byte aligned tensors")
+    except AfslError:
+        _pending_devices.clear()
+        raise
+    _pending_devices.append(t.device.index)
     return p
 
 
-def stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def stream_ptr():
+    """The launch stream argument: resolved by call() to the current stream of the device that owns the tensors
+    (the reference picks ``cuda:{gpu_index}`` without ``set_device``, src/train_test.py:44-45, so the current
+    device need not be the tensors' device)."""
+    return _STREAM
 
 
 def call(name: str, *args) -> None:
+    """Launch one libafsl entry point on the device of its tensor arguments (all must share one device), on that
+    device's current stream."""
     lib = load()
-    rc = getattr(lib, name)(*args)
+    devices = set(_pending_devices)
+    _pending_devices.clear()
+    if len(devices) > 1:
+        raise AfslError(f"{name}: tensor arguments live on different devices {sorted(devices)}")
+    dev = devices.pop() if devices else torch.cuda.current_device()
+    fn = getattr(lib, name)
+    if dev == torch.cuda.current_device():
+        rc = fn(*[torch.cuda.current_stream(dev).cuda_stream if a is _STREAM else a for a in args])
+    else:
+        with torch.cuda.device(dev):              # grid sizing and the launch itself follow cudaGetDevice()
+            rc = fn(*[torch.cuda.current_stream(dev).cuda_stream if a is _STREAM else a for a in args])
     if rc != 0:
         raise AfslError(f"{name} failed (code {rc}): {lib.afsl_last_error().decode()}")

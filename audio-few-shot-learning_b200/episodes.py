@@ -23,7 +23,7 @@ import torch.nn.functional as F
 
 from . import ops
 from .loops.loss import draw_keep_reference, draw_keep_vectorised
-from .utils.augmentations import SpecAugment
+from .utils.augmentations import SpecAugment, SpecAugParams
 
 
 @dataclass
@@ -83,6 +83,7 @@ class EpisodeRunner:
         self._stage: Optional[EpisodeBatch] = None     # device staging buffers of the prefetched next batch
         self._prefetched: Optional[EpisodeBatch] = None
         self._copy_stream = None
+        self._pending_rnd = None                       # (batch, randomness) drawn ahead for the next train_step
         if use_cuda_graph:
             self._prefetch_done = torch.cuda.Event()
             self._inputs_consumed = torch.cuda.Event()
@@ -98,7 +99,9 @@ class EpisodeRunner:
         """Host-side SpecAugment parameters of E sets (datasets/batch_creation.py:111-121), or None."""
         if self.specaug is None or not augment:
             return None
-        return self.specaug.draw_batch(e, n, t_len, replay_reference_rng=self.replay)
+        # the warp spline is always evaluated on the host with the reference's op sequence (also in CUDA-graph mode,
+        # where the result refreshes a static buffer): the warped view is the reference's up to the last bit of the blend
+        return self.specaug.draw_batch(e, n, t_len, replay_reference_rng=self.replay).with_spline(t_len)
 
     def _views(self, spec: torch.Tensor, params, out: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
         """[E,N,1,F,T] -> list of V tensors [E,N,1,F,T]; ``params``: SpecAugParams (host or device tensors) or None.
@@ -106,7 +109,7 @@ class EpisodeRunner:
         if params is None:
             return [spec]
         e, n = spec.shape[:2]
-        views = self.specaug.apply_batch(spec.reshape(e * n, *spec.shape[2:]), params, exact_spline=self.replay, out=out)
+        views = self.specaug.apply_batch(spec.reshape(e * n, *spec.shape[2:]), params, exact_spline=True, out=out)
         return [views[v].view(e, n, *spec.shape[2:]) for v in range(4)]
 
     def _both_views(self, batch: EpisodeBatch, rnd: Dict[str, object]):
@@ -146,24 +149,48 @@ class EpisodeRunner:
         cfg = self.cfg
         e, ns = batch.support.shape[:2]
         nq, t_len = batch.query.shape[1], batch.support.shape[-1]
-        rnd: Dict[str, object] = {"sup": self._draw_views(e, ns, t_len, True),
-                                  "qry": self._draw_views(e, nq, t_len, cfg["train_query_augmentations"])}
-        views = 4 if rnd["qry"] is not None else 1
-        if cfg["use_contrastive"] and hasattr(self.model, "attention_model"):
+        aug_q = cfg["train_query_augmentations"]
+        fused = cfg["use_contrastive"] and hasattr(self.model, "attention_model")
+        use_cpl = cfg["use_contrastive"] and cfg["loss"]["cpl"]["use"]
+        views = 4 if (self.specaug is not None and aug_q) else 1
+        ql = batch.query_labels
+        if self.concat_views:
+            ql = ql.repeat(1, views)
+        rnd: Dict[str, object] = {}
+        if self.replay:
+            # episode by episode, each generator consumed in the reference's order: SpecAugment support, SpecAugment
+            # query (torch randint + NumPy), view shuffle (Python random), CPL negatives (torch randperm)
+            sup, qry, perms, keeps = [], [], [], []
+            m = int(cfg["loss"]["cpl"]["m_param"]) if use_cpl else 0
+            ql_host = ql.cpu()
+            for i in range(e):
+                sup.append(self._draw_views(1, ns, t_len, True))
+                qry.append(self._draw_views(1, nq, t_len, aug_q))
+                if fused:
+                    rest = list(range(1, views))
+                    random.shuffle(rest)
+                    perms.append([0] + rest)
+                if use_cpl:
+                    keeps.append(draw_keep_reference(ql_host[i], m))
+            rnd["sup"] = SpecAugParams.cat(sup) if sup[0] is not None else None
+            rnd["qry"] = SpecAugParams.cat(qry) if qry[0] is not None else None
+            if fused:
+                rnd["perm"] = torch.tensor(perms, dtype=torch.int64)
+            if use_cpl:
+                rnd["keep"] = ops.pack_keep(torch.stack(keeps))
+            return rnd
+        rnd["sup"] = self._draw_views(e, ns, t_len, True)
+        rnd["qry"] = self._draw_views(e, nq, t_len, aug_q)
+        if fused:
             perms = []
             for _ in range(e):
                 rest = list(range(1, views))
                 random.shuffle(rest)
                 perms.append([0] + rest)
             rnd["perm"] = torch.tensor(perms, dtype=torch.int64)
-        if cfg["use_contrastive"] and cfg["loss"]["cpl"]["use"]:
+        if use_cpl:
             m = int(cfg["loss"]["cpl"]["m_param"])
-            ql = batch.query_labels
-            if self.concat_views:
-                ql = ql.repeat(1, views)
-            if self.replay:
-                rnd["keep"] = ops.pack_keep(torch.stack([draw_keep_reference(row, m) for row in ql.cpu()]))
-            elif m < ql.shape[1] // batch.n_way:               # balanced synthetic / sampled episodes
+            if m < ql.shape[1] // batch.n_way:                 # balanced synthetic / sampled episodes
                 rnd["keep"] = ops.pack_keep(draw_keep_vectorised(ql.cpu(), m, batch.n_way))
         return rnd
 
@@ -176,15 +203,15 @@ class EpisodeRunner:
             elif v is None:
                 out[k] = None
             else:                                              # SpecAugParams
-                out[k] = type(v)(v.warp_p.to(device=device, dtype=torch.int32), v.warp_d.to(device=device, dtype=torch.int32),
-                                 v.time_masks.to(device=device, dtype=torch.int32),
-                                 v.freq_masks.to(device=device, dtype=torch.int32), v.set_size)
+                mv = lambda t, dt: None if t is None else t.to(device=device, dtype=dt, non_blocking=True)
+                out[k] = type(v)(mv(v.warp_p, torch.int32), mv(v.warp_d, torch.int32), mv(v.time_masks, torch.int32),
+                                 mv(v.freq_masks, torch.int32), v.set_size, mv(v.set_ids, torch.int32),
+                                 mv(v.src_x, torch.float32))
         return out
 
     def _train_compute(self, batch: EpisodeBatch, rnd: Dict[str, object]) -> Dict[str, torch.Tensor]:
         """Device part of one step: views -> encoder -> fusion -> fused head (+ CPL / angular) -> backward."""
         cfg, model = self.cfg, self.model
-        model.n_way = batch.n_way
         s_views, q_views = self._both_views(batch, rnd)
         sl, ql = batch.support_labels, batch.query_labels
         if self.concat_views:                                   # loops/loops.py:33-37
@@ -219,11 +246,12 @@ class EpisodeRunner:
         model = self.model
         model.train()
         device = next(model.parameters()).device
-        rnd = self._draw_step_randomness(batch)
+        if self._pending_rnd is not None and self._pending_rnd[0] is batch:
+            rnd = self._pending_rnd[1]                      # drawn while the previous step was running on the GPU
+        else:
+            rnd = self._draw_step_randomness(batch)
+        self._pending_rnd = None
         if self.use_cuda_graph:
-            if self.replay:
-                raise ValueError("use_cuda_graph needs replay_reference_rng=False: the reference-exact warp spline is "
-                                 "evaluated on the host from the drawn control points")
             out = self._graph_step(batch, rnd, device)
             if next_batch is not None:
                 self._prefetch(next_batch, device)
@@ -235,6 +263,9 @@ class EpisodeRunner:
             self.grad_sync()
         if self.optimizer is not None:
             self.optimizer.step()
+        if next_batch is not None:
+            # the following step's host draws (same generators, same order) overlap this step's device work
+            self._pending_rnd = (next_batch, self._draw_step_randomness(next_batch))
         return out
 
     # ------------------------------------------------------------------ CUDA-graph replay of the device part
@@ -284,6 +315,8 @@ class EpisodeRunner:
                 dst[k].warp_d.copy_(v.warp_d, non_blocking=True)
                 dst[k].time_masks.copy_(v.time_masks, non_blocking=True)
                 dst[k].freq_masks.copy_(v.freq_masks, non_blocking=True)
+                if v.src_x is not None:
+                    dst[k].src_x.copy_(v.src_x, non_blocking=True)
 
     def _capture(self, batch: EpisodeBatch, rnd: Dict[str, object], device):
         """Static buffers + three eager warm-up steps on a side stream (cuDNN autotuning, lazy initialisation),
@@ -294,6 +327,9 @@ class EpisodeRunner:
                          (s_batch.query, batch.query), (s_batch.query_labels, batch.query_labels)):
             dst.copy_(src)
         s_rnd = self._rnd_to(rnd, device)
+        # the warm-up passes must leave no trace: BatchNorm running statistics / num_batches_tracked are put back
+        # afterwards, so the first batch of a new shape is folded into them once (by the first replay), not four times
+        buffers = [(b, b.detach().clone()) for b in self.model.buffers()]
         side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
@@ -301,6 +337,9 @@ class EpisodeRunner:
                 for prm in self.model.parameters():
                     prm.grad = None
                 self._train_compute(s_batch, s_rnd)
+            with torch.no_grad():
+                for buf, saved in buffers:
+                    buf.copy_(saved)
         torch.cuda.current_stream(device).wait_stream(side)
         torch.cuda.synchronize(device)
         for prm in self.model.parameters():
@@ -382,6 +421,30 @@ class EpisodeRunner:
         graph.replay()
         return s_out
 
+    def _draw_eval_views(self, batch: EpisodeBatch, t_len: int, augment_query: bool, counts):
+        """SpecAugment parameters of E evaluation tasks -> (support, query) or None where a set is not augmented.
+        ``counts``: query rows per task for packed multi-segment tasks (ragged sets), None for [E,Nq,...] queries.
+        With ``replay_reference_rng`` the generators are consumed task by task, support then query - the order of E
+        successive ``sample_episode`` calls (datasets/batch_creation.py:111-115)."""
+        if self.specaug is None:
+            return None, None
+        e, ns = batch.support.shape[:2]
+        nq = batch.query.shape[1]
+        sa = self.specaug
+        if self.replay:
+            sup, qry = [], []
+            for i in range(e):
+                sup.append(sa.draw_batch(1, ns, t_len, True))
+                if augment_query:
+                    qry.append(sa.draw_batch(1, nq, t_len, True) if counts is None else sa.draw_ragged([counts[i]], t_len, True))
+            sup_p = SpecAugParams.cat(sup).with_spline(t_len)
+            return sup_p, (SpecAugParams.cat(qry).with_spline(t_len) if augment_query else None)
+        sup_p = sa.draw_batch(e, ns, t_len, False).with_spline(t_len)
+        if not augment_query:
+            return sup_p, None
+        qry_p = sa.draw_batch(e, nq, t_len, False) if counts is None else sa.draw_ragged(counts, t_len, False)
+        return sup_p, qry_p.with_spline(t_len)
+
     @torch.no_grad()
     def eval_step(self, batch: EpisodeBatch, augment_query: bool = False, clip_ids: Optional[torch.Tensor] = None,
                   seg_offsets: Optional[torch.Tensor] = None, tie_strategy: str = "") -> np.ndarray:
@@ -392,26 +455,24 @@ class EpisodeRunner:
         model = self.model
         model.eval()
         device = next(model.parameters()).device
-        model.n_way = batch.n_way
         t_len = batch.support.shape[-1]
         if seg_offsets is None:
-            rnd = {"sup": self._draw_views(*batch.support.shape[:2], t_len, True),
-                   "qry": self._draw_views(*batch.query.shape[:2], t_len, augment_query)}
-            if self.use_cuda_graph and not self.replay:
+            sup_p, qry_p = self._draw_eval_views(batch, t_len, augment_query, None)
+            rnd = {"sup": sup_p, "qry": qry_p}
+            if self.use_cuda_graph:
                 correct, per_task = self._eval_graph_step(batch, rnd, device)
             else:
                 correct, per_task = self._eval_compute(batch.to(device), self._rnd_to(rnd, device))
             return correct.cpu().numpy().astype(np.float64) / per_task
         batch = batch.to(device)
-        s_views = self._views(batch.support, self._draw_views(*batch.support.shape[:2], t_len, True))
+        # one SpecAugment draw per task, shared by all its query segments (batch_creation.py:113-115)
+        counts = (seg_offsets[1:] - seg_offsets[:-1]).tolist()
+        sup_p, q_params = self._draw_eval_views(batch, t_len, augment_query, counts)
+        s_views = self._views(batch.support, sup_p)
         sl = batch.support_labels
         if self.concat_views:
             sl = sl.repeat(1, len(s_views))
         support_features = model.compute_features(s_views)
-        # one SpecAugment draw per task, shared by all its query segments (batch_creation.py:113-115)
-        counts = (seg_offsets[1:] - seg_offsets[:-1]).tolist()
-        q_params = (self.specaug.draw_ragged(counts, t_len, replay_reference_rng=self.replay)
-                    if self.specaug is not None and augment_query else None)
         q_views = self._views(batch.query, q_params)
         feats = model(q_views)[0]                                # packed rows
         ql = batch.query_labels[0]

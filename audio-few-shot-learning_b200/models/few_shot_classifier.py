@@ -25,7 +25,6 @@ class FewShotClassifier(nn.Module):
         self.support_labels = torch.tensor(())
         self.feature_centering = feature_centering if feature_centering is not None else torch.tensor(0)
         self.feature_normalization = feature_normalization
-        self.n_way: Optional[int] = None      # optional hint; skips the unique() synchronisation
 
     @abstractmethod
     def forward(self, query_images: Tensor) -> Tensor:
@@ -59,7 +58,7 @@ class FewShotClassifier(nn.Module):
         self.support_labels = support_labels
         self.support_features = self.compute_features(support_images)
         self._raise_error_if_features_are_multi_dimensional(self.support_features)
-        self.prototypes = compute_prototypes(self.support_features, support_labels, self.n_way)
+        self.prototypes = compute_prototypes(self.support_features, support_labels)
 
     @staticmethod
     def _raise_error_if_features_are_multi_dimensional(features: Tensor):

@@ -301,9 +301,16 @@ class SelfAttention(nn.Module):
 
     def forward(self, x):
         lead = x.shape[:-2]                            # [N] or [E, N]
-        if x.is_cuda and FUSED_VIEW_FUSION and ops.view_fusion_supported(self.encoder_layer, x.shape[-2]):
+        if FUSED_VIEW_FUSION:
+            # the view fusion is a head kernel of this build: no eager / CPU path is taken silently
+            if not x.is_cuda:
+                raise RuntimeError("SelfAttention runs on the libafsl view-fusion kernel: CUDA tensors only (no CPU fallback)")
+            if not ops.view_fusion_supported(self.encoder_layer, x.shape[-2]):
+                raise NotImplementedError("view-fusion kernel supports embed_dim=64, num_heads=1, ffn_dim=256, post-norm ReLU "
+                                          f"and 1/2/4/8 views; got {self.embed_dim}/{self.num_heads}/{self.ffn_dim}, "
+                                          f"{x.shape[-2]} views")
             y = ops.view_fusion(x, self.encoder_layer)                 # libafsl kernel (fwd + bwd)
-        else:                                          # other layer shapes / CPU unit tests: stock module
+        else:                                          # A/B switch for measurements and tests only (never set by the package)
             y = self.encoder_layer(x.reshape(-1, *x.shape[-2:]))
         return y.reshape(*lead, -1)                    # views side by side == cat(y[:, i, :])
 

@@ -31,6 +31,28 @@ class SpecAugParams:
     freq_masks: torch.Tensor   # int64 [sets, num_mask, 2]
     set_size: int
     set_ids: Optional[torch.Tensor] = None   # int64 [samples]: ragged sets (then set_size is unused)
+    src_x: Optional[torch.Tensor] = None     # fp32 [samples, T]: the warp spline evaluated on the host (reference-exact)
+
+    def with_spline(self, spec_len: int) -> "SpecAugParams":
+        """Attach the reference-exact source coordinates of the time warp (``warp_source_x``; a few vectorised torch-CPU
+        ops on [samples, T]), so that the kernel does not evaluate the spline itself."""
+        self.src_x = warp_source_x(self.warp_p, self.warp_d, spec_len)
+        return self
+
+    @staticmethod
+    def cat(parts: "List[SpecAugParams]") -> "SpecAugParams":
+        """Parameters of several draws back to back (sets keep their order; ragged set ids are renumbered)."""
+        ids = None
+        if parts[0].set_ids is not None:
+            offs, chunks = 0, []
+            for p in parts:
+                chunks.append(p.set_ids + offs)
+                offs += p.time_masks.shape[0]
+            ids = torch.cat(chunks)
+        return SpecAugParams(torch.cat([p.warp_p for p in parts]), torch.cat([p.warp_d for p in parts]),
+                             torch.cat([p.time_masks for p in parts]), torch.cat([p.freq_masks for p in parts]),
+                             parts[0].set_size, ids,
+                             torch.cat([p.src_x for p in parts]) if parts[0].src_x is not None else None)
 
 
 class SpecAugment():
@@ -121,7 +143,9 @@ class SpecAugment():
     def apply_batch(self, spec: torch.Tensor, params: SpecAugParams, views_mask: int = 0b1111,
                     exact_spline: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """spec [N,1,F,T] on the GPU -> [4,N,1,F,T] = (copy, time-warp, time-mask, freq-mask)."""
-        src_x = warp_source_x(params.warp_p, params.warp_d, spec.shape[-1]) if exact_spline else None
+        src_x = params.src_x
+        if src_x is None and exact_spline:
+            src_x = warp_source_x(params.warp_p, params.warp_d, spec.shape[-1])
         return ops.specaug_views(spec, params.warp_p, params.warp_d, params.time_masks, params.freq_masks,
                                  float(self.mask_value), params.set_size, src_x=src_x, views_mask=views_mask, out=out,
                                  set_ids=params.set_ids)

@@ -430,6 +430,54 @@ def eval_throughput(runner, device, world, rank, tasks_per_step, steps):
     return out
 
 
+def tf32_variant(args, device, world, rank, episodes, host, barrier):
+    """Second, LABELLED line: the same step with cuDNN TF32 convolutions allowed (PyTorch's default, i.e. what the
+    reference itself would run on this GPU).  Fresh model with the headline's initial weights; reports throughput with
+    device-resident inputs and the first step's loss next to the fp32 run's for the same batch and seeds."""
+    import random
+    import numpy as np
+    import torch.distributed as dist
+    from afsl_b200 import parallel
+    from afsl_b200.episodes import EpisodeRunner
+    out = {}
+    first = {}
+    for allow in (False, True):
+        torch.backends.cudnn.allow_tf32 = allow
+        model = build_model(device)
+        for m in model.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        torch.manual_seed(4321); np.random.seed(4321); random.seed(4321)
+        runner = EpisodeRunner(model, EXPERIMENT_CONFIG, None, replay_reference_rng=False, use_cuda_graph=False)
+        first[allow] = runner.train_step(host[0])["loss"].double().cpu()
+    dev_loss = float(((first[True] - first[False]).abs() / first[False].abs()).max())
+    torch.backends.cudnn.allow_tf32 = True
+    model = build_model(device)
+    opt = torch.optim.Adam(model.parameters(), lr=EXPERIMENT_CONFIG["lr"])
+    runner = EpisodeRunner(model, EXPERIMENT_CONFIG, opt, replay_reference_rng=False, use_cuda_graph=not args.no_graph)
+    dp = parallel.EpisodeDataParallel(model)
+    runner.grad_sync = dp.sync_gradients if world > 1 else None
+    resident = [b.to(device) for b in host]
+    for i in range(args.warmup):
+        runner.train_step(resident[i % len(resident)])
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(args.steps):
+        runner.train_step(resident[i % len(resident)])
+    b.record()
+    barrier()
+    t = torch.tensor([a.elapsed_time(b)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    torch.backends.cudnn.allow_tf32 = False
+    return {"label": "cuDNN TF32 convolutions allowed (NOT the headline; parity suite validates fp32 only)",
+            "dtype": "tf32-conv", "value": world * episodes * args.steps / (ms * 1e-3), "unit": "episodes/s",
+            "ms_per_step": ms / args.steps,
+            "max_rel_loss_deviation_vs_fp32_first_step": dev_loss}
+
+
 def run_b200(args):
     import torch.distributed as dist
     import afsl_b200.ops as ops
@@ -440,6 +488,11 @@ def run_b200(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     torch.backends.cudnn.benchmark = True
+    # the headline is fp32 end to end: cuDNN's TF32 convolution / RNN kernels are switched off (PyTorch's default allows
+    # them), matching the fp32 arithmetic every parity test checks; matmuls are fp32 by PyTorch's own default.
+    # `--tf32` measures the TF32-convolution variant as a second, labelled line under extra_metrics.
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     pk, pk_src = peaks()
     E = args.episodes
 
@@ -502,6 +555,9 @@ def run_b200(args):
     e2e_value = world * E * args.steps / (e2e_ms * 1e-3)
     h2d_bytes = host[0].nbytes() * world            # whole job, like `value`
 
+    tf32_line = None
+    if not args.skip_tf32:
+        tf32_line = tf32_variant(args, device, world, rank, E, host, barrier)
     del host
     evals = eval_throughput(runner, device, world, rank, args.eval_tasks, max(2, args.steps // 2)) if not args.skip_eval else {}
 
@@ -543,7 +599,7 @@ def run_b200(args):
         "roofline": roofs.get("proto_head_fwd_bwd"),
         "kernels": roofs,
         "cpu_baseline": cpu,
-        "extra_metrics": evals,
+        "extra_metrics": dict(evals, **({"tf32_conv_variant": tf32_line} if tf32_line else {})),
     }
     print(json.dumps(line))
     if world > 1:
@@ -556,8 +612,8 @@ def main():
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--episodes", type=int, default=32, help="episodes per step per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
@@ -565,6 +621,7 @@ def main():
     ap.add_argument("--skip-eval", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-kernels", action="store_true")
+    ap.add_argument("--skip-tf32", action="store_true", help="skip the labelled TF32-convolution variant")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -51,7 +51,7 @@ def save(name, **arrays):
             v = v.detach().cpu().numpy()
         out[k] = np.asarray(v)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
-    print("wrote", name, {k: tuple(v.shape) for k, v in out.items()})
+    print("wrote", name, {k: tuple(v.shape) for k, v in out.items() if not k.startswith(("w_", "init_", "after_"))})
 
 
 # ------------------------------------------------------------------ head
@@ -463,9 +463,174 @@ def gen_sampler_wav():
     save("sampler_wav", dataset_seed=3, **out)
 
 
+# ------------------------------------------------------------------ multi-segment evaluation loop (config 4)
+def class_patterns(classes, t_len, seed, scale=0.4):
+    """[classes, 1, 128, t_len]: one smooth rank-one pattern per class (deterministic in ``seed``)."""
+    g = torch.Generator().manual_seed(10_000 + seed)
+    f = torch.nn.functional.avg_pool1d(torch.randn(classes, 1, 128 + 8, generator=g), 9, 1)[:, 0]
+    t = torch.nn.functional.avg_pool1d(torch.randn(classes, 1, t_len + 8, generator=g), 9, 1)[:, 0]
+    return (scale * 9.0 * f.unsqueeze(2) * t.unsqueeze(1)).unsqueeze(1)
+
+
+class FakeMultiSegSpecDataset(FakeMultiSegDataset):
+    """FakeMultiSegDataset with full-length spectrograms (the conv stack needs T >= 81) and an optional SpecAugment config."""
+
+    def __init__(self, cfg, classes=7, per_class=9, t_len=157, seed=0):
+        super().__init__(cfg, classes=classes, per_class=per_class, t_len=t_len, seed=seed)
+        self.specaug_use = bool(cfg["specaug_params"]["use"])
+        # class structure (a rank-one time-frequency pattern per class on top of the noise), so that the tasks are not
+        # pure chance and the argmax over prototypes is not decided by the last bits of near-identical distances
+        patterns = class_patterns(classes, t_len, seed)
+        for label_name, idx in zip(self.data_df["label"].tolist(), self.data_df["index_column"].tolist()):
+            self.clips[idx] = self.clips[idx] + patterns[self.class_to_label[label_name]]
+
+
+def _multiseg_models(kind):
+    """(model, experiment_config): 'concat' = Conv4, no views (ContrastivePrototypicalNetworksWithoutAttention);
+    'fused' = Hybrid + SpecAugment support/query views + self-attention fusion (ContrastivePrototypicalNetworks)."""
+    from models.main_modules import EncoderModule, ProjectionHead, SelfAttention, StandardCNN
+    from models.prototypical import ContrastivePrototypicalNetworks, ContrastivePrototypicalNetworksWithoutAttention
+    if kind == "concat":
+        cfg = {"encoder_name": "CNN", "specaug_params": {"use": False}}
+        mc = {"Projection": {"input_dim": 64, "hidden_dim": 16, "output_dim": 64}}
+
+        class Enc(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.encoder = StandardCNN(1, (1, 1, 128, 157), 64, [3, 3], 64)
+
+            def forward(self, views):
+                return [self.encoder(v) for v in views]
+        return ContrastivePrototypicalNetworksWithoutAttention(Enc(), ProjectionHead(mc)), cfg
+    cfg = {"encoder_name": "Hybrid",
+           "specaug_params": {"use": True, "mask_param": 16, "W": 22, "num_mask": 1, "mask_value": 0, "p": 0.282}}
+    mc = {"Hybrid": {"in_channels": 1, "seq_layers": 1, "seq_type": "RNN", "bidirectional": False, "hidden_channels": 64,
+                     "pool_dim": [3, 3], "out_dim": 64},
+          "Attention": {"embed_dim": 64, "num_heads": 1, "ffn_dim": 256, "dropout": 0.1},
+          "Projection": {"input_dim": 256, "hidden_dim": 16, "output_dim": 64}}
+    return ContrastivePrototypicalNetworks(EncoderModule(cfg, mc), SelfAttention(mc), ProjectionHead(mc)), cfg
+
+
+def _perturb_bn(model, seed):
+    """Non-trivial running statistics / affine parameters, as a trained checkpoint would have."""
+    g = torch.Generator().manual_seed(seed)
+    for m in model.modules():
+        if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
+            with torch.no_grad():
+                m.weight.copy_(torch.rand(m.weight.shape, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+
+
+def gen_multiseg_eval():
+    """The reference's own evaluate_multisegment_loop (loops/loops.py:250-283) on a multi-segment fake dataset, for the three
+    tie strategies: per-task accuracies (recorded by wrapping the reference's calculate_majority_vote_accuracy, which still
+    runs unmodified), the returned mean / std, the per-segment predictions and top-2 score margins.  The model is in eval
+    mode, as after contrastive_training_loop (whose last call is the validation).  The sampling seed is the first one from 41
+    whose smallest top-2 margin is >= 1e-4 (scores are ~0.1 in magnitude, fp32 convolution noise ~1e-7): the comparison
+    of per-task accuracies across devices must not hinge on the last bits of near-tied distances."""
+    import loops.loops as L
+    for kind in ("concat", "fused"):
+        torch.manual_seed(600 if kind == "concat" else 601)
+        model, cfg = _multiseg_models(kind)
+        _perturb_bn(model, 77)
+        model.eval()
+        ds = FakeMultiSegSpecDataset(cfg, seed=12)
+        margins, preds = [], []
+
+        def hook(_m, _inp, out):
+            top2 = torch.topk(out, 2, dim=1).values
+            margins.append(top2[:, 0] - top2[:, 1])
+            preds.append(torch.max(out, 1)[1])
+        handle = model.register_forward_hook(hook)
+        per_task, out = [], {}
+        original = L.calculate_majority_vote_accuracy
+
+        def recording(*a, **k):
+            acc = original(*a, **k)
+            per_task.append(acc)
+            return acc
+        L.calculate_majority_vote_accuracy = recording
+        n_tasks, ways, shots, queries = 6, 5, 3, 4
+        augment = cfg["specaug_params"]["use"]
+
+        def run(seed, strat):
+            per_task.clear(); margins.clear(); preds.clear()
+            random.seed(seed); np.random.seed(seed); torch.manual_seed(seed)
+            return L.evaluate_multisegment_loop(ds, ways, shots, queries, n_tasks, model, "cpu", strat, None, augment)
+        try:
+            seed = 41
+            while True:
+                run(seed, "")
+                if float(torch.cat(margins).min()) >= 1e-4:
+                    break
+                seed += 1
+            for strat in ("", "min_label", "max_posterior"):
+                msg = run(seed, strat)
+                key = strat or "first"
+                out[f"acc_{key}"] = np.array(per_task, dtype=np.float64)
+                out[f"mean_{key}"] = msg["mean_accuracy"]
+                out[f"std_{key}"] = msg["accuracy_std"]
+        finally:
+            L.calculate_majority_vote_accuracy = original
+            handle.remove()
+        save(f"multiseg_eval_{kind}", dataset_seed=12, rng_seed=seed, n_tasks=n_tasks, ways=ways, shots=shots, queries=queries,
+             margins=torch.cat(margins), pred=torch.cat(preds), rows_per_task=np.array([m.numel() for m in margins]),
+             **out, **{"w_" + k: v for k, v in model.state_dict().items()})
+
+
+# ------------------------------------------------------------------ 2000-task accuracy identity (north-star target)
+class FakeManyClassDataset(FakeDataset):
+    """24 classes x 12 single-segment clips: enough for 20-way 5-shot 5-query tasks."""
+
+    def __init__(self, cfg, seed=0, t_len=157):
+        super().__init__(cfg, classes=24, per_class=12, t_len=t_len, seed=seed)
+        patterns = class_patterns(24, t_len, seed)
+        self.items = self.items + patterns.repeat_interleave(12, dim=0).unsqueeze(1)
+
+
+def gen_tasks2000():
+    """The reference's evaluate_single_segment (loops/loops.py:84-121) over 2000 sampled tasks for each of
+    (W, K) in {5, 20} x {1, 5}, Q = 5, Conv4 ProtoNet in eval mode with fixed weights (BASELINE config 5 / config 1 model).
+    Per-task accuracies are recovered from a forward hook on the model (scores -> argmax == labels is what
+    evaluate_on_one_task computes; asserted against the returned mean / std).  Also stored: the eval-mode embedding of every
+    dataset item (so the head can be checked on the reference's own embeddings) and the smallest top-2 margin per config."""
+    import loops.loops as L
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(700)
+    model, cfg = _multiseg_models("concat")
+    _perturb_bn(model, 78)
+    model.eval()
+    ds = FakeManyClassDataset(cfg, seed=13)
+    with torch.no_grad():
+        emb = torch.cat([model.backbone([ds.items[i:i + 32, 0]])[0] for i in range(0, ds.items.shape[0], 32)])
+    out = {}
+    n_tasks = int(os.environ.get("AFSL_N_TASKS", "2000"))
+    for ways, shots in ((5, 1), (5, 5), (20, 1), (20, 5)):
+        accs, margins = [], []
+        labels = torch.arange(ways).repeat_interleave(5)
+
+        def hook(_m, _inp, scores):
+            top2 = torch.topk(scores, 2, dim=1).values
+            margins.append(float((top2[:, 0] - top2[:, 1]).min()))
+            accs.append(int((torch.max(scores, 1)[1] == labels).sum()) / labels.numel())
+        handle = model.register_forward_hook(hook)
+        random.seed(1000 + ways * 10 + shots)
+        mean, std = L.evaluate_single_segment(model, ds, n_tasks, "cpu", ways, shots, 5, None, False)
+        handle.remove()
+        accs = np.array(accs, dtype=np.float64)
+        assert accs.size == n_tasks and np.mean(accs) == mean and np.std(accs) == std
+        key = f"{ways}w{shots}s"
+        out.update({f"acc_{key}": accs, f"mean_{key}": mean, f"std_{key}": std, f"margin_{key}": np.array(margins)})
+        print(key, mean, std, min(margins), flush=True)
+    save("tasks2000_cnn", dataset_seed=13, n_tasks=n_tasks, embeddings=emb, **out,
+         **{"w_" + k: v for k, v in model.state_dict().items()})
+
+
 if __name__ == "__main__":
     import_reference()
     torch.set_num_threads(1)            # fixed reduction order for the fixtures
-    which = sys.argv[1:] or ["head", "cpl", "specaug", "vote", "modules", "epoch", "epoch_first", "sampler", "sampler_wav"]
+    which = sys.argv[1:] or ["head", "cpl", "specaug", "vote", "modules", "epoch", "epoch_first", "sampler", "sampler_wav", "multiseg_eval"]
     for name in which:
         globals()["gen_" + name]()

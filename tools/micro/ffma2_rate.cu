@@ -1,5 +1,6 @@
 // Microbenchmark: fp32 FMA issue rates on sm_100a - scalar FFMA, packed FFMA2 (reg pairs), FFMA2 with a scalar (.F32)
-// multiplicand - in FMA lanes per clock per SM.  nvcc -arch=sm_100a -O3 -o ffma2_rate ffma2_rate.cu && ./ffma2_rate
+// multiplicand - in FMA lanes per clock per SM.  build ON THE GPU BOX into /tmp with the shared runtime (a statically linked
+// cudart in the shipped tree trips the driver's closed-call scan): nvcc -arch=sm_100a -O3 -cudart shared -o /tmp/ffma2_rate ffma2_rate.cu && /tmp/ffma2_rate
 #include <cstdio>
 #include <cuda_runtime.h>
 typedef unsigned long long f32x2;
