@@ -257,6 +257,9 @@ def _stack_views(spec_list: Sequence[torch.Tensor], e: int, n: int) -> torch.Ten
     return torch.cat([x.reshape(e * n, *x.shape[2:]) for x in spec_list], dim=0)
 
 
+MAX_SAMPLES_PER_CALL = 8192      # samples per encoder call on the batched path (see EncoderModule.forward)
+
+
 class EncoderModule(nn.Module):
     """Applies the encoder to every view (models/main_modules.py:10-23).
 
@@ -280,7 +283,14 @@ class EncoderModule(nn.Module):
         stacked = _stack_views(spec_list, e, n)
         set_group_size(self.encoder, n)
         try:
-            feats = self.encoder(stacked)
+            # whole groups per cuDNN call, at most MAX_SAMPLES_PER_CALL samples: BatchNorm statistics are per group (or the
+            # running ones), so splitting the batch changes nothing numerically, and the 64-channel stage-2 tensors stay
+            # below 2^31 elements (beyond that cuDNN's fp32 convolutions fall back to kernels ~20x slower)
+            per_call = max(n, (MAX_SAMPLES_PER_CALL // n) * n)
+            if stacked.shape[0] <= per_call:
+                feats = self.encoder(stacked)
+            else:
+                feats = torch.cat([self.encoder(stacked[lo:lo + per_call]) for lo in range(0, stacked.shape[0], per_call)])
         finally:
             set_group_size(self.encoder, None)
         return [f.view(e, n, -1) for f in feats.chunk(len(spec_list), dim=0)]

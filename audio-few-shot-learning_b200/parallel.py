@@ -40,32 +40,63 @@ def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 class EpisodeDataParallel:
-    """Keeps replicas in sync: broadcast parameters once, then one flat all-reduce of gradients per step."""
+    """Keeps replicas in sync: broadcast parameters and buffers once, then one flat all-reduce of gradients per step.
+
+    ``sync_gradients`` costs three launches whatever the number of parameters: one gather of all gradients into the flat
+    bucket (``torch.cat(out=)``), one ``all_reduce`` (NCCL averages in the collective itself), one multi-tensor copy back
+    into the ``.grad`` tensors (``torch._foreach_copy_``).  ``local_episodes`` / ``total_episodes`` weight a rank's
+    gradient by its share of the step's episodes, so unequal shards (``shard_range``) still give the global episode mean.
+    """
 
     def __init__(self, module: torch.nn.Module):
         self.module = module
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.params: List[torch.nn.Parameter] = [p for p in module.parameters() if p.requires_grad]
         self._flat: Optional[torch.Tensor] = None
+        self._views: List[torch.Tensor] = []
+        self._nccl = dist.is_initialized() and dist.get_backend() == "nccl"
         if self.world > 1:
             for t in list(module.parameters()) + list(module.buffers()):
                 dist.broadcast(t.data, src=0)
 
-    def sync_gradients(self) -> None:
+    def _bucket(self, like: torch.Tensor) -> None:
+        total = sum(p.numel() for p in self.params)
+        self._flat = torch.zeros(total, device=like.device, dtype=torch.float32)
+        self._views, off = [], 0
+        for p in self.params:
+            self._views.append(self._flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+    def sync_gradients(self, local_episodes: Optional[int] = None, total_episodes: Optional[int] = None) -> None:
         """Average gradients over ranks with a single all-reduce (mean over all episodes of the step)."""
         if self.world == 1:
             return
-        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
         if self._flat is None:
-            self._flat = torch.empty(sum(g.numel() for g in grads), device=grads[0].device, dtype=torch.float32)
+            self._bucket(next(p for p in self.params))
+        for p in self.params:                                   # parameters this step did not touch contribute zeros
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        grads = [p.grad for p in self.params]
         torch.cat([g.reshape(-1) for g in grads], out=self._flat)
-        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
-        self._flat.div_(self.world)
-        off = 0
-        for p, g in zip(self.params, grads):
-            n = g.numel()
-            p.grad = self._flat[off:off + n].view_as(p).clone() if p.grad is None else p.grad.copy_(self._flat[off:off + n].view_as(p))
-            off += n
+        weight = 1.0
+        if local_episodes is not None and total_episodes:
+            weight = local_episodes * self.world / float(total_episodes)     # 1.0 for equal shards
+        if weight != 1.0:
+            self._flat.mul_(weight)
+        if self._nccl:
+            dist.all_reduce(self._flat, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
+            self._flat.div_(self.world)
+        torch._foreach_copy_(grads, self._views)
+
+    def sync_buffers(self) -> None:
+        """Rank 0's buffers (BatchNorm running statistics) to every rank: call before evaluation / checkpointing, since
+        each rank folds only its own episodes into the running statistics."""
+        if self.world == 1:
+            return
+        for b in self.module.buffers():
+            dist.broadcast(b.data, src=0)
 
 
 def gather_accuracies(local_acc: np.ndarray, total: int) -> np.ndarray:
