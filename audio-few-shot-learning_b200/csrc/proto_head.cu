@@ -523,6 +523,11 @@ int launch(const HeadParams& p, bool bwd, cudaStream_t stream, const char* name)
     const int rc = launch_head_warp(p, bwd, stream, name, &handled);
     if (rc != AFSL_OK || handled) return rc;
   }
+  {   // many-way forward of fixed-size tasks: the q.p contraction on the tcgen05 tensor cores (proto_head_mma.cu)
+    bool handled = false;
+    const int rc = launch_head_mma(p, bwd, stream, name, &handled);
+    if (rc != AFSL_OK || handled) return rc;
+  }
   {   // many-way forward: register batches of query rows against shared-memory prototypes (proto_head_wide.cu)
     bool handled = false;
     const int rc = launch_head_wide(p, bwd, stream, name, &handled);

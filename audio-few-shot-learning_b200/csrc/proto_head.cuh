@@ -35,5 +35,8 @@ struct HeadParams {
 int launch_head_warp(const HeadParams& p, bool bwd, cudaStream_t stream, const char* name, bool* handled);
 // proto_head_wide.cu: forward launches of many-way episodes (W >= 8, D in {128,256}); same contract
 int launch_head_wide(const HeadParams& p, bool bwd, cudaStream_t stream, const char* name, bool* handled);
+// proto_head_mma.cu: forward launches of fixed-size many-way tasks (8 <= W <= 24, 25 < Nq <= 128, D in {64,128,256}) with the
+// query x prototype contraction on tcgen05 tensor cores in 3-pass split TF32; same contract
+int launch_head_mma(const HeadParams& p, bool bwd, cudaStream_t stream, const char* name, bool* handled);
 
 }  // namespace afsl

@@ -106,6 +106,7 @@ def test_head_batched_vs_oracle(ops, monkeypatch, ways, shots, nq, dim, path):
     both kernel families: one warp per episode (registers; small W*D) and one CTA per episode (any shape)."""
     monkeypatch.setenv("AFSL_HEAD_WARP", "1" if path == "warp" else "0")
     monkeypatch.setenv("AFSL_HEAD_WIDE", "1" if path == "warp" else "0")     # many-way forward: register-batch kernel / lane groups
+    monkeypatch.setenv("AFSL_HEAD_MMA", "1" if path == "warp" else "0")      # many-way forward: tcgen05 kernel / fp32-pipe kernels
     e = 37
     gen = torch.Generator().manual_seed(ways * 1000 + dim)
     s = torch.randn(e, ways * shots, dim, generator=gen)
@@ -127,6 +128,53 @@ def test_head_batched_vs_oracle(ops, monkeypatch, ways, shots, nq, dim, path):
         close(sg.grad[i], sc.grad)
         close(qg.grad[i], qc.grad)
         assert int(correct[i]) == ohead.evaluate_task(ohead.l2_scores(qc, pr), ql[i])[0]
+
+
+@pytest.mark.parametrize("ways,shots,nq,dim", [(20, 5, 5, 256), (20, 1, 5, 256), (20, 5, 5, 64), (20, 1, 5, 64), (20, 5, 5, 128),
+                                               (10, 3, 7, 128), (24, 2, 5, 256), (8, 4, 16, 64)])
+def test_head_many_way_tensor_core_kernel(ops, monkeypatch, ways, shots, nq, dim):
+    """proto_head_mma.cu (tcgen05, 3-pass split TF32) on 333 tasks per launch - several tasks per persistent CTA, so
+    every barrier phase, both accumulators and both pipeline stages are reused - against the oracle task by task
+    (scores / posterior / loss 1e-5, prototypes exact to rounding, argmax and #correct equal) and against the fp32-pipe
+    kernel on the same inputs; also the given-prototypes entry (afsl_proto_scores_fwd_f32)."""
+    e = 333
+    gen = torch.Generator().manual_seed(ways * 100 + dim + shots)
+    s = torch.randn(e, ways * shots, dim, generator=gen)
+    q = torch.randn(e, ways * nq, dim, generator=gen)
+    sl = torch.stack([torch.arange(ways).repeat_interleave(shots)[torch.randperm(ways * shots, generator=gen)] for _ in range(e)])
+    ql = torch.randint(0, ways, (e, ways * nq), generator=gen)
+    out = {}
+    for mma in ("1", "0"):
+        monkeypatch.setenv("AFSL_HEAD_MMA", mma)
+        pred, post, correct, scores = ops.proto_eval(s.cuda(), sl.cuda(), q.cuda(), ql.cuda(), n_way=ways, want_scores=True)
+        loss, protos, corr2 = ops.proto_head(s.cuda(), sl.cuda(), q.cuda(), ql.cuda(), n_way=ways)
+        sc2 = ops.l2_scores(q.cuda(), protos)
+        torch.cuda.synchronize()
+        out[mma] = [x.cpu() for x in (pred, post, correct, scores, loss, protos, corr2, sc2)]
+    pred, post, correct, scores, loss, protos, corr2, sc2 = out["1"]
+    assert torch.equal(correct, corr2)
+    flips = 0
+    for i in range(e):
+        pr = ohead.prototypes(s[i], sl[i])
+        sc = ohead.l2_scores(q[i], pr)
+        po, pd = torch.max(sc, 1)
+        close(protos[i], pr)
+        close(scores.view(e, ways * nq, ways)[i], sc)
+        close(sc2[i], sc)
+        close(post.view(e, -1)[i], po)
+        close(loss[i], ohead.fsl_loss(pr, q[i], ql[i]))
+        same = pred.view(e, -1)[i].long() == pd
+        if not bool(same.all()):                      # only a tie closer than fp32 rounding of the distances may differ
+            top2 = torch.topk(sc, 2, dim=1).values
+            assert float((top2[:, 0] - top2[:, 1])[~same].max()) < 1e-5 * float(sc.abs().max())
+            flips += int((~same).sum())
+        else:
+            assert int(correct[i]) == int((pd == ql[i]).sum())
+    agree = float((out["1"][0] == out["0"][0]).float().mean())
+    print(f"[{ways}w{shots}s q{nq} D={dim}] argmax flips vs oracle on near-ties: {flips} of {e * ways * nq} rows; "
+          f"agreement with the fp32-pipe kernel {agree:.6f}")
+    assert flips <= 2 and agree > 0.9999
+    close(out["1"][3], out["0"][3])
 
 
 @pytest.mark.parametrize("ways,shots,dim,wide", [(5, 5, 64, 1), (20, 5, 256, 1), (20, 5, 256, 0), (20, 1, 64, 1), (20, 1, 64, 0),
@@ -224,6 +272,59 @@ def test_cpl_batched_vs_oracle(ops, monkeypatch, ways, per, dim, m, path):
 
 
 # ------------------------------------------------------------------ angular (restated-oracle parity: PML unpinned)
+def _pml():
+    """pytorch_metric_learning when the box has it (runtime probe; it is in neither the reference's
+    requirements.txt nor this image, so normally None -> the angular results are 'restated-oracle parity')."""
+    try:
+        import pytorch_metric_learning
+        from pytorch_metric_learning import losses, miners
+        return pytorch_metric_learning, losses, miners
+    except ImportError:
+        return None
+
+
+def test_angular_oracle_provenance(ops):
+    """Says, in the test log, which oracle pins the angular loss on this box, and - when the real package is importable -
+    checks the restatement (oracle/angular.py) and the kernel against pytorch_metric_learning itself, driven exactly like
+    the reference wrapper does (loops/loss.py:63-97)."""
+    from oracle import angular as oang
+    pml = _pml()
+    if pml is None:
+        print("pytorch_metric_learning NOT importable here: angular parity is restated-oracle parity (oracle/angular.py)")
+        pytest.skip("pytorch_metric_learning not installed: restated-oracle parity only")
+    mod, losses, miners = pml
+    print("pytorch_metric_learning", mod.__version__, "importable: angular parity pinned to the real package")
+    gen = torch.Generator().manual_seed(123)
+    ways, per, dim = 5, 5, 64
+    for angle in (0.0, 15.0):
+        for anchors in (True, False):
+            protos = torch.nn.functional.normalize(torch.randn(ways, dim, generator=gen), dim=-1)
+            queries = torch.nn.functional.normalize(torch.randn(ways * per, dim, generator=gen) + 0.5 * protos.repeat_interleave(per, 0), dim=-1)
+            labels = torch.arange(ways).repeat_interleave(per)
+            loss_fn, miner = losses.AngularLoss(), miners.AngularMiner(angle=angle)
+            pc, qc = protos.clone().requires_grad_(True), queries.clone().requires_grad_(True)
+            proto_labels = torch.arange(ways)
+            if anchors:                                                            # loops/loss.py:68-83
+                a, pp, nn_ = miner(pc, proto_labels, qc, labels)
+                emb = pc[a]
+                ref = torch.cat([qc[pp], qc[nn_]])
+                ref_labels = torch.cat([labels[pp], labels[nn_]])
+                want = loss_fn(emb, proto_labels[a], ref_emb=ref, ref_labels=ref_labels)
+            else:                                                                  # loops/loss.py:84-96
+                x = torch.cat([pc, qc])
+                y = torch.cat([proto_labels, labels])
+                want = loss_fn(x, y, miner(x, y))
+            want.backward()
+            got_oracle = oang.angular_loss_class(protos, queries, labels, angle, anchors)
+            close(got_oracle, want.detach(), rtol=1e-6)
+            pg, qg = protos.cuda().requires_grad_(True), queries.cuda().requires_grad_(True)
+            got = ops.angular_loss(pg, qg, labels.cuda(), angle, 40.0, anchors, False)
+            got.backward()
+            close(got, want.detach(), rtol=2e-5)
+            close(pg.grad, pc.grad, rtol=1e-4)
+            close(qg.grad, qc.grad, rtol=1e-4)
+
+
 @pytest.mark.parametrize("anchors", [True, False])
 @pytest.mark.parametrize("angle", [0.0, 15.0, 30.0])
 @pytest.mark.parametrize("unit_protos", [True, False])
