@@ -48,6 +48,8 @@ SIGNATURES = {
     "afsl_stage1_finalize_f64": [_P, _I, _P, _P, _P, _F, _D, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "afsl_stage1_dw_f32": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _D, _I, _P, _P, _P, _P, _P],
     "afsl_eval_vote_i32": [_P, _P, _P, _P, _P, _I, _P, _P, _I, _P],
+    "afsl_linear_fwd_f32": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "afsl_linear_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
 }
 
 _lib = None
@@ -75,6 +77,8 @@ def load() -> ctypes.CDLL:
     lib.afsl_stage1_acc_slots.restype = c_int
     lib.afsl_gbn_nhwc_parts.restype = c_int
     lib.afsl_gbn_nhwc_parts.argtypes = [c_int]
+    lib.afsl_linear_bwd_workspace_floats.restype = c_longlong
+    lib.afsl_linear_bwd_workspace_floats.argtypes = [c_int, c_int, c_int]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

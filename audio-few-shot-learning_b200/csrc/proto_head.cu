@@ -523,9 +523,11 @@ int launch(const HeadParams& p, bool bwd, cudaStream_t stream, const char* name)
     const int rc = launch_head_warp(p, bwd, stream, name, &handled);
     if (rc != AFSL_OK || handled) return rc;
   }
-  {   // many-way forward of fixed-size tasks: the q.p contraction on the tcgen05 tensor cores (proto_head_mma.cu)
+  {   // many-way forward of fixed-size tasks: TMA-fed ring, q.p on the tcgen05 tensor cores (proto_head_tma.cu)
     bool handled = false;
-    const int rc = launch_head_mma(p, bwd, stream, name, &handled);
+    int rc = launch_head_tma(p, bwd, stream, name, &handled);
+    if (rc != AFSL_OK || handled) return rc;
+    rc = launch_head_mma(p, bwd, stream, name, &handled);      // its LDG-fed predecessor, AFSL_HEAD_MMA=2 only
     if (rc != AFSL_OK || handled) return rc;
   }
   {   // many-way forward: register batches of query rows against shared-memory prototypes (proto_head_wide.cu)

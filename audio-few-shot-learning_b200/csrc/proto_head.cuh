@@ -38,5 +38,7 @@ int launch_head_wide(const HeadParams& p, bool bwd, cudaStream_t stream, const c
 // proto_head_mma.cu: forward launches of fixed-size many-way tasks (8 <= W <= 24, 25 < Nq <= 128, D in {64,128,256}) with the
 // query x prototype contraction on tcgen05 tensor cores in 3-pass split TF32; same contract
 int launch_head_mma(const HeadParams& p, bool bwd, cudaStream_t stream, const char* name, bool* handled);
+// proto_head_tma.cu: the same shapes with every byte arriving through a TMA-filled shared-memory ring (the default)
+int launch_head_tma(const HeadParams& p, bool bwd, cudaStream_t stream, const char* name, bool* handled);
 
 }  // namespace afsl

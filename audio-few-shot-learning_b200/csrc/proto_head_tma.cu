@@ -1,0 +1,493 @@
+// Prototype head forward for MANY-WAY tasks: TMA-fed, tcgen05 tensor cores, TMEM accumulators (sm_100a).
+//
+// Same arithmetic and reference as proto_head_wide.cu / proto_head_mma.cu (models/util_functions.py:6-19: per-class mean of
+// the support rows in ascending row order; few_shot_classifier.py:108-116: -torch.cdist, in the matmul form
+// |q|^2 + |p|^2 - 2 q.p clamped at 0 that cdist itself uses beyond 25 rows; loops/loss.py:24-37: log-softmax + NLL;
+// loops/loops.py:79: first-index argmax, #correct).  This is the shape of the path that is a real dense contraction
+// (Nq = 100 rows x W = 20 prototypes x D = 64..256 per task, thousands of tasks: SURVEY 8d config 5), so q.p runs on
+// `tcgen05.mma.kind::tf32` in split precision: the tensor core reads the RAW fp32 rows TMA delivered (it truncates them to
+// TF32 itself: hi), the CUDA cores only derive lo = rna_tf32(x - trunc_tf32(x)), and
+//     q.p = lo.lo + lo.hi + hi.lo + hi.hi          (four passes, fp32 accumulation in TMEM, ~22 bits per product).
+//
+// One persistent CTA per SM; every byte comes in through ONE ring of 16 KB shared-memory stages filled by TMA
+// (cp.async.bulk.tensor.2d, 128-byte swizzle = the UMMA operand layout), 6-8 stages (~80-100 KB) ahead of the consumers and
+// across task boundaries - Little's law at ~1.2 us loaded latency needs ~50 KB in flight per SM, and no load latency is ever
+// exposed.  A stage holds one k-block (32 columns) of either the task's support rows or its query rows.  Roles (mbarriers
+// only, no CTA barrier in the task loop):
+//   warp 9     loader    one lane: arms the stage's mbarrier with the byte count and issues the TMA box
+//   warps 0-7  producers two groups of four warps take alternate stages.  Support stage: per-class sums straight out of
+//                        the swizzled rows (thread = class x 16-byte chunk, rows of a class in ascending order from a
+//                        per-task bucket list) -> prototype chunk, |p|^2, the split prototype tiles (B operand);
+//                        query stage: lo tile (ring of four) for the raw tile, |q|^2
+//   warp 8     issuer    one lane: 16 MMAs (128 x 32 x 8) per query stage, tcgen05.commit hands the stage back to the loader
+//   warps 10-13 epilogue tcgen05.ld of the 128 x 32 accumulator (thread = query row): distances, first-index argmax,
+//                        log-softmax / NLL, #correct; two accumulators, so task t's epilogue overlaps task t+1's stages
+#include <cstdlib>
+
+#include "proto_head.cuh"
+#include "tc_common.cuh"
+
+namespace afsl {
+namespace {
+
+using namespace tc;
+
+constexpr unsigned kFullMask = 0xffffffffu;
+constexpr int kProducerWarps = 8;
+constexpr int kProducers = kProducerWarps * 32;
+constexpr int kGroups = 2;                                      // producer groups taking alternate stages
+constexpr int kGroupWarps = kProducerWarps / kGroups;
+constexpr int kGroupThreads = kGroupWarps * 32;                 // 128
+constexpr int kIssuerWarp = 8;
+constexpr int kLoaderWarp = 9;
+constexpr int kEpiWarp0 = 10;
+constexpr int kEpiWarps = 4;
+constexpr int kTmaThreads = (kEpiWarp0 + kEpiWarps) * 32;       // 448
+constexpr int kTileM = 128;                                     // query rows per accumulator (TMEM lanes)
+constexpr int kTileN = 32;                                      // prototype slots per accumulator (TMEM columns)
+constexpr int kMaxWays = 24;                                    // B tiles hold 24 rows (3 KB); the MMA's slots 24..31 read on into
+                                                                // the next tile / the lo ring: garbage columns nobody looks at
+constexpr int kBlockK = 32;                                     // fp32 per 128-byte swizzle row = one stage's columns
+constexpr int kTile = kTileM * 128;                             // bytes of one [128 x 32] fp32 tile = one ring stage
+constexpr int kBTile = kMaxWays * 128;
+constexpr int kLoRing = 4;
+constexpr int kMaxRing = 9;
+constexpr int kMaxSupportRows = kTileM;
+constexpr uint32_t kIdesc = idesc_tf32(kTileM, kTileN);
+
+struct TmaBars {
+  uint64_t tma_full[kMaxRing];    // stage filled by TMA (transaction bytes)
+  uint64_t ready[kMaxRing];       // stage processed by its producer group (4 warps)
+  uint64_t empty[kMaxRing];       // stage free again (issuer: plain arrive for support stages, tcgen05.commit for query stages)
+  uint64_t lo_free[kLoRing];      // lo tile free again (tcgen05.commit)
+  uint64_t b_empty;               // the task's MMAs are done with the prototype tiles
+  uint64_t acc_full[2], epi_done[2], meta_full[2];
+};
+
+struct TmaMeta {
+  TmaBars bars;
+  uint32_t tmem_base;
+  float qq[2][kGroups][kTileM];          // |q|^2 partial sums: the k-blocks each producer group handled
+  float pp[2][kGroups][kTileN];
+  float part[kEpiWarps];
+  int hits[kEpiWarps];
+  int cnt[2][kTileN];                    // rows per class
+  int warp_cnt[kProducerWarps][kTileN];  // rows per class inside each producer warp's 32-row slice
+};
+
+// waiting roles that are not on the critical path (loader, epilogue) sleep between polls instead of competing with the
+// producers for issue slots
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!done) __nanosleep(64);
+  } while (!done);
+}
+
+__device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory"); }
+__device__ __forceinline__ void epilogue_bar() { asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
+
+template <int kD, int kRing>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_q) {
+  constexpr int kKB = kD / kBlockK;
+  static_assert(kKB % kGroups == 0, "stages of a task must split evenly over the producer groups");
+  extern __shared__ __align__(1024) uint8_t smem_tma_raw[];
+  uint8_t* smem = smem_tma_raw + ((1024u - (smem_u32(smem_tma_raw) & 1023u)) & 1023u);     // 1 KB: swizzle atoms
+  const uint32_t ring = smem_u32(smem);                                        // [kRing][16 KB] raw rows as TMA wrote them
+  const uint32_t b_base = ring + kRing * kTile;                                // [kKB][hi, lo][3 KB] split prototypes
+  const uint32_t lo_base = b_base + kKB * 2 * kBTile;                          // [kLoRing][16 KB] lo tiles of query stages
+  TmaMeta* meta = reinterpret_cast<TmaMeta*>(smem + kRing * kTile + kKB * 2 * kBTile + kLoRing * kTile);
+  uint8_t* rows_base = reinterpret_cast<uint8_t*>(meta + 1);                   // [2][W][row_stride]: bucketed support rows
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int W = p.W, Nq = p.Nq;
+  const int sup_rows = p.support ? p.Ns : W;                                   // given prototypes: one "support row" per class
+  const int row_stride = (sup_rows + 7) & ~7;                                  // a class's row list is read 8 ids at a time
+
+  if (tid == 0) {
+    for (int s = 0; s < kRing; ++s) {
+      mbar_init(&meta->bars.tma_full[s], 1);
+      mbar_init(&meta->bars.ready[s], kGroupWarps);
+      mbar_init(&meta->bars.empty[s], 1);
+    }
+    for (int s = 0; s < kLoRing; ++s) mbar_init(&meta->bars.lo_free[s], 1);
+    mbar_init(&meta->bars.b_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&meta->bars.acc_full[i], 1);
+      mbar_init(&meta->bars.epi_done[i], kEpiWarps);
+      mbar_init(&meta->bars.meta_full[i], kProducerWarps);
+    }
+    fence_barrier_init();
+    prefetch_tensormap(&map_s);
+    prefetch_tensormap(&map_q);
+  }
+  // prototype slots W..23 of every B tile stay zero for the whole launch
+  for (int i = tid; i < kKB * 2 * kBTile / 16; i += kTmaThreads) sts4(b_base + i * 16, make_float4(0.f, 0.f, 0.f, 0.f));
+  if (warp == kIssuerWarp) tmem_alloc<64>(&meta->tmem_base);
+  fence_async_proxy();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = meta->tmem_base;
+
+  if (warp == kLoaderWarp) {
+    // =============================================================== loader
+    if (lane == 0) {
+      uint32_t c = 0;
+      for (int e = blockIdx.x; e < p.E; e += gridDim.x) {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const CUtensorMap* map = half ? &map_q : &map_s;
+          const int rows = half ? Nq : sup_rows;
+#pragma unroll 1
+          for (int kb = 0; kb < kKB; ++kb, ++c) {
+            const uint32_t s = c % kRing;
+            mbar_wait_relaxed(&meta->bars.empty[s], ((c / kRing) & 1) ^ 1);
+            mbar_arrive_expect_tx(&meta->bars.tma_full[s], (uint32_t)rows * 128u);
+            tma_load_2d(ring + s * kTile, map, kb * kBlockK, e * rows, &meta->bars.tma_full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp < kProducerWarps) {
+    // =============================================================== producers
+    const int grp = warp / kGroupWarps, gtid = tid & (kGroupThreads - 1);
+    uint32_t c = 0;                        // stages issued so far (all tasks); this group handles those with (kb & 1) == grp
+    uint32_t qc = 0;                       // query stages so far -> lo ring slot
+    int it = 0;
+    // this thread's support label of the first task (row = tid); the next task's is fetched one task ahead
+    int next_lab = -1;
+    if (tid < sup_rows && blockIdx.x < p.E) next_lab = p.support ? p.s_labels[(size_t)blockIdx.x * p.Ns + tid] : tid;
+    for (int e = blockIdx.x; e < p.E; e += gridDim.x, ++it) {
+      const int par = it & 1;
+      mbar_wait(&meta->bars.epi_done[par], ((it >> 1) & 1) ^ 1);     // |p|^2, |q|^2, bucket of parity `par` are free
+      // ---------------------------------------------------------- bucket the support rows by class, ascending rows
+      const int my_lab = next_lab;
+      {
+        const int en = e + gridDim.x;
+        next_lab = -1;
+        if (tid < sup_rows && en < p.E) next_lab = p.support ? p.s_labels[(size_t)en * p.Ns + tid] : tid;
+      }
+      uint8_t* rows = rows_base + (size_t)par * W * row_stride;
+      const bool valid = my_lab >= 0 && my_lab < W;                  // other labels are left out, as in the fp32-pipe kernels
+      if (warp * 32 < sup_rows) {
+        for (int w = 0; w < W; ++w) {
+          const unsigned m = __ballot_sync(kFullMask, my_lab == w);
+          if (lane == 0) meta->warp_cnt[warp][w] = __popc(m);
+        }
+      } else if (lane < W) {
+        meta->warp_cnt[warp][lane] = 0;
+      }
+      producer_bar();
+      {
+        const unsigned same = __match_any_sync(kFullMask, my_lab);
+        if (valid) {
+          int pos = __popc(same & ((1u << lane) - 1u));
+          for (int wj = 0; wj < warp; ++wj) pos += meta->warp_cnt[wj][my_lab];
+          rows[my_lab * row_stride + pos] = (uint8_t)tid;
+        }
+        if (tid < W) {
+          int n = 0;
+          for (int wj = 0; wj < kProducerWarps; ++wj) n += meta->warp_cnt[wj][tid];
+          meta->cnt[par][tid] = n;
+        }
+      }
+      producer_bar();
+      // ---------------------------------------------------------- support stages: prototypes, |p|^2, split prototype tiles
+      {
+        // item = (class w, 16-byte chunk j): 8 W items over the group's 128 threads, two rounds
+        float pp_acc[2] = {0.f, 0.f};
+        int n_it[2];
+        float rcp_it[2], fn_it[2];
+        const uint8_t* rows_it[2];
+#pragma unroll
+        for (int rnd = 0; rnd < 2; ++rnd) {
+          const int w = (gtid + rnd * kGroupThreads) >> 3;
+          n_it[rnd] = w < W ? meta->cnt[par][w] : 0;
+          rows_it[rnd] = rows + (w < W ? w : 0) * row_stride;
+          // mean = sum / n through a refined reciprocal and one residual correction (the division's own fast path, without
+          // its per-element reciprocal): n == 0 gives 0 * inf = NaN, as the reference's empty mean
+          fn_it[rnd] = (float)n_it[rnd];
+          const float r0 = __frcp_rn(fn_it[rnd]);
+          rcp_it[rnd] = r0;
+        }
+#pragma unroll 1
+        for (int kb = 0; kb < kKB; ++kb, ++c) {
+          if ((kb & 1) != grp) continue;
+          const uint32_t s = c % kRing;
+          mbar_wait(&meta->bars.tma_full[s], (c / kRing) & 1);
+          if (kb == grp) mbar_wait(&meta->bars.b_empty, (it & 1) ^ 1);       // previous task's MMAs are done with the tiles
+          const uint32_t stage = ring + s * kTile;
+#pragma unroll
+          for (int rnd = 0; rnd < 2; ++rnd) {
+            const int item = gtid + rnd * kGroupThreads;
+            const int w = item >> 3, j = item & 7;
+            const bool act = w < W;
+            const int n = n_it[rnd];
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            // 8 rows per step: one 64-bit read of the row ids, 8 independent 128-bit reads, then the adds in row order
+            for (int i0 = 0; i0 < n; i0 += 8) {
+              const uint2 ids = *reinterpret_cast<const uint2*>(rows_it[rnd] + i0);
+              float4 v[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const uint32_t r = ((u < 4 ? ids.x : ids.y) >> (8 * (u & 3))) & 0xffu;
+                v[u] = lds4(stage + sw128((int)(i0 + u < n ? r : 0u), j));
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u)
+                if (i0 + u < n) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+            }
+            float sq = 0.f;
+            if (act) {
+              const float rc = rcp_it[rnd], fn = fn_it[rnd];
+              auto mean = [&](float sum) { const float q0 = sum * rc; return fmaf(fmaf(-q0, fn, sum), rc, q0); };
+              acc = make_float4(mean(acc.x), mean(acc.y), mean(acc.z), mean(acc.w));
+              if (p.protos_out && p.support)
+                *reinterpret_cast<float4*>(p.protos_out + ((size_t)e * W + w) * kD + kb * kBlockK + 4 * j) = acc;
+              sq = fmaf(acc.x, acc.x, fmaf(acc.y, acc.y, fmaf(acc.z, acc.z, acc.w * acc.w)));
+              const uint32_t off = sw128(w, j);
+              sts4(b_base + (kb * 2 + 0) * kBTile + off, acc);               // hi: the tensor core truncates it itself
+              sts4(b_base + (kb * 2 + 1) * kBTile + off, lo_of_raw(acc));
+            }
+            sq += __shfl_xor_sync(kFullMask, sq, 1);
+            sq += __shfl_xor_sync(kFullMask, sq, 2);
+            sq += __shfl_xor_sync(kFullMask, sq, 4);
+            pp_acc[rnd] += sq;
+          }
+          fence_async_proxy();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&meta->bars.ready[s]);
+        }
+#pragma unroll
+        for (int rnd = 0; rnd < 2; ++rnd) {
+          const int item = gtid + rnd * kGroupThreads;
+          if ((item & 7) == 0 && (item >> 3) < kTileN) meta->pp[par][grp][item >> 3] = pp_acc[rnd];
+        }
+      }
+      // ---------------------------------------------------------- query stages: lo tile for the raw tile, |q|^2
+      {
+        const int r0 = gtid >> 3, j = gtid & 7;                              // rows r0 + 16 t: 2 KB apart, same swizzle phase
+        const uint32_t off0 = sw128(r0, j);
+        float qacc[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) qacc[t] = 0.f;
+#pragma unroll 1
+        for (int kb = 0; kb < kKB; ++kb, ++c, ++qc) {
+          if ((kb & 1) != grp) continue;
+          const uint32_t s = c % kRing, ls = qc % kLoRing;
+          mbar_wait(&meta->bars.tma_full[s], (c / kRing) & 1);
+          const uint32_t src = ring + s * kTile + off0, dst = lo_base + ls * kTile + off0;
+          // rows >= Nq of the tile were never written by TMA: whatever they hold only reaches accumulator rows nobody reads
+          float4 v[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v[t] = lds4(src + t * 2048);
+          mbar_wait(&meta->bars.lo_free[ls], ((qc / kLoRing) & 1) ^ 1);      // the MMAs of query stage qc - 4 are done with the slot
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            sts4(dst + t * 2048, lo_of_raw(v[t]));
+            qacc[t] = fmaf(v[t].x, v[t].x, fmaf(v[t].y, v[t].y, fmaf(v[t].z, v[t].z, fmaf(v[t].w, v[t].w, qacc[t]))));
+          }
+          fence_async_proxy();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&meta->bars.ready[s]);
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          float x = qacc[t];
+          x += __shfl_xor_sync(kFullMask, x, 1);
+          x += __shfl_xor_sync(kFullMask, x, 2);
+          x += __shfl_xor_sync(kFullMask, x, 4);
+          if (j == 0) meta->qq[par][grp][r0 + 16 * t] = x;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&meta->bars.meta_full[par]);
+    }
+  } else if (warp == kIssuerWarp) {
+    // =============================================================== MMA issuer
+    // The whole warp runs the (warp-uniform) control flow and the barrier waits; one elected lane issues.  The descriptors
+    // of a stage are four 32-bit words computed once, each MMA adds a constant: ~4 instructions per MMA on the issuing
+    // thread (a 128 x 32 x 8 MMA occupies the tensor pipe for 16 cycles, so the issue loop must not cost more than that).
+    uint32_t c = 0, qc = 0;
+    int it = 0;
+    for (int e = blockIdx.x; e < p.E; e += gridDim.x, ++it) {
+      const int par = it & 1;
+#pragma unroll 1
+      for (int kb = 0; kb < kKB; ++kb, ++c) {                               // support stages: consumed by the producers only
+        const uint32_t s = c % kRing;
+        mbar_wait(&meta->bars.ready[s], (c / kRing) & 1);
+        if (elect_one()) mbar_arrive(&meta->bars.empty[s]);
+      }
+      mbar_wait(&meta->bars.epi_done[par], ((it >> 1) & 1) ^ 1);            // accumulator `par` drained (task it-2)
+      const uint32_t acc = tmem + par * kTileN;
+#pragma unroll 1
+      for (int kb = 0; kb < kKB; ++kb, ++c, ++qc) {
+        const uint32_t s = c % kRing, ls = qc % kLoRing;
+        mbar_wait(&meta->bars.ready[s], (c / kRing) & 1);
+        fence_after();
+        if (elect_one()) {
+          const uint32_t a_hi = desc_lo(ring + s * kTile), a_lo = desc_lo(lo_base + ls * kTile);
+          const uint32_t b_hi = desc_lo(b_base + kb * 2 * kBTile), b_lo = desc_lo(b_base + (kb * 2 + 1) * kBTile);
+          // small terms first: lo.lo, lo.hi, hi.lo, hi.hi; a K step of 8 fp32 = 32 bytes = 2 descriptor units
+          mma_tf32_lo(acc, a_lo, b_lo, kIdesc, kb != 0);
+#pragma unroll
+          for (int k = 1; k < kBlockK / 8; ++k) mma_tf32_lo(acc, a_lo + 2 * k, b_lo + 2 * k, kIdesc, 1u);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 8; ++k) mma_tf32_lo(acc, a_lo + 2 * k, b_hi + 2 * k, kIdesc, 1u);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 8; ++k) mma_tf32_lo(acc, a_hi + 2 * k, b_lo + 2 * k, kIdesc, 1u);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 8; ++k) mma_tf32_lo(acc, a_hi + 2 * k, b_hi + 2 * k, kIdesc, 1u);
+          commit(&meta->bars.empty[s]);
+          commit(&meta->bars.lo_free[ls]);
+          if (kb == kKB - 1) {
+            commit(&meta->bars.acc_full[par]);
+            commit(&meta->bars.b_empty);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =============================================================== epilogue: thread = query row
+    const int quad = warp & 3;                                              // TMEM lanes 32 quad .. 32 quad + 31
+    const int row = quad * 32 + lane;
+    int it = 0;
+    for (int e = blockIdx.x; e < p.E; e += gridDim.x, ++it) {
+      const int par = it & 1, ph = (it >> 1) & 1;
+      mbar_wait_relaxed(&meta->bars.meta_full[par], ph);
+      mbar_wait_relaxed(&meta->bars.acc_full[par], ph);
+      fence_after();
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + par * kTileN, v);
+      const bool live = row < Nq;
+      const float qq = meta->qq[par][0][live ? row : 0] + meta->qq[par][1][live ? row : 0];
+      const int y = (live && p.q_labels) ? p.q_labels[(size_t)e * Nq + row] : -1;
+      const bool need_scores = p.scores != nullptr || p.loss != nullptr;
+      float m = -INFINITY, vy = 0.f, se = 1.f;
+      int am = 0x7fffffff;
+      if (need_scores) {
+        float sc[kMaxWays];
+#pragma unroll
+        for (int w = 0; w < kMaxWays; ++w) {
+          // |q|^2 + |p|^2 - 2 q.p clamped at 0, as at::_euclidean_dist; -sqrt = the score
+          const int wc = w < W ? w : 0;
+          const float pw2 = meta->pp[par][0][wc] + meta->pp[par][1][wc];
+          const float d2 = fmaxf(fmaf(-2.f, __uint_as_float(v[w]), qq) + pw2, 0.f);
+          const float s = -sqrtf(d2);
+          sc[w] = s;
+          if (w < W) {
+            if (s > m) { m = s; am = w; }                                   // first index among equal maxima, like torch.max
+            if (s != s && am == 0x7fffffff) am = w;                         // NaN row: keep something defined
+            if (w == y) vy = s;
+          }
+        }
+        if (p.loss) {
+          se = 0.f;
+#pragma unroll
+          for (int w = 0; w < kMaxWays; ++w)
+            if (w < W) se += expf(sc[w] - m);
+        }
+        if (live && p.scores) {
+          float* dst = p.scores + ((size_t)e * Nq + row) * W;
+#pragma unroll
+          for (int w = 0; w < kMaxWays; ++w)
+            if (w < W) dst[w] = sc[w];
+        }
+      } else {
+        // evaluation only (labels, posterior, #correct): the smallest squared distance wins, one square root per row
+        float best = INFINITY;
+#pragma unroll
+        for (int w = 0; w < kMaxWays; ++w) {
+          const int wc = w < W ? w : 0;
+          const float pw2 = meta->pp[par][0][wc] + meta->pp[par][1][wc];
+          const float d2 = fmaxf(fmaf(-2.f, __uint_as_float(v[w]), qq) + pw2, 0.f);
+          if (w < W) {
+            if (d2 < best) { best = d2; am = w; }
+            if (d2 != d2 && am == 0x7fffffff) am = w;
+          }
+        }
+        m = -sqrtf(best);
+      }
+      float nll = 0.f;
+      int hit = 0;
+      if (live) {
+        const size_t r = (size_t)e * Nq + row;
+        if (p.pred) p.pred[r] = am;
+        if (p.posterior) p.posterior[r] = m;
+        if (p.loss && y >= 0 && y < W) nll = -((vy - m) - logf(se));        // log_softmax then NLL
+        hit = (am == y);
+      }
+      if (p.loss || p.correct) {
+        nll = warp_sum(nll);
+        for (int o = 16; o > 0; o >>= 1) hit += __shfl_xor_sync(kFullMask, hit, o);
+        if (lane == 0) { meta->part[quad] = nll; meta->hits[quad] = hit; }
+        epilogue_bar();
+        if (quad == 0 && lane == 0) {
+          if (p.loss) p.loss[e] = (meta->part[0] + meta->part[1] + meta->part[2] + meta->part[3]) / (float)Nq;
+          if (p.correct) p.correct[e] = meta->hits[0] + meta->hits[1] + meta->hits[2] + meta->hits[3];
+        }
+        epilogue_bar();
+      }
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&meta->bars.epi_done[par]);
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == kIssuerWarp) tmem_free<64>(tmem);
+}
+
+template <int kD, int kRing>
+int launch_variant(const HeadParams& p, const CUtensorMap& ms, const CUtensorMap& mq, int sup_rows, cudaStream_t stream,
+                   const char* name) {
+  static_assert(kRing <= kMaxRing, "ring too deep for the barrier arrays");
+  auto fn = head_tma_fwd_kernel<kD, kRing>;
+  const size_t bytes = (size_t)kRing * kTile + (size_t)(kD / kBlockK) * 2 * kBTile + (size_t)kLoRing * kTile + sizeof(TmaMeta) +
+                       2 * (size_t)p.W * ((sup_rows + 7) & ~7) + 1024 + 16;
+  if (int rc = opt_in_smem(fn, bytes, name)) return rc;
+  int sms = kNumSMs, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.E < sms ? p.E : sms;
+  fn<<<grid, kTmaThreads, bytes, stream>>>(p, ms, mq);
+  AFSL_CHECK_LAUNCH(name);
+  return AFSL_OK;
+}
+
+}  // namespace
+
+// Forward launches of fixed-size many-way tasks: 8 <= W <= 24, 25 < Nq <= 128 (the reference's cdist is in its matmul form
+// there too), D in {64, 128, 256}, support block (<= 128 rows) or given prototypes.  AFSL_HEAD_MMA=0 disables it (the parity
+// tests run this kernel and the fp32-pipe kernels on the same cases), AFSL_HEAD_MMA=2 selects the LDG-fed variant
+// (proto_head_mma.cu).
+int launch_head_tma(const HeadParams& p, bool bwd, cudaStream_t stream, const char* name, bool* handled) {
+  *handled = false;
+  if (bwd || !p.queries || p.q_offsets || !(p.support || p.protos_in)) return AFSL_OK;
+  if (p.W < 8 || p.W > kMaxWays || p.Nq <= 25 || p.Nq > kTileM) return AFSL_OK;
+  if (p.D != 64 && p.D != 128 && p.D != 256) return AFSL_OK;
+  const int sup_rows = p.support ? p.Ns : p.W;
+  if (sup_rows > kMaxSupportRows) return AFSL_OK;
+  const char* env = getenv("AFSL_HEAD_MMA");
+  if (env && atoi(env) != 1) return AFSL_OK;
+  const int ring_stages = p.D == 256 ? 6 : p.D == 128 ? 7 : 8;
+  const size_t bytes = (size_t)ring_stages * kTile + (size_t)(p.D / kBlockK) * 2 * kBTile + (size_t)kLoRing * kTile +
+                       sizeof(TmaMeta) + 2 * (size_t)p.W * ((sup_rows + 7) & ~7) + 1024 + 16;
+  if (bytes > 220 * 1024) return AFSL_OK;          // very long support blocks: the fp32-pipe kernels take the launch
+  *handled = true;
+  CUtensorMap ms, mq;
+  const float* sup = p.support ? p.support : p.protos_in;
+  if (int rc = make_tensor_map_f32(&ms, sup, (uint64_t)p.E * sup_rows, (uint64_t)p.D, (uint32_t)sup_rows, name)) return rc;
+  if (int rc = make_tensor_map_f32(&mq, p.queries, (uint64_t)p.E * p.Nq, (uint64_t)p.D, (uint32_t)p.Nq, name)) return rc;
+  if (p.D == 256) return launch_variant<256, 6>(p, ms, mq, sup_rows, stream, name);
+  if (p.D == 128) return launch_variant<128, 7>(p, ms, mq, sup_rows, stream, name);
+  return launch_variant<64, 8>(p, ms, mq, sup_rows, stream, name);
+}
+
+}  // namespace afsl

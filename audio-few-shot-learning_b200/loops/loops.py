@@ -87,8 +87,9 @@ def evaluate_on_one_task(model, support_images, support_labels, query_images, qu
 
 
 def evaluate_single_segment(model, dataset, num_val_tasks, device, n_classes, k_support, k_query, feat_extractor,
-                            eval_query_augmentation):
-    """(mean, std) of the per-task accuracies over ``num_val_tasks`` sampled tasks (loops/loops.py:84-121)."""
+                            eval_query_augmentation, return_accuracies: bool = False):
+    """(mean, std) of the per-task accuracies over ``num_val_tasks`` sampled tasks (loops/loops.py:84-121);
+    ``return_accuracies`` (extension) appends the per-task list - what a rank contributes to a sharded evaluation."""
     accuracies = []
     model.eval()
     with torch.no_grad():
@@ -100,6 +101,8 @@ def evaluate_single_segment(model, dataset, num_val_tasks, device, n_classes, k_
             correct, total = evaluate_on_one_task(model, [t.to(device) for t in support_list], support_labels.to(device),
                                                   [t.to(device) for t in query_list], query_labels.to(device))
             accuracies.append(correct / total)
+    if return_accuracies:
+        return np.mean(accuracies), np.std(accuracies), accuracies
     return np.mean(accuracies), np.std(accuracies)
 
 
@@ -107,9 +110,11 @@ def contrastive_training_loop(model, train_dataset, validation_dataset, optimize
                               cpl_loss_fn, l_param, epochs, train_scheduler, patience, results_path, project_prototypes,
                               normalize_prototypes, n_train_classes, n_validation_classes, k_support_train, k_support_validation,
                               k_query_train, k_query_validation, feat_extractor, use_contrastive, train_query_augmentations,
-                              validation_query_augmentations, episodes_per_step: int = 1, runner=None):
+                              validation_query_augmentations, episodes_per_step: int = 1, runner=None, accuracy_sync=None):
     """Epoch loop with early stopping on the validation accuracy; reloads and returns the best model
-    (loops/loops.py:124-167).  The checkpoint lives at experiments/<results_path>/model.pt like the reference's."""
+    (loops/loops.py:124-167).  The checkpoint lives at experiments/<results_path>/model.pt like the reference's.
+    ``accuracy_sync`` (extension, multi-GPU): maps this rank's validation accuracy to the one every rank must act on
+    (rank 0's), so that all ranks stop at the same epoch."""
     folder = os.path.join(PROJECT_PATH, "experiments", results_path)
     os.makedirs(folder, exist_ok=True)
     checkpoint = os.path.join(folder, "model.pt")
@@ -128,6 +133,8 @@ def contrastive_training_loop(model, train_dataset, validation_dataset, optimize
                                               n_classes=n_validation_classes, k_support=k_support_validation,
                                               k_query=k_query_validation, feat_extractor=feat_extractor,
                                               eval_query_augmentation=validation_query_augmentations)
+        if accuracy_sync is not None:
+            accuracy = accuracy_sync(accuracy)
         stopper(val_accuracy=accuracy, model=model, epoch=epoch)
         if stopper.early_stop:
             print("Early Stopping.")
@@ -153,8 +160,9 @@ def calculate_majority_vote_accuracy(predicted_labels, spectrogram_ids, query_la
 
 
 def evaluate_multisegment_loop(test_dataset, n_classes, k_support, k_query, num_test_tasks, trained_model, device, tie_strategy,
-                               feat_extractor, eval_query_augmentation):
-    """{"mean_accuracy", "accuracy_std"} over multi-segment test tasks (loops/loops.py:250-283)."""
+                               feat_extractor, eval_query_augmentation, return_accuracies: bool = False):
+    """{"mean_accuracy", "accuracy_std"} over multi-segment test tasks (loops/loops.py:250-283); ``return_accuracies``
+    (extension) adds the per-task list under "accuracies"."""
     accuracies = []
     for _ in range(num_test_tasks):
         support_list, support_labels, query_list, query_labels, audio_ids = sample_episode(
@@ -172,4 +180,7 @@ def evaluate_multisegment_loop(test_dataset, n_classes, k_support, k_query, num_
             accuracies.append(calculate_majority_vote_accuracy(predicted_labels=predicted_labels, spectrogram_ids=audio_ids,
                                                                query_labels=query_labels, tie_strategy=tie_strategy,
                                                                posterior_values=posterior_values))
-    return {"mean_accuracy": np.mean(accuracies), "accuracy_std": np.std(accuracies)}
+    msg = {"mean_accuracy": np.mean(accuracies), "accuracy_std": np.std(accuracies)}
+    if return_accuracies:
+        msg["accuracies"] = accuracies
+    return msg

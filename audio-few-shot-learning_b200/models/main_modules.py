@@ -339,5 +339,6 @@ class ProjectionHead(nn.Module):
         self.ln2 = nn.LayerNorm(self.output_dim)
 
     def forward(self, x):
-        x = self.fc2(F.relu(self.fc1(x)))
-        return ops.l2_normalize(x, eps=1e-12)          # libafsl kernel; CUDA only, no eager fallback
+        # three libafsl launches (fc1 + ReLU, fc2, L2 normalise), forward and backward; CUDA only, no eager fallback
+        h = ops.linear(x, self.fc1.weight, self.fc1.bias, relu=True)
+        return ops.l2_normalize(ops.linear(h, self.fc2.weight, self.fc2.bias), eps=1e-12)

@@ -243,6 +243,48 @@ def l2_normalize(x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
     return _L2Normalize.apply(_f32(x), eps)
 
 
+# ---------------------------------------------------------------------------------- Linear (projection head)
+class _Linear(torch.autograd.Function):
+    """y = x w^T + b (optionally ReLU) on the libafsl SGEMM; x [M,K], w [N,K], b [N]."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        m, k = x.shape
+        n = weight.shape[0]
+        y = torch.empty(m, n, device=x.device, dtype=torch.float32)
+        call("afsl_linear_fwd_f32", ptr(x), ptr(weight), ptr(bias), ptr(y), m, n, k, int(relu), stream_ptr())
+        ctx.save_for_backward(x, weight, y if relu else None)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, d_y):
+        x, weight, y_relu = ctx.saved_tensors
+        m, k = x.shape
+        n = weight.shape[0]
+        d_y = _f32(d_y)
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        d_x = torch.empty_like(x) if need_x else None
+        d_w = torch.empty_like(weight) if need_w else None
+        d_b = torch.empty(n, device=x.device, dtype=torch.float32) if need_b else None
+        if m == 0:
+            return (torch.zeros_like(x) if need_x else None, torch.zeros_like(weight) if need_w else None,
+                    torch.zeros(n, device=x.device) if need_b else None, None)
+        ws = torch.empty(int(_lib.load().afsl_linear_bwd_workspace_floats(m, n, k)), device=x.device, dtype=torch.float32)
+        call("afsl_linear_bwd_f32", ptr(x), ptr(weight), ptr(y_relu), ptr(d_y), ptr(d_x), ptr(d_w), ptr(d_b), ptr(ws), m, n, k,
+             stream_ptr())
+        return d_x, d_w, d_b, None
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+    """F.linear(x, weight, bias) (then ReLU when ``relu``) over the last dimension, any leading dimensions."""
+    lead = x.shape[:-1]
+    if x.shape[-1] != weight.shape[1]:
+        raise ValueError(f"linear: input features {x.shape[-1]} vs weight {tuple(weight.shape)}")
+    y = _Linear.apply(_f32(x.reshape(-1, x.shape[-1])), _f32(weight), _f32(bias) if bias is not None else None, relu)
+    return y.view(*lead, weight.shape[0])
+
+
 # ---------------------------------------------------------------------------------- CPL
 class _Cpl(torch.autograd.Function):
     @staticmethod

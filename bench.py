@@ -149,6 +149,14 @@ def kernel_rooflines(device, peak_gbs, episodes):
                      "frac": bytes_per_launch / sec / 1e9 / peak_gbs, "traffic": traffic.get(name), "ms": sec * 1e3,
                      "units": units, "bytes_per_launch": bytes_per_launch, "launches": launches, **extra}
 
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    fp32_peak = sms * 128 * 2 * peaks_clock_mhz() * 1e6 / 1e12
+
+    def entry_fp32(name, flops, sec, units):
+        out[name] = {"bound": "fp32", "achieved": flops / sec / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                     "frac": flops / sec / 1e12 / fp32_peak, "traffic": traffic.get(name), "ms": sec * 1e3, "units": units,
+                     "flops_per_launch": flops, "launches": 1}
+
     st = stream_ptr()
     # ---- SpecAugment: 4 views written; algorithmic bytes 4*N*F*T*(1+V) per launch (10.05 MB / 25-sample set)
     sets, n = 256, 256 * 25
@@ -159,9 +167,12 @@ def kernel_rooflines(device, peak_gbs, episodes):
     tm = torch.tensor([[[40, 12]]], device=device, dtype=torch.int32).repeat(sets, 1, 1).contiguous()
     fm = torch.tensor([[[60, 9]]], device=device, dtype=torch.int32).repeat(sets, 1, 1).contiguous()
     lo, w = _row_tables(MELS, device)
-    sec = timed(lambda: call("afsl_specaug_views_f32", ptr(x), ptr(views), ptr(wp), ptr(wd), None, ptr(lo), ptr(w), None,
+    # the warp spline evaluated on the host with the reference's op sequence, as EpisodeRunner passes it (exact path)
+    from afsl_b200.utils.augmentations import warp_source_x
+    sx = warp_source_x(wp.cpu().long(), wd.cpu().long(), T_LEN).to(device).contiguous()
+    sec = timed(lambda: call("afsl_specaug_views_f32", ptr(x), ptr(views), ptr(wp), ptr(wd), ptr(sx), ptr(lo), ptr(w), None,
                              ptr(tm), ptr(fm), 1, 0.0, n, 25, MELS, T_LEN, 15, st))
-    entry("specaug_views", 4.0 * n * MELS * T_LEN * 5, sec, f"{sets} sets x 25 samples [1,128,157]")
+    entry("specaug_views", 4.0 * n * MELS * T_LEN * 5 + 4.0 * n * T_LEN, sec, f"{sets} sets x 25 samples [1,128,157], host spline")
     del x, views
     # ---- fused head, D=256, 5w5s5q
     e, d, ns, nq, ways = 16384, 256, 25, 25, N_WAY
@@ -292,7 +303,6 @@ def kernel_rooflines(device, peak_gbs, episodes):
     y1 = torch.empty(n1, ph, pw, 64, device=device)
     arg1 = torch.empty(n1, ph, pw, 64, device=device, dtype=torch.uint8)
     dy1 = torch.randn_like(y1)
-    sms = torch.cuda.get_device_properties(device).multi_processor_count
     parts1 = max(1, (4 * sms + g - 1) // g)
     mom = torch.empty(g, parts1, 54, device=device, dtype=torch.float64)
     parts_b = max(1, (4 * sms + g - 1) // g)
@@ -304,11 +314,43 @@ def kernel_rooflines(device, peak_gbs, episodes):
                              ptr(partial), parts_b, g, grp, h, wd_, 1, 1, st), reps=10)
     fp32_peak = sms * 128 * 2 * peaks_clock_mhz() * 1e6 / 1e12
 
-    def entry_fp32(name, flops, sec, units):
-        out[name] = {"bound": "fp32", "achieved": flops / sec / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
-                     "frac": flops / sec / 1e12 / fp32_peak, "traffic": traffic.get(name), "ms": sec * 1e3, "units": units,
-                     "flops_per_launch": flops, "launches": 1}
-
+    # ---- view fusion (one post-norm encoder layer over V = 4 views, d = 64, FFN 256): the one head kernel that is fp32-FMA
+    #      bound (397 312 flop per sample forward; backward ~2x forward + the weight gradients), at the bench step's
+    #      size (N = 800 samples: 32 episodes x 25 rows) and at a size that fills the GPU (N = 409 600)
+    lib = _lib.load()
+    wf, pf = int(lib.afsl_view_fusion_weight_floats()), int(lib.afsl_view_fusion_param_floats())
+    layer = torch.nn.TransformerEncoderLayer(d_model=64, nhead=1, dim_feedforward=256, dropout=0.0, batch_first=True).to(device)
+    from afsl_b200.ops import _FUSION_PARAMS
+    named = dict(layer.named_parameters())
+    prm = [named[k].detach() for k in _FUSION_PARAMS]
+    packed = torch.cat([t_.reshape(-1) for t_ in prm] + [prm[0].t().reshape(-1), prm[2].t().reshape(-1), prm[4].t().reshape(-1),
+                                                         prm[6].t().reshape(-1)]).float().contiguous()
+    assert packed.numel() == wf
+    for nf in (800, 409600):
+        xf = torch.randn(nf, 4, 64, device=device)
+        yf, dyf, dxf = torch.empty_like(xf), torch.randn_like(xf), torch.empty_like(xf)
+        gridf = int(lib.afsl_view_fusion_grid(nf, 4))
+        partial_f = torch.zeros(gridf, pf, device=device)
+        t_ff = timed(lambda: call("afsl_view_fusion_fwd_f32", ptr(xf), ptr(packed), ptr(yf), None, None, None, None, nf, 4, 64, 256, st))
+        t_fb = timed(lambda: call("afsl_view_fusion_bwd_f32", ptr(xf), ptr(packed), ptr(dyf), None, None, None, None, ptr(dxf),
+                                  ptr(partial_f), nf, 4, 64, 256, st))
+        entry_fp32(f"fusion_fwd_n{nf}", 397312.0 * nf, t_ff, f"{nf} samples x 4 views x 64")
+        entry_fp32(f"fusion_bwd_n{nf}", 3.0 * 397312.0 * nf, t_fb, f"{nf} samples x 4 views x 64 (dx + weight gradients: ~3x the forward flops)")
+        del xf, yf, dyf, dxf
+    # ---- majority vote (E2): 16 bytes per query segment (pred, clip id, label, posterior) + 8 per task out
+    tasks_v, clips_v = 65536, 25
+    seg = torch.randint(1, 9, (tasks_v, clips_v), device=device)
+    rows_v = int(seg.sum())
+    offs_v = torch.cat([torch.zeros(1, dtype=torch.int64, device=device), seg.sum(1).cumsum(0)]).to(torch.int32)
+    cid_v = torch.repeat_interleave(torch.arange(clips_v, device=device).repeat(tasks_v), seg.reshape(-1)).to(torch.int32)
+    lab_v = (cid_v // 5).to(torch.int32)
+    pred_v = torch.randint(0, 5, (rows_v,), device=device, dtype=torch.int32)
+    post_v = -torch.rand(rows_v, device=device)
+    corr_v, ncl_v = torch.empty(tasks_v, device=device, dtype=torch.int32), torch.empty(tasks_v, device=device, dtype=torch.int32)
+    t_v = timed(lambda: call("afsl_eval_vote_i32", ptr(pred_v), ptr(cid_v), ptr(lab_v), ptr(post_v), ptr(offs_v), 1, ptr(corr_v),
+                             ptr(ncl_v), tasks_v, st))
+    entry("eval_vote", 16.0 * rows_v + 12.0 * tasks_v, t_v, f"{tasks_v} tasks x 25 clips x U{{1..8}} segments ({rows_v} rows), min_label",
+          tasks_per_s=tasks_v / t_v)
     shape1 = f"{g} groups x 25 x [1,128,157] -> [42,52,64] channels-last"
     entry_fp32("stage1_fwd", 2.0 * 90 * n1 * ph * pw * 64, t_f, shape1)
     entry("stage1_moments", 4.0 * x1.numel(), t_m, shape1)       # one pass over the 1-channel input, 14 FMA per pixel
@@ -344,6 +386,103 @@ def cpu_episode_runner(threads):
         q = torch.randn(N_WAY * K_QUERY, 1, MELS, T_LEN, generator=gen)
         return oep.train_step(net, opt, s, sl, q, ql, EXPERIMENT_CONFIG)
     return one_episode
+
+
+def head_baselines(device, threads):
+    """SURVEY 8d's other baselines for the head alone, given embeddings (5-way 5-shot 5-query, D = 256):
+    (i) the CPU oracle port, episode by episode like the reference (prototypes, -cdist, log-softmax/NLL, backward);
+    (ii) the same op chain in eager PyTorch ON THE B200, episode by episode (what the reference itself would launch);
+    (iii) libafsl's fused head on the same episodes in one launch pair."""
+    import afsl_b200.ops as ops
+    from oracle import head as ohead
+    torch.set_num_threads(threads)
+    e, d, ways = 256, 256, N_WAY
+    gen = torch.Generator().manual_seed(5)
+    s = torch.randn(e, ways * K_SHOT, d, generator=gen)
+    q = torch.randn(e, ways * K_QUERY, d, generator=gen)
+    sl = torch.arange(ways).repeat_interleave(K_SHOT)
+    ql = torch.arange(ways).repeat_interleave(K_QUERY)
+
+    def chain(si, qi, sli, qli):
+        si, qi = si.clone().requires_grad_(True), qi.clone().requires_grad_(True)
+        loss = ohead.fsl_loss(ohead.prototypes(si, sli), qi, qli)
+        loss.backward()
+        return loss
+    n_cpu = 64
+    chain(s[0], q[0], sl, ql)
+    t0 = time.perf_counter()
+    for i in range(n_cpu):
+        chain(s[i], q[i], sl, ql)
+    cpu_eps = n_cpu / (time.perf_counter() - t0)
+    sg, qg, slg, qlg = s.to(device), q.to(device), sl.to(device), ql.to(device)
+    for i in range(8):
+        chain(sg[i], qg[i], slg, qlg)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(e):
+        chain(sg[i], qg[i], slg, qlg)
+    torch.cuda.synchronize()
+    eager_eps = e / (time.perf_counter() - t0)
+    big = 16384
+    sb = torch.randn(big, ways * K_SHOT, d, device=device).requires_grad_(True)
+    qb = torch.randn(big, ways * K_QUERY, d, device=device).requires_grad_(True)
+    slb, qlb = slg.expand(big, -1).contiguous(), qlg.expand(big, -1).contiguous()
+    for _ in range(3):
+        ops.proto_head(sb, slb, qb, qlb, n_way=ways)[0].sum().backward()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        sb.grad = qb.grad = None
+        ops.proto_head(sb, slb, qb, qlb, n_way=ways)[0].sum().backward()
+    b.record()
+    torch.cuda.synchronize()
+    fused_eps = 5 * big / (a.elapsed_time(b) * 1e-3)
+    return {"workload": "head only on given embeddings: prototypes + -cdist + log-softmax/NLL, forward + backward, 5w5s5q D=256",
+            "unit": "episodes/s",
+            "cpu_oracle_port": {"value": cpu_eps, "cores": threads, "sample": f"{n_cpu} episodes, one at a time"},
+            "eager_pytorch_on_b200": {"value": eager_eps, "sample": f"{e} episodes, one at a time (the reference's launch pattern)"},
+            "libafsl_autograd": {"value": fused_eps, "sample": f"{big} episodes per launch pair through ops.proto_head (autograd wrapper included)"}}
+
+
+def cpu_eval_baselines(threads):
+    """CPU oracle port of evaluate_single_segment / evaluate_multisegment_loop per task (loops/loops.py:66-121,250-283) on
+    the bench model (Hybrid + SpecAugment support/query views + view fusion, eval mode): tasks/s on a bounded sample."""
+    import numpy as np
+    from oracle import episode as oep
+    from oracle import modules as om
+    torch.set_num_threads(threads)
+    torch.manual_seed(1234)
+    net = om.FusedViewsNet(om.ViewEncoder(om.build_encoder("Hybrid", T_LEN)), om.ViewFusion(64, 1, 256, 0.1),
+                           om.Projection(256, 512, 256)).eval()
+    gen = torch.Generator().manual_seed(17)
+    sl = torch.arange(N_WAY).repeat_interleave(K_SHOT)
+    ql = torch.arange(N_WAY).repeat_interleave(K_QUERY)
+    rng = np.random.RandomState(3)
+
+    def single():
+        s = torch.randn(N_WAY * K_SHOT, 1, MELS, T_LEN, generator=gen)
+        q = torch.randn(N_WAY * K_QUERY, 1, MELS, T_LEN, generator=gen)
+        return oep.eval_task(net, oep.make_views(s, EXPERIMENT_CONFIG, True), sl, oep.make_views(q, EXPERIMENT_CONFIG, True), ql)
+
+    def multi():
+        seg = rng.randint(1, 9, size=N_WAY * K_QUERY)
+        rows = int(seg.sum())
+        s = torch.randn(N_WAY * K_SHOT, 1, MELS, T_LEN, generator=gen)
+        q = torch.randn(rows, 1, MELS, T_LEN, generator=gen)
+        ids = torch.from_numpy(np.repeat(np.arange(N_WAY * K_QUERY), seg))
+        labels = torch.from_numpy(np.repeat(np.arange(N_WAY).repeat(K_QUERY), seg))
+        return oep.eval_task(net, oep.make_views(s, EXPERIMENT_CONFIG, True), sl, oep.make_views(q, EXPERIMENT_CONFIG, True), labels,
+                             clip_ids=ids, tie_strategy="min_label")
+    out = {}
+    for name, fn, n in (("single_segment", single, 4), ("multi_segment", multi, 2)):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        out[name] = {"value": n / (time.perf_counter() - t0), "unit": "tasks/s", "cores": threads, "kind": "port",
+                     "sample": f"{n} tasks after 1 warm-up, oracle/episode.py::eval_task"}
+    return out
 
 
 def run_reference(args):
@@ -581,6 +720,9 @@ def run_b200(args):
         cpu = {"value": n_cpu / dt, "unit": "episodes/s", "cores": threads, "kind": "port",
                "sample": f"{n_cpu} episodes after 1 warm-up, one optimizer step each; oracle/episode.py (torch-CPU port "
                          "of loops/loops.py:26-61, pinned to the reference by tests/golden)"}
+    baselines = None
+    if world == 1 and not args.skip_cpu:
+        baselines = {"head_only": head_baselines(device, os.cpu_count() or 1), "cpu_eval_per_task": cpu_eval_baselines(os.cpu_count() or 1)}
     line = {
         "metric": "episodes/sec (train fwd+bwd)", "value": value, "unit": "episodes/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -599,6 +741,7 @@ def run_b200(args):
         "roofline": roofs.get("proto_head_fwd_bwd"),
         "kernels": roofs,
         "cpu_baseline": cpu,
+        "baselines": baselines,
         "extra_metrics": dict(evals, **({"tf32_conv_variant": tf32_line} if tf32_line else {})),
     }
     print(json.dumps(line))

@@ -302,6 +302,20 @@ int afsl_stage1_dw_f32(const float* partial, int parts, int G, const double* S, 
                        double count, int per_group, float* d_w, float* d_gamma, float* d_beta, float* d_bias,
                        void* stream);
 
+/* ---------------------------------------------------------------------------
+ * F2: the Linear layers of ProjectionHead (models/main_modules.py:231-255: fc1 -> ReLU -> fc2 -> L2 normalise;
+ * the closing normalisation is afsl_l2_normalize_*).  Replaces torch.nn.functional.linear / cuBLAS on this path.
+ * fwd: y[M,N] = x[M,K] . w[N,K]^T + bias[N] [opt], ReLU when relu != 0.
+ * bwd: with g = d_y masked by (y_relu > 0) when y_relu (the forward's ReLU output) is given:
+ *      d_x[M,K] = g . w [opt], d_w[N,K] = g^T . x [opt], d_bias[N] = column sums of g [opt].
+ *      workspace: afsl_linear_bwd_workspace_floats(M,N,K) floats (row-split partial sums, reduced in fixed order).
+ * ------------------------------------------------------------------------- */
+int afsl_linear_fwd_f32(const float* x, const float* w, const float* bias, float* y, int M, int N, int K, int relu,
+                        void* stream);
+long long afsl_linear_bwd_workspace_floats(int M, int N, int K);
+int afsl_linear_bwd_f32(const float* x, const float* w, const float* y_relu, const float* d_y, float* d_x, float* d_w,
+                        float* d_bias, float* workspace, int M, int N, int K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -628,6 +628,68 @@ def gen_tasks2000():
          **{"w_" + k: v for k, v in model.state_dict().items()})
 
 
+# ------------------------------------------------------------------ epoch loop / early stopping control flow
+LOOP_SCRIPTS = {
+    # name: (validation accuracies per epoch, patience, epochs)
+    "improves_then_stalls": ([0.30, 0.42, 0.41, 0.42, 0.40, 0.39, 0.38, 0.37], 3, 8),
+    "never_stops": ([0.2, 0.3, 0.25, 0.35, 0.3], 4, 5),
+    "stops_at_patience_one": ([0.5, 0.4, 0.6], 1, 3),
+}
+
+
+def scripted_loop(loop_fn, module, script, patience, epochs, tmpdir):
+    """Run an epoch loop (the reference's or the mirror's contrastive_training_loop) with its training epoch and
+    validation replaced by scripts: every "training epoch" adds 1 to the single weight of a toy model, validation returns
+    the scripted accuracy.  Returns what the loop did: printed lines, weight of the returned model, scheduler steps."""
+    import contextlib
+    import io
+    model = torch.nn.Linear(1, 1, bias=False)
+    with torch.no_grad():
+        model.weight.fill_(0.0)
+    opt = torch.optim.SGD(model.parameters(), lr=1.0)
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[2, 4], gamma=0.5)
+    calls = {"train": 0, "val": 0}
+
+    def fake_training_epoch(model, **kw):
+        calls["train"] += 1
+        with torch.no_grad():
+            model.weight.add_(1.0)
+        return {"loss": 1.0 / calls["train"], "fsl_loss": 0.5, "cpl_loss": float("nan")}
+
+    def fake_validation(model, **kw):
+        calls["val"] += 1
+        return script[calls["val"] - 1], 0.0
+    saved = (module.training_epoch, module.evaluate_single_segment)
+    module.training_epoch, module.evaluate_single_segment = fake_training_epoch, fake_validation
+    out = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(out):
+            trained = loop_fn(model, None, None, opt, 1, 1, "cpu", None, None, 0.0, epochs, sched, patience, tmpdir, False, False,
+                              5, 5, 5, 5, 5, 5, None, False, False, False)
+    finally:
+        module.training_epoch, module.evaluate_single_segment = saved
+    lines = [ln.replace(tmpdir, "<dir>") for ln in out.getvalue().splitlines()]
+    return {"lines": lines, "weight": float(trained.weight.item()), "train_calls": calls["train"], "val_calls": calls["val"],
+            "scheduler_last_epoch": int(sched.last_epoch), "lr": float(opt.param_groups[0]["lr"])}
+
+
+def gen_training_loop():
+    """The REFERENCE's contrastive_training_loop + EarlyStopping (loops/loops.py:124-167, callbacks/early_stopping.py:15-70)
+    driven by scripted validation accuracies: epochs run, early-stopping messages, checkpoint reload, scheduler steps."""
+    import json
+    import tempfile
+    if not hasattr(np, "Inf"):
+        np.Inf = np.inf                                 # the reference predates numpy 2.0 (early_stopping.py:38)
+    import loops.loops as L
+    out = {}
+    for name, (script, patience, epochs) in LOOP_SCRIPTS.items():
+        with tempfile.TemporaryDirectory() as tmp:
+            out[name] = scripted_loop(L.contrastive_training_loop, L, script, patience, epochs, tmp)
+        print(name, out[name]["train_calls"], out[name]["weight"])
+    with open(os.path.join(HERE, "training_loop_control_flow.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+
+
 if __name__ == "__main__":
     import_reference()
     torch.set_num_threads(1)            # fixed reduction order for the fixtures

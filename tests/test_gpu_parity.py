@@ -133,8 +133,8 @@ def test_head_batched_vs_oracle(ops, monkeypatch, ways, shots, nq, dim, path):
 @pytest.mark.parametrize("ways,shots,nq,dim", [(20, 5, 5, 256), (20, 1, 5, 256), (20, 5, 5, 64), (20, 1, 5, 64), (20, 5, 5, 128),
                                                (10, 3, 7, 128), (24, 2, 5, 256), (8, 4, 16, 64)])
 def test_head_many_way_tensor_core_kernel(ops, monkeypatch, ways, shots, nq, dim):
-    """proto_head_mma.cu (tcgen05, 3-pass split TF32) on 333 tasks per launch - several tasks per persistent CTA, so
-    every barrier phase, both accumulators and both pipeline stages are reused - against the oracle task by task
+    """proto_head_tma.cu / proto_head_mma.cu (tcgen05, split-precision TF32) on 333 tasks per launch - several tasks per
+    persistent CTA, so every barrier phase, both accumulators and all ring stages are reused - against the oracle task by task
     (scores / posterior / loss 1e-5, prototypes exact to rounding, argmax and #correct equal) and against the fp32-pipe
     kernel on the same inputs; also the given-prototypes entry (afsl_proto_scores_fwd_f32)."""
     e = 333
@@ -144,37 +144,42 @@ def test_head_many_way_tensor_core_kernel(ops, monkeypatch, ways, shots, nq, dim
     sl = torch.stack([torch.arange(ways).repeat_interleave(shots)[torch.randperm(ways * shots, generator=gen)] for _ in range(e)])
     ql = torch.randint(0, ways, (e, ways * nq), generator=gen)
     out = {}
-    for mma in ("1", "0"):
+    for mma in ("1", "2", "0"):            # TMA-fed tcgen05 kernel (default), LDG-fed tcgen05 kernel, fp32-pipe kernel
         monkeypatch.setenv("AFSL_HEAD_MMA", mma)
         pred, post, correct, scores = ops.proto_eval(s.cuda(), sl.cuda(), q.cuda(), ql.cuda(), n_way=ways, want_scores=True)
         loss, protos, corr2 = ops.proto_head(s.cuda(), sl.cuda(), q.cuda(), ql.cuda(), n_way=ways)
         sc2 = ops.l2_scores(q.cuda(), protos)
         torch.cuda.synchronize()
         out[mma] = [x.cpu() for x in (pred, post, correct, scores, loss, protos, corr2, sc2)]
-    pred, post, correct, scores, loss, protos, corr2, sc2 = out["1"]
-    assert torch.equal(correct, corr2)
-    flips = 0
+    oracle = []
     for i in range(e):
         pr = ohead.prototypes(s[i], sl[i])
         sc = ohead.l2_scores(q[i], pr)
-        po, pd = torch.max(sc, 1)
-        close(protos[i], pr)
-        close(scores.view(e, ways * nq, ways)[i], sc)
-        close(sc2[i], sc)
-        close(post.view(e, -1)[i], po)
-        close(loss[i], ohead.fsl_loss(pr, q[i], ql[i]))
-        same = pred.view(e, -1)[i].long() == pd
-        if not bool(same.all()):                      # only a tie closer than fp32 rounding of the distances may differ
-            top2 = torch.topk(sc, 2, dim=1).values
-            assert float((top2[:, 0] - top2[:, 1])[~same].max()) < 1e-5 * float(sc.abs().max())
-            flips += int((~same).sum())
-        else:
-            assert int(correct[i]) == int((pd == ql[i]).sum())
-    agree = float((out["1"][0] == out["0"][0]).float().mean())
-    print(f"[{ways}w{shots}s q{nq} D={dim}] argmax flips vs oracle on near-ties: {flips} of {e * ways * nq} rows; "
-          f"agreement with the fp32-pipe kernel {agree:.6f}")
-    assert flips <= 2 and agree > 0.9999
-    close(out["1"][3], out["0"][3])
+        oracle.append((pr, sc, ohead.fsl_loss(pr, q[i], ql[i])))
+    for mma in ("1", "2"):
+        pred, post, correct, scores, loss, protos, corr2, sc2 = out[mma]
+        assert torch.equal(correct, corr2)
+        flips = 0
+        for i in range(e):
+            pr, sc, lo = oracle[i]
+            po, pd = torch.max(sc, 1)
+            close(protos[i], pr)
+            close(scores.view(e, ways * nq, ways)[i], sc)
+            close(sc2[i], sc)
+            close(post.view(e, -1)[i], po)
+            close(loss[i], lo)
+            same = pred.view(e, -1)[i].long() == pd
+            if not bool(same.all()):                      # only a tie closer than fp32 rounding of the distances may differ
+                top2 = torch.topk(sc, 2, dim=1).values
+                assert float((top2[:, 0] - top2[:, 1])[~same].max()) < 1e-5 * float(sc.abs().max())
+                flips += int((~same).sum())
+            else:
+                assert int(correct[i]) == int((pd == ql[i]).sum())
+        agree = float((pred == out["0"][0]).float().mean())
+        print(f"[{ways}w{shots}s q{nq} D={dim}, AFSL_HEAD_MMA={mma}] argmax flips vs oracle on near-ties: {flips} of "
+              f"{e * ways * nq} rows; agreement with the fp32-pipe kernel {agree:.6f}")
+        assert flips <= 2 and agree > 0.9999
+        close(scores, out["0"][3])
 
 
 @pytest.mark.parametrize("ways,shots,dim,wide", [(5, 5, 64, 1), (20, 5, 256, 1), (20, 5, 256, 0), (20, 1, 64, 1), (20, 1, 64, 0),
@@ -1371,3 +1376,92 @@ def test_ops_follow_the_tensors_device(ops):
     assert torch.equal(l0.cpu(), l1.cpu()) and torch.equal(p0.cpu(), p1.cpu()) and torch.equal(c0.cpu(), c1.cpu())
     with pytest.raises(AfslError, match="different devices"):
         ops.proto_head(s.cuda(0), lab.cuda(0), q.cuda(1), lab.cuda(1), n_way=5)
+
+
+# ------------------------------------------------------------------ config-driven driver (src/train_test.py)
+@pytest.mark.parametrize("multi_segm,eps", [(False, 1), (True, 4)])
+def test_train_test_driver_on_synthetic_episodes(ops, tmp_path, multi_segm, eps):
+    """afsl_b200.train_test (mirror of src/train_test.py:20-181) end to end from the two JSON files: model built from the
+    configs, contrastive_training_loop with early stopping and checkpoint reload, then the single- or multi-segment test.
+    On the class-structured synthetic dataset two short epochs must beat chance clearly (5-way: 0.2)."""
+    import copy
+    import json
+    import bench
+    from afsl_b200 import train_test
+    cfg = copy.deepcopy(bench.EXPERIMENT_CONFIG)
+    cfg.update({"dataset_name": "synthetic", "device": "cuda", "gpu_index": 0, "multi_segm": multi_segm, "tie_strategy": "min_label",
+                "n_way_train": 5, "n_way_validation": 5, "n_way_test": 5, "n_shot_train": 3, "n_shot_validation": 3,
+                "n_shot_test": 3, "n_query_train": 3, "n_query_validation": 3, "n_query_test": 3, "num_epochs": 2,
+                "n_training_tasks": 8, "n_testing_tasks": 6, "patience": 5, "scheduler_milestones": [1], "scheduler_gamma": 0.5,
+                "experiment_folder": str(tmp_path / "exp"), "validation_query_augmentations": True, "test_query_augmentations": True,
+                "waveaug_params": {"use": False},
+                "synthetic": {"classes": 8, "per_class": 8, "t_len": 157, "max_segments": 3 if multi_segm else 1, "scale": 1.0}})
+    mcfg = copy.deepcopy(bench.MODEL_CONFIG)
+    mcfg["Projection"] = {"input_dim": 256, "hidden_dim": 64, "output_dim": 64}
+    e_path, m_path = tmp_path / "experiment_config.json", tmp_path / "model_config.json"
+    e_path.write_text(json.dumps(cfg)); m_path.write_text(json.dumps(mcfg))
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        msgs = train_test.main(["-e", str(e_path), "-m", str(m_path), "--runs", "1", "--episodes-per-step", str(eps), "--seed", "3"])
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert (tmp_path / "exp" / "model.pt").exists()
+    msg = msgs[0]
+    mean = msg["mean_accuracy"] if multi_segm else msg[0]
+    print("driver test message:", msg)
+    assert 0.35 < float(mean) <= 1.0
+
+
+# ------------------------------------------------------------------ F2: projection head on the libafsl Linear kernels
+def test_projection_head_vs_reference_fixture(ops):
+    """ProjectionHead (fc1 -> ReLU -> fc2 -> L2 normalise, all libafsl kernels: afsl_linear_* + afsl_l2_normalize_*) against
+    what the REFERENCE's module produced (tests/golden/modules_projection.npz): output, input gradient, parameter gradients."""
+    from afsl_b200.models.main_modules import ProjectionHead
+    g = load_golden("modules_projection")
+    proj = ProjectionHead({"Projection": {"input_dim": 256, "hidden_dim": 128, "output_dim": 256}})
+    proj.load_state_dict({k[2:]: t(v) for k, v in g.items() if k.startswith("w_")})
+    proj = proj.cuda()
+    x = dev(g["x"]).requires_grad_(True)
+    before = ops.launch_count()
+    y = proj(x)
+    y.backward(dev(g["gy"]))
+    assert ops.launch_count() - before >= 6          # 3 forward launches + normalise / two Linear backward passes
+    close(y, t(g["y"]))
+    close(x.grad, t(g["dx"]))
+    for name, prm in proj.named_parameters():
+        if "g_" + name in g:
+            close(prm.grad, t(g["g_" + name]))
+        else:
+            assert prm.grad is None                  # ln1 / ln2 exist in the state dict but are never applied
+
+
+@pytest.mark.parametrize("m,n,k,relu,bias", [(960, 512, 256, True, True), (960, 256, 512, False, True), (37, 64, 64, True, False),
+                                             (9001, 130, 70, True, True), (1, 256, 256, False, True), (20000, 64, 256, True, True)])
+def test_linear_vs_torch(ops, m, n, k, relu, bias):
+    """afsl_linear_{fwd,bwd}_f32 (register-tiled fp32 SGEMM; dw / db row-split with a fixed-order reduce beyond 4096 rows)
+    against F.linear (+ ReLU) in float64 on the CPU: output and all three gradients."""
+    gen = torch.Generator().manual_seed(m + n + k)
+    x = torch.randn(m, k, generator=gen)
+    w = torch.randn(n, k, generator=gen) / k ** 0.5
+    b = torch.randn(n, generator=gen) if bias else None
+    gy = torch.randn(m, n, generator=gen)
+    xg, wg = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    bg = b.cuda().requires_grad_(True) if bias else None
+    y = ops.linear(xg, wg, bg, relu=relu)
+    y.backward(gy.cuda())
+    xd, wd = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    bd = b.double().requires_grad_(True) if bias else None
+    yd = torch.nn.functional.linear(xd, wd, bd)
+    if relu:
+        yd = torch.relu(yd)
+    yd.backward(gy.double())
+    close(y, yd.float())
+    close(xg.grad, xd.grad.float())
+    close(wg.grad, wd.grad.float())
+    if bias:
+        close(bg.grad, bd.grad.float())
+    # determinism (fixed-order split reduction)
+    xg2, wg2 = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    ops.linear(xg2, wg2, bg.detach() if bias else None, relu=relu).backward(gy.cuda())
+    assert torch.equal(wg2.grad, wg.grad) and torch.equal(xg2.grad, xg.grad)

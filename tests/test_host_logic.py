@@ -327,3 +327,24 @@ def test_sample_episode_waveform_input_matches_reference():
     ds.waveaug_use = True
     with pytest.raises(NotImplementedError):
         sample_episode(ds, 4, 2, 3, False, "cpu", mel, False)
+
+
+# ------------------------------------------------------------------ epoch loop / early stopping vs the reference's control flow
+@pytest.mark.parametrize("name", ["improves_then_stalls", "never_stops", "stops_at_patience_one"])
+def test_contrastive_training_loop_control_flow_matches_reference(name, tmp_path):
+    """loops.contrastive_training_loop + callbacks.EarlyStopping driven by scripted validation accuracies do exactly what the
+    REFERENCE's loop did with the same script (tests/golden/training_loop_control_flow.json, generated by running
+    /root/reference/loops/loops.py:124-167 itself): same printed lines (epoch headers, loss dictionaries, checkpoint and
+    early-stopping messages), same number of epochs, the best checkpoint reloaded into the returned model, same scheduler
+    position and learning rate."""
+    import json
+    from conftest import GOLDEN, golden_module
+    import afsl_b200.loops.loops as loops
+    with open(os.path.join(GOLDEN, "training_loop_control_flow.json")) as fh:
+        want = json.load(fh)[name]
+    mg = golden_module()
+    script, patience, epochs = mg.LOOP_SCRIPTS[name]
+    got = mg.scripted_loop(loops.contrastive_training_loop, loops, script, patience, epochs, str(tmp_path))
+    assert got["lines"] == want["lines"]
+    for key in ("weight", "train_calls", "val_calls", "scheduler_last_epoch", "lr"):
+        assert got[key] == want[key], key
