@@ -11,9 +11,9 @@ SpecAugment runs on the GPU kernel, so the views are produced after the move to 
 ``EpisodeRunner``: index selection is one pass over a per-class index table built once per dataset instead of
 one pandas filter per class per episode.
 
-``input_type == 'wav'`` follows the reference too: 5-second splits of the waveform (``variable_wav_splits``), the
-caller's ``feat_extractor`` (torchaudio ``MelSpectrogram``, a library op) on the device, ``10*log10(x + eps)`` and the
-dataset's global normalisation.  Waveform augmentation (``waveaug_use``) needs torch_audiomentations, which is not
+``input_type == 'wav'`` follows the reference too: 5-second splits of the waveform (``variable_wav_splits``), then the log-mel
+front end with the caller's ``feat_extractor`` configuration (torchaudio ``MelSpectrogram``): on the GPU ONE libafsl launch
+(``afsl_logmel_f32``: STFT, power, the transform's own mel filters, ``10*log10(x + eps)``, the dataset's global normalisation).  Waveform augmentation (``waveaug_use``) needs torch_audiomentations, which is not
 part of this build, and raises.
 """
 from __future__ import annotations
@@ -24,6 +24,7 @@ from typing import Dict, List, Tuple
 import numpy as np
 import torch
 
+from .. import ops
 from ..episodes import EpisodeBatch
 from ..utils.augmentations import SpecAugment
 
@@ -91,9 +92,21 @@ def variable_wav_splits(sample):
 
 
 def mel_spec_function_gpu(x, mel_transform):
-    """Log-mel spectrogram in dB of a waveform batch (datasets/batch_creation.py:215-218)."""
+    """Log-mel spectrogram in dB of a waveform batch (datasets/batch_creation.py:215-218).  On the GPU with the
+    reference's MelSpectrogram configuration this is the one-launch libafsl front end (STFT, power, mel filters, dB);
+    on the CPU, or with another transform, the torchaudio module itself is applied."""
+    if x.is_cuda and ops.log_mel_supported(mel_transform):
+        return ops.log_mel(x, mel_transform)[:, 0]
     mel_spec = mel_transform(x)
     return 20.0 / 2 * torch.log10(mel_spec + torch.finfo(mel_spec.dtype).eps)
+
+
+def log_mel_normalized(x, mel_transform, mean, std):
+    """``((mel_spec_function_gpu(x) - mean) / std).unsqueeze(1)`` (datasets/batch_creation.py:138-143): one libafsl launch
+    on the GPU (normalisation fused into the front-end kernel), the eager chain elsewhere."""
+    if x.is_cuda and ops.log_mel_supported(mel_transform):
+        return ops.log_mel(x, mel_transform, float(mean), float(std))
+    return ((mel_spec_function_gpu(x, mel_transform=mel_transform) - mean) / std).unsqueeze(1)
 
 
 def _sample_wav_episode(dataset, n_classes, k_support, k_query, is_test, device, feat_extractor, augment_query):
@@ -129,7 +142,7 @@ def _sample_wav_episode(dataset, n_classes, k_support, k_query, is_test, device,
             query_counter += 1
     mean, std = dataset.get_normalization_stats()
     stacked = torch.cat(support_set + query_set, dim=0).to(device)
-    spectrograms = ((mel_spec_function_gpu(stacked, mel_transform=feat_extractor) - mean) / std).unsqueeze(1)
+    spectrograms = log_mel_normalized(stacked, feat_extractor, mean, std)
     n_support = n_classes * k_support
     return ([spectrograms[:n_support]], torch.tensor(support_labels), [spectrograms[n_support:]], torch.tensor(query_labels),
             torch.tensor(audio_ids))

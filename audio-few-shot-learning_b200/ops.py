@@ -718,6 +718,54 @@ def stage1_conv_bn_relu_pool(x: torch.Tensor, conv: torch.nn.Conv2d, bn: torch.n
                          mean_u.float().contiguous(), rstd.float().contiguous(), empty, empty, 1, n, False)
 
 
+# ---------------------------------------------------------------------------------- waveform front end
+def log_mel_supported(mel_transform) -> bool:
+    """True for a torchaudio MelSpectrogram configured as the reference's (src/train_test.py:123-129)."""
+    spec, scale = getattr(mel_transform, "spectrogram", None), getattr(mel_transform, "mel_scale", None)
+    if spec is None or scale is None:
+        return False
+    return (spec.n_fft == 1024 and spec.win_length == 1024 and spec.hop_length > 0 and spec.power == 2.0 and spec.center
+            and spec.pad_mode == "reflect" and not spec.normalized and spec.onesided and spec.pad == 0
+            and tuple(scale.fb.shape) == (513, 128))
+
+
+def _mel_bands(mel_transform, device):
+    """The transform's dense [513,128] filterbank as bands (first bin, length, offset, packed weights), cached on it."""
+    cache = getattr(mel_transform, "_afsl_bands", None)
+    if cache is None or cache[0].device != torch.device(device):
+        fb = mel_transform.mel_scale.fb.detach().float().cpu()
+        starts, lens, offs, weights, off = [], [], [], [], 0
+        for m in range(fb.shape[1]):
+            nz = torch.nonzero(fb[:, m]).flatten()
+            lo, hi = (int(nz[0]), int(nz[-1])) if nz.numel() else (0, -1)
+            starts.append(lo); lens.append(hi - lo + 1); offs.append(off)
+            weights.append(fb[lo:hi + 1, m])
+            off += hi - lo + 1
+        i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=device)
+        cache = (i32(starts), i32(lens), i32(offs), torch.cat(weights + [torch.zeros(4)]).to(device).contiguous(),
+                 mel_transform.spectrogram.window.detach().float().to(device).contiguous())
+        mel_transform._afsl_bands = cache
+    return cache
+
+
+@torch.no_grad()
+def log_mel(wave: torch.Tensor, mel_transform, mean: float = 0.0, std: float = 1.0) -> torch.Tensor:
+    """wave [N,L] -> normalised log-mel spectrogram in dB [N,1,128,T] in one libafsl launch:
+    ``((20/2 * log10(mel_transform(wave) + eps)) - mean) / std`` with eps = float32 machine epsilon
+    (datasets/batch_creation.py:138-143,215-218)."""
+    if not log_mel_supported(mel_transform):
+        raise NotImplementedError("log_mel needs the reference's MelSpectrogram (n_fft 1024, 128 mels, power 2, centred, reflect)")
+    wave = _f32(wave)
+    n, length = wave.shape
+    hop = int(mel_transform.spectrogram.hop_length)
+    t = length // hop + 1
+    starts, lens, offs, weights, window = _mel_bands(mel_transform, wave.device)
+    out = torch.empty(n, 1, 128, t, device=wave.device, dtype=torch.float32)
+    call("afsl_logmel_f32", ptr(wave), ptr(window), ptr(starts), ptr(lens), ptr(offs), ptr(weights), ptr(out), n, length, t, 1024,
+         hop, 128, float(torch.finfo(torch.float32).eps), float(mean), float(std), stream_ptr())
+    return out
+
+
 # ---------------------------------------------------------------------------------- majority vote
 @torch.no_grad()
 def eval_vote(pred, clip_ids, labels, posterior, seg_offsets, tie_strategy: str = "min_label"):

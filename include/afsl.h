@@ -316,6 +316,17 @@ long long afsl_linear_bwd_workspace_floats(int M, int N, int K);
 int afsl_linear_bwd_f32(const float* x, const float* w, const float* y_relu, const float* d_y, float* d_x, float* d_w,
                         float* d_bias, float* workspace, int M, int N, int K, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * f-4: waveform front end (datasets/batch_creation.py:138-143,215-218 with the MelSpectrogram of src/train_test.py:123-129):
+ * wave [N,L] (16 kHz) -> out [N,1,128,T], T = L/hop + 1:
+ *   STFT (n_fft = 1024, window [1024] as given, centred frames, reflect padding) -> |X|^2 -> mel filters in band form
+ *   (filter m: fb_len[m] weights fb_w[fb_off[m] ..] on bins fb_start[m] ..) -> 10 log10(mel + eps) -> (x - mean) / std.
+ * One launch; the window and the filterbank are the reference transform's own tensors.
+ * ------------------------------------------------------------------------- */
+int afsl_logmel_f32(const float* wave, const float* window, const int32_t* fb_start, const int32_t* fb_len,
+                    const int32_t* fb_off, const float* fb_w, float* out, int N, int L, int T, int n_fft, int hop,
+                    int n_mels, float eps, float mean, float std, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

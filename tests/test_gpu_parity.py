@@ -1465,3 +1465,40 @@ def test_linear_vs_torch(ops, m, n, k, relu, bias):
     xg2, wg2 = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
     ops.linear(xg2, wg2, bg.detach() if bias else None, relu=relu).backward(gy.cuda())
     assert torch.equal(wg2.grad, wg.grad) and torch.equal(xg2.grad, xg.grad)
+
+
+# ------------------------------------------------------------------ f-4: waveform front end
+def test_log_mel_front_end_vs_torchaudio_and_reference(ops):
+    """afsl_logmel_f32 (STFT + power + mel filters + dB + z-normalisation in one launch) against the eager torchaudio chain
+    of the reference (datasets/batch_creation.py:138-143,215-218) on the GPU and on the CPU, and - through sample_episode on
+    'wav' input - against what the REFERENCE's sample_episode produced (tests/golden/sampler_wav.npz).  Values are dB /
+    13.25 (about +-3): bound 2e-5 absolute on the normalised log-mel (fp32 FFT rounding differs from cuFFT's / pocketfft's)."""
+    import random
+    torchaudio = pytest.importorskip("torchaudio")
+    from afsl_b200.datasets.batch_creation import sample_episode
+    from test_host_logic import _FakeWavDataset
+    mel = torchaudio.transforms.MelSpectrogram(sample_rate=16000, n_mels=128, n_fft=1024, hop_length=512, power=2.0)
+    gen = torch.Generator().manual_seed(4)
+    wave = torch.randn(7, 80000, generator=gen) * 0.1
+    wave[3] *= 1e-3                                                  # a quiet clip: mel energies near the eps floor
+    wave[5, 40000:] = 0.0                                            # digital silence: exactly log10(eps)
+    mean, std = -21.5, 13.25
+    want_cpu = ((20.0 / 2 * torch.log10(mel(wave) + torch.finfo(torch.float32).eps) - mean) / std).unsqueeze(1)
+    mel_gpu = mel.cuda()
+    want_gpu = ((20.0 / 2 * torch.log10(mel_gpu(wave.cuda()) + torch.finfo(torch.float32).eps) - mean) / std).unsqueeze(1)
+    before = ops.launch_count()
+    got = ops.log_mel(wave.cuda(), mel_gpu, mean, std)
+    assert ops.launch_count() - before == 1 and got.shape == (7, 1, 128, 157)
+    close(got, want_gpu, rtol=0, scale=2e-5)
+    close(got, want_cpu, rtol=0, scale=2e-5)
+    # the sampler on waveform input, on the GPU, against the reference's own sample_episode
+    g = load_golden("sampler_wav")
+    ds = _FakeWavDataset(int(g["dataset_seed"]))
+    fp = lambda x: x[:, 0, ::16, ::20].reshape(x.shape[0], -1)
+    for name, is_test in (("train", False), ("test", True)):
+        random.seed(int(g[f"{name}_seed"]))
+        s_list, s_lab, q_list, q_lab, ids = sample_episode(ds, 4, 2, 3, is_test, "cuda", mel_gpu, False)
+        assert list(q_list[0].shape) == g[f"{name}_shape"].tolist() and q_list[0].is_cuda
+        close(fp(s_list[0]), t(g[f"{name}_support"]), rtol=0, scale=2e-5)
+        close(fp(q_list[0]), t(g[f"{name}_query"]), rtol=0, scale=2e-5)
+        assert torch.equal(q_lab, t(g[f"{name}_query_labels"])) and torch.equal(ids, t(g[f"{name}_audio_ids"]))
