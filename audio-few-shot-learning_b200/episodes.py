@@ -447,8 +447,10 @@ class EpisodeRunner:
 
     @torch.no_grad()
     def eval_step(self, batch: EpisodeBatch, augment_query: bool = False, clip_ids: Optional[torch.Tensor] = None,
-                  seg_offsets: Optional[torch.Tensor] = None, tie_strategy: str = "") -> np.ndarray:
-        """Per-task accuracies (float64 numpy, ``correct/total`` like loops/loops.py:114,277).
+                  seg_offsets: Optional[torch.Tensor] = None, tie_strategy: str = "", as_tensor: bool = False):
+        """Per-task accuracies (float64 numpy, ``correct/total`` like loops/loops.py:114,277).  ``as_tensor`` returns them
+        as a float64 device tensor instead, without synchronising: the host goes on to draw the next step's parameters
+        while the GPU works (collect the tensors and convert once at the end).
 
         Single-segment: ``batch.query`` is [E,Nq,...].  Multi-segment: ``batch.query`` is
         [1,rows,...] packed over tasks, with ``seg_offsets`` [E+1] and ``clip_ids`` [rows]."""
@@ -463,6 +465,8 @@ class EpisodeRunner:
                 correct, per_task = self._eval_graph_step(batch, rnd, device)
             else:
                 correct, per_task = self._eval_compute(batch.to(device), self._rnd_to(rnd, device))
+            if as_tensor:
+                return correct.double() / per_task
             return correct.cpu().numpy().astype(np.float64) / per_task
         batch = batch.to(device)
         # one SpecAugment draw per task, shared by all its query segments (batch_creation.py:113-115)
@@ -480,4 +484,6 @@ class EpisodeRunner:
         pred, post, _, _ = ops.proto_eval(support_features, sl, feats, ql, n_way=batch.n_way,
                                           q_offsets=seg_offsets.to(feats.device), max_rows=max_rows)
         correct, clips = ops.eval_vote(pred, clip_ids, ql, post, seg_offsets, tie_strategy)
+        if as_tensor:
+            return correct.double() / clips.double()
         return correct.cpu().numpy().astype(np.float64) / clips.cpu().numpy().astype(np.float64)

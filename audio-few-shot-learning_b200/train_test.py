@@ -156,6 +156,7 @@ def main(argv=None):
     rank, world, local = parallel.init_from_env()
     if world > 1:
         device = f"cuda:{local}"
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))        # torchrun pins OMP_NUM_THREADS=1
     elif experiment_config["device"] == "cuda":
         device = f"cuda:{experiment_config['gpu_index']}"                     # src/train_test.py:40-45
     else:

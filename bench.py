@@ -49,6 +49,17 @@ MODEL_CONFIG = {
 }
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """Print the one JSON line on the real stdout (see main)."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -507,7 +518,7 @@ def run_reference(args):
                                        "oracle/episode.py torch-CPU port of loops/loops.py:26-61"},
             "e2e": {"value": value, "unit": "episodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def eval_throughput(runner, device, world, rank, tasks_per_step, steps):
@@ -544,8 +555,8 @@ def eval_throughput(runner, device, world, rank, tasks_per_step, steps):
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        accs = [fn(i) for i in range(steps)]
-        acc = parallel.gather_accuracies(np.concatenate(accs), world * steps * e)
+        accs = [fn(i) for i in range(steps)]                                  # device tensors: no host sync per step
+        acc = parallel.gather_accuracies(torch.cat(accs).cpu().numpy(), world * steps * e)
         b.record()
         if world > 1:
             dist.barrier()
@@ -558,11 +569,11 @@ def eval_throughput(runner, device, world, rank, tasks_per_step, steps):
                 "mean_accuracy": float(acc.mean())}
 
     # test_query_augmentations = true (README.md:92): the view-fusion model needs the four query views at test time too
-    out["test_tasks_per_s"] = dict(timed(lambda i: runner.eval_step(single[i % 2], augment_query=True), e), unit="tasks/s",
+    out["test_tasks_per_s"] = dict(timed(lambda i: runner.eval_step(single[i % 2], augment_query=True, as_tensor=True), e), unit="tasks/s",
                                    workload="5-way 5-shot 5-query single-segment tasks, SpecAugment support + query views, "
                                             "eval-mode encoder")
     out["multiseg_tasks_per_s"] = dict(timed(lambda i: runner.eval_step(multi, augment_query=True, clip_ids=clip_ids,
-                                                                        seg_offsets=offsets_dev, tie_strategy="min_label"), e),
+                                                                        seg_offsets=offsets_dev, tie_strategy="min_label", as_tensor=True), e),
                                        unit="tasks/s",
                                        rows_per_step_per_gpu=rows,
                                        workload="5-way 5-shot, 25 query clips x U{1..8} segments per task, majority vote (min_label)")
@@ -625,6 +636,9 @@ def run_b200(args):
 
     rank, world, local = parallel.init_from_env("nccl")
     torch.cuda.set_device(local)
+    # torchrun pins OMP_NUM_THREADS=1; the host side of a step (randomness draws, the reference-exact warp spline) is
+    # vectorised torch-CPU work: give every rank its share of the host cores
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(1, world)))
     device = torch.device("cuda", local)
     torch.backends.cudnn.benchmark = True
     # the headline is fp32 end to end: cuDNN's TF32 convolution / RNN kernels are switched off (PyTorch's default allows
@@ -744,15 +758,20 @@ def run_b200(args):
         "baselines": baselines,
         "extra_metrics": dict(evals, **({"tf32_conv_variant": tf32_line} if tf32_line else {})),
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
-    # stdout carries exactly one JSON line: NCCL's own log lines (e.g. the version banner under NCCL_DEBUG=VERSION) go to stderr
+    # stdout carries exactly one JSON line: everything else - Python prints and C-level writes such as NCCL's version banner,
+    # which ignores NCCL_DEBUG_FILE - is sent to stderr by pointing file descriptor 1 at it until the line is printed
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)

@@ -6,10 +6,10 @@
 set -u
 tag=${1:-r1}; shift || true
 kernels=("$@")
-[ ${#kernels[@]} -eq 0 ] && kernels=(head_warp_kernel:4:head_fwd head_warp_kernel:27:head_bwd cpl_warp_kernel:4:cpl_fwd cpl_warp_kernel:27:cpl_bwd specaug_tile_kernel:4:specaug_tile angular_warp_kernel:2:angular_fwd angular_warp_kernel:10:angular_bwd head_wide_fwd_kernel:27:head_wide_20w5s_d256)
+[ ${#kernels[@]} -eq 0 ] && kernels=(head_warp_kernel:4:head_fwd head_warp_kernel:27:head_bwd cpl_warp_kernel:4:cpl_fwd cpl_warp_kernel:27:cpl_bwd specaug_tile_kernel:4:specaug_tile angular_warp_kernel:2:angular_fwd angular_warp_kernel:10:angular_bwd head_tma_fwd_kernel:50:head_tma_20w5s_d256 head_tma_fwd_kernel:4:head_tma_20w5s_d64 fusion_fwd_kernel:27:fusion_fwd_n409600 fusion_bwd_kernel:27:fusion_bwd_n409600 vote_kernel:4:eval_vote)
 out=gpurun_out
 mkdir -p $out
-BENCH="python bench.py --steps 2 --warmup 3 --episodes 32 --skip-cpu --skip-kernels --skip-eval"
+BENCH="python bench.py --steps 2 --warmup 3 --episodes 32 --skip-cpu --skip-kernels --skip-eval --skip-tf32"
 $BENCH > $out/${tag}_bench_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --graph-profiling node -c 8000 --csv --log-file $out/${tag}_launches.csv \
     $BENCH > $out/${tag}_launches.log 2>&1

@@ -3,7 +3,8 @@
 #     bash tools/sanitize.sh [memcheck|racecheck|initcheck|synccheck]      (default: memcheck)
 # ONE tool per gpurun call (B200_PROFILING.md: several sanitizer tools in one call have wedged the GPU).  The target is the
 # GPU parity suite restricted to the kernel-level tests (head, CPL, angular, SpecAugment, vote, view fusion, normalise) -
-# every libafsl entry point, every kernel family, through the C ABI - at its small shapes.  The program must have exited 0
+# every libafsl entry point, every kernel family, through the C ABI - at its small shapes.  (Round 2: the pool answered
+# "compute-sanitizer is closed on this pool", rc 86 - see profiles/r2_sanitizer_note.txt; the script is kept for pools where it runs.)  The program must have exited 0
 # without the sanitizer first (same call, `&&`).  Log -> gpurun_out/sanitize_<tool>.log; copy the summary to profiles/.
 set -u
 tool=${1:-memcheck}
