@@ -9,11 +9,12 @@
 // TF32 itself: hi), the CUDA cores only derive lo = rna_tf32(x - trunc_tf32(x)), and
 //     q.p = lo.lo + lo.hi + hi.lo + hi.hi          (four passes, fp32 accumulation in TMEM, ~22 bits per product).
 //
-// One persistent CTA per SM; every byte comes in through ONE ring of 16 KB shared-memory stages filled by TMA
-// (cp.async.bulk.tensor.2d, 128-byte swizzle = the UMMA operand layout), 6-8 stages (~80-100 KB) ahead of the consumers and
-// across task boundaries - Little's law at ~1.2 us loaded latency needs ~50 KB in flight per SM, and no load latency is ever
-// exposed.  A stage holds one k-block (32 columns) of either the task's support rows or its query rows.  Roles (mbarriers
-// only, no CTA barrier in the task loop):
+// One persistent CTA per SM; every byte comes in through ONE ring of shared-memory stages filled by TMA
+// (cp.async.bulk.tensor.2d, 128-byte swizzle = the UMMA operand layout), ~80-100 KB ahead of the consumers and across task
+// boundaries - Little's law at ~1.2 us loaded latency needs ~50 KB in flight per SM, and no load latency is ever exposed.
+// A stage holds kPair k-blocks (32 columns each, one TMA box per k-block) of either the task's support rows or its query
+// rows; kPair = 2 halves the barrier round trips, proxy fences and reductions per task.  Roles (mbarriers only, no CTA
+// barrier in the task loop):
 //   warp 9     loader    one lane: arms the stage's mbarrier with the byte count and issues the TMA box
 //   warps 0-7  producers two groups of four warps take alternate stages.  Support stage: per-class sums straight out of
 //                        the swizzled rows (thread = class x 16-byte chunk, rows of a class in ascending order from a
@@ -50,7 +51,7 @@ constexpr int kMaxWays = 24;                                    // B tiles hold 
 constexpr int kBlockK = 32;                                     // fp32 per 128-byte swizzle row = one stage's columns
 constexpr int kTile = kTileM * 128;                             // bytes of one [128 x 32] fp32 tile = one ring stage
 constexpr int kBTile = kMaxWays * 128;
-constexpr int kLoRing = 4;
+constexpr int kMaxLoRing = 4;
 constexpr int kMaxRing = 9;
 constexpr int kMaxSupportRows = kTileM;
 constexpr uint32_t kIdesc = idesc_tf32(kTileM, kTileN);
@@ -59,7 +60,7 @@ struct TmaBars {
   uint64_t tma_full[kMaxRing];    // stage filled by TMA (transaction bytes)
   uint64_t ready[kMaxRing];       // stage processed by its producer group (4 warps)
   uint64_t empty[kMaxRing];       // stage free again (issuer: plain arrive for support stages, tcgen05.commit for query stages)
-  uint64_t lo_free[kLoRing];      // lo tile free again (tcgen05.commit)
+  uint64_t lo_free[kMaxLoRing];   // lo tiles of a query stage free again (tcgen05.commit)
   uint64_t b_empty;               // the task's MMAs are done with the prototype tiles
   uint64_t acc_full[2], epi_done[2], meta_full[2];
 };
@@ -92,17 +93,20 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
 __device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory"); }
 __device__ __forceinline__ void epilogue_bar() { asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 
-template <int kD, int kRing>
+template <int kD, int kRing, int kPair, int kLo>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_q) {
   constexpr int kKB = kD / kBlockK;
-  static_assert(kKB % kGroups == 0, "stages of a task must split evenly over the producer groups");
+  constexpr int kSt = kKB / kPair;                  // ring stages per phase (support / query) of a task: kPair k-blocks each
+  constexpr int kStageB = kPair * kTile;            // bytes of a ring stage (and of a lo-ring slot)
+  static_assert(kKB % kPair == 0 && kLo <= kMaxLoRing && kRing <= kMaxRing, "bad stage configuration");
+  // a task has 2 kSt stages, so its first stage always has an even index: the group that owns a stage is (index & 1)
   extern __shared__ __align__(1024) uint8_t smem_tma_raw[];
   uint8_t* smem = smem_tma_raw + ((1024u - (smem_u32(smem_tma_raw) & 1023u)) & 1023u);     // 1 KB: swizzle atoms
-  const uint32_t ring = smem_u32(smem);                                        // [kRing][16 KB] raw rows as TMA wrote them
-  const uint32_t b_base = ring + kRing * kTile;                                // [kKB][hi, lo][3 KB] split prototypes
-  const uint32_t lo_base = b_base + kKB * 2 * kBTile;                          // [kLoRing][16 KB] lo tiles of query stages
-  TmaMeta* meta = reinterpret_cast<TmaMeta*>(smem + kRing * kTile + kKB * 2 * kBTile + kLoRing * kTile);
+  const uint32_t ring = smem_u32(smem);                                        // [kRing][kPair][16 KB] raw rows as TMA wrote them
+  const uint32_t b_base = ring + kRing * kStageB;                                // [kKB][hi, lo][3 KB] split prototypes
+  const uint32_t lo_base = b_base + kKB * 2 * kBTile;                          // [kLo][kPair][16 KB] lo tiles of query stages
+  TmaMeta* meta = reinterpret_cast<TmaMeta*>(smem + kRing * kStageB + kKB * 2 * kBTile + kLo * kStageB);
   uint8_t* rows_base = reinterpret_cast<uint8_t*>(meta + 1);                   // [2][W][row_stride]: bucketed support rows
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = p.W, Nq = p.Nq;
@@ -115,7 +119,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
       mbar_init(&meta->bars.ready[s], kGroupWarps);
       mbar_init(&meta->bars.empty[s], 1);
     }
-    for (int s = 0; s < kLoRing; ++s) mbar_init(&meta->bars.lo_free[s], 1);
+    for (int s = 0; s < kLo; ++s) mbar_init(&meta->bars.lo_free[s], 1);
     mbar_init(&meta->bars.b_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&meta->bars.acc_full[i], 1);
@@ -145,11 +149,13 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
           const CUtensorMap* map = half ? &map_q : &map_s;
           const int rows = half ? Nq : sup_rows;
 #pragma unroll 1
-          for (int kb = 0; kb < kKB; ++kb, ++c) {
+          for (int st = 0; st < kSt; ++st, ++c) {
             const uint32_t s = c % kRing;
             mbar_wait_relaxed(&meta->bars.empty[s], ((c / kRing) & 1) ^ 1);
-            mbar_arrive_expect_tx(&meta->bars.tma_full[s], (uint32_t)rows * 128u);
-            tma_load_2d(ring + s * kTile, map, kb * kBlockK, e * rows, &meta->bars.tma_full[s]);
+            mbar_arrive_expect_tx(&meta->bars.tma_full[s], (uint32_t)rows * 128u * kPair);
+#pragma unroll
+            for (int i = 0; i < kPair; ++i)
+              tma_load_2d(ring + s * kStageB + i * kTile, map, (st * kPair + i) * kBlockK, e * rows, &meta->bars.tma_full[s]);
           }
         }
       }
@@ -216,44 +222,52 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
           const float r0 = __frcp_rn(fn_it[rnd]);
           rcp_it[rnd] = r0;
         }
+        bool tiles_free = false;
 #pragma unroll 1
-        for (int kb = 0; kb < kKB; ++kb, ++c) {
-          if ((kb & 1) != grp) continue;
+        for (int st = 0; st < kSt; ++st, ++c) {
+          if ((int)(c & 1) != grp) continue;
           const uint32_t s = c % kRing;
           mbar_wait(&meta->bars.tma_full[s], (c / kRing) & 1);
-          if (kb == grp) mbar_wait(&meta->bars.b_empty, (it & 1) ^ 1);       // previous task's MMAs are done with the tiles
-          const uint32_t stage = ring + s * kTile;
+          if (!tiles_free) {                                                 // previous task's MMAs are done with the tiles
+            mbar_wait(&meta->bars.b_empty, (it & 1) ^ 1);
+            tiles_free = true;
+          }
 #pragma unroll
           for (int rnd = 0; rnd < 2; ++rnd) {
             const int item = gtid + rnd * kGroupThreads;
             const int w = item >> 3, j = item & 7;
             const bool act = w < W;
             const int n = n_it[rnd];
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            // 8 rows per step: one 64-bit read of the row ids, 8 independent 128-bit reads, then the adds in row order
-            for (int i0 = 0; i0 < n; i0 += 8) {
-              const uint2 ids = *reinterpret_cast<const uint2*>(rows_it[rnd] + i0);
-              float4 v[8];
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                const uint32_t r = ((u < 4 ? ids.x : ids.y) >> (8 * (u & 3))) & 0xffu;
-                v[u] = lds4(stage + sw128((int)(i0 + u < n ? r : 0u), j));
-              }
-#pragma unroll
-              for (int u = 0; u < 8; ++u)
-                if (i0 + u < n) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
-            }
             float sq = 0.f;
-            if (act) {
-              const float rc = rcp_it[rnd], fn = fn_it[rnd];
-              auto mean = [&](float sum) { const float q0 = sum * rc; return fmaf(fmaf(-q0, fn, sum), rc, q0); };
-              acc = make_float4(mean(acc.x), mean(acc.y), mean(acc.z), mean(acc.w));
-              if (p.protos_out && p.support)
-                *reinterpret_cast<float4*>(p.protos_out + ((size_t)e * W + w) * kD + kb * kBlockK + 4 * j) = acc;
-              sq = fmaf(acc.x, acc.x, fmaf(acc.y, acc.y, fmaf(acc.z, acc.z, acc.w * acc.w)));
-              const uint32_t off = sw128(w, j);
-              sts4(b_base + (kb * 2 + 0) * kBTile + off, acc);               // hi: the tensor core truncates it itself
-              sts4(b_base + (kb * 2 + 1) * kBTile + off, lo_of_raw(acc));
+#pragma unroll
+            for (int i = 0; i < kPair; ++i) {
+              const int kb = st * kPair + i;
+              const uint32_t stage = ring + s * kStageB + i * kTile;
+              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+              // 8 rows per step: one 64-bit read of the row ids, 8 independent 128-bit reads, then the adds in row order
+              for (int i0 = 0; i0 < n; i0 += 8) {
+                const uint2 ids = *reinterpret_cast<const uint2*>(rows_it[rnd] + i0);
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                  const uint32_t r = ((u < 4 ? ids.x : ids.y) >> (8 * (u & 3))) & 0xffu;
+                  v[u] = lds4(stage + sw128((int)(i0 + u < n ? r : 0u), j));
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                  if (i0 + u < n) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+              }
+              if (act) {
+                const float rc = rcp_it[rnd], fn = fn_it[rnd];
+                auto mean = [&](float sum) { const float q0 = sum * rc; return fmaf(fmaf(-q0, fn, sum), rc, q0); };
+                acc = make_float4(mean(acc.x), mean(acc.y), mean(acc.z), mean(acc.w));
+                if (p.protos_out && p.support)
+                  *reinterpret_cast<float4*>(p.protos_out + ((size_t)e * W + w) * kD + kb * kBlockK + 4 * j) = acc;
+                sq = fmaf(acc.x, acc.x, fmaf(acc.y, acc.y, fmaf(acc.z, acc.z, fmaf(acc.w, acc.w, sq))));
+                const uint32_t off = sw128(w, j);
+                sts4(b_base + (kb * 2 + 0) * kBTile + off, acc);             // hi: the tensor core truncates it itself
+                sts4(b_base + (kb * 2 + 1) * kBTile + off, lo_of_raw(acc));
+              }
             }
             sq += __shfl_xor_sync(kFullMask, sq, 1);
             sq += __shfl_xor_sync(kFullMask, sq, 2);
@@ -278,20 +292,23 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
 #pragma unroll
         for (int t = 0; t < 8; ++t) qacc[t] = 0.f;
 #pragma unroll 1
-        for (int kb = 0; kb < kKB; ++kb, ++c, ++qc) {
-          if ((kb & 1) != grp) continue;
-          const uint32_t s = c % kRing, ls = qc % kLoRing;
+        for (int st = 0; st < kSt; ++st, ++c, ++qc) {
+          if ((int)(c & 1) != grp) continue;
+          const uint32_t s = c % kRing, ls = qc % kLo;
           mbar_wait(&meta->bars.tma_full[s], (c / kRing) & 1);
-          const uint32_t src = ring + s * kTile + off0, dst = lo_base + ls * kTile + off0;
-          // rows >= Nq of the tile were never written by TMA: whatever they hold only reaches accumulator rows nobody reads
-          float4 v[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) v[t] = lds4(src + t * 2048);
-          mbar_wait(&meta->bars.lo_free[ls], ((qc / kLoRing) & 1) ^ 1);      // the MMAs of query stage qc - 4 are done with the slot
+          for (int i = 0; i < kPair; ++i) {
+            const uint32_t src = ring + s * kStageB + i * kTile + off0, dst = lo_base + ls * kStageB + i * kTile + off0;
+            // rows >= Nq of the tile were never written by TMA: whatever they hold only reaches accumulator rows nobody reads
+            float4 v[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            sts4(dst + t * 2048, lo_of_raw(v[t]));
-            qacc[t] = fmaf(v[t].x, v[t].x, fmaf(v[t].y, v[t].y, fmaf(v[t].z, v[t].z, fmaf(v[t].w, v[t].w, qacc[t]))));
+            for (int t = 0; t < 8; ++t) v[t] = lds4(src + t * 2048);
+            if (i == 0) mbar_wait(&meta->bars.lo_free[ls], ((qc / kLo) & 1) ^ 1);   // MMAs of query stage qc - kLo are done with the slot
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              sts4(dst + t * 2048, lo_of_raw(v[t]));
+              qacc[t] = fmaf(v[t].x, v[t].x, fmaf(v[t].y, v[t].y, fmaf(v[t].z, v[t].z, fmaf(v[t].w, v[t].w, qacc[t]))));
+            }
           }
           fence_async_proxy();
           __syncwarp();
@@ -319,7 +336,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
     for (int e = blockIdx.x; e < p.E; e += gridDim.x, ++it) {
       const int par = it & 1;
 #pragma unroll 1
-      for (int kb = 0; kb < kKB; ++kb, ++c) {                               // support stages: consumed by the producers only
+      for (int st = 0; st < kSt; ++st, ++c) {                               // support stages: consumed by the producers only
         const uint32_t s = c % kRing;
         mbar_wait(&meta->bars.ready[s], (c / kRing) & 1);
         if (elect_one()) mbar_arrive(&meta->bars.empty[s]);
@@ -327,26 +344,30 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
       mbar_wait(&meta->bars.epi_done[par], ((it >> 1) & 1) ^ 1);            // accumulator `par` drained (task it-2)
       const uint32_t acc = tmem + par * kTileN;
 #pragma unroll 1
-      for (int kb = 0; kb < kKB; ++kb, ++c, ++qc) {
-        const uint32_t s = c % kRing, ls = qc % kLoRing;
+      for (int st = 0; st < kSt; ++st, ++c, ++qc) {
+        const uint32_t s = c % kRing, ls = qc % kLo;
         mbar_wait(&meta->bars.ready[s], (c / kRing) & 1);
         fence_after();
         if (elect_one()) {
-          const uint32_t a_hi = desc_lo(ring + s * kTile), a_lo = desc_lo(lo_base + ls * kTile);
-          const uint32_t b_hi = desc_lo(b_base + kb * 2 * kBTile), b_lo = desc_lo(b_base + (kb * 2 + 1) * kBTile);
-          // small terms first: lo.lo, lo.hi, hi.lo, hi.hi; a K step of 8 fp32 = 32 bytes = 2 descriptor units
-          mma_tf32_lo(acc, a_lo, b_lo, kIdesc, kb != 0);
 #pragma unroll
-          for (int k = 1; k < kBlockK / 8; ++k) mma_tf32_lo(acc, a_lo + 2 * k, b_lo + 2 * k, kIdesc, 1u);
+          for (int i = 0; i < kPair; ++i) {
+            const int kb = st * kPair + i;
+            const uint32_t a_hi = desc_lo(ring + s * kStageB + i * kTile), a_lo = desc_lo(lo_base + ls * kStageB + i * kTile);
+            const uint32_t b_hi = desc_lo(b_base + kb * 2 * kBTile), b_lo = desc_lo(b_base + (kb * 2 + 1) * kBTile);
+            // small terms first: lo.lo, lo.hi, hi.lo, hi.hi; a K step of 8 fp32 = 32 bytes = 2 descriptor units
+            mma_tf32_lo(acc, a_lo, b_lo, kIdesc, kb != 0);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 8; ++k) mma_tf32_lo(acc, a_lo + 2 * k, b_hi + 2 * k, kIdesc, 1u);
+            for (int k = 1; k < kBlockK / 8; ++k) mma_tf32_lo(acc, a_lo + 2 * k, b_lo + 2 * k, kIdesc, 1u);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 8; ++k) mma_tf32_lo(acc, a_hi + 2 * k, b_lo + 2 * k, kIdesc, 1u);
+            for (int k = 0; k < kBlockK / 8; ++k) mma_tf32_lo(acc, a_lo + 2 * k, b_hi + 2 * k, kIdesc, 1u);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 8; ++k) mma_tf32_lo(acc, a_hi + 2 * k, b_hi + 2 * k, kIdesc, 1u);
+            for (int k = 0; k < kBlockK / 8; ++k) mma_tf32_lo(acc, a_hi + 2 * k, b_lo + 2 * k, kIdesc, 1u);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 8; ++k) mma_tf32_lo(acc, a_hi + 2 * k, b_hi + 2 * k, kIdesc, 1u);
+          }
           commit(&meta->bars.empty[s]);
           commit(&meta->bars.lo_free[ls]);
-          if (kb == kKB - 1) {
+          if (st == kSt - 1) {
             commit(&meta->bars.acc_full[par]);
             commit(&meta->bars.b_empty);
           }
@@ -445,13 +466,14 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
   if (warp == kIssuerWarp) tmem_free<64>(tmem);
 }
 
-template <int kD, int kRing>
+template <int kD, int kRing, int kPair, int kLo>
 int launch_variant(const HeadParams& p, const CUtensorMap& ms, const CUtensorMap& mq, int sup_rows, cudaStream_t stream,
-                   const char* name) {
-  static_assert(kRing <= kMaxRing, "ring too deep for the barrier arrays");
-  auto fn = head_tma_fwd_kernel<kD, kRing>;
-  const size_t bytes = (size_t)kRing * kTile + (size_t)(kD / kBlockK) * 2 * kBTile + (size_t)kLoRing * kTile + sizeof(TmaMeta) +
+                   const char* name, bool* handled) {
+  auto fn = head_tma_fwd_kernel<kD, kRing, kPair, kLo>;
+  const size_t bytes = (size_t)(kRing + kLo) * kPair * kTile + (size_t)(kD / kBlockK) * 2 * kBTile + sizeof(TmaMeta) +
                        2 * (size_t)p.W * ((sup_rows + 7) & ~7) + 1024 + 16;
+  if (bytes > 220 * 1024) return AFSL_OK;          // very long support blocks: the fp32-pipe kernels take the launch
+  *handled = true;
   if (int rc = opt_in_smem(fn, bytes, name)) return rc;
   int sms = kNumSMs, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -476,18 +498,21 @@ int launch_head_tma(const HeadParams& p, bool bwd, cudaStream_t stream, const ch
   if (sup_rows > kMaxSupportRows) return AFSL_OK;
   const char* env = getenv("AFSL_HEAD_MMA");
   if (env && atoi(env) != 1) return AFSL_OK;
-  const int ring_stages = p.D == 256 ? 6 : p.D == 128 ? 7 : 8;
-  const size_t bytes = (size_t)ring_stages * kTile + (size_t)(p.D / kBlockK) * 2 * kBTile + (size_t)kLoRing * kTile +
-                       sizeof(TmaMeta) + 2 * (size_t)p.W * ((sup_rows + 7) & ~7) + 1024 + 16;
-  if (bytes > 220 * 1024) return AFSL_OK;          // very long support blocks: the fp32-pipe kernels take the launch
-  *handled = true;
   CUtensorMap ms, mq;
   const float* sup = p.support ? p.support : p.protos_in;
   if (int rc = make_tensor_map_f32(&ms, sup, (uint64_t)p.E * sup_rows, (uint64_t)p.D, (uint32_t)sup_rows, name)) return rc;
   if (int rc = make_tensor_map_f32(&mq, p.queries, (uint64_t)p.E * p.Nq, (uint64_t)p.D, (uint32_t)p.Nq, name)) return rc;
-  if (p.D == 256) return launch_variant<256, 6>(p, ms, mq, sup_rows, stream, name);
-  if (p.D == 128) return launch_variant<128, 7>(p, ms, mq, sup_rows, stream, name);
-  return launch_variant<64, 8>(p, ms, mq, sup_rows, stream, name);
+  // ring stages hold two k-blocks at D >= 128 (half as many barrier round trips per task: 0.54 -> 0.61 of HBM at 20w5s
+  // D = 256) and one at D = 64, where a pair would leave one stage per phase and so no overlap between the producer groups
+  // (measured 0.40 against 0.41); AFSL_HEAD_PAIR=1 / 2 forces one / two (the parity tests run both)
+  const char* pair_env = getenv("AFSL_HEAD_PAIR");
+  const bool pair = pair_env ? atoi(pair_env) == 2 : p.D >= 128;
+  if (p.D == 256) return pair ? launch_variant<256, 3, 2, 2>(p, ms, mq, sup_rows, stream, name, handled)
+                              : launch_variant<256, 6, 1, 4>(p, ms, mq, sup_rows, stream, name, handled);
+  if (p.D == 128) return pair ? launch_variant<128, 3, 2, 2>(p, ms, mq, sup_rows, stream, name, handled)
+                              : launch_variant<128, 7, 1, 4>(p, ms, mq, sup_rows, stream, name, handled);
+  return pair ? launch_variant<64, 4, 2, 2>(p, ms, mq, sup_rows, stream, name, handled)
+              : launch_variant<64, 8, 1, 4>(p, ms, mq, sup_rows, stream, name, handled);
 }
 
 }  // namespace afsl

@@ -146,8 +146,10 @@ def test_head_many_way_tensor_core_kernel(ops, monkeypatch, ways, shots, nq, dim
     sl = torch.stack([torch.arange(ways).repeat_interleave(shots)[torch.randperm(ways * shots, generator=gen)] for _ in range(e)])
     ql = torch.randint(0, ways, (e, ways * nq), generator=gen)
     out = {}
-    for mma in ("1", "2", "0"):            # TMA-fed tcgen05 kernel (default), LDG-fed tcgen05 kernel, fp32-pipe kernel
-        monkeypatch.setenv("AFSL_HEAD_MMA", mma)
+    # TMA-fed tcgen05 kernel with one / two k-blocks per ring stage, LDG-fed tcgen05 kernel, fp32-pipe kernel
+    for mma in ("1", "1p", "2", "0"):
+        monkeypatch.setenv("AFSL_HEAD_MMA", mma[0])
+        monkeypatch.setenv("AFSL_HEAD_PAIR", "2" if mma == "1p" else "1")
         pred, post, correct, scores = ops.proto_eval(s.cuda(), sl.cuda(), q.cuda(), ql.cuda(), n_way=ways, want_scores=True)
         loss, protos, corr2 = ops.proto_head(s.cuda(), sl.cuda(), q.cuda(), ql.cuda(), n_way=ways)
         sc2 = ops.l2_scores(q.cuda(), protos)
@@ -158,7 +160,7 @@ def test_head_many_way_tensor_core_kernel(ops, monkeypatch, ways, shots, nq, dim
         pr = ohead.prototypes(s[i], sl[i])
         sc = ohead.l2_scores(q[i], pr)
         oracle.append((pr, sc, ohead.fsl_loss(pr, q[i], ql[i])))
-    for mma in ("1", "2"):
+    for mma in ("1", "1p", "2"):
         pred, post, correct, scores, loss, protos, corr2, sc2 = out[mma]
         assert torch.equal(correct, corr2)
         flips = 0
