@@ -279,6 +279,11 @@ int launch(const AngParams& p, bool bwd, cudaStream_t stream, const char* name) 
   AFSL_REQUIRE(p.protos && p.queries && p.labels, "%s: null pointer", name);
   AFSL_REQUIRE(p.E >= 0 && p.Nq > 0 && p.W > 0 && p.D > 0, "%s: bad sizes E=%d Nq=%d W=%d D=%d", name, p.E, p.Nq, p.W, p.D);
   if (p.E == 0) return AFSL_OK;
+  {
+    bool handled = false;
+    const int rc = launch_angular_tc(p, bwd, stream, name, &handled);
+    if (rc != AFSL_OK || handled) return rc;
+  }
   const char* warp_env = getenv("AFSL_ANGULAR_WARP");   // read per launch so the tests can exercise both paths
   if (!warp_env || atoi(warp_env) != 0) {
     bool handled = false;

@@ -1,5 +1,5 @@
 // Parameter block shared by the angular-loss kernels (angular.cu: one CTA per episode, any shape;
-// angular_warp.cu: one warp per episode, Dp = 64 and at most 32 pooled rows).
+// angular_warp.cu: one warp per episode, Dp = 64 and at most 32 pooled rows; angular_tc.cu: tensor cores, anchors branch).
 #pragma once
 
 #include "afsl_common.cuh"
@@ -24,5 +24,7 @@ struct AngParams {
 
 // angular_warp.cu: launches the warp-per-episode kernel when the shape fits it; *handled says whether it did
 int launch_angular_warp(const AngParams& p, bool bwd, cudaStream_t stream, const char* name, bool* handled);
+// angular_tc.cu: the tensor-core kernel (anchors branch, Dp = 64, W <= 8, W + Nq <= 31), four episodes per tcgen05 tile
+int launch_angular_tc(const AngParams& p, bool bwd, cudaStream_t stream, const char* name, bool* handled);
 
 }  // namespace afsl

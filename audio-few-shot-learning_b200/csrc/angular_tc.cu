@@ -1,0 +1,550 @@
+// Angular loss, prototypes-as-anchors branch (AngularLossClass.forward, loops/loss.py:68-83 + the pytorch_metric_learning
+// miner / loss restated in oracle/angular.py), Dp = 64 and W + Nq <= 31 pooled rows, on the tensor cores.
+//
+// What the loss needs per episode is the Gram matrix of its 30 pooled rows (forward) and, in the backward, the product
+// dL/dGram . X: three 30 x 30 x 64 contractions that kept the one-warp-per-episode kernel (angular_warp.cu) at 0.07-0.11 of
+// the HBM roofline on the fp32 pipe.  Here FOUR episodes share one 128-row tcgen05 tile, split TF32 (x = hi + lo, three
+// passes lo.hi + hi.lo + hi.hi with fp32 accumulation in TMEM, ~2^-22 per product):
+//
+//   rows 32 e + i of the tile: prototypes (i < W), queries (W <= i < N), zero rows, and row 31 = ones, so that column 31 of
+//   the Gram block is the component sum the miner's pairwise_distance epsilon needs;
+//   MMA 1   D1[128 x 128] = X X^T (raw rows; the 32 x 32 diagonal blocks are the episodes' Gram matrices, norms = sqrt of
+//           the diagonal);
+//   E1      one warp per episode, lane = row: tcgen05.ld of its 32 Gram entries, normalisation, mining counts from ballots,
+//           the weighted log-sum-exp of its (prototype, query) pair with the negatives unrolled over registers, loss; in the
+//           backward dL/dGram rows (transposed through the warp's scratch, per-class sums in ascending row order:
+//           deterministic), with the row normalisation's backward folded in:
+//           G3[i][j] = r_i r_j G'[i][j] + delta_ij r_i (drho_i - r_i <x^_i, dx^_i>),  so that  dX = G3 X  exactly;
+//   MMA 2   (dX)^T of two episodes per instruction: D2[2 x 64 dims][2 x 32 rows] = X^T-tiles . G3-rows^T, every operand
+//           K-major (the producers keep a transposed copy of the tile: tools/micro/umma_layout_probe.cu);
+//   E2      lane = embedding dimension, columns = rows: coalesced 128-byte stores of dP / dQ.
+//
+// One persistent CTA per SM, warp-specialised, mbarriers only: 4 producer warps (LDG.128 straight from HBM a tile ahead,
+// hi / lo split, transposed copy), 2 x 4 E1 warps (alternate tiles, two D1 accumulators), 4 E2 warps, 1 issuer warp.
+#include "angular.cuh"
+#include "tc_common.cuh"
+
+namespace afsl {
+namespace {
+
+using namespace tc;
+
+constexpr int kD = 64;
+constexpr int kBlk = 32;                      // tile rows (and TMEM lanes) per episode
+constexpr int kEp = 4;                        // episodes per tile
+constexpr int kMaxW = 8;
+constexpr int kOnesRow = 31;
+constexpr int kTile = 128 * 128;              // bytes of a [128 x 32 fp32] swizzled tile
+constexpr int kLs = 36;                       // row stride (floats) of the per-warp scratch matrices: conflict-free
+constexpr float kNormEps = 1e-12f;            // F.normalize
+constexpr float kPairEps = 1e-6f;             // F.pairwise_distance
+constexpr unsigned kFull = 0xffffffffu;
+
+constexpr int kProducerWarps = 4, kE1Warps = 8, kE2Warps = 4;
+constexpr int kFirstE1 = kProducerWarps, kFirstE2 = kFirstE1 + kE1Warps, kIssuer = kFirstE2 + kE2Warps;
+constexpr int kThreadsBwd = (kIssuer + 1) * 32;                 // 544
+constexpr int kThreadsFwd = kThreadsBwd;                        // the forward keeps the layout (E2 warps exit at once)
+
+// per-E1-warp scratch (floats)
+struct Scratch {
+  float sg[kBlk * kLs];        // Gram rows (raw), later the T rows (dL/dGram of the pairs, row = positive)
+  float sp[kMaxW * kLs];       // per-class column sums of T = prototype rows of dL/dGram
+  float rinv[kBlk], nrm[kBlk], csn[kBlk], gdi[kBlk], nu[kBlk], gs[kBlk];
+  int manc[kMaxW];
+};
+
+struct Bars {
+  uint64_t x_full, x_free, xt_full, xt_free, gp_full, gp_free, d2_full, d2_free;
+  uint64_t d1_full[2], d1_free[2];
+  uint32_t tmem_base;
+};
+
+constexpr uint32_t kXH = 0, kXL = 2 * kTile, kXTH = 4 * kTile, kXTL = 6 * kTile, kGPH = 8 * kTile, kGPL = 9 * kTile;
+constexpr uint32_t kOpBytesBwd = 10 * kTile, kOpBytesFwd = 4 * kTile;
+
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    if (!done) __nanosleep(32);
+  } while (!done);
+}
+__device__ __forceinline__ void sts1(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float bitf(uint32_t v) { return __uint_as_float(v); }
+
+// ---------------------------------------------------------------------------------------------------------------- E1
+// One warp, lane = row of the episode's block.  `tm` = TMEM address of the block's 32 Gram columns in this warp's lanes.
+template <bool kBwd>
+__device__ __forceinline__ void e1_episode(const AngParams& p, int ep, int lab_in, uint32_t tm, Scratch* sc, uint64_t* d1_free,
+                                           uint64_t* gp_free, uint32_t gp_parity, uint32_t gph_row, uint32_t gpl_row) {
+  const int lane = threadIdx.x & 31;
+  const int W = p.W, N = p.W + p.Nq;
+  const bool qv = lane >= W && lane < N && lab_in >= 0 && lab_in < W;
+  const int lab = lane < W ? lane : (qv ? lab_in : -1);
+  const int a = qv ? lab : 0;
+  const float c4 = 4.f * p.t2, cneg = -2.f * (1.f + p.t2);
+
+  float g[32], pa[32];
+  {
+    uint32_t v[32];
+    tmem_ld32(tm, v);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) g[k] = bitf(v[k]);
+  }
+  if (!kBwd) {                                                  // the accumulator is free as soon as it is in registers
+    fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(d1_free);
+  }
+  // ---- raw Gram rows to the scratch: diagonal (norms), prototype rows for every lane
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    *reinterpret_cast<float4*>(sc->sg + lane * kLs + 4 * c) = make_float4(g[4 * c], g[4 * c + 1], g[4 * c + 2], g[4 * c + 3]);
+  __syncwarp();
+  const float gii = sc->sg[lane * kLs + lane];
+  const float nrm = sqrtf(fmaxf(gii, 0.f));
+  const float ri = 1.f / fmaxf(nrm, kNormEps);
+  const float cs = g[kOnesRow] * ri;                            // component sum of the normalised row
+  const float gdi = gii * ri * ri;
+  sc->rinv[lane] = ri; sc->nrm[lane] = nrm; sc->csn[lane] = cs; sc->gdi[lane] = gdi;
+  if (lane < kMaxW) sc->manc[lane] = 0;
+  __syncwarp();
+  const float ra_inv = sc->rinv[a];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4 r4 = *reinterpret_cast<const float4*>(sc->rinv + 4 * c);
+    const float4 s4 = *reinterpret_cast<const float4*>(sc->sg + a * kLs + 4 * c);
+    g[4 * c] *= ri * r4.x; g[4 * c + 1] *= ri * r4.y; g[4 * c + 2] *= ri * r4.z; g[4 * c + 3] *= ri * r4.w;
+    pa[4 * c] = s4.x * ra_inv * r4.x; pa[4 * c + 1] = s4.y * ra_inv * r4.y;
+    pa[4 * c + 2] = s4.z * ra_inv * r4.z; pa[4 * c + 3] = s4.w * ra_inv * r4.w;
+  }
+  const float gaq = sc->sg[a * kLs + lane] * ra_inv * ri;       // cos(prototype a, this query)
+
+  // ---- masks: queries of the episode, lanes of my class, my pair's negatives
+  const unsigned allq = __ballot_sync(kFull, qv);
+  const unsigned sameq = __match_any_sync(kFull, lab) & allq;
+  const unsigned negmask = qv ? (allq & ~sameq) : 0u;
+  unsigned cm[kMaxW];
+#pragma unroll
+  for (int w = 0; w < kMaxW; ++w) cm[w] = __ballot_sync(kFull, qv && lab == w);
+
+  // ---- mining (AngularMiner): negatives of my pair that pass the angle test; times my row was mined as a negative
+  const float deps = (float)kD * kPairEps * kPairEps;
+  const float ap2 = sc->gdi[a] + gdi - 2.f * gaq + 2.f * kPairEps * (sc->csn[a] - cs) + deps;
+  const float ap = sqrtf(fmaxf(ap2, 0.f));
+  int count = 0, wneg = 0;
+  if (p.miner_tan == 0.f) {
+    // angle 0: atan(ap / (2 nc)) > 0 iff ap > 0: every negative of a pair with distinct anchor / positive passes
+    const bool on = qv && !p.miner_never && ap > 0.f;
+    const unsigned onmask = __ballot_sync(kFull, on);
+    count = on ? __popc(negmask) : 0;
+    wneg = qv ? __popc(onmask & ~sameq) : 0;
+  } else {
+    const float ra = sc->nrm[a], rq = nrm;
+    const float sum_norm = sqrtf(fmaxf(ra * ra + rq * rq + 2.f * ra * rq * gaq, 0.f));
+    const float inv = 1.f / fmaxf(sum_norm, kNormEps);
+    const float cc = sum_norm > kNormEps ? 1.f : (sum_norm * inv) * (sum_norm * inv);
+    const float csum_c = (ra * sc->csn[a] + rq * cs) * inv;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float dot = (ra * pa[k] + rq * g[k]) * inv;
+      const float nc2 = sc->gdi[k] + cc - 2.f * dot + 2.f * kPairEps * (sc->csn[k] - csum_c) + deps;
+      const float nc = sqrtf(fmaxf(nc2, 0.f));
+      // atan(ap / (2 nc)) > angle without the arctangent and the division: ap > 2 nc tan(angle)
+      const bool pass = ((negmask >> k) & 1u) && !p.miner_never && ap > 2.f * nc * p.miner_tan;
+      count += pass;
+      const unsigned b = __ballot_sync(kFull, pass);
+      if (lane == k) wneg = __popc(b);
+    }
+  }
+  if (count) atomicAdd(&sc->manc[a], count);
+  const float nu_i = qv ? (float)(count + wneg) : 0.f;
+  sc->nu[lane] = nu_i;
+  __syncwarp();
+
+  // ---- my pair: weighted log-sum-exp over the negatives, with the appended zero
+  const float omega = qv ? (float)sc->manc[a] * nu_i : 0.f;
+  const float base = cneg * gaq;
+  float mx = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4 nu4 = *reinterpret_cast<const float4*>(sc->nu + 4 * c);
+    float4 rho = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (!p.normalize_ref) rho = *reinterpret_cast<const float4*>(sc->nrm + 4 * c);
+    const float nuv[4] = {nu4.x, nu4.y, nu4.z, nu4.w}, rv[4] = {rho.x, rho.y, rho.z, rho.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = 4 * c + u;
+      const float f = fmaf(c4 * rv[u], pa[k] + g[k], base);
+      pa[k] = f;
+      const bool use = ((negmask >> k) & 1u) && nuv[u] > 0.f;
+      mx = use ? fmaxf(mx, f) : mx;
+    }
+  }
+  float tot = __expf(-mx);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4 nu4 = *reinterpret_cast<const float4*>(sc->nu + 4 * c);
+    const float nuv[4] = {nu4.x, nu4.y, nu4.z, nu4.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = 4 * c + u;
+      const float w = ((negmask >> k) & 1u) ? nuv[u] : 0.f;
+      const float ex = w * __expf(pa[k] - mx);
+      pa[k] = ex;
+      tot += ex;
+    }
+  }
+  const float term = omega > 0.f ? omega * (mx + logf(tot)) : 0.f;
+  const float num = warp_sum(term), den = warp_sum(omega);
+  if (!kBwd) {
+    if (lane == 0) p.loss[ep] = den > 0.f ? num / den : 0.f;
+    return;
+  }
+
+  // ---- backward.  T_i[k] = 4 t2 rho_k g_k: dL/dGram[i][k] of my pair (and of its anchor's row), gsum = sum_k g_k
+  const float scale = den > 0.f ? p.d_loss[ep] / den : 0.f;
+  const float coef = omega > 0.f ? scale * omega / tot : 0.f;
+  float gsum = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float4 rho = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (!p.normalize_ref) rho = *reinterpret_cast<const float4*>(sc->nrm + 4 * c);
+    const float rv[4] = {rho.x, rho.y, rho.z, rho.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = 4 * c + u;
+      const float gk = coef * pa[k];
+      gsum += gk;
+      pa[k] = c4 * rv[u] * gk;
+    }
+  }
+  sc->gs[lane] = gsum;
+  __syncwarp();                                                 // every lane is done with the Gram rows in sg
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    *reinterpret_cast<float4*>(sc->sg + lane * kLs + 4 * c) = make_float4(pa[4 * c], pa[4 * c + 1], pa[4 * c + 2], pa[4 * c + 3]);
+  __syncwarp();
+  // per-class column sums (rows of a class in ascending order): pr[w] = dL/dGram[prototype w][this lane's row]
+  float pr[kMaxW];
+#pragma unroll
+  for (int w = 0; w < kMaxW; ++w) {
+    pr[w] = 0.f;
+    if (w < W) {
+      for (unsigned m = cm[w]; m != 0; m &= m - 1) pr[w] += sc->sg[(__ffs(m) - 1) * kLs + lane];
+      sc->sp[w * kLs + lane] = pr[w];
+    }
+  }
+  __syncwarp();
+  // own Gram row again (normalised) from the accumulator, then the accumulator is free
+  {
+    uint32_t v[32];
+    tmem_ld32(tm, v);
+    fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(d1_free);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float4 r4 = *reinterpret_cast<const float4*>(sc->rinv + 4 * c);
+      g[4 * c] = bitf(v[4 * c]) * ri * r4.x; g[4 * c + 1] = bitf(v[4 * c + 1]) * ri * r4.y;
+      g[4 * c + 2] = bitf(v[4 * c + 2]) * ri * r4.z; g[4 * c + 3] = bitf(v[4 * c + 3]) * ri * r4.w;
+    }
+  }
+  // symmetric G'[i][k] = dL/dGram[i][k] + dL/dGram[k][i], row i = this lane
+  const bool isp = lane < W;
+  const int prow = isp ? lane : 0;
+  float drho = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4 sp4 = *reinterpret_cast<const float4*>(sc->sp + prow * kLs + 4 * c);
+    const float4 gs4 = *reinterpret_cast<const float4*>(sc->gs + 4 * c);
+    const float spv[4] = {sp4.x, sp4.y, sp4.z, sp4.w}, gsv[4] = {gs4.x, gs4.y, gs4.z, gs4.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = 4 * c + u;
+      const float col = sc->sg[k * kLs + lane];                 // T_k[i]
+      drho = fmaf(col, g[k], drho);
+      const float vq = pa[k] + col;
+      const float vp = ((sameq >> k) & 1u) ? cneg * gsv[u] : spv[u];
+      pa[k] = qv ? vq : (isp ? vp : 0.f);
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < kMaxW; ++w)
+    if (w < W) {
+      if (qv) pa[w] = (w == lab) ? cneg * gsum : pr[w];
+      drho = fmaf(pr[w], g[w], drho);                           // pr[lab] = 0: my own class never uses me as a negative
+    }
+  drho = (!p.normalize_ref && qv && nrm > 0.f) ? drho / nrm : 0.f;
+  float dot = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) dot = fmaf(pa[k], g[k], dot);
+  if (!(nrm > kNormEps)) dot = 0.f;                             // F.normalize clamps the norm: no projection term there
+  const float cdiag = ri * (drho - ri * dot);
+  // G3 row -> B operand of MMA 2 (hi = the raw value, the tensor core truncates it; lo = the rounded remainder)
+  mbar_wait_sleep(gp_free, gp_parity);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4 r4 = *reinterpret_cast<const float4*>(sc->rinv + 4 * c);
+    float4 v = make_float4(ri * r4.x * pa[4 * c], ri * r4.y * pa[4 * c + 1], ri * r4.z * pa[4 * c + 2], ri * r4.w * pa[4 * c + 3]);
+    if ((lane >> 2) == c) {
+      const int u = lane & 3;
+      if (u == 0) v.x += cdiag;
+      if (u == 1) v.y += cdiag;
+      if (u == 2) v.z += cdiag;
+      if (u == 3) v.w += cdiag;
+    }
+    const uint32_t off = ((uint32_t)((c ^ lane) & 7) << 4);     // sw128 inside this lane's row
+    sts4(gph_row + off, v);
+    sts4(gpl_row + off, lo_of_raw(v));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------ kernel
+template <bool kBwd>
+__global__ void __launch_bounds__(kThreadsBwd, 1) angular_tc_kernel(const AngParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_ang_raw[];
+  uint8_t* smem = smem_ang_raw + ((1024u - (smem_u32(smem_ang_raw) & 1023u)) & 1023u);
+  const uint32_t base = smem_u32(smem);
+  constexpr uint32_t kOps = kBwd ? kOpBytesBwd : kOpBytesFwd;
+  Scratch* scratch = reinterpret_cast<Scratch*>(smem + kOps);
+  Bars* bars = reinterpret_cast<Bars*>(scratch + kE1Warps);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int W = p.W, Nq = p.Nq, N = W + Nq;
+  const int tiles = (p.E + kEp - 1) / kEp;
+
+  if (tid == 0) {
+    mbar_init(&bars->x_full, kProducerWarps);
+    mbar_init(&bars->x_free, 1);
+    mbar_init(&bars->xt_full, kProducerWarps);
+    mbar_init(&bars->xt_free, 1);
+    mbar_init(&bars->gp_full, 4);
+    mbar_init(&bars->gp_free, 1);
+    mbar_init(&bars->d2_full, 1);
+    mbar_init(&bars->d2_free, kE2Warps);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars->d1_full[b], 1);
+      mbar_init(&bars->d1_free[b], 4);
+    }
+    fence_barrier_init();
+  }
+  // operand tiles start as zeros (pad rows stay zero for the whole launch), row 31 of every block of X is ones
+  for (uint32_t i = tid; i < kOps / 16; i += blockDim.x) sts4(base + i * 16, make_float4(0.f, 0.f, 0.f, 0.f));
+  __syncthreads();
+  for (int i = tid; i < kEp * 2 * 8; i += blockDim.x) {
+    const int e = i >> 4, kb = (i >> 3) & 1, c = i & 7;
+    sts4(base + kXH + kb * kTile + sw128(e * kBlk + kOnesRow, c), make_float4(1.f, 1.f, 1.f, 1.f));
+  }
+  if (warp == kIssuer) tmem_alloc<512>(&bars->tmem_base);
+  fence_async_proxy();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp < kProducerWarps) {
+    // =========================================================== producers: warp = episode slot of the tile
+    const int e = warp;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const int ep = tile * kEp + e;
+      const bool valid = ep < p.E;
+      const float* prow = p.protos + (size_t)(valid ? ep : 0) * W * kD;
+      const float* qrow = p.queries + (size_t)(valid ? ep : 0) * Nq * kD;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int ci = lane + 32 * j, r = ci >> 3, cc = ci & 7;
+          v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid && r < N) {
+            const float* src = (r < W ? prow + r * kD : qrow + (r - W) * kD) + 32 * h + 4 * cc;
+            v[j] = ldg_stream(reinterpret_cast<const float4*>(src));
+          }
+        }
+        if (h == 0) mbar_wait(&bars->x_free, (it & 1) ^ 1);             // MMA 1 of the previous tile is done with X
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int ci = lane + 32 * j, r = ci >> 3, cc = ci & 7;
+          if (r < N) {
+            const uint32_t off = h * kTile + sw128(e * kBlk + r, cc);
+            sts4(base + kXH + off, v[j]);
+            sts4(base + kXL + off, lo_of_raw(v[j]));
+          }
+        }
+      }
+      fence_async_proxy();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->x_full);
+      if (kBwd) {
+        // transposed copy of my block: XT[e][d][j] = X[j][d] (lane = row j reads its own row, conflict-free both ways)
+        mbar_wait(&bars->xt_free, (it & 1) ^ 1);                        // MMA 2 of the previous tile is done with XT
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 hv = lds4(base + kXH + h * kTile + sw128(e * kBlk + lane, c));
+            const float4 lv = lo_of_raw(hv);
+            const float hvv[4] = {hv.x, hv.y, hv.z, hv.w}, lvv[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int d = 32 * h + 4 * c + u;
+              const uint32_t off = (uint32_t)e * (kD * 128) + sw128(d, lane >> 2) + (lane & 3) * 4;
+              sts1(base + kXTH + off, hvv[u]);
+              sts1(base + kXTL + off, lvv[u]);
+            }
+          }
+        fence_async_proxy();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->xt_full);
+      }
+    }
+  } else if (warp == kIssuer) {
+    // =========================================================== MMA issuer (warp-uniform control flow, one elected lane)
+    constexpr uint32_t kIdesc1 = idesc_tf32(128, 128), kIdesc2 = idesc_tf32(128, 64);
+    const int my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto mma1 = [&](int it) {
+      const int b = it & 1;
+      mbar_wait(&bars->x_full, it & 1);
+      mbar_wait(&bars->d1_free[b], ((it >> 1) & 1) ^ 1);
+      fence_after();
+      if (elect_one()) {
+        const uint32_t acc = tmem + b * 128;
+        uint32_t first = 0;
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {                          // small terms first: lo.hi, hi.lo, hi.hi
+          const uint32_t pa_ = pass == 0 ? kXL : kXH, pb_ = pass == 1 ? kXL : kXH;
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint32_t da = desc_lo(base + pa_ + kb * kTile), db = desc_lo(base + pb_ + kb * kTile);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              mma_tf32_lo(acc, da + 2 * k, db + 2 * k, kIdesc1, first);
+              first = 1;
+            }
+          }
+        }
+        commit(&bars->x_free);
+        commit(&bars->d1_full[b]);
+      }
+      __syncwarp();
+    };
+    if (my_tiles > 0) mma1(0);
+    for (int it = 0; it < my_tiles; ++it) {
+      if (it + 1 < my_tiles) mma1(it + 1);
+      if (kBwd) {
+        mbar_wait(&bars->xt_full, it & 1);
+        mbar_wait(&bars->gp_full, it & 1);
+        mbar_wait(&bars->d2_free, (it & 1) ^ 1);
+        fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {                                 // two episodes per instruction
+            const uint32_t acc = tmem + 256 + s * 64;
+            uint32_t first = 0;
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint32_t pa_ = pass == 0 ? kXTL : kXTH, pb_ = pass == 1 ? kGPL : kGPH;
+              const uint32_t da = desc_lo(base + pa_ + s * kTile), db = desc_lo(base + pb_ + s * (kTile / 2));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                mma_tf32_lo(acc, da + 2 * k, db + 2 * k, kIdesc2, first);
+                first = 1;
+              }
+            }
+          }
+          commit(&bars->xt_free);
+          commit(&bars->gp_free);
+          commit(&bars->d2_full);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < kFirstE2) {
+    // =========================================================== E1: set = (warp - 4) / 4 takes the tiles of its parity
+    const int set = (warp - kFirstE1) >> 2, quad = warp & 3;           // quad = episode slot = TMEM lane quarter
+    Scratch* sc = scratch + (warp - kFirstE1);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != set) continue;
+      const int ep = tile * kEp + quad;
+      const bool valid = ep < p.E;
+      int lab = -1;
+      if (valid && lane >= W && lane < N) lab = p.labels[(size_t)ep * Nq + (lane - W)];
+      mbar_wait_sleep(&bars->d1_full[set], (it >> 1) & 1);
+      fence_after();
+      const uint32_t row = (uint32_t)(quad * kBlk + lane) * 128u;
+      if (valid) {
+        e1_episode<kBwd>(p, ep, lab, tmem + ((uint32_t)(quad * 32) << 16) + set * 128 + quad * 32, sc, &bars->d1_free[set],
+                         &bars->gp_free, (it & 1) ^ 1, base + kGPH + row, base + kGPL + row);
+      } else {
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->d1_free[set]);
+        if (kBwd) mbar_wait_sleep(&bars->gp_free, (it & 1) ^ 1);
+      }
+      if (kBwd) {
+        fence_async_proxy();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->gp_full);
+      }
+    }
+  } else if (kBwd) {
+    // =========================================================== E2: lane = embedding dimension, columns = rows
+    const int quad = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      mbar_wait_sleep(&bars->d2_full, it & 1);
+      fence_after();
+      uint32_t v[2][32];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + 256 + s * 64 + (quad >> 1) * 32, v[s]);
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->d2_free);
+      const int d = (quad & 1) * 32 + lane;
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int ep = tile * kEp + 2 * s + (quad >> 1);
+        if (ep >= p.E) continue;
+        float* dp = p.d_protos + (size_t)ep * W * kD + d;
+        float* dq = p.d_queries + (size_t)ep * Nq * kD + d;
+#pragma unroll
+        for (int i = 0; i < 31; ++i) {
+          if (i < W) dp[i * kD] = bitf(v[s][i]);
+          else if (i < N) dq[(i - W) * kD] = bitf(v[s][i]);
+        }
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == kIssuer) tmem_free<512>(tmem);
+}
+
+}  // namespace
+
+// Anchors branch, Dp = 64, W <= 8, W + Nq <= 31.  AFSL_ANGULAR_TC=0 leaves the launch to the fp32-pipe kernels (the parity
+// tests run all of them on the same cases).
+int launch_angular_tc(const AngParams& p, bool bwd, cudaStream_t stream, const char* name, bool* handled) {
+  *handled = false;
+  if (!p.anchors || p.D != kD || p.W > kMaxW || p.W + p.Nq > kOnesRow) return AFSL_OK;
+  const char* env = getenv("AFSL_ANGULAR_TC");
+  if (env && atoi(env) == 0) return AFSL_OK;
+  *handled = true;
+  const size_t bytes = (bwd ? kOpBytesBwd : kOpBytesFwd) + kE1Warps * sizeof(Scratch) + sizeof(Bars) + 1024;
+  auto fn = bwd ? angular_tc_kernel<true> : angular_tc_kernel<false>;
+  if (int rc = opt_in_smem(fn, bytes, name)) return rc;
+  int sms = kNumSMs, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = (p.E + kEp - 1) / kEp;
+  fn<<<tiles < sms ? tiles : sms, kThreadsBwd, bytes, stream>>>(p);
+  AFSL_CHECK_LAUNCH(name);
+  return AFSL_OK;
+}
+
+}  // namespace afsl

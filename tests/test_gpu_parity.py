@@ -337,11 +337,14 @@ def test_angular_oracle_provenance(ops):
 @pytest.mark.parametrize("anchors", [True, False])
 @pytest.mark.parametrize("angle", [0.0, 15.0, 30.0])
 @pytest.mark.parametrize("unit_protos", [True, False])
-@pytest.mark.parametrize("path", ["warp", "cta"])
+@pytest.mark.parametrize("path", ["tc", "warp", "cta"])
 def test_angular_vs_restated_oracle(ops, monkeypatch, anchors, angle, unit_protos, path):
     from oracle import angular as oang
+    if path == "tc" and not anchors:
+        pytest.skip("the tensor-core kernel covers the prototypes-as-anchors branch")
+    monkeypatch.setenv("AFSL_ANGULAR_TC", "1" if path == "tc" else "0")
     monkeypatch.setenv("AFSL_ANGULAR_WARP", "1" if path == "warp" else "0")
-    e, ways, per, dim = 6, 5, 5, 64
+    e, ways, per, dim = (1203 if path == "tc" else 6), 5, 5, 64
     gen = torch.Generator().manual_seed(int(angle) * 10 + int(anchors) + 100 * int(unit_protos))
     protos = torch.randn(e, ways, dim, generator=gen)
     if unit_protos:
@@ -352,7 +355,8 @@ def test_angular_vs_restated_oracle(ops, monkeypatch, anchors, angle, unit_proto
     pg, qg = protos.cuda().requires_grad_(True), queries.cuda().requires_grad_(True)
     loss = ops.angular_loss(pg, qg, labels.cuda(), angle, 40.0, anchors, False)
     (loss * wl.cuda()).sum().backward()
-    for i in range(e):
+    # the tensor-core kernel runs 1203 episodes (several tiles per CTA, a partial last tile); the oracle checks a sample
+    for i in (range(e) if e <= 6 else [0, 1, 2, 3, 4, 5, 591, 592, 593, 1199, 1200, 1201, 1202]):
         pc, qc = protos[i].clone().requires_grad_(True), queries[i].clone().requires_grad_(True)
         lo = oang.angular_loss_class(pc, qc, labels[i], angle, anchors)
         (lo * wl[i]).backward()
@@ -360,6 +364,42 @@ def test_angular_vs_restated_oracle(ops, monkeypatch, anchors, angle, unit_proto
         zero = lambda g, like: torch.zeros_like(like) if g is None else g      # nothing mined -> constant zero loss
         close(pg.grad[i], zero(pc.grad, pc), rtol=2e-5)
         close(qg.grad[i], zero(qc.grad, qc), rtol=2e-5)
+
+
+@pytest.mark.parametrize("ways,nq,angle,normalize_ref", [(5, 25, 0.0, False), (5, 25, 20.0, False), (3, 12, 0.0, True),
+                                                         (8, 23, 10.0, False), (4, 27, 0.0, False), (5, 25, 35.0, True)])
+def test_angular_tensor_core_vs_fp32_kernels(ops, monkeypatch, ways, nq, angle, normalize_ref):
+    """The tcgen05 kernel against the warp-per-episode fp32 kernel (itself checked against the oracle above) on every
+    episode of a multi-tile launch: unbalanced random labels, non-unit prototypes AND queries (the reference rows enter
+    the loss un-normalised unless normalize_ref), several (W, Nq); and against the oracle on a sample."""
+    from oracle import angular as oang
+    e, dim = 777, 64
+    gen = torch.Generator().manual_seed(ways * 1000 + nq * 10 + int(angle))
+    protos = torch.randn(e, ways, dim, generator=gen) * (0.5 + torch.rand(e, ways, 1, generator=gen))
+    labels = torch.randint(0, ways, (e, nq), generator=gen)
+    labels[:, :ways] = torch.arange(ways)                      # every class occurs (loops/loss.py:65 asserts it)
+    queries = torch.randn(e, nq, dim, generator=gen) + 0.7 * torch.gather(protos, 1, labels.unsqueeze(-1).expand(-1, -1, dim))
+    queries = queries * (0.8 + 0.4 * torch.rand(e, nq, 1, generator=gen))
+    wl = torch.rand(e, generator=gen) + 0.5
+    got = {}
+    for path in ("tc", "warp"):
+        monkeypatch.setenv("AFSL_ANGULAR_TC", "1" if path == "tc" else "0")
+        monkeypatch.setenv("AFSL_ANGULAR_WARP", "1")
+        pg, qg = protos.cuda().requires_grad_(True), queries.cuda().requires_grad_(True)
+        loss = ops.angular_loss(pg, qg, labels.cuda(), angle, 40.0, True, normalize_ref)
+        (loss * wl.cuda()).sum().backward()
+        got[path] = (loss.detach().cpu(), pg.grad.cpu(), qg.grad.cpu())
+    close(got["tc"][0], got["warp"][0], rtol=1e-5)
+    close(got["tc"][1], got["warp"][1], rtol=2e-5)
+    close(got["tc"][2], got["warp"][2], rtol=2e-5)
+    for i in (0, 333, 776):
+        pc, qc = protos[i].clone().requires_grad_(True), queries[i].clone().requires_grad_(True)
+        lo = oang.angular_loss_class(pc, qc, labels[i], angle, True, normalize_ref=normalize_ref)
+        (lo * wl[i]).backward()
+        close(got["tc"][0][i], lo, rtol=1e-5)
+        zero = lambda g, like: torch.zeros_like(like) if g is None else g
+        close(got["tc"][1][i], zero(pc.grad, pc), rtol=2e-5)
+        close(got["tc"][2][i], zero(qc.grad, qc), rtol=2e-5)
 
 
 # ------------------------------------------------------------------ SpecAugment
