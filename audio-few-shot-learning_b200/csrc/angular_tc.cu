@@ -19,8 +19,12 @@
 //           K-major (the producers keep a transposed copy of the tile: tools/micro/umma_layout_probe.cu);
 //   E2      lane = embedding dimension, columns = rows: coalesced 128-byte stores of dP / dQ.
 //
-// One persistent CTA per SM, warp-specialised, mbarriers only: 4 producer warps (LDG.128 straight from HBM a tile ahead,
-// hi / lo split, transposed copy), 2 x 4 E1 warps (alternate tiles, two D1 accumulators), 4 E2 warps, 1 issuer warp.
+// One persistent CTA per SM, 17 warps, mbarriers only: 4 producer warps (warp = episode slot: 16 LDG.128 per lane straight
+// from HBM, issued a tile ahead and held in registers across the transposed copy of the current tile; hi / lo split), 4 E2
+// warps, 2 x 4 E1 warps (alternate tiles, two D1 accumulators), 1 issuer warp.  Every role is a compact LOOP over 4-column
+// chunks (tcgen05.ld.x4 re-reads the accumulator instead of holding 32-wide register arrays): the first version, fully
+// unrolled over 32 columns, was 8000 SASS instructions executed once per tile and bound by instruction fetch (no_inst stalls,
+// profiles/r2q_*).
 #include "angular.cuh"
 #include "tc_common.cuh"
 
@@ -40,15 +44,14 @@ constexpr float kNormEps = 1e-12f;            // F.normalize
 constexpr float kPairEps = 1e-6f;             // F.pairwise_distance
 constexpr unsigned kFull = 0xffffffffu;
 
-constexpr int kProducerWarps = 4, kE1Warps = 8, kE2Warps = 4;
-constexpr int kFirstE1 = kProducerWarps, kFirstE2 = kFirstE1 + kE1Warps, kIssuer = kFirstE2 + kE2Warps;
-constexpr int kThreadsBwd = (kIssuer + 1) * 32;                 // 544
-constexpr int kThreadsFwd = kThreadsBwd;                        // the forward keeps the layout (E2 warps exit at once)
+constexpr int kProducerWarps = 4, kE2Warps = 4, kE1Warps = 8;
+constexpr int kFirstE2 = kProducerWarps, kFirstE1 = kFirstE2 + kE2Warps, kIssuer = kFirstE1 + kE1Warps;
+constexpr int kThreads = (kIssuer + 1) * 32;                    // 544
 
 // per-E1-warp scratch (floats)
 struct Scratch {
-  float sg[kBlk * kLs];        // Gram rows (raw), later the T rows (dL/dGram of the pairs, row = positive)
-  float sp[kMaxW * kLs];       // per-class column sums of T = prototype rows of dL/dGram
+  float fx[kBlk * kLs];        // per-lane rows: exponents -> exponentials -> T (dL/dGram of the pairs, row = positive)
+  float sp[kMaxW * kLs];       // raw Gram rows of the prototypes, later the per-class column sums of T
   float rinv[kBlk], nrm[kBlk], csn[kBlk], gdi[kBlk], nu[kBlk], gs[kBlk];
   int manc[kMaxW];
 };
@@ -73,7 +76,15 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
   } while (!done);
 }
 __device__ __forceinline__ void sts1(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
-__device__ __forceinline__ float bitf(uint32_t v) { return __uint_as_float(v); }
+// four consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ float4 tmem_ld4(uint32_t taddr) {
+  uint32_t a, b, c, d;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  return make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c), __uint_as_float(d));
+}
+__device__ __forceinline__ float pick(const float4& t, int u) { return u == 0 ? t.x : u == 1 ? t.y : u == 2 ? t.z : t.w; }
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
 // ---------------------------------------------------------------------------------------------------------------- E1
 // One warp, lane = row of the episode's block.  `tm` = TMEM address of the block's 32 Gram columns in this warp's lanes.
@@ -86,42 +97,27 @@ __device__ __forceinline__ void e1_episode(const AngParams& p, int ep, int lab_i
   const int lab = lane < W ? lane : (qv ? lab_in : -1);
   const int a = qv ? lab : 0;
   const float c4 = 4.f * p.t2, cneg = -2.f * (1.f + p.t2);
+  float* fx_row = sc->fx + lane * kLs;
 
-  float g[32], pa[32];
-  {
-    uint32_t v[32];
-    tmem_ld32(tm, v);
-#pragma unroll
-    for (int k = 0; k < 32; ++k) g[k] = bitf(v[k]);
+  // ---- raw Gram row: diagonal (norm), column 31 (component sum); the prototypes' rows go to the scratch for every lane
+  float gii = 0.f, srow = 0.f;
+#pragma unroll 2
+  for (int c = 0; c < 8; ++c) {
+    const float4 t = tmem_ld4(tm + 4 * c);
+    if (c == (lane >> 2)) gii = pick(t, lane & 3);
+    if (c == 7) srow = t.w;
+    if (lane < W) *reinterpret_cast<float4*>(sc->sp + lane * kLs + 4 * c) = t;
   }
-  if (!kBwd) {                                                  // the accumulator is free as soon as it is in registers
-    fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(d1_free);
-  }
-  // ---- raw Gram rows to the scratch: diagonal (norms), prototype rows for every lane
-#pragma unroll
-  for (int c = 0; c < 8; ++c)
-    *reinterpret_cast<float4*>(sc->sg + lane * kLs + 4 * c) = make_float4(g[4 * c], g[4 * c + 1], g[4 * c + 2], g[4 * c + 3]);
-  __syncwarp();
-  const float gii = sc->sg[lane * kLs + lane];
   const float nrm = sqrtf(fmaxf(gii, 0.f));
   const float ri = 1.f / fmaxf(nrm, kNormEps);
-  const float cs = g[kOnesRow] * ri;                            // component sum of the normalised row
+  const float cs = srow * ri;                                   // component sum of the normalised row
   const float gdi = gii * ri * ri;
   sc->rinv[lane] = ri; sc->nrm[lane] = nrm; sc->csn[lane] = cs; sc->gdi[lane] = gdi;
   if (lane < kMaxW) sc->manc[lane] = 0;
   __syncwarp();
   const float ra_inv = sc->rinv[a];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const float4 r4 = *reinterpret_cast<const float4*>(sc->rinv + 4 * c);
-    const float4 s4 = *reinterpret_cast<const float4*>(sc->sg + a * kLs + 4 * c);
-    g[4 * c] *= ri * r4.x; g[4 * c + 1] *= ri * r4.y; g[4 * c + 2] *= ri * r4.z; g[4 * c + 3] *= ri * r4.w;
-    pa[4 * c] = s4.x * ra_inv * r4.x; pa[4 * c + 1] = s4.y * ra_inv * r4.y;
-    pa[4 * c + 2] = s4.z * ra_inv * r4.z; pa[4 * c + 3] = s4.w * ra_inv * r4.w;
-  }
-  const float gaq = sc->sg[a * kLs + lane] * ra_inv * ri;       // cos(prototype a, this query)
+  const float* pa_row = sc->sp + a * kLs;                       // raw Gram row of my prototype
+  const float gaq = pa_row[lane] * ra_inv * ri;                 // cos(prototype a, this query)
 
   // ---- masks: queries of the episode, lanes of my class, my pair's negatives
   const unsigned allq = __ballot_sync(kFull, qv);
@@ -148,16 +144,23 @@ __device__ __forceinline__ void e1_episode(const AngParams& p, int ep, int lab_i
     const float inv = 1.f / fmaxf(sum_norm, kNormEps);
     const float cc = sum_norm > kNormEps ? 1.f : (sum_norm * inv) * (sum_norm * inv);
     const float csum_c = (ra * sc->csn[a] + rq * cs) * inv;
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      const float4 t = tmem_ld4(tm + 4 * c), r4 = ld4(sc->rinv + 4 * c), s4 = ld4(pa_row + 4 * c);
+      const float4 gd4 = ld4(sc->gdi + 4 * c), cs4 = ld4(sc->csn + 4 * c);
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const float dot = (ra * pa[k] + rq * g[k]) * inv;
-      const float nc2 = sc->gdi[k] + cc - 2.f * dot + 2.f * kPairEps * (sc->csn[k] - csum_c) + deps;
-      const float nc = sqrtf(fmaxf(nc2, 0.f));
-      // atan(ap / (2 nc)) > angle without the arctangent and the division: ap > 2 nc tan(angle)
-      const bool pass = ((negmask >> k) & 1u) && !p.miner_never && ap > 2.f * nc * p.miner_tan;
-      count += pass;
-      const unsigned b = __ballot_sync(kFull, pass);
-      if (lane == k) wneg = __popc(b);
+      for (int u = 0; u < 4; ++u) {
+        const int k = 4 * c + u;
+        const float gk = pick(t, u) * ri * pick(r4, u), pk = pick(s4, u) * ra_inv * pick(r4, u);
+        const float dot = (ra * pk + rq * gk) * inv;
+        const float nc2 = pick(gd4, u) + cc - 2.f * dot + 2.f * kPairEps * (pick(cs4, u) - csum_c) + deps;
+        const float nc = sqrtf(fmaxf(nc2, 0.f));
+        // atan(ap / (2 nc)) > angle without the arctangent and the division: ap > 2 nc tan(angle)
+        const bool pass = ((negmask >> k) & 1u) && !p.miner_never && ap > 2.f * nc * p.miner_tan;
+        count += pass;
+        const unsigned b = __ballot_sync(kFull, pass);
+        if (lane == k) wneg = __popc(b);
+      }
     }
   }
   if (count) atomicAdd(&sc->manc[a], count);
@@ -169,34 +172,38 @@ __device__ __forceinline__ void e1_episode(const AngParams& p, int ep, int lab_i
   const float omega = qv ? (float)sc->manc[a] * nu_i : 0.f;
   const float base = cneg * gaq;
   float mx = 0.f;
-#pragma unroll
+#pragma unroll 2
   for (int c = 0; c < 8; ++c) {
-    const float4 nu4 = *reinterpret_cast<const float4*>(sc->nu + 4 * c);
+    const float4 t = tmem_ld4(tm + 4 * c), r4 = ld4(sc->rinv + 4 * c), s4 = ld4(pa_row + 4 * c), nu4 = ld4(sc->nu + 4 * c);
     float4 rho = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (!p.normalize_ref) rho = *reinterpret_cast<const float4*>(sc->nrm + 4 * c);
-    const float nuv[4] = {nu4.x, nu4.y, nu4.z, nu4.w}, rv[4] = {rho.x, rho.y, rho.z, rho.w};
+    if (!p.normalize_ref) rho = ld4(sc->nrm + 4 * c);
+    float f[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int k = 4 * c + u;
-      const float f = fmaf(c4 * rv[u], pa[k] + g[k], base);
-      pa[k] = f;
-      const bool use = ((negmask >> k) & 1u) && nuv[u] > 0.f;
-      mx = use ? fmaxf(mx, f) : mx;
+      const float rk = pick(r4, u);
+      f[u] = fmaf(c4 * pick(rho, u), (pick(s4, u) * ra_inv + pick(t, u) * ri) * rk, base);
+      const bool use = ((negmask >> (4 * c + u)) & 1u) && pick(nu4, u) > 0.f;
+      mx = use ? fmaxf(mx, f[u]) : mx;
     }
+    *reinterpret_cast<float4*>(fx_row + 4 * c) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+  if (!kBwd) {                                                  // the accumulator is not needed any more
+    fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(d1_free);
   }
   float tot = __expf(-mx);
-#pragma unroll
+#pragma unroll 2
   for (int c = 0; c < 8; ++c) {
-    const float4 nu4 = *reinterpret_cast<const float4*>(sc->nu + 4 * c);
-    const float nuv[4] = {nu4.x, nu4.y, nu4.z, nu4.w};
+    const float4 f4 = ld4(fx_row + 4 * c), nu4 = ld4(sc->nu + 4 * c);
+    float ex[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int k = 4 * c + u;
-      const float w = ((negmask >> k) & 1u) ? nuv[u] : 0.f;
-      const float ex = w * __expf(pa[k] - mx);
-      pa[k] = ex;
-      tot += ex;
+      const float w = ((negmask >> (4 * c + u)) & 1u) ? pick(nu4, u) : 0.f;
+      ex[u] = w * __expf(pick(f4, u) - mx);
+      tot += ex[u];
     }
+    if (kBwd) *reinterpret_cast<float4*>(fx_row + 4 * c) = make_float4(ex[0], ex[1], ex[2], ex[3]);
   }
   const float term = omega > 0.f ? omega * (mx + logf(tot)) : 0.f;
   const float num = warp_sum(term), den = warp_sum(omega);
@@ -209,103 +216,93 @@ __device__ __forceinline__ void e1_episode(const AngParams& p, int ep, int lab_i
   const float scale = den > 0.f ? p.d_loss[ep] / den : 0.f;
   const float coef = omega > 0.f ? scale * omega / tot : 0.f;
   float gsum = 0.f;
-#pragma unroll
+#pragma unroll 2
   for (int c = 0; c < 8; ++c) {
+    const float4 e4 = ld4(fx_row + 4 * c);
     float4 rho = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (!p.normalize_ref) rho = *reinterpret_cast<const float4*>(sc->nrm + 4 * c);
-    const float rv[4] = {rho.x, rho.y, rho.z, rho.w};
+    if (!p.normalize_ref) rho = ld4(sc->nrm + 4 * c);
+    float tk[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int k = 4 * c + u;
-      const float gk = coef * pa[k];
+      const float gk = coef * pick(e4, u);
       gsum += gk;
-      pa[k] = c4 * rv[u] * gk;
+      tk[u] = c4 * pick(rho, u) * gk;
     }
+    *reinterpret_cast<float4*>(fx_row + 4 * c) = make_float4(tk[0], tk[1], tk[2], tk[3]);
   }
   sc->gs[lane] = gsum;
-  __syncwarp();                                                 // every lane is done with the Gram rows in sg
-#pragma unroll
-  for (int c = 0; c < 8; ++c)
-    *reinterpret_cast<float4*>(sc->sg + lane * kLs + 4 * c) = make_float4(pa[4 * c], pa[4 * c + 1], pa[4 * c + 2], pa[4 * c + 3]);
-  __syncwarp();
+  __syncwarp();                                                 // T rows complete; every lane is done with the prototype rows
   // per-class column sums (rows of a class in ascending order): pr[w] = dL/dGram[prototype w][this lane's row]
-  float pr[kMaxW];
+  {
+    float pr[kMaxW];
 #pragma unroll
-  for (int w = 0; w < kMaxW; ++w) {
-    pr[w] = 0.f;
-    if (w < W) {
-      for (unsigned m = cm[w]; m != 0; m &= m - 1) pr[w] += sc->sg[(__ffs(m) - 1) * kLs + lane];
-      sc->sp[w * kLs + lane] = pr[w];
+    for (int w = 0; w < kMaxW; ++w) pr[w] = 0.f;
+    unsigned any = 0;
+#pragma unroll
+    for (int w = 0; w < kMaxW; ++w) any |= cm[w];
+    while (any) {                                               // one row of every class per round: W independent chains
+      any = 0;
+#pragma unroll
+      for (int w = 0; w < kMaxW; ++w)
+        if (cm[w]) {
+          pr[w] += sc->fx[(__ffs(cm[w]) - 1) * kLs + lane];
+          cm[w] &= cm[w] - 1;
+          any |= cm[w];
+        }
     }
+#pragma unroll
+    for (int w = 0; w < kMaxW; ++w)
+      if (w < W) sc->sp[w * kLs + lane] = pr[w];
   }
   __syncwarp();
-  // own Gram row again (normalised) from the accumulator, then the accumulator is free
-  {
-    uint32_t v[32];
-    tmem_ld32(tm, v);
-    fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(d1_free);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float4 r4 = *reinterpret_cast<const float4*>(sc->rinv + 4 * c);
-      g[4 * c] = bitf(v[4 * c]) * ri * r4.x; g[4 * c + 1] = bitf(v[4 * c + 1]) * ri * r4.y;
-      g[4 * c + 2] = bitf(v[4 * c + 2]) * ri * r4.z; g[4 * c + 3] = bitf(v[4 * c + 3]) * ri * r4.w;
-    }
-  }
-  // symmetric G'[i][k] = dL/dGram[i][k] + dL/dGram[k][i], row i = this lane
+  // symmetric G'[i][k] = dL/dGram[i][k] + dL/dGram[k][i] of row i = this lane, scaled into the B operand of MMA 2:
+  // G3[i][k] = r_i r_k G'[i][k] (hi = the raw value, the tensor core truncates it; lo = the rounded remainder)
   const bool isp = lane < W;
-  const int prow = isp ? lane : 0;
-  float drho = 0.f;
-#pragma unroll
+  const float* sp_row = sc->sp + (isp ? lane : 0) * kLs;
+  float drho = 0.f, dot = 0.f;
+  mbar_wait_sleep(gp_free, gp_parity);                          // MMA 2 of the previous tile is done with the operand
+#pragma unroll 2
   for (int c = 0; c < 8; ++c) {
-    const float4 sp4 = *reinterpret_cast<const float4*>(sc->sp + prow * kLs + 4 * c);
-    const float4 gs4 = *reinterpret_cast<const float4*>(sc->gs + 4 * c);
-    const float spv[4] = {sp4.x, sp4.y, sp4.z, sp4.w}, gsv[4] = {gs4.x, gs4.y, gs4.z, gs4.w};
+    const float4 t = tmem_ld4(tm + 4 * c), r4 = ld4(sc->rinv + 4 * c), t4 = ld4(fx_row + 4 * c), sp4 = ld4(sp_row + 4 * c);
+    const float4 gs4 = ld4(sc->gs + 4 * c);
+    float o[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int k = 4 * c + u;
-      const float col = sc->sg[k * kLs + lane];                 // T_k[i]
-      drho = fmaf(col, g[k], drho);
-      const float vq = pa[k] + col;
-      const float vp = ((sameq >> k) & 1u) ? cneg * gsv[u] : spv[u];
-      pa[k] = qv ? vq : (isp ? vp : 0.f);
+      const float gk = pick(t, u) * ri * pick(r4, u);           // cos(row i, row k)
+      const float col = sc->fx[k * kLs + lane];                 // T_k[i]
+      drho = fmaf(col, gk, drho);
+      const float vq = pick(t4, u) + col;
+      const float vp = ((sameq >> k) & 1u) ? cneg * pick(gs4, u) : pick(sp4, u);
+      float val = qv ? vq : (isp ? vp : 0.f);
+      if (c < 2 && k < W) {                                     // prototype columns of a query's row
+        const float prk = sc->sp[k * kLs + lane];               // 0 for my own class: it never uses me as a negative
+        if (qv) val = (k == lab) ? cneg * gsum : prk;
+        drho = fmaf(prk, gk, drho);
+      }
+      dot = fmaf(val, gk, dot);
+      o[u] = ri * pick(r4, u) * val;
     }
-  }
-#pragma unroll
-  for (int w = 0; w < kMaxW; ++w)
-    if (w < W) {
-      if (qv) pa[w] = (w == lab) ? cneg * gsum : pr[w];
-      drho = fmaf(pr[w], g[w], drho);                           // pr[lab] = 0: my own class never uses me as a negative
-    }
-  drho = (!p.normalize_ref && qv && nrm > 0.f) ? drho / nrm : 0.f;
-  float dot = 0.f;
-#pragma unroll
-  for (int k = 0; k < 32; ++k) dot = fmaf(pa[k], g[k], dot);
-  if (!(nrm > kNormEps)) dot = 0.f;                             // F.normalize clamps the norm: no projection term there
-  const float cdiag = ri * (drho - ri * dot);
-  // G3 row -> B operand of MMA 2 (hi = the raw value, the tensor core truncates it; lo = the rounded remainder)
-  mbar_wait_sleep(gp_free, gp_parity);
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const float4 r4 = *reinterpret_cast<const float4*>(sc->rinv + 4 * c);
-    float4 v = make_float4(ri * r4.x * pa[4 * c], ri * r4.y * pa[4 * c + 1], ri * r4.z * pa[4 * c + 2], ri * r4.w * pa[4 * c + 3]);
-    if ((lane >> 2) == c) {
-      const int u = lane & 3;
-      if (u == 0) v.x += cdiag;
-      if (u == 1) v.y += cdiag;
-      if (u == 2) v.z += cdiag;
-      if (u == 3) v.w += cdiag;
-    }
+    const float4 v = make_float4(o[0], o[1], o[2], o[3]);
     const uint32_t off = ((uint32_t)((c ^ lane) & 7) << 4);     // sw128 inside this lane's row
     sts4(gph_row + off, v);
     sts4(gpl_row + off, lo_of_raw(v));
   }
+  fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(d1_free);
+  // the diagonal carries the backward of the row normalisation: r_i (drho_i - r_i <x^_i, dx^_i>); G'[i][i] itself is 0
+  drho = (!p.normalize_ref && qv && nrm > 0.f) ? drho / nrm : 0.f;
+  if (!(nrm > kNormEps)) dot = 0.f;                             // F.normalize clamps the norm: no projection term there
+  const float cdiag = ri * (drho - ri * dot);
+  const uint32_t doff = ((uint32_t)(((lane >> 2) ^ lane) & 7) << 4) + (lane & 3) * 4;
+  sts1(gph_row + doff, cdiag);
+  sts1(gpl_row + doff, rna_tf32(cdiag - trunc_tf32(cdiag)));
 }
 
 // ------------------------------------------------------------------------------------------------------------ kernel
 template <bool kBwd>
-__global__ void __launch_bounds__(kThreadsBwd, 1) angular_tc_kernel(const AngParams p) {
+__global__ void __launch_bounds__(kThreads, 1) angular_tc_kernel(const AngParams p) {
   extern __shared__ __align__(1024) uint8_t smem_ang_raw[];
   uint8_t* smem = smem_ang_raw + ((1024u - (smem_u32(smem_ang_raw) & 1023u)) & 1023u);
   const uint32_t base = smem_u32(smem);
@@ -348,59 +345,95 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) angular_tc_kernel(const AngPar
   if (warp < kProducerWarps) {
     // =========================================================== producers: warp = episode slot of the tile
     const int e = warp;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+    const int n16 = N * 16, w16 = W * 16;                               // 16-byte chunks of the block / of its prototypes
+    float4 v[16];
+    auto load_tile = [&](int tile) {
       const int ep = tile * kEp + e;
-      const bool valid = ep < p.E;
-      const float* prow = p.protos + (size_t)(valid ? ep : 0) * W * kD;
-      const float* qrow = p.queries + (size_t)(valid ? ep : 0) * Nq * kD;
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        float4 v[8];
+      const bool valid = tile < tiles && ep < p.E;
+      const float4* p4 = reinterpret_cast<const float4*>(p.protos) + (size_t)(valid ? ep : 0) * w16;
+      const float4* q4 = reinterpret_cast<const float4*>(p.queries) + (size_t)(valid ? ep : 0) * (n16 - w16);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int ci = lane + 32 * j, r = ci >> 3, cc = ci & 7;
-          v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (valid && r < N) {
-            const float* src = (r < W ? prow + r * kD : qrow + (r - W) * kD) + 32 * h + 4 * cc;
-            v[j] = ldg_stream(reinterpret_cast<const float4*>(src));
-          }
-        }
-        if (h == 0) mbar_wait(&bars->x_free, (it & 1) ^ 1);             // MMA 1 of the previous tile is done with X
+      for (int j = 0; j < 16; ++j) {
+        const int ci = lane + 32 * j;                                   // row ci / 16, 16-byte chunk ci % 16 of the block
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid && ci < n16) v[j] = ldg_stream(ci < w16 ? p4 + ci : q4 + (ci - w16));
+      }
+    };
+    int it = 0;
+    load_tile(blockIdx.x);
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      mbar_wait(&bars->x_free, (it & 1) ^ 1);                           // MMA 1 of the previous tile is done with X
+      {
+        const int cc = lane & 15;
+        const uint32_t half = base + (cc >> 3) * kTile;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int ci = lane + 32 * j, r = ci >> 3, cc = ci & 7;
+        for (int j = 0; j < 16; ++j) {
+          const int r = (lane >> 4) + 2 * j;
           if (r < N) {
-            const uint32_t off = h * kTile + sw128(e * kBlk + r, cc);
-            sts4(base + kXH + off, v[j]);
-            sts4(base + kXL + off, lo_of_raw(v[j]));
+            const uint32_t off = half + sw128(e * kBlk + r, cc & 7);
+            sts4(off + kXH, v[j]);
+            sts4(off + kXL, lo_of_raw(v[j]));
           }
         }
       }
       fence_async_proxy();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->x_full);
+      load_tile(tile + gridDim.x);                                      // next tile's rows fly while this one is finished
       if (kBwd) {
         // transposed copy of my block: XT[e][d][j] = X[j][d] (lane = row j reads its own row, conflict-free both ways)
         mbar_wait(&bars->xt_free, (it & 1) ^ 1);                        // MMA 2 of the previous tile is done with XT
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h)
+        for (int hc = 0; hc < 16; ++hc) {
+          const int h = hc >> 3, c = hc & 7;
+          const float4 hv = lds4(base + kXH + h * kTile + sw128(e * kBlk + lane, c));
+          const float4 lv = lo_of_raw(hv);
+          const uint32_t col = (uint32_t)e * (kD * 128) + (lane & 3) * 4;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 hv = lds4(base + kXH + h * kTile + sw128(e * kBlk + lane, c));
-            const float4 lv = lo_of_raw(hv);
-            const float hvv[4] = {hv.x, hv.y, hv.z, hv.w}, lvv[4] = {lv.x, lv.y, lv.z, lv.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int d = 32 * h + 4 * c + u;
-              const uint32_t off = (uint32_t)e * (kD * 128) + sw128(d, lane >> 2) + (lane & 3) * 4;
-              sts1(base + kXTH + off, hvv[u]);
-              sts1(base + kXTL + off, lvv[u]);
-            }
+          for (int u = 0; u < 4; ++u) {
+            const int d = 4 * hc + u;
+            const uint32_t off = col + sw128(d, lane >> 2);
+            sts1(base + kXTH + off, pick(hv, u));
+            sts1(base + kXTL + off, pick(lv, u));
           }
+        }
         fence_async_proxy();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->xt_full);
+      }
+    }
+  } else if (warp < kFirstE1) {
+    // =========================================================== E2: lane = embedding dimension, columns = rows
+    if (kBwd) {
+      const int quad = warp & 3;
+      const int d = (quad & 1) * 32 + lane;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        mbar_wait_sleep(&bars->d2_full, it & 1);
+        fence_after();
+#pragma unroll 1
+        for (int s2 = 0; s2 < 2; ++s2) {
+          const int ep = tile * kEp + 2 * s2 + (quad >> 1);
+          const bool valid = ep < p.E;
+          const uint32_t ta = tmem + ((uint32_t)(quad * 32) << 16) + 256 + s2 * 64 + (quad >> 1) * 32;
+          // row i of the block lives at dp + i * 64 (prototypes) or dqm + i * 64 (queries)
+          const size_t dp = (size_t)(valid ? ep : 0) * W * kD + d, dqm = (size_t)(valid ? ep : 0) * Nq * kD + d;
+#pragma unroll 2
+          for (int c = 0; c < 8; ++c) {
+            const float4 t = tmem_ld4(ta + 4 * c);
+            if (valid) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int i = 4 * c + u;
+                if (i < W) p.d_protos[dp + i * kD] = pick(t, u);
+                else if (i < N) p.d_queries[dqm + (i - W) * kD] = pick(t, u);
+              }
+            }
+          }
+        }
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->d2_free);
       }
     }
   } else if (warp == kIssuer) {
@@ -464,7 +497,7 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) angular_tc_kernel(const AngPar
         __syncwarp();
       }
     }
-  } else if (warp < kFirstE2) {
+  } else {
     // =========================================================== E1: set = (warp - 4) / 4 takes the tiles of its parity
     const int set = (warp - kFirstE1) >> 2, quad = warp & 3;           // quad = episode slot = TMEM lane quarter
     Scratch* sc = scratch + (warp - kFirstE1);
@@ -493,33 +526,6 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) angular_tc_kernel(const AngPar
         if (lane == 0) mbar_arrive(&bars->gp_full);
       }
     }
-  } else if (kBwd) {
-    // =========================================================== E2: lane = embedding dimension, columns = rows
-    const int quad = warp & 3;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-      mbar_wait_sleep(&bars->d2_full, it & 1);
-      fence_after();
-      uint32_t v[2][32];
-#pragma unroll
-      for (int s = 0; s < 2; ++s) tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + 256 + s * 64 + (quad >> 1) * 32, v[s]);
-      fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->d2_free);
-      const int d = (quad & 1) * 32 + lane;
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const int ep = tile * kEp + 2 * s + (quad >> 1);
-        if (ep >= p.E) continue;
-        float* dp = p.d_protos + (size_t)ep * W * kD + d;
-        float* dq = p.d_queries + (size_t)ep * Nq * kD + d;
-#pragma unroll
-        for (int i = 0; i < 31; ++i) {
-          if (i < W) dp[i * kD] = bitf(v[s][i]);
-          else if (i < N) dq[(i - W) * kD] = bitf(v[s][i]);
-        }
-      }
-    }
   }
   fence_before();
   __syncthreads();
@@ -542,7 +548,7 @@ int launch_angular_tc(const AngParams& p, bool bwd, cudaStream_t stream, const c
   int sms = kNumSMs, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = (p.E + kEp - 1) / kEp;
-  fn<<<tiles < sms ? tiles : sms, kThreadsBwd, bytes, stream>>>(p);
+  fn<<<tiles < sms ? tiles : sms, kThreads, bytes, stream>>>(p);
   AFSL_CHECK_LAUNCH(name);
   return AFSL_OK;
 }
