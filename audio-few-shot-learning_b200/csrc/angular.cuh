@@ -20,6 +20,7 @@ struct AngParams {
   float* d_protos;        // [E,W,D]
   float* d_queries;       // [E,Nq,D]
   int E, Nq, W, D;
+  long long* dbg;         // angular_tc.cu timeline buffer (AFSL_ANGULAR_DBG), else null
 };
 
 // angular_warp.cu: launches the warp-per-episode kernel when the shape fits it; *handled says whether it did

@@ -19,9 +19,10 @@
 //           K-major (the producers keep a transposed copy of the tile: tools/micro/umma_layout_probe.cu);
 //   E2      lane = embedding dimension, columns = rows: coalesced 128-byte stores of dP / dQ.
 //
-// One persistent CTA per SM, 17 warps, mbarriers only: 4 producer warps (warp = episode slot: 16 LDG.128 per lane straight
-// from HBM, issued a tile ahead and held in registers across the transposed copy of the current tile; hi / lo split), 4 E2
-// warps, 2 x 4 E1 warps (alternate tiles, two D1 accumulators), 1 issuer warp.  Every role is a compact LOOP over 4-column
+// One persistent CTA per SM, 17 warps, mbarriers only: 2 x 4 producer / E2 warps (warp = episode slot, the two sets take
+// alternate tiles: 16 LDG.128 per lane straight from HBM, issued TWO tiles ahead and held in registers - two tiles = 61 KB
+// in flight per SM; hi / lo split; transposed copy; E2 of the set's previous tile), 2 x 4 E1 warps (alternate tiles, two D1
+// accumulators), 1 issuer warp.  Every role is a compact LOOP over 4-column
 // chunks (tcgen05.ld.x4 re-reads the accumulator instead of holding 32-wide register arrays): the first version, fully
 // unrolled over 32 columns, was 8000 SASS instructions executed once per tile and bound by instruction fetch (no_inst stalls,
 // profiles/r2q_*).
@@ -44,8 +45,8 @@ constexpr float kNormEps = 1e-12f;            // F.normalize
 constexpr float kPairEps = 1e-6f;             // F.pairwise_distance
 constexpr unsigned kFull = 0xffffffffu;
 
-constexpr int kProducerWarps = 4, kE2Warps = 4, kE1Warps = 8;
-constexpr int kFirstE2 = kProducerWarps, kFirstE1 = kFirstE2 + kE2Warps, kIssuer = kFirstE1 + kE1Warps;
+constexpr int kPeWarps = 8, kE1Warps = 8;                      // two sets of four each, alternating tiles
+constexpr int kFirstE1 = kPeWarps, kIssuer = kFirstE1 + kE1Warps;
 constexpr int kThreads = (kIssuer + 1) * 32;                    // 544
 
 // per-E1-warp scratch (floats)
@@ -57,8 +58,10 @@ struct Scratch {
 };
 
 struct Bars {
-  uint64_t x_full, x_free, xt_full, xt_free, gp_full, gp_free, d2_full, d2_free;
-  uint64_t d1_full[2], d1_free[2];
+  // mbarrier waits only tell adjacent phases apart, so a barrier that a role observes every OTHER tile (the two producer
+  // sets, the two E1 sets) exists once per tile parity: index = tile iteration & 1, phase = iteration >> 1
+  uint64_t x_full, xt_full, gp_full, gp_free;
+  uint64_t x_free[2], xt_free[2], xt_done[2], d2_full[2], d2_free[2], d1_full[2], d1_free[2];
   uint32_t tmem_base;
 };
 
@@ -86,11 +89,22 @@ __device__ __forceinline__ float4 tmem_ld4(uint32_t taddr) {
 __device__ __forceinline__ float pick(const float4& t, int u) { return u == 0 ? t.x : u == 1 ? t.y : u == 2 ? t.z : t.w; }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
+// timeline of CTA 0 (AFSL_ANGULAR_DBG=1): SM clock at event `ev` of tile iteration `it`, one warp per role
+#define DBG(ev)                                                                                              \
+  do {                                                                                                       \
+    if (p.dbg && blockIdx.x == 0 && (threadIdx.x & 127) == 0 && it < 24) p.dbg[it * 32 + (ev)] = clock64(); \
+  } while (0)
+
 // ---------------------------------------------------------------------------------------------------------------- E1
 // One warp, lane = row of the episode's block.  `tm` = TMEM address of the block's 32 Gram columns in this warp's lanes.
 template <bool kBwd>
 __device__ __forceinline__ void e1_episode(const AngParams& p, int ep, int lab_in, uint32_t tm, Scratch* sc, uint64_t* d1_free,
-                                           uint64_t* gp_free, uint32_t gp_parity, uint32_t gph_row, uint32_t gpl_row) {
+                                           uint64_t* gp_free, uint32_t gp_parity, uint32_t gph_row, uint32_t gpl_row,
+                                           long long* dbg) {
+#define DBGE(ev)                                         \
+  do {                                                   \
+    if (dbg && (threadIdx.x & 31) == 0) dbg[ev] = clock64(); \
+  } while (0)
   const int lane = threadIdx.x & 31;
   const int W = p.W, N = p.W + p.Nq;
   const bool qv = lane >= W && lane < N && lab_in >= 0 && lab_in < W;
@@ -115,6 +129,7 @@ __device__ __forceinline__ void e1_episode(const AngParams& p, int ep, int lab_i
   sc->rinv[lane] = ri; sc->nrm[lane] = nrm; sc->csn[lane] = cs; sc->gdi[lane] = gdi;
   if (lane < kMaxW) sc->manc[lane] = 0;
   __syncwarp();
+  DBGE(13);
   const float ra_inv = sc->rinv[a];
   const float* pa_row = sc->sp + a * kLs;                       // raw Gram row of my prototype
   const float gaq = pa_row[lane] * ra_inv * ri;                 // cos(prototype a, this query)
@@ -167,6 +182,7 @@ __device__ __forceinline__ void e1_episode(const AngParams& p, int ep, int lab_i
   const float nu_i = qv ? (float)(count + wneg) : 0.f;
   sc->nu[lane] = nu_i;
   __syncwarp();
+  DBGE(14);
 
   // ---- my pair: weighted log-sum-exp over the negatives, with the appended zero
   const float omega = qv ? (float)sc->manc[a] * nu_i : 0.f;
@@ -192,6 +208,7 @@ __device__ __forceinline__ void e1_episode(const AngParams& p, int ep, int lab_i
     __syncwarp();
     if (lane == 0) mbar_arrive(d1_free);
   }
+  DBGE(15);
   float tot = __expf(-mx);
 #pragma unroll 2
   for (int c = 0; c < 8; ++c) {
@@ -207,6 +224,7 @@ __device__ __forceinline__ void e1_episode(const AngParams& p, int ep, int lab_i
   }
   const float term = omega > 0.f ? omega * (mx + logf(tot)) : 0.f;
   const float num = warp_sum(term), den = warp_sum(omega);
+  DBGE(16);
   if (!kBwd) {
     if (lane == 0) p.loss[ep] = den > 0.f ? num / den : 0.f;
     return;
@@ -232,6 +250,7 @@ __device__ __forceinline__ void e1_episode(const AngParams& p, int ep, int lab_i
   }
   sc->gs[lane] = gsum;
   __syncwarp();                                                 // T rows complete; every lane is done with the prototype rows
+  DBGE(17);
   // per-class column sums (rows of a class in ascending order): pr[w] = dL/dGram[prototype w][this lane's row]
   {
     float pr[kMaxW];
@@ -260,7 +279,9 @@ __device__ __forceinline__ void e1_episode(const AngParams& p, int ep, int lab_i
   const bool isp = lane < W;
   const float* sp_row = sc->sp + (isp ? lane : 0) * kLs;
   float drho = 0.f, dot = 0.f;
+  DBGE(18);
   mbar_wait_sleep(gp_free, gp_parity);                          // MMA 2 of the previous tile is done with the operand
+  DBGE(19);
 #pragma unroll 2
   for (int c = 0; c < 8; ++c) {
     const float4 t = tmem_ld4(tm + 4 * c), r4 = ld4(sc->rinv + 4 * c), t4 = ld4(fx_row + 4 * c), sp4 = ld4(sp_row + 4 * c);
@@ -314,15 +335,16 @@ __global__ void __launch_bounds__(kThreads, 1) angular_tc_kernel(const AngParams
   const int tiles = (p.E + kEp - 1) / kEp;
 
   if (tid == 0) {
-    mbar_init(&bars->x_full, kProducerWarps);
-    mbar_init(&bars->x_free, 1);
-    mbar_init(&bars->xt_full, kProducerWarps);
-    mbar_init(&bars->xt_free, 1);
+    mbar_init(&bars->x_full, 4);
+    mbar_init(&bars->xt_full, 4);
     mbar_init(&bars->gp_full, 4);
     mbar_init(&bars->gp_free, 1);
-    mbar_init(&bars->d2_full, 1);
-    mbar_init(&bars->d2_free, kE2Warps);
     for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars->x_free[b], 1);
+      mbar_init(&bars->xt_free[b], 1);
+      mbar_init(&bars->xt_done[b], 4);
+      mbar_init(&bars->d2_full[b], 1);
+      mbar_init(&bars->d2_free[b], 4);
       mbar_init(&bars->d1_full[b], 1);
       mbar_init(&bars->d1_free[b], 4);
     }
@@ -342,9 +364,9 @@ __global__ void __launch_bounds__(kThreads, 1) angular_tc_kernel(const AngParams
   fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp < kProducerWarps) {
-    // =========================================================== producers: warp = episode slot of the tile
-    const int e = warp;
+  if (warp < kPeWarps) {
+    // =========================================================== producers + E2: warp & 3 = episode slot, warp / 4 = set
+    const int set = warp >> 2, e = warp & 3;
     const int n16 = N * 16, w16 = W * 16;                               // 16-byte chunks of the block / of its prototypes
     float4 v[16];
     auto load_tile = [&](int tile) {
@@ -359,10 +381,42 @@ __global__ void __launch_bounds__(kThreads, 1) angular_tc_kernel(const AngParams
         if (valid && ci < n16) v[j] = ldg_stream(ci < w16 ? p4 + ci : q4 + (ci - w16));
       }
     };
-    int it = 0;
-    load_tile(blockIdx.x);
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-      mbar_wait(&bars->x_free, (it & 1) ^ 1);                           // MMA 1 of the previous tile is done with X
+    auto e2_tile = [&](int tile, int it) {                              // lane = embedding dimension, columns = rows
+      const int d = (e & 1) * 32 + lane;
+      mbar_wait(&bars->d2_full[it & 1], (it >> 1) & 1);
+      fence_after();
+#pragma unroll 1
+      for (int s2 = 0; s2 < 2; ++s2) {
+        const int ep = tile * kEp + 2 * s2 + (e >> 1);
+        const bool valid = ep < p.E;
+        const uint32_t ta = tmem + ((uint32_t)(e * 32) << 16) + 256 + s2 * 64 + (e >> 1) * 32;
+        const size_t dp = (size_t)(valid ? ep : 0) * W * kD + d, dq = (size_t)(valid ? ep : 0) * Nq * kD + d;
+#pragma unroll 2
+        for (int c = 0; c < 8; ++c) {
+          const float4 t = tmem_ld4(ta + 4 * c);
+          if (valid) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int i = 4 * c + u;
+              if (i < W) p.d_protos[dp + i * kD] = pick(t, u);
+              else if (i < N) p.d_queries[dq + (i - W) * kD] = pick(t, u);
+            }
+          }
+        }
+      }
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->d2_free[it & 1]);
+    };
+    int it = set, prev_tile = -1, prev_it = -1;
+    int tile = blockIdx.x + set * gridDim.x;
+    load_tile(tile);
+    for (; tile < tiles; tile += 2 * gridDim.x, it += 2) {
+      DBG(0);
+      if (it > 0) mbar_wait(&bars->x_free[(it - 1) & 1], ((it - 1) >> 1) & 1);   // MMA 1 of the previous tile is done with X
+      // ... and so is the other set's transposed copy, which reads X
+      if (kBwd && it > 0) mbar_wait(&bars->xt_done[(it - 1) & 1], ((it - 1) >> 1) & 1);
+      DBG(1);
       {
         const int cc = lane & 15;
         const uint32_t half = base + (cc >> 3) * kTile;
@@ -379,10 +433,15 @@ __global__ void __launch_bounds__(kThreads, 1) angular_tc_kernel(const AngParams
       fence_async_proxy();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->x_full);
-      load_tile(tile + gridDim.x);                                      // next tile's rows fly while this one is finished
+      DBG(2);
+      load_tile(tile + 2 * gridDim.x);                                  // the set's next tile flies while this one is finished
+      DBG(3);
       if (kBwd) {
+        if (prev_tile >= 0) e2_tile(prev_tile, prev_it);                // its MMA 2 completed long ago
+        DBG(5);
         // transposed copy of my block: XT[e][d][j] = X[j][d] (lane = row j reads its own row, conflict-free both ways)
-        mbar_wait(&bars->xt_free, (it & 1) ^ 1);                        // MMA 2 of the previous tile is done with XT
+        if (it > 0) mbar_wait(&bars->xt_free[(it - 1) & 1], ((it - 1) >> 1) & 1);   // MMA 2 of the previous tile is done with XT
+        DBG(6);
 #pragma unroll 1
         for (int hc = 0; hc < 16; ++hc) {
           const int h = hc >> 3, c = hc & 7;
@@ -399,43 +458,16 @@ __global__ void __launch_bounds__(kThreads, 1) angular_tc_kernel(const AngParams
         }
         fence_async_proxy();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->xt_full);
-      }
-    }
-  } else if (warp < kFirstE1) {
-    // =========================================================== E2: lane = embedding dimension, columns = rows
-    if (kBwd) {
-      const int quad = warp & 3;
-      const int d = (quad & 1) * 32 + lane;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-        mbar_wait_sleep(&bars->d2_full, it & 1);
-        fence_after();
-#pragma unroll 1
-        for (int s2 = 0; s2 < 2; ++s2) {
-          const int ep = tile * kEp + 2 * s2 + (quad >> 1);
-          const bool valid = ep < p.E;
-          const uint32_t ta = tmem + ((uint32_t)(quad * 32) << 16) + 256 + s2 * 64 + (quad >> 1) * 32;
-          // row i of the block lives at dp + i * 64 (prototypes) or dqm + i * 64 (queries)
-          const size_t dp = (size_t)(valid ? ep : 0) * W * kD + d, dqm = (size_t)(valid ? ep : 0) * Nq * kD + d;
-#pragma unroll 2
-          for (int c = 0; c < 8; ++c) {
-            const float4 t = tmem_ld4(ta + 4 * c);
-            if (valid) {
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int i = 4 * c + u;
-                if (i < W) p.d_protos[dp + i * kD] = pick(t, u);
-                else if (i < N) p.d_queries[dqm + (i - W) * kD] = pick(t, u);
-              }
-            }
-          }
+        if (lane == 0) {
+          mbar_arrive(&bars->xt_full);
+          mbar_arrive(&bars->xt_done[it & 1]);
         }
-        fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->d2_free);
+        DBG(7);
+        prev_tile = tile;
+        prev_it = it;
       }
     }
+    if (kBwd && prev_tile >= 0) e2_tile(prev_tile, prev_it);
   } else if (warp == kIssuer) {
     // =========================================================== MMA issuer (warp-uniform control flow, one elected lane)
     constexpr uint32_t kIdesc1 = idesc_tf32(128, 128), kIdesc2 = idesc_tf32(128, 64);
@@ -445,6 +477,7 @@ __global__ void __launch_bounds__(kThreads, 1) angular_tc_kernel(const AngParams
       mbar_wait(&bars->x_full, it & 1);
       mbar_wait(&bars->d1_free[b], ((it >> 1) & 1) ^ 1);
       fence_after();
+      DBG(8);
       if (elect_one()) {
         const uint32_t acc = tmem + b * 128;
         uint32_t first = 0;
@@ -461,7 +494,7 @@ __global__ void __launch_bounds__(kThreads, 1) angular_tc_kernel(const AngParams
             }
           }
         }
-        commit(&bars->x_free);
+        commit(&bars->x_free[b]);
         commit(&bars->d1_full[b]);
       }
       __syncwarp();
@@ -472,8 +505,9 @@ __global__ void __launch_bounds__(kThreads, 1) angular_tc_kernel(const AngParams
       if (kBwd) {
         mbar_wait(&bars->xt_full, it & 1);
         mbar_wait(&bars->gp_full, it & 1);
-        mbar_wait(&bars->d2_free, (it & 1) ^ 1);
+        if (it > 0) mbar_wait(&bars->d2_free[(it - 1) & 1], ((it - 1) >> 1) & 1);
         fence_after();
+        DBG(10);
         if (elect_one()) {
 #pragma unroll
           for (int s = 0; s < 2; ++s) {                                 // two episodes per instruction
@@ -490,9 +524,9 @@ __global__ void __launch_bounds__(kThreads, 1) angular_tc_kernel(const AngParams
               }
             }
           }
-          commit(&bars->xt_free);
+          commit(&bars->xt_free[it & 1]);
           commit(&bars->gp_free);
-          commit(&bars->d2_full);
+          commit(&bars->d2_full[it & 1]);
         }
         __syncwarp();
       }
@@ -510,10 +544,12 @@ __global__ void __launch_bounds__(kThreads, 1) angular_tc_kernel(const AngParams
       if (valid && lane >= W && lane < N) lab = p.labels[(size_t)ep * Nq + (lane - W)];
       mbar_wait_sleep(&bars->d1_full[set], (it >> 1) & 1);
       fence_after();
+      DBG(12);
       const uint32_t row = (uint32_t)(quad * kBlk + lane) * 128u;
       if (valid) {
         e1_episode<kBwd>(p, ep, lab, tmem + ((uint32_t)(quad * 32) << 16) + set * 128 + quad * 32, sc, &bars->d1_free[set],
-                         &bars->gp_free, (it & 1) ^ 1, base + kGPH + row, base + kGPL + row);
+                         &bars->gp_free, (it & 1) ^ 1, base + kGPH + row, base + kGPL + row,
+                         (p.dbg && blockIdx.x == 0 && quad == 0 && it < 24) ? p.dbg + it * 32 : nullptr);
       } else {
         fence_before();
         __syncwarp();
@@ -525,6 +561,7 @@ __global__ void __launch_bounds__(kThreads, 1) angular_tc_kernel(const AngParams
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->gp_full);
       }
+      DBG(20);
     }
   }
   fence_before();
@@ -548,6 +585,27 @@ int launch_angular_tc(const AngParams& p, bool bwd, cudaStream_t stream, const c
   int sms = kNumSMs, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = (p.E + kEp - 1) / kEp;
+  if (getenv("AFSL_ANGULAR_DBG")) {
+    // timeline of CTA 0 (tools/angular_bench.py --timeline): SM clocks of every pipeline event of its first 24 tiles
+    AngParams q = p;
+    long long host[24 * 32];
+    if (cudaMalloc(&q.dbg, sizeof(host)) != cudaSuccess) return AFSL_ECUDA;
+    cudaMemsetAsync(q.dbg, 0, sizeof(host), stream);
+    fn<<<tiles < sms ? tiles : sms, kThreads, bytes, stream>>>(q);
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(host, q.dbg, sizeof(host), cudaMemcpyDeviceToHost);
+    cudaFree(q.dbg);
+    long long t0 = 0;
+    for (long long t : host) if (t && (!t0 || t < t0)) t0 = t;
+    fprintf(stderr, "angular_tc %s timeline (clocks since the first event; columns = events 0..20)\n", bwd ? "bwd" : "fwd");
+    for (int it = 0; it < 24; ++it) {
+      fprintf(stderr, "it %2d:", it);
+      for (int ev = 0; ev <= 20; ++ev) fprintf(stderr, " %6lld", host[it * 32 + ev] ? host[it * 32 + ev] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+    AFSL_CHECK_LAUNCH(name);
+    return AFSL_OK;
+  }
   fn<<<tiles < sms ? tiles : sms, kThreads, bytes, stream>>>(p);
   AFSL_CHECK_LAUNCH(name);
   return AFSL_OK;

@@ -19,6 +19,9 @@ if "--angle" in args:
     i = args.index("--angle"); angle = float(args[i + 1]); del args[i:i + 2]
 if "--episodes" in args:
     i = args.index("--episodes"); e = int(args[i + 1]); del args[i:i + 2]
+timeline = "--timeline" in args
+if timeline:
+    args.remove("--timeline")
 variants = args or ["tc", "warp"]
 dev = torch.device("cuda", 0)
 pk = bench.peaks()[0]["hbm_gbs"]
@@ -50,6 +53,11 @@ def timed(fn, reps=20):
 
 for v in variants:
     os.environ["AFSL_ANGULAR_TC"] = "1" if v == "tc" else "0"
+    if timeline and v == "tc":          # one instrumented launch of each kernel: CTA 0's pipeline events on stderr
+        os.environ["AFSL_ANGULAR_DBG"] = "1"
+        call("afsl_angular_fwd_f32", ptr(pa), ptr(qa), ptr(ql), angle, 40.0, 1, 0, ptr(loss), e, nq, ways, d, st)
+        call("afsl_angular_bwd_f32", ptr(pa), ptr(qa), ptr(ql), angle, 40.0, 1, 0, ptr(dl), ptr(dpa), ptr(dqa), e, nq, ways, d, st)
+        del os.environ["AFSL_ANGULAR_DBG"]
     af = lambda: call("afsl_angular_fwd_f32", ptr(pa), ptr(qa), ptr(ql), angle, 40.0, 1, 0, ptr(loss), e, nq, ways, d, st)
     ab = lambda: call("afsl_angular_bwd_f32", ptr(pa), ptr(qa), ptr(ql), angle, 40.0, 1, 0, ptr(dl), ptr(dpa), ptr(dqa), e, nq,
                       ways, d, st)
