@@ -425,6 +425,9 @@ __global__ void __launch_bounds__(kThreads, 1) angular_tc_kernel(const AngParams
 
   if (warp < kPeWarps) {
     // =========================================================== producers + E2: warp & 3 = episode slot, warp / 4 = set
+    // 17 warps leave 96 registers per thread; this role holds a 64-register prefetch and takes the 16 registers per thread
+    // that the E1 warps hand back (setmaxnreg moves registers inside the CTA's own allocation only)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     const int set = warp >> 2, e = warp & 3;
     const int n16 = N * 16, w16 = W * 16;                               // 16-byte chunks of the block / of its prototypes
     const uint32_t xb = base + kX + (uint32_t)set * 2 * kTile;          // this set's X buffer: h0 tile, h1 at + kTile
@@ -520,8 +523,7 @@ __global__ void __launch_bounds__(kThreads, 1) angular_tc_kernel(const AngParams
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh->x_full[set]);
       DBG(2);
-      load_tile(tile + 2 * gridDim.x);                                  // the set's next tile flies while this one is finished
-      DBG(3);
+      if (!kBwd) load_tile(tile + 2 * gridDim.x);                       // the set's next tile flies during the other set's turn
       if (kBwd) {
         if (prev_tile >= 0) e2_tile(prev_tile, prev_it);                // its MMA 2 completed long ago
         DBG(5);
@@ -547,6 +549,10 @@ __global__ void __launch_bounds__(kThreads, 1) angular_tc_kernel(const AngParams
         DBG(7);
         prev_tile = tile;
         prev_it = it;
+        // the 64 prefetch registers are live only from here to the split of the set's next tile (held across E2 and the
+        // transposed copy they spilled, and every spill store waited for its load: 13000 clocks per tile)
+        load_tile(tile + 2 * gridDim.x);
+        DBG(3);
       }
     }
     if (kBwd && prev_tile >= 0) e2_tile(prev_tile, prev_it);
@@ -612,6 +618,7 @@ __global__ void __launch_bounds__(kThreads, 1) angular_tc_kernel(const AngParams
     }
   } else {
     // =========================================================== E1: set = (warp - 8) / 4 takes the tiles of its parity
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     const int set = (warp - kFirstE1) >> 2, quad = warp & 3;           // quad = episode slot = TMEM lane quarter
     Scratch* sc = scratch + (warp - kFirstE1);
     int it = 0;
