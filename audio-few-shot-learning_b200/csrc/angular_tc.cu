@@ -240,35 +240,58 @@ __device__ __forceinline__ void e1_episode(const AngParams& p, int ep, int lab_i
   // ---- my pair: weighted log-sum-exp over the negatives, with the appended zero
   const float omega = qv ? (float)sc->manc[a] * nu_i : 0.f;
   const float base = cneg * gaq;
-  float mx = 0.f;
-#pragma unroll 2
-  for (int c = 0; c < 8; ++c) {
-    const float4 g4 = ld4(gn_row + 4 * c), s4 = ld4(pa_row + 4 * c), nu4 = ld4(sc->nu + 4 * c);
-    float4 rho = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (!p.normalize_ref) rho = ld4(sc->nrm + 4 * c);
-    float f[4];
+  float mx = 0.f, tot = 1.f;
+  if (!kBwd) {
+    // forward only: ONE pass, running maximum with rescaling of the running sum (the appended zero is the initial term)
+#pragma unroll 4
+    for (int c = 0; c < 8; ++c) {
+      const float4 g4 = ld4(gn_row + 4 * c), s4 = ld4(pa_row + 4 * c), nu4 = ld4(sc->nu + 4 * c);
+      float4 rho = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (!p.normalize_ref) rho = ld4(sc->nrm + 4 * c);
+      float f[4], m_new = mx;
+      bool use[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      f[u] = fmaf(c4 * pick(rho, u), pick(s4, u) + pick(g4, u), base);
-      const bool use = ((negmask >> (4 * c + u)) & 1u) && pick(nu4, u) > 0.f;
-      mx = use ? fmaxf(mx, f[u]) : mx;
-    }
-    *reinterpret_cast<float4*>(fx_row + 4 * c) = make_float4(f[0], f[1], f[2], f[3]);
-  }
-  DBGE(15);
-  float tot = __expf(-mx);
-#pragma unroll 2
-  for (int c = 0; c < 8; ++c) {
-    const float4 f4 = ld4(fx_row + 4 * c), nu4 = ld4(sc->nu + 4 * c);
-    float ex[4];
+      for (int u = 0; u < 4; ++u) {
+        f[u] = fmaf(c4 * pick(rho, u), pick(s4, u) + pick(g4, u), base);
+        use[u] = ((negmask >> (4 * c + u)) & 1u) && pick(nu4, u) > 0.f;
+        m_new = use[u] ? fmaxf(m_new, f[u]) : m_new;
+      }
+      float part = 0.f;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      // a select, not a product with a zero weight: the exponent of a masked column may overflow
-      const bool use = ((negmask >> (4 * c + u)) & 1u) && pick(nu4, u) > 0.f;
-      ex[u] = use ? pick(nu4, u) * __expf(pick(f4, u) - mx) : 0.f;
-      tot += ex[u];
+      for (int u = 0; u < 4; ++u) part += use[u] ? pick(nu4, u) * __expf(f[u] - m_new) : 0.f;   // a select: see below
+      tot = fmaf(tot, __expf(mx - m_new), part);
+      mx = m_new;
     }
-    if (kBwd) *reinterpret_cast<float4*>(fx_row + 4 * c) = make_float4(ex[0], ex[1], ex[2], ex[3]);
+  } else {
+  #pragma unroll 2
+    for (int c = 0; c < 8; ++c) {
+      const float4 g4 = ld4(gn_row + 4 * c), s4 = ld4(pa_row + 4 * c), nu4 = ld4(sc->nu + 4 * c);
+      float4 rho = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (!p.normalize_ref) rho = ld4(sc->nrm + 4 * c);
+      float f[4];
+  #pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        f[u] = fmaf(c4 * pick(rho, u), pick(s4, u) + pick(g4, u), base);
+        const bool use = ((negmask >> (4 * c + u)) & 1u) && pick(nu4, u) > 0.f;
+        mx = use ? fmaxf(mx, f[u]) : mx;
+      }
+      *reinterpret_cast<float4*>(fx_row + 4 * c) = make_float4(f[0], f[1], f[2], f[3]);
+    }
+    DBGE(15);
+    tot = __expf(-mx);
+  #pragma unroll 2
+    for (int c = 0; c < 8; ++c) {
+      const float4 f4 = ld4(fx_row + 4 * c), nu4 = ld4(sc->nu + 4 * c);
+      float ex[4];
+  #pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        // a select, not a product with a zero weight: the exponent of a masked column may overflow
+        const bool use = ((negmask >> (4 * c + u)) & 1u) && pick(nu4, u) > 0.f;
+        ex[u] = use ? pick(nu4, u) * __expf(pick(f4, u) - mx) : 0.f;
+        tot += ex[u];
+      }
+      if (kBwd) *reinterpret_cast<float4*>(fx_row + 4 * c) = make_float4(ex[0], ex[1], ex[2], ex[3]);
+    }
   }
   const float term = omega > 0.f ? omega * (mx + logf(tot)) : 0.f;
   const float num = warp_sum(term), den = warp_sum(omega);
