@@ -29,6 +29,8 @@ SIGNATURES = {
     "afsl_l2_normalize_bwd_f32": [_P, _P, _P, _I, _I, _F, _P],
     "afsl_cpl_fwd_f32": [_P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _P],
     "afsl_cpl_bwd_f32": [_P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _I, _P],
+    "afsl_cpl_fwd_save_f32": [_P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _I, _P],
+    "afsl_cpl_bwd_saved_f32": [_P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "afsl_angular_fwd_f32": [_P, _P, _P, _F, _F, _I, _I, _P, _I, _I, _I, _I, _P],
     "afsl_angular_bwd_f32": [_P, _P, _P, _F, _F, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P],
     "afsl_specaug_views_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _I, _I, _I, _I, _I, _P],
@@ -80,6 +82,8 @@ def load() -> ctypes.CDLL:
     lib.afsl_gbn_nhwc_parts.argtypes = [c_int]
     lib.afsl_linear_bwd_workspace_floats.restype = c_longlong
     lib.afsl_linear_bwd_workspace_floats.argtypes = [c_int, c_int, c_int]
+    lib.afsl_cpl_saved_supported.restype = c_int
+    lib.afsl_cpl_saved_supported.argtypes = [c_int, c_int, c_int]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

@@ -386,3 +386,35 @@ extern "C" int afsl_cpl_bwd_f32(const float* protos, const float* queries, const
   p.d_loss = d_loss; p.d_protos = d_protos; p.d_queries = d_queries; p.E = E; p.Nq = Nq; p.W = W; p.D = D;
   return afsl::launch(p, true, (cudaStream_t)stream, "afsl_cpl_bwd_f32");
 }
+
+// ---- the same pair with the forward's similarity matrix handed to the backward (warp family only: 5-way, D in {64, 128, 256})
+extern "C" int afsl_cpl_saved_supported(int Nq, int W, int D) {
+  const char* warp_env = getenv("AFSL_CPL_WARP");
+  if (warp_env && atoi(warp_env) == 0) return 0;
+  return afsl::cpl_warp_supported(Nq, W, D) ? 1 : 0;
+}
+
+extern "C" int afsl_cpl_fwd_save_f32(const float* protos, const float* queries, const int32_t* labels, const uint32_t* keep,
+                                      float temperature, float* loss, float* sim, float* qinv, int E, int Nq, int W, int D,
+                                      void* stream) {
+  AFSL_REQUIRE(loss && sim && qinv, "afsl_cpl_fwd_save_f32: null pointer");
+  AFSL_REQUIRE(afsl_cpl_saved_supported(Nq, W, D), "afsl_cpl_fwd_save_f32: shape Nq=%d W=%d D=%d is not taken by the warp kernels "
+               "(ask afsl_cpl_saved_supported first)", Nq, W, D);
+  afsl::CplParams p{};
+  p.protos = protos; p.queries = queries; p.labels = labels; p.keep = keep; p.temperature = temperature;
+  p.loss = loss; p.sim_out = sim; p.qinv_out = qinv; p.E = E; p.Nq = Nq; p.W = W; p.D = D;
+  return afsl::launch(p, false, (cudaStream_t)stream, "afsl_cpl_fwd_save_f32");
+}
+
+extern "C" int afsl_cpl_bwd_saved_f32(const float* protos, const float* queries, const int32_t* labels, const uint32_t* keep,
+                                       float temperature, const float* sim, const float* qinv, const float* d_loss,
+                                       float* d_protos, float* d_queries, int E, int Nq, int W, int D, void* stream) {
+  AFSL_REQUIRE(sim && qinv && d_loss && d_protos && d_queries, "afsl_cpl_bwd_saved_f32: null pointer");
+  AFSL_REQUIRE(afsl_cpl_saved_supported(Nq, W, D), "afsl_cpl_bwd_saved_f32: shape Nq=%d W=%d D=%d is not taken by the warp kernels",
+               Nq, W, D);
+  afsl::CplParams p{};
+  p.protos = protos; p.queries = queries; p.labels = labels; p.keep = keep; p.temperature = temperature;
+  p.sim_in = sim; p.qinv_in = qinv; p.d_loss = d_loss; p.d_protos = d_protos; p.d_queries = d_queries;
+  p.E = E; p.Nq = Nq; p.W = W; p.D = D;
+  return afsl::launch(p, true, (cudaStream_t)stream, "afsl_cpl_bwd_saved_f32");
+}

@@ -35,8 +35,9 @@ __device__ __forceinline__ f32x2 lds_pair(const float* p) {
 
 
 
-template <int kW, int kV, int kB, bool kBwd>
-__global__ void __launch_bounds__(kCtaThreads, kBwd ? (kV == 8 ? 3 : kV == 4 ? 4 : 5) : (kV == 8 ? 4 : kV == 4 ? 6 : 8)) cpl_warp_kernel(const CplParams p) {
+template <int kW, int kV, int kB, bool kBwd, bool kSaved>
+__global__ void __launch_bounds__(kCtaThreads, kBwd ? (kV == 8 ? (kSaved ? 4 : 3) : kV == 4 ? (kSaved ? 5 : 4) : (kSaved ? 6 : 5))
+                                                    : (kV == 8 ? 4 : kV == 4 ? 6 : 8)) cpl_warp_kernel(const CplParams p) {
   extern __shared__ __align__(16) float smem_raw[];
   constexpr int kH = kV / 2, kD = kV * 32, kC = kW + 1, kVals = kB * kC, kN = pow2_ceil(kVals);
   static_assert(kVals <= 32, "a batch of rows must fit one value per lane");
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(kCtaThreads, kBwd ? (kV == 8 ? 3 : kV == 4 ? 4
   const uint32_t* keep_e = p.keep ? p.keep + (size_t)e * Nq * words : nullptr;
 
   const float* qry = p.queries + (size_t)e * Nq * kD;
-  const int total = kBwd ? 2 * nq_pad : nq_pad;          // the backward walks the rows twice
+  const int total = kBwd ? 2 * nq_pad : nq_pad;          // the backward walks the rows twice (once with saved similarities)
   auto row_ptr = [&](int t) -> const float* {
     const int r = t < nq_pad ? t : t - nq_pad;
     return qry + (size_t)min(r, Nq - 1) * kD;
@@ -95,11 +96,17 @@ __global__ void __launch_bounds__(kCtaThreads, kBwd ? (kV == 8 ? 3 : kV == 4 ? 4
   }
   f32x2 buf[kB][kH];
 #pragma unroll
-  for (int u = 0; u < kB; ++u) load_row<kV>(row_ptr(u), lane, buf[u]);
+  for (int u = 0; u < kB; ++u) load_row<kV>(row_ptr((kSaved ? nq_pad : 0) + u), lane, buf[u]);
+  if (kSaved) {
+    // the forward's similarity matrix and reciprocal norms: no dot-product walk over the queries
+    const float* gs = p.sim_in + (size_t)e * kW * Nq;
+    for (int k = lane; k < kW * Nq; k += 32) sim[k] = gs[k];
+    for (int k = lane; k < nq_pad; k += 32) qinv[k] = k < Nq ? p.qinv_in[(size_t)e * Nq + k] : 1.f;
+  }
   __syncwarp();
 
   // ------------------------------------------------------------------ pass 1: C[w,j] = <p^_w, q^_j> / T
-  for (int t0 = 0; t0 < nq_pad; t0 += kB) {
+  for (int t0 = 0; t0 < (kSaved ? 0 : nq_pad); t0 += kB) {
     float part[kN];
 #pragma unroll
     for (int u = 0; u < kB; ++u) {
@@ -138,6 +145,11 @@ __global__ void __launch_bounds__(kCtaThreads, kBwd ? (kV == 8 ? 3 : kV == 4 ? 4
     }
   }
   __syncwarp();
+  if (!kBwd && p.sim_out) {
+    float* gs = p.sim_out + (size_t)e * kW * Nq;
+    for (int k = lane; k < kW * Nq; k += 32) gs[k] = sim[k];
+    for (int k = lane; k < Nq; k += 32) p.qinv_out[(size_t)e * Nq + k] = qinv[k];
+  }
 
   const float inv_t = 1.f / p.temperature;
   // g = d_loss / Nq^2 ; the stored pairs are g * dL/dC / T (and that times 1/|q_j|)
@@ -346,16 +358,17 @@ __global__ void __launch_bounds__(kCtaThreads, kBwd ? (kV == 8 ? 3 : kV == 4 ? 4
 using KernelFn = void (*)(const CplParams);
 
 template <int kW, int kV>
-void variant(bool bwd, KernelFn& fn) {
+void variant(bool bwd, bool saved, KernelFn& fn) {
   constexpr int kB = 32 / (kW + 1) < 6 ? 32 / (kW + 1) : 6;
-  fn = bwd ? cpl_warp_kernel<kW, kV, kB, true> : cpl_warp_kernel<kW, kV, kB, false>;
+  fn = bwd ? (saved ? cpl_warp_kernel<kW, kV, kB, true, true> : cpl_warp_kernel<kW, kV, kB, true, false>)
+           : cpl_warp_kernel<kW, kV, kB, false, false>;
 }
 
-bool pick_variant(int W, int D, bool bwd, KernelFn& fn) {
-#define AFSL_WV(W_, D_)                  \
-  if (W == W_ && D == D_) {              \
-    variant<W_, D_ / 32>(bwd, fn);       \
-    return true;                         \
+bool pick_variant(int W, int D, bool bwd, bool saved, KernelFn& fn) {
+#define AFSL_WV(W_, D_)                      \
+  if (W == W_ && D == D_) {                  \
+    variant<W_, D_ / 32>(bwd, saved, fn);    \
+    return true;                             \
   }
   AFSL_WV(5, 256) AFSL_WV(5, 128) AFSL_WV(5, 64)
 #undef AFSL_WV
@@ -364,13 +377,22 @@ bool pick_variant(int W, int D, bool bwd, KernelFn& fn) {
 
 }  // namespace
 
+static size_t warp_smem_bytes(int Nq, int W, int D) {
+  const int kb = 32 / (W + 1) < 6 ? 32 / (W + 1) : 6;
+  const int nq_pad = (Nq + kb - 1) / kb * kb;
+  return (size_t)kWarpsPerCta * slice_words(W * D, W, Nq, nq_pad) * sizeof(float);
+}
+
+bool cpl_warp_supported(int Nq, int W, int D) {
+  KernelFn fn = nullptr;
+  return Nq > 0 && pick_variant(W, D, false, false, fn) && warp_smem_bytes(Nq, W, D) <= 64 * 1024;
+}
+
 int launch_cpl_warp(const CplParams& p, bool bwd, cudaStream_t stream, const char* name, bool* handled) {
   *handled = false;
   KernelFn fn = nullptr;
-  if (!pick_variant(p.W, p.D, bwd, fn)) return AFSL_OK;
-  const int kb = 32 / (p.W + 1) < 6 ? 32 / (p.W + 1) : 6;
-  const int nq_pad = (p.Nq + kb - 1) / kb * kb;
-  const size_t bytes = (size_t)kWarpsPerCta * slice_words(p.W * p.D, p.W, p.Nq, nq_pad) * sizeof(float);
+  if (!pick_variant(p.W, p.D, bwd, bwd && p.sim_in != nullptr, fn)) return AFSL_OK;
+  const size_t bytes = warp_smem_bytes(p.Nq, p.W, p.D);
   if (bytes > 64 * 1024) return AFSL_OK;            // very long query lists: the CTA-per-episode kernel takes them
   *handled = true;
   if (int rc = opt_in_smem(fn, bytes, name)) return rc;

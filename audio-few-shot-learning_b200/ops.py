@@ -7,6 +7,7 @@ implementation here on purpose (see _lib.py).
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -292,21 +293,37 @@ class _Cpl(torch.autograd.Function):
         e, w, d = protos.shape
         nq = queries.shape[1]
         loss = torch.empty(e, device=protos.device, dtype=torch.float32)
-        call("afsl_cpl_fwd_f32", ptr(protos), ptr(queries), ptr(labels), ptr(keep), float(temperature), ptr(loss), e, nq, w,
-             d, stream_ptr())
-        ctx.save_for_backward(protos, queries, labels, keep)
+        # when a backward will follow and the warp kernels take the shape, the forward hands its similarity matrix and
+        # reciprocal norms to the backward (0.6 KB per episode), which then walks the query rows once instead of twice
+        needs_grad = protos.requires_grad or queries.requires_grad
+        saved = (needs_grad and os.environ.get("AFSL_CPL_SAVE", "1") != "0"       # the parity tests run both backwards
+                 and bool(_lib.load().afsl_cpl_saved_supported(nq, w, d)))
+        sim = qinv = None
+        if saved:
+            sim = torch.empty(e, w, nq, device=protos.device, dtype=torch.float32)
+            qinv = torch.empty(e, nq, device=protos.device, dtype=torch.float32)
+            call("afsl_cpl_fwd_save_f32", ptr(protos), ptr(queries), ptr(labels), ptr(keep), float(temperature), ptr(loss),
+                 ptr(sim), ptr(qinv), e, nq, w, d, stream_ptr())
+        else:
+            call("afsl_cpl_fwd_f32", ptr(protos), ptr(queries), ptr(labels), ptr(keep), float(temperature), ptr(loss), e, nq,
+                 w, d, stream_ptr())
+        ctx.save_for_backward(protos, queries, labels, keep, sim, qinv)
         ctx.temperature = float(temperature)
         return loss
 
     @staticmethod
     def backward(ctx, d_loss):
-        protos, queries, labels, keep = ctx.saved_tensors
+        protos, queries, labels, keep, sim, qinv = ctx.saved_tensors
         e, w, d = protos.shape
         nq = queries.shape[1]
         d_protos, d_queries = torch.empty_like(protos), torch.empty_like(queries)
         d_loss = _f32(d_loss)
-        call("afsl_cpl_bwd_f32", ptr(protos), ptr(queries), ptr(labels), ptr(keep), ctx.temperature, ptr(d_loss),
-             ptr(d_protos), ptr(d_queries), e, nq, w, d, stream_ptr())
+        if sim is not None:
+            call("afsl_cpl_bwd_saved_f32", ptr(protos), ptr(queries), ptr(labels), ptr(keep), ctx.temperature, ptr(sim),
+                 ptr(qinv), ptr(d_loss), ptr(d_protos), ptr(d_queries), e, nq, w, d, stream_ptr())
+        else:
+            call("afsl_cpl_bwd_f32", ptr(protos), ptr(queries), ptr(labels), ptr(keep), ctx.temperature, ptr(d_loss),
+                 ptr(d_protos), ptr(d_queries), e, nq, w, d, stream_ptr())
         return d_protos, d_queries, None, None, None
 
 

@@ -228,6 +228,19 @@ def kernel_rooflines(device, peak_gbs, episodes):
     entry("cpl_fwd", (4.0 * d * (nq + ways) + 4 * nq + 4) * e, t_cf, f"{e} episodes Nq=25 Dp=256")
     entry("cpl_bwd", (4.0 * d * 2 * (nq + ways) + 4 * nq + 4) * e, t_cb, f"{e} episodes Nq=25 Dp=256")
     entry("cpl_fwd_bwd", (4.0 * d * 3 * (nq + ways) + nq * nq / 8) * e, t_cf + t_cb, f"{e} episodes Nq=25 Dp=256", launches=2)
+    # the pair the autograd op launches: the forward also writes C [E,W,Nq] and 1/|q| [E,Nq], the backward reads them back
+    # and walks the query rows once
+    sim, qinv = torch.empty(e, ways, nq, device=device), torch.empty(e, nq, device=device)
+    cfs = lambda: call("afsl_cpl_fwd_save_f32", ptr(p), ptr(q), ptr(ql), None, 9.2361, ptr(loss), ptr(sim), ptr(qinv), e, nq,
+                       ways, d, st)
+    cbs = lambda: call("afsl_cpl_bwd_saved_f32", ptr(p), ptr(q), ptr(ql), None, 9.2361, ptr(sim), ptr(qinv), ptr(dl), ptr(dp),
+                       ptr(dq), e, nq, ways, d, st)
+    t_cfs, t_cbs = timed(cfs), timed(cbs)
+    saved_bytes = 4.0 * (ways * nq + nq)
+    entry("cpl_fwd_save", (4.0 * d * (nq + ways) + 4 * nq + 4 + saved_bytes) * e, t_cfs, f"{e} episodes Nq=25 Dp=256")
+    entry("cpl_bwd_saved", (4.0 * d * 2 * (nq + ways) + 4 * nq + 4 + saved_bytes) * e, t_cbs, f"{e} episodes Nq=25 Dp=256")
+    entry("cpl_save_fwd_bwd", (4.0 * d * 3 * (nq + ways) + nq * nq / 8 + 2 * saved_bytes) * e, t_cfs + t_cbs,
+          f"{e} episodes Nq=25 Dp=256", launches=2)
     del s, ds, dq, p, dp
     # ---- angular loss (config 3: prototypes as anchors, miner angle 0, alpha 40 deg), Dp=64, Nq=25:
     #      4*Dp*3*(Nq+W) B per episode fwd+bwd (23 KB); Gram-matrix / mining arithmetic dominates

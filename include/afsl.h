@@ -127,6 +127,19 @@ int afsl_cpl_fwd_f32(const float* protos, const float* queries, const int32_t* l
 int afsl_cpl_bwd_f32(const float* protos, const float* queries, const int32_t* labels,
                      const uint32_t* keep, float temperature, const float* d_loss, float* d_protos,
                      float* d_queries, int E, int Nq, int W, int D, void* stream);
+/* The same pair with the forward's similarity matrix handed to the backward: afsl_cpl_fwd_save_f32 also writes
+ * sim [E,W,Nq] = C and qinv [E,Nq] = 1/|q_j| (negative where the norm was clamped), afsl_cpl_bwd_saved_f32 takes
+ * them back and walks the query rows ONCE instead of twice (what torch.autograd does for the reference: loss.py:118-165
+ * keeps its similarity matrix alive for the backward).  Only for the shapes afsl_cpl_saved_supported(Nq, W, D) accepts
+ * (5-way, D in {64,128,256}: the warp-per-episode kernels); elsewhere use the pair above. */
+int afsl_cpl_saved_supported(int Nq, int W, int D);
+int afsl_cpl_fwd_save_f32(const float* protos, const float* queries, const int32_t* labels,
+                          const uint32_t* keep, float temperature, float* loss, float* sim, float* qinv,
+                          int E, int Nq, int W, int D, void* stream);
+int afsl_cpl_bwd_saved_f32(const float* protos, const float* queries, const int32_t* labels,
+                           const uint32_t* keep, float temperature, const float* sim, const float* qinv,
+                           const float* d_loss, float* d_protos, float* d_queries, int E, int Nq, int W,
+                           int D, void* stream);
 
 /* ---------------------------------------------------------------------------
  * Angular loss.  Replaces AngularLossClass.forward, loops/loss.py:48-97

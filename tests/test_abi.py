@@ -44,7 +44,7 @@ def test_ctypes_table_matches_header(lib):
     bound = set(lib.SIGNATURES) | {"afsl_version", "afsl_last_error", "afsl_launch_count",
                                    "afsl_view_fusion_weight_floats", "afsl_view_fusion_param_floats",
                                    "afsl_stage1_channels", "afsl_stage1_acc_slots", "afsl_gbn_nhwc_parts",
-                                   "afsl_linear_bwd_workspace_floats"}
+                                   "afsl_linear_bwd_workspace_floats", "afsl_cpl_saved_supported"}
     assert bound == set(decl), (bound ^ set(decl))
     for name, argtypes in lib.SIGNATURES.items():
         args = decl[name]

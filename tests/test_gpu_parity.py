@@ -230,10 +230,12 @@ def test_l2_normalize(ops):
 
 
 # ------------------------------------------------------------------ CPL
-@pytest.mark.parametrize("path", ["warp", "cta"])
+@pytest.mark.parametrize("path", ["warp", "warp_recompute", "cta"])
 @pytest.mark.parametrize("name", golden_names("cpl_"))
 def test_cpl_vs_reference(ops, monkeypatch, name, path):
-    monkeypatch.setenv("AFSL_CPL_WARP", "1" if path == "warp" else "0")
+    # warp: the forward hands its similarity matrix to the backward; warp_recompute: the backward recomputes it
+    monkeypatch.setenv("AFSL_CPL_WARP", "0" if path == "cta" else "1")
+    monkeypatch.setenv("AFSL_CPL_SAVE", "0" if path == "warp_recompute" else "1")
     g = load_golden(name)
     p = dev(g["prototypes"]).requires_grad_(True)
     q = dev(g["queries"]).requires_grad_(True)
@@ -254,12 +256,14 @@ def test_cpl_vs_reference(ops, monkeypatch, name, path):
         close(q2.grad, t(g["d_queries"]))
 
 
-@pytest.mark.parametrize("path", ["warp", "cta"])
+@pytest.mark.parametrize("path", ["warp", "warp_recompute", "cta"])
 @pytest.mark.parametrize("ways,per,dim,m", [(5, 6, 256, 3), (5, 5, 256, 5), (5, 20, 64, 5), (5, 9, 128, 2), (4, 7, 64, 3)])
 def test_cpl_batched_vs_oracle(ops, monkeypatch, ways, per, dim, m, path):
     """E episodes at once == the closed-form oracle episode by episode, sampled-negative masks included,
-    through both kernel families (one warp per episode for 5-way; one CTA per episode for any shape)."""
-    monkeypatch.setenv("AFSL_CPL_WARP", "1" if path == "warp" else "0")
+    through both kernel families (one warp per episode for 5-way, with the forward's similarities saved for the backward
+    or recomputed by it; one CTA per episode for any shape)."""
+    monkeypatch.setenv("AFSL_CPL_WARP", "0" if path == "cta" else "1")
+    monkeypatch.setenv("AFSL_CPL_SAVE", "0" if path == "warp_recompute" else "1")
     e, temp = 19, 2.6981
     gen = torch.Generator().manual_seed(77 + ways * per)
     p = torch.randn(e, ways, dim, generator=gen)
