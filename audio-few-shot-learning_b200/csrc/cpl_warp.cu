@@ -7,7 +7,9 @@
 // combined by one transposing butterfly, which leaves lane u*(W+1)+w with <p^_w, q_u>, so the division by the
 // norm and the temperature happens once per matrix entry.  The W x Nq similarity matrix lives in the warp's
 // shared-memory slice; the masked log-sum-exp of row i runs on lane i.  The backward builds dL/dC column by
-// column (lane j), then walks the query rows a second time (L2 hits) to store dQ and accumulate dP in registers.
+// column (lane j), then walks the query rows a second time (L2 hits) to store dQ and accumulate dP in registers -
+// or ONCE, when the forward saved C and 1/|q| for it (afsl_cpl_fwd_save_f32 / afsl_cpl_bwd_saved_f32, what the autograd
+// op launches: 0.58 -> 0.71 of the HBM roofline at Dp = 256; 128 registers for a fourth CTA per SM spill 628 bytes).
 // Without a sampled-negative mask (M >= per-class count, the reference's default M = 5 at 5 queries per class)
 // every row of class w sees the same negatives, so their exp-sum S_w is computed once per class and the
 // row statistics / dL/dC follow from it with O(W) work per lane instead of O(Nq) (same value, regrouped sums).
@@ -36,8 +38,7 @@ __device__ __forceinline__ f32x2 lds_pair(const float* p) {
 
 
 template <int kW, int kV, int kB, bool kBwd, bool kSaved>
-__global__ void __launch_bounds__(kCtaThreads, kBwd ? (kV == 8 ? (kSaved ? 4 : 3) : kV == 4 ? (kSaved ? 5 : 4) : (kSaved ? 6 : 5))
-                                                    : (kV == 8 ? 4 : kV == 4 ? 6 : 8)) cpl_warp_kernel(const CplParams p) {
+__global__ void __launch_bounds__(kCtaThreads, kBwd ? (kV == 8 ? 3 : kV == 4 ? 4 : 5) : (kV == 8 ? 4 : kV == 4 ? 6 : 8)) cpl_warp_kernel(const CplParams p) {
   extern __shared__ __align__(16) float smem_raw[];
   constexpr int kH = kV / 2, kD = kV * 32, kC = kW + 1, kVals = kB * kC, kN = pow2_ceil(kVals);
   static_assert(kVals <= 32, "a batch of rows must fit one value per lane");
