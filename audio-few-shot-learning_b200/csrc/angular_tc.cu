@@ -58,7 +58,7 @@ struct Scratch {
   float gn[kBlk * kLs];        // cosine rows of the block; in the backward the lane's own row becomes its B row
   float fx[kBlk * kLs];        // per-lane rows: exponents -> exponentials -> T (dL/dGram of the pairs, row = positive)
   float sp[kMaxW * kLs];       // per-class column sums of T = prototype rows of dL/dGram
-  float nrm[kBlk], csn[kBlk], gdi[kBlk], nu[kBlk], gs[kBlk];
+  float nrm[kBlk], csn[kBlk], gdi[kBlk], nu[kBlk], gs[kBlk], coef[kBlk];
   int manc[kMaxW];
 };
 
@@ -86,16 +86,8 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
     if (!done) __nanosleep(32);
   } while (!done);
 }
-__device__ __forceinline__ void sts_u16(uint32_t addr, unsigned short v) {
-  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
-}
 __device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b) {
   asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
-}
-__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
 }
 // 16 consecutive accumulator columns of this thread's TMEM lane
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
@@ -240,7 +232,7 @@ __device__ __forceinline__ void e1_episode(const AngParams& p, int ep, int lab_i
   // ---- my pair: weighted log-sum-exp over the negatives, with the appended zero
   const float omega = qv ? (float)sc->manc[a] * nu_i : 0.f;
   const float base = cneg * gaq;
-  float mx = 0.f, tot = 1.f;
+  float mx = 0.f, tot = 1.f, gsum_un = 0.f;
   if (!kBwd) {
     // forward only: ONE pass, running maximum with rescaling of the running sum (the appended zero is the initial term)
 #pragma unroll 4
@@ -279,19 +271,25 @@ __device__ __forceinline__ void e1_episode(const AngParams& p, int ep, int lab_i
     }
     DBGE(15);
     tot = __expf(-mx);
-  #pragma unroll 2
+    float sumex = 0.f;
+#pragma unroll 2
     for (int c = 0; c < 8; ++c) {
       const float4 f4 = ld4(fx_row + 4 * c), nu4 = ld4(sc->nu + 4 * c);
-      float ex[4];
-  #pragma unroll
+      float4 rho = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (!p.normalize_ref) rho = ld4(sc->nrm + 4 * c);
+      float tu[4];
+#pragma unroll
       for (int u = 0; u < 4; ++u) {
         // a select, not a product with a zero weight: the exponent of a masked column may overflow
         const bool use = ((negmask >> (4 * c + u)) & 1u) && pick(nu4, u) > 0.f;
-        ex[u] = use ? pick(nu4, u) * __expf(pick(f4, u) - mx) : 0.f;
-        tot += ex[u];
+        const float ex = use ? pick(nu4, u) * __expf(pick(f4, u) - mx) : 0.f;
+        sumex += ex;
+        tu[u] = c4 * pick(rho, u) * ex;     // dL/dGram[i][k] of my pair up to the row's coefficient (applied where it is read)
       }
-      if (kBwd) *reinterpret_cast<float4*>(fx_row + 4 * c) = make_float4(ex[0], ex[1], ex[2], ex[3]);
+      *reinterpret_cast<float4*>(fx_row + 4 * c) = make_float4(tu[0], tu[1], tu[2], tu[3]);
     }
+    tot += sumex;
+    gsum_un = sumex;
   }
   const float term = omega > 0.f ? omega * (mx + logf(tot)) : 0.f;
   const float num = warp_sum(term), den = warp_sum(omega);
@@ -301,24 +299,12 @@ __device__ __forceinline__ void e1_episode(const AngParams& p, int ep, int lab_i
     return;
   }
 
-  // ---- backward.  T_i[k] = 4 t2 rho_k g_k: dL/dGram[i][k] of my pair (and of its anchor's row), gsum = sum_k g_k
+  // ---- backward.  T_i[k] = coef_i 4 t2 rho_k nu_k exp(f_k - m): dL/dGram[i][k] of my pair (and of its anchor's row); the
+  //      scratch rows hold it without coef_i, which is known only now; gsum = sum_k g_k
   const float scale = den > 0.f ? p.d_loss[ep] / den : 0.f;
   const float coef = omega > 0.f ? scale * omega / tot : 0.f;
-  float gsum = 0.f;
-#pragma unroll 2
-  for (int c = 0; c < 8; ++c) {
-    const float4 e4 = ld4(fx_row + 4 * c);
-    float4 rho = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (!p.normalize_ref) rho = ld4(sc->nrm + 4 * c);
-    float tk[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float gk = coef * pick(e4, u);
-      gsum += gk;
-      tk[u] = c4 * pick(rho, u) * gk;
-    }
-    *reinterpret_cast<float4*>(fx_row + 4 * c) = make_float4(tk[0], tk[1], tk[2], tk[3]);
-  }
+  const float gsum = coef * gsum_un;
+  sc->coef[lane] = coef;
   sc->gs[lane] = gsum;
   __syncwarp();                                                 // T rows complete; every lane is done with the prototype rows
   DBGE(17);
@@ -335,7 +321,7 @@ __device__ __forceinline__ void e1_episode(const AngParams& p, int ep, int lab_i
 #pragma unroll
       for (int w = 0; w < kMaxW; ++w)
         if (cm[w]) {
-          pr[w] += sc->fx[(__ffs(cm[w]) - 1) * kLs + lane];
+          pr[w] = fmaf(sc->coef[__ffs(cm[w]) - 1], sc->fx[(__ffs(cm[w]) - 1) * kLs + lane], pr[w]);
           cm[w] &= cm[w] - 1;
           any |= cm[w];
         }
@@ -354,14 +340,15 @@ __device__ __forceinline__ void e1_episode(const AngParams& p, int ep, int lab_i
 #pragma unroll 2
   for (int c = 0; c < 8; ++c) {
     const float4 g4 = ld4(gn_row + 4 * c), t4 = ld4(fx_row + 4 * c), sp4 = ld4(sp_row + 4 * c), gs4 = ld4(sc->gs + 4 * c);
+    const float4 cf4 = ld4(sc->coef + 4 * c);
     float o[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int k = 4 * c + u;
       const float gk = pick(g4, u);                             // cos(row i, row k)
-      const float col = sc->fx[k * kLs + lane];                 // T_k[i]
+      const float col = pick(cf4, u) * sc->fx[k * kLs + lane];  // T_k[i]
       drho = fmaf(col, gk, drho);
-      const float vq = pick(t4, u) + col;
+      const float vq = fmaf(coef, pick(t4, u), col);
       const float vp = ((sameq >> k) & 1u) ? cneg * pick(gs4, u) : pick(sp4, u);
       float val = qv ? vq : (isp ? vp : 0.f);
       if (c < 2 && k < W) {                                     // prototype columns of a query's row
@@ -458,13 +445,15 @@ __global__ void __launch_bounds__(kThreads, 1) angular_tc_kernel(const AngParams
     auto load_tile = [&](int tile) {
       const int ep = tile * kEp + e;
       const bool valid = tile < tiles && ep < p.E;
-      const float4* p4 = reinterpret_cast<const float4*>(p.protos) + (size_t)(valid ? ep : 0) * w16;
-      const float4* q4 = reinterpret_cast<const float4*>(p.queries) + (size_t)(valid ? ep : 0) * (n16 - w16);
+      // chunk ci = lane + 32 j of the block (row ci / 16, 16-byte chunk ci % 16): the first 16 W chunks are the episode's
+      // prototype rows, the rest its query rows; W <= 8, so only j < 4 can still be prototypes
+      const float4* p4 = reinterpret_cast<const float4*>(p.protos) + (size_t)(valid ? ep : 0) * w16 + lane;
+      const float4* q4 = reinterpret_cast<const float4*>(p.queries) + (size_t)(valid ? ep : 0) * (n16 - w16) + lane - w16;
+      const int lim = valid ? n16 - lane : 0;                           // chunk j exists when 32 j < lim
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int ci = lane + 32 * j;                                   // row ci / 16, 16-byte chunk ci % 16 of the block
         v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid && ci < n16) v[j] = ldg_stream(ci < w16 ? p4 + ci : q4 + (ci - w16));
+        if (32 * j < lim) v[j] = ldg_stream((j < 4 && lane + 32 * j < w16 ? p4 : q4) + 32 * j);
       }
     };
     auto e2_tile = [&](int tile, int it) {                              // lane = embedding dimension, columns = rows
@@ -552,18 +541,31 @@ __global__ void __launch_bounds__(kThreads, 1) angular_tc_kernel(const AngParams
         DBG(5);
         if (it > 0) mbar_wait(&sh->xt_free[(it - 1) & 1], ((it - 1) >> 1) & 1);   // MMA 2 of the previous tile is done with XT
         DBG(6);
-        // transposed copy of my block: XT[64 (e / 2) + d][32 (e % 2) + j] = x^_j[d]; lane = row j reads its own row
-#pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-          const uint4 a0 = lds_u4(xb + sw128(e * kBlk + lane, c)), a1 = lds_u4(xb + kTile + sw128(e * kBlk + lane, c));
-          const uint32_t w0[4] = {a0.x, a0.y, a0.z, a0.w}, w1[4] = {a1.x, a1.y, a1.z, a1.w};
+        // transposed copy of my block: XT[64 (e / 2) + d][32 (e % 2) + j] = x^_j[d].  ldmatrix.trans hands every lane the
+        // transposed 8 x 8 fp16 tiles of four row groups at once: lane i gets dim 8 c + i / 4 of rows 8 t + 2 (i % 4), + 1
+        // as one 32-bit word per t - four conflict-free 4-byte stores per 8 dims (the first version moved single halves:
+        // 16 st.shared.u16 per lane and 8 dims, 4400 instructions per tile)
+        {
+          const uint32_t src = xb + (uint32_t)(e * kBlk + lane) * 128;
+          const uint32_t dst = base + kXT + (uint32_t)(64 * (e >> 1) + (lane >> 2)) * 128 + (lane & 3) * 4;
+          uint32_t ct[4];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int row = 64 * (e >> 1) + 8 * c + u;                  // row & 7 = u
-            // byte 64 (e & 1) + 2 lane of the row: 16-byte chunk 4 (e & 1) + lane / 8, swizzled with the row
-            const uint32_t off = (uint32_t)row * 128 + ((uint32_t)(((4 * (e & 1) + (lane >> 3)) ^ u) & 7) << 4) + (lane & 7) * 2;
-            sts_u16(base + kXT + off, (unsigned short)(w0[u >> 1] >> (16 * (u & 1))));
-            sts_u16(base + kXT + kTile + off, (unsigned short)(w1[u >> 1] >> (16 * (u & 1))));
+          for (int t = 0; t < 4; ++t) ct[t] = (uint32_t)(((4 * (e & 1) + t) ^ (lane >> 2)) & 7) << 4;
+#pragma unroll 1
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t sa = src + ((uint32_t)((c ^ lane) & 7) << 4);
+#pragma unroll
+            for (int comp = 0; comp < 2; ++comp) {
+              uint32_t r0, r1, r2, r3;
+              asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                           : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                           : "r"(sa + comp * kTile));
+              const uint32_t da = dst + c * 1024 + comp * kTile;
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(da + ct[0]), "r"(r0) : "memory");
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(da + ct[1]), "r"(r1) : "memory");
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(da + ct[2]), "r"(r2) : "memory");
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(da + ct[3]), "r"(r3) : "memory");
+            }
           }
         }
         fence_async_proxy();
