@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(kThreads, 1) angular_tc_kernel(const AngParams
     asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(base + kX + (b * 2) * kTile + sw128(e * kBlk + kOnesRow, c)), "r"(one2)
                  : "memory");
   }
-  if (warp == kIssuer) tmem_alloc<512>(&sh->tmem_base);
+  if (warp == kIssuer) tmem_alloc<kBwd ? 512 : 256>(&sh->tmem_base);       // D1 x 2 (+ D2 x 2 K halves in the backward)
   fence_async_proxy();
   fence_before();
   __syncthreads();
@@ -675,7 +675,7 @@ __global__ void __launch_bounds__(kThreads, 1) angular_tc_kernel(const AngParams
   }
   fence_before();
   __syncthreads();
-  if (warp == kIssuer) tmem_free<512>(tmem);
+  if (warp == kIssuer) tmem_free<kBwd ? 512 : 256>(tmem);
 }
 
 }  // namespace
