@@ -93,14 +93,19 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
 __device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory"); }
 __device__ __forceinline__ void epilogue_bar() { asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 
-template <int kD, int kRing, int kPair, int kLo>
+template <int kD, int kRing, int kPair, int kLo, bool kOneSup>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_q) {
   constexpr int kKB = kD / kBlockK;
   constexpr int kSt = kKB / kPair;                  // ring stages per phase (support / query) of a task: kPair k-blocks each
   constexpr int kStageB = kPair * kTile;            // bytes of a ring stage (and of a lo-ring slot)
+  // support blocks of at most 32 rows (20-way 1-shot, given prototypes): ALL their k-blocks share ONE ring stage, 4 KB apart
+  // (8 x 4 KB = a stage at D = 256) - the support phase of a task is one barrier round trip instead of kSt
+  // (one k-block per stage at D = 256 has 16 KB stages: it keeps the per-k-block support stages)
+  constexpr bool kOne = kOneSup && kKB * 4096 <= kStageB;
+  constexpr int kSupSt = kOne ? 1 : kSt, kSupPair = kOne ? kKB : kPair, kSupStride = kOne ? 4096 : kTile;
   static_assert(kKB % kPair == 0 && kLo <= kMaxLoRing && kRing <= kMaxRing, "bad stage configuration");
-  // a task has 2 kSt stages, so its first stage always has an even index: the group that owns a stage is (index & 1)
+  // the producer group that owns a stage is (global stage index & 1)
   extern __shared__ __align__(1024) uint8_t smem_tma_raw[];
   uint8_t* smem = smem_tma_raw + ((1024u - (smem_u32(smem_tma_raw) & 1023u)) & 1023u);     // 1 KB: swizzle atoms
   const uint32_t ring = smem_u32(smem);                                        // [kRing][kPair][16 KB] raw rows as TMA wrote them
@@ -149,13 +154,14 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
           const CUtensorMap* map = half ? &map_q : &map_s;
           const int rows = half ? Nq : sup_rows;
 #pragma unroll 1
-          for (int st = 0; st < kSt; ++st, ++c) {
+          const int stages = half ? kSt : kSupSt, per = half ? kPair : kSupPair;
+          const uint32_t stride = half ? kTile : kSupStride;
+          for (int st = 0; st < stages; ++st, ++c) {
             const uint32_t s = c % kRing;
             mbar_wait_relaxed(&meta->bars.empty[s], ((c / kRing) & 1) ^ 1);
-            mbar_arrive_expect_tx(&meta->bars.tma_full[s], (uint32_t)rows * 128u * kPair);
-#pragma unroll
-            for (int i = 0; i < kPair; ++i)
-              tma_load_2d(ring + s * kStageB + i * kTile, map, (st * kPair + i) * kBlockK, e * rows, &meta->bars.tma_full[s]);
+            mbar_arrive_expect_tx(&meta->bars.tma_full[s], (uint32_t)rows * 128u * per);
+            for (int i = 0; i < per; ++i)
+              tma_load_2d(ring + s * kStageB + i * stride, map, (st * per + i) * kBlockK, e * rows, &meta->bars.tma_full[s]);
           }
         }
       }
@@ -224,7 +230,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
         }
         bool tiles_free = false;
 #pragma unroll 1
-        for (int st = 0; st < kSt; ++st, ++c) {
+        for (int st = 0; st < kSupSt; ++st, ++c) {
           if ((int)(c & 1) != grp) continue;
           const uint32_t s = c % kRing;
           mbar_wait(&meta->bars.tma_full[s], (c / kRing) & 1);
@@ -240,9 +246,9 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
             const int n = n_it[rnd];
             float sq = 0.f;
 #pragma unroll
-            for (int i = 0; i < kPair; ++i) {
-              const int kb = st * kPair + i;
-              const uint32_t stage = ring + s * kStageB + i * kTile;
+            for (int i = 0; i < kSupPair; ++i) {
+              const int kb = st * kSupPair + i;
+              const uint32_t stage = ring + s * kStageB + i * kSupStride;
               float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
               // 8 rows per step: one 64-bit read of the row ids, 8 independent 128-bit reads, then the adds in row order
               for (int i0 = 0; i0 < n; i0 += 8) {
@@ -336,7 +342,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
     for (int e = blockIdx.x; e < p.E; e += gridDim.x, ++it) {
       const int par = it & 1;
 #pragma unroll 1
-      for (int st = 0; st < kSt; ++st, ++c) {                               // support stages: consumed by the producers only
+      for (int st = 0; st < kSupSt; ++st, ++c) {                            // support stages: consumed by the producers only
         const uint32_t s = c % kRing;
         mbar_wait(&meta->bars.ready[s], (c / kRing) & 1);
         if (elect_one()) mbar_arrive(&meta->bars.empty[s]);
@@ -466,10 +472,10 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
   if (warp == kIssuerWarp) tmem_free<64>(tmem);
 }
 
-template <int kD, int kRing, int kPair, int kLo>
+template <int kD, int kRing, int kPair, int kLo, bool kOneSup>
 int launch_variant(const HeadParams& p, const CUtensorMap& ms, const CUtensorMap& mq, int sup_rows, cudaStream_t stream,
                    const char* name, bool* handled) {
-  auto fn = head_tma_fwd_kernel<kD, kRing, kPair, kLo>;
+  auto fn = head_tma_fwd_kernel<kD, kRing, kPair, kLo, kOneSup>;
   const size_t bytes = (size_t)(kRing + kLo) * kPair * kTile + (size_t)(kD / kBlockK) * 2 * kBTile + sizeof(TmaMeta) +
                        2 * (size_t)p.W * ((sup_rows + 7) & ~7) + 1024 + 16;
   if (bytes > 220 * 1024) return AFSL_OK;          // very long support blocks: the fp32-pipe kernels take the launch
@@ -507,12 +513,16 @@ int launch_head_tma(const HeadParams& p, bool bwd, cudaStream_t stream, const ch
   // (measured 0.40 against 0.41); AFSL_HEAD_PAIR=1 / 2 forces one / two (the parity tests run both)
   const char* pair_env = getenv("AFSL_HEAD_PAIR");
   const bool pair = pair_env ? atoi(pair_env) == 2 : p.D >= 128;
-  if (p.D == 256) return pair ? launch_variant<256, 3, 2, 2>(p, ms, mq, sup_rows, stream, name, handled)
-                              : launch_variant<256, 6, 1, 4>(p, ms, mq, sup_rows, stream, name, handled);
-  if (p.D == 128) return pair ? launch_variant<128, 3, 2, 2>(p, ms, mq, sup_rows, stream, name, handled)
-                              : launch_variant<128, 7, 1, 4>(p, ms, mq, sup_rows, stream, name, handled);
-  return pair ? launch_variant<64, 4, 2, 2>(p, ms, mq, sup_rows, stream, name, handled)
-              : launch_variant<64, 8, 1, 4>(p, ms, mq, sup_rows, stream, name, handled);
+  // support blocks of at most 32 rows in one ring stage (AFSL_HEAD_ONESUP=0 keeps them on one stage per k-block group)
+  const char* one_env = getenv("AFSL_HEAD_ONESUP");
+  const bool one = sup_rows <= 32 && !(one_env && atoi(one_env) == 0);
+#define AFSL_TMA_VARIANT(D_, R_, P_, L_) \
+  (one ? launch_variant<D_, R_, P_, L_, true>(p, ms, mq, sup_rows, stream, name, handled) \
+       : launch_variant<D_, R_, P_, L_, false>(p, ms, mq, sup_rows, stream, name, handled))
+  if (p.D == 256) return pair ? AFSL_TMA_VARIANT(256, 3, 2, 2) : AFSL_TMA_VARIANT(256, 6, 1, 4);
+  if (p.D == 128) return pair ? AFSL_TMA_VARIANT(128, 3, 2, 2) : AFSL_TMA_VARIANT(128, 7, 1, 4);
+  return pair ? AFSL_TMA_VARIANT(64, 4, 2, 2) : AFSL_TMA_VARIANT(64, 8, 1, 4);
+#undef AFSL_TMA_VARIANT
 }
 
 }  // namespace afsl

@@ -146,10 +146,12 @@ def test_head_many_way_tensor_core_kernel(ops, monkeypatch, ways, shots, nq, dim
     sl = torch.stack([torch.arange(ways).repeat_interleave(shots)[torch.randperm(ways * shots, generator=gen)] for _ in range(e)])
     ql = torch.randint(0, ways, (e, ways * nq), generator=gen)
     out = {}
-    # TMA-fed tcgen05 kernel with one / two k-blocks per ring stage, LDG-fed tcgen05 kernel, fp32-pipe kernel
-    for mma in ("1", "1p", "2", "0"):
+    # TMA-fed tcgen05 kernel with one / two k-blocks per ring stage (support blocks of <= 32 rows in ONE stage; "1o": one
+    # stage per k-block group for them too), LDG-fed tcgen05 kernel, fp32-pipe kernel
+    for mma in ("1", "1p", "1o", "2", "0"):
         monkeypatch.setenv("AFSL_HEAD_MMA", mma[0])
-        monkeypatch.setenv("AFSL_HEAD_PAIR", "2" if mma == "1p" else "1")
+        monkeypatch.setenv("AFSL_HEAD_PAIR", "1" if mma == "1" else "2")
+        monkeypatch.setenv("AFSL_HEAD_ONESUP", "0" if mma == "1o" else "1")
         pred, post, correct, scores = ops.proto_eval(s.cuda(), sl.cuda(), q.cuda(), ql.cuda(), n_way=ways, want_scores=True)
         loss, protos, corr2 = ops.proto_head(s.cuda(), sl.cuda(), q.cuda(), ql.cuda(), n_way=ways)
         sc2 = ops.l2_scores(q.cuda(), protos)
@@ -160,7 +162,7 @@ def test_head_many_way_tensor_core_kernel(ops, monkeypatch, ways, shots, nq, dim
         pr = ohead.prototypes(s[i], sl[i])
         sc = ohead.l2_scores(q[i], pr)
         oracle.append((pr, sc, ohead.fsl_loss(pr, q[i], ql[i])))
-    for mma in ("1", "1p", "2"):
+    for mma in ("1", "1p", "1o", "2"):
         pred, post, correct, scores, loss, protos, corr2, sc2 = out[mma]
         assert torch.equal(correct, corr2)
         flips = 0
@@ -404,6 +406,36 @@ def test_angular_tensor_core_vs_fp32_kernels(ops, monkeypatch, ways, nq, angle, 
         zero = lambda g, like: torch.zeros_like(like) if g is None else g
         close(got["tc"][1][i], zero(pc.grad, pc), rtol=2e-5)
         close(got["tc"][2][i], zero(qc.grad, qc), rtol=2e-5)
+
+
+def test_angular_tensor_core_full_size_properties(ops, monkeypatch):
+    """16387 episodes (every CTA runs ~28 tiles, the last tile is partial) through the tcgen05 kernel: repeated launches are
+    bit-identical (no race between the producer / epilogue / issuer roles), and permuting the episodes permutes losses and
+    gradients bit for bit (an episode's result does not depend on its tile, its slot in the tile or its neighbours)."""
+    monkeypatch.setenv("AFSL_ANGULAR_TC", "1")
+    e, ways, per, dim = 16387, 5, 5, 64
+    gen = torch.Generator().manual_seed(2026)
+    protos = torch.nn.functional.normalize(torch.randn(e, ways, dim, generator=gen), dim=-1).cuda()
+    queries = torch.nn.functional.normalize(torch.randn(e, ways * per, dim, generator=gen), dim=-1).cuda()
+    labels = torch.arange(ways).repeat_interleave(per).expand(e, -1).contiguous().cuda()
+    wl = (torch.rand(e, generator=gen) + 0.5).cuda()
+
+    def run(p, q, w):
+        pg, qg = p.clone().requires_grad_(True), q.clone().requires_grad_(True)
+        loss = ops.angular_loss(pg, qg, labels, 0.0, 40.0, True, False)
+        (loss * w).sum().backward()
+        return loss.detach(), pg.grad, qg.grad
+
+    first = run(protos, queries, wl)
+    for _ in range(2):
+        again = run(protos, queries, wl)
+        for a, b in zip(first, again):
+            assert torch.equal(a, b)
+    perm = torch.randperm(e, generator=gen).cuda()
+    shuffled = run(protos[perm].contiguous(), queries[perm].contiguous(), wl[perm].contiguous())
+    for a, b in zip(first, shuffled):
+        assert torch.equal(a[perm], b)
+    assert torch.isfinite(first[0]).all() and float(first[0].min()) > 0
 
 
 # ------------------------------------------------------------------ SpecAugment
