@@ -513,9 +513,12 @@ int launch_head_tma(const HeadParams& p, bool bwd, cudaStream_t stream, const ch
   // (measured 0.40 against 0.41); AFSL_HEAD_PAIR=1 / 2 forces one / two (the parity tests run both)
   const char* pair_env = getenv("AFSL_HEAD_PAIR");
   const bool pair = pair_env ? atoi(pair_env) == 2 : p.D >= 128;
-  // support blocks of at most 32 rows in one ring stage (AFSL_HEAD_ONESUP=0 keeps them on one stage per k-block group)
+  // support blocks of at most 32 rows in ONE ring stage: one barrier round trip for the support phase, but one producer
+  // group then reduces all k-blocks while the other idles - a small gain at D = 64 (20w1s: 0.975 -> 0.948 ms per 48828
+  // tasks), a loss at D = 256 (0.614 -> 0.802 ms per 12207 tasks), so only D = 64 takes it by default; AFSL_HEAD_ONESUP=1 / 0
+  // forces it on / off (the parity test runs both)
   const char* one_env = getenv("AFSL_HEAD_ONESUP");
-  const bool one = sup_rows <= 32 && !(one_env && atoi(one_env) == 0);
+  const bool one = sup_rows <= 32 && (one_env ? atoi(one_env) != 0 : p.D == 64);
 #define AFSL_TMA_VARIANT(D_, R_, P_, L_) \
   (one ? launch_variant<D_, R_, P_, L_, true>(p, ms, mq, sup_rows, stream, name, handled) \
        : launch_variant<D_, R_, P_, L_, false>(p, ms, mq, sup_rows, stream, name, handled))

@@ -151,7 +151,7 @@ def test_head_many_way_tensor_core_kernel(ops, monkeypatch, ways, shots, nq, dim
     for mma in ("1", "1p", "1o", "2", "0"):
         monkeypatch.setenv("AFSL_HEAD_MMA", mma[0])
         monkeypatch.setenv("AFSL_HEAD_PAIR", "1" if mma == "1" else "2")
-        monkeypatch.setenv("AFSL_HEAD_ONESUP", "0" if mma == "1o" else "1")
+        monkeypatch.setenv("AFSL_HEAD_ONESUP", "0" if mma == "1o" else "1")       # "1": forced on for every D
         pred, post, correct, scores = ops.proto_eval(s.cuda(), sl.cuda(), q.cuda(), ql.cuda(), n_way=ways, want_scores=True)
         loss, protos, corr2 = ops.proto_head(s.cuda(), sl.cuda(), q.cuda(), ql.cuda(), n_way=ways)
         sc2 = ops.l2_scores(q.cuda(), protos)
