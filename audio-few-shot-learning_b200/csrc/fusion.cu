@@ -114,15 +114,28 @@ __device__ inline void gemm_tile(const float* __restrict__ A, int lda, const flo
       if (kAccum) acc[i] = *reinterpret_cast<const float4*>(C + (size_t)min(r0 + i, rows - 1) * ldc + cg * 4);
       else acc[i] = bias ? __ldg(reinterpret_cast<const float4*>(bias) + cg) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const float* a0 = A + (size_t)r0 * lda;
-#pragma unroll 4
-    for (int k = 0; k < K; ++k) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(B + (size_t)k * ldb) + cg);
+    // four k per step: one 128-bit shared-memory read per row (a broadcast: the lanes of a warp share the row group) and
+    // four 128-bit weight reads feed 64 FMAs - the first version read A element by element (5 loads per 16 FMAs: bound
+    // by the load / store unit, not the FMA pipe).  Same fmaf sequence per output, so the results are bit-identical.
+    const float* ar[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ar[i] = A + (size_t)(r0 + min(i, rows - 1 - r0)) * lda;
+    static_assert(K % 4 == 0, "K must be a multiple of 4");
+#pragma unroll 2
+    for (int k = 0; k < K; k += 4) {
+      float4 a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(ar[i] + k);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) b[kk] = __ldg(reinterpret_cast<const float4*>(B + (size_t)(k + kk) * ldb) + cg);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float a = a0[(size_t)min(i, rows - 1 - r0) * lda + k];
-        acc[i].x = fmaf(a, b.x, acc[i].x); acc[i].y = fmaf(a, b.y, acc[i].y);
-        acc[i].z = fmaf(a, b.z, acc[i].z); acc[i].w = fmaf(a, b.w, acc[i].w);
+        const float av[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          acc[i].x = fmaf(av[kk], b[kk].x, acc[i].x); acc[i].y = fmaf(av[kk], b[kk].y, acc[i].y);
+          acc[i].z = fmaf(av[kk], b[kk].z, acc[i].z); acc[i].w = fmaf(av[kk], b[kk].w, acc[i].w);
+        }
       }
     }
 #pragma unroll
@@ -135,19 +148,33 @@ __device__ inline void gemm_tile(const float* __restrict__ A, int lda, const flo
 template <int K>
 __device__ inline void grad_weights(const float* __restrict__ G, int ldg, const float* __restrict__ A, int lda, int rows, int N,
                                     float* __restrict__ part, float* __restrict__ bias_part) {
+  // register tile of 4 outputs n x 4 inputs k per thread: two 128-bit shared-memory reads feed 16 FMAs per row (the first
+  // version had one output per thread: a scalar and a 128-bit read per 4 FMAs).  Rows are added in ascending order per
+  // element as before: bit-identical.
   constexpr int K4 = K / 4;
-  for (int item = threadIdx.x; item < N * K4; item += kThreads) {
-    const int n = item / K4, kg = item - n * K4;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int N4 = N >> 2;
+  for (int item = threadIdx.x; item < N4 * K4; item += kThreads) {
+    const int ng = item / K4, kg = item - ng * K4;
+    float4 acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int m = 0; m < rows; ++m) {
-      const float g = G[(size_t)m * ldg + n];
+      const float4 g = *reinterpret_cast<const float4*>(G + (size_t)m * ldg + ng * 4);
       const float4 a = *reinterpret_cast<const float4*>(A + (size_t)m * lda + kg * 4);
-      acc.x = fmaf(g, a.x, acc.x); acc.y = fmaf(g, a.y, acc.y); acc.z = fmaf(g, a.z, acc.z); acc.w = fmaf(g, a.w, acc.w);
+      const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[j].x = fmaf(gv[j], a.x, acc[j].x); acc[j].y = fmaf(gv[j], a.y, acc[j].y);
+        acc[j].z = fmaf(gv[j], a.z, acc[j].z); acc[j].w = fmaf(gv[j], a.w, acc[j].w);
+      }
     }
-    float4* dst = reinterpret_cast<float4*>(part + (size_t)n * K) + kg;
-    float4 cur = *dst;
-    cur.x += acc.x; cur.y += acc.y; cur.z += acc.z; cur.w += acc.w;
-    *dst = cur;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float4* dst = reinterpret_cast<float4*>(part + (size_t)(ng * 4 + j) * K) + kg;
+      float4 cur = *dst;
+      cur.x += acc[j].x; cur.y += acc[j].y; cur.z += acc[j].z; cur.w += acc[j].w;
+      *dst = cur;
+    }
   }
   for (int n = threadIdx.x; n < N; n += kThreads) {
     float acc = 0.f;
