@@ -101,35 +101,37 @@ __device__ inline Tile carve(float* b, bool bwd) {
 
 // C[m][n] = (bias[n] | C[m][n]) + sum_k A[m][k] * B[k*ldb + n],  m < rows, n < N (N % 4 == 0)
 // A, C in shared memory; B in global memory with contiguous n (coalesced 128-bit reads through L1).
-template <int K, bool kAccum>
+template <int K, bool kAccum, int kR = 4>
 __device__ inline void gemm_tile(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                                  const float* __restrict__ bias, float* __restrict__ C, int ldc, int rows, int N) {
+  // kR rows x 4 columns per thread: 4 rows for the wide outputs (N = 192 / 256), 2 rows for N = 64, where 4 would leave
+  // half of the CTA's threads without rows of the 32-token tile
   const int ncg = N >> 2, nrg = kThreads / ncg;
   const int cg = threadIdx.x % ncg, rg = threadIdx.x / ncg;
   if (rg >= nrg) return;
-  for (int r0 = rg * 4; r0 < rows; r0 += nrg * 4) {
-    float4 acc[4];
+  for (int r0 = rg * kR; r0 < rows; r0 += nrg * kR) {
+    float4 acc[kR];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kR; ++i) {
       if (kAccum) acc[i] = *reinterpret_cast<const float4*>(C + (size_t)min(r0 + i, rows - 1) * ldc + cg * 4);
       else acc[i] = bias ? __ldg(reinterpret_cast<const float4*>(bias) + cg) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     // four k per step: one 128-bit shared-memory read per row (a broadcast: the lanes of a warp share the row group) and
-    // four 128-bit weight reads feed 64 FMAs - the first version read A element by element (5 loads per 16 FMAs: bound
+    // four 128-bit weight reads feed 16 kR FMAs - the first version read A element by element (5 loads per 16 FMAs: bound
     // by the load / store unit, not the FMA pipe).  Same fmaf sequence per output, so the results are bit-identical.
-    const float* ar[4];
+    const float* ar[kR];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) ar[i] = A + (size_t)(r0 + min(i, rows - 1 - r0)) * lda;
+    for (int i = 0; i < kR; ++i) ar[i] = A + (size_t)(r0 + min(i, rows - 1 - r0)) * lda;
     static_assert(K % 4 == 0, "K must be a multiple of 4");
 #pragma unroll 2
     for (int k = 0; k < K; k += 4) {
-      float4 a[4], b[4];
+      float4 a[kR], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(ar[i] + k);
+      for (int i = 0; i < kR; ++i) a[i] = *reinterpret_cast<const float4*>(ar[i] + k);
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) b[kk] = __ldg(reinterpret_cast<const float4*>(B + (size_t)(k + kk) * ldb) + cg);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < kR; ++i) {
         const float av[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
@@ -139,7 +141,7 @@ __device__ inline void gemm_tile(const float* __restrict__ A, int lda, const flo
       }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < kR; ++i)
       if (r0 + i < rows) *reinterpret_cast<float4*>(C + (size_t)(r0 + i) * ldc + cg * 4) = acc[i];
   }
 }
@@ -297,7 +299,7 @@ __device__ inline void tile_forward(const FusionParams& p, const Tile& t, int to
     t.ctx[(size_t)m * ldD + j] = acc;
   }
   __syncthreads();
-  gemm_tile<kD, false>(t.ctx, ldD, w + O::wo_t, kD, w + O::bo, t.x1, ldD, rows, kD);     // sa -> x1 buffer
+  gemm_tile<kD, false, 2>(t.ctx, ldD, w + O::wo_t, kD, w + O::bo, t.x1, ldD, rows, kD);     // sa -> x1 buffer
   __syncthreads();
   residual_layernorm(t.x, t.x1, p.drop1, (size_t)tok0 * kD, w + O::g1, w + O::be1, t.x1, t.r1h, t.rs1, rows);
   __syncthreads();
@@ -310,7 +312,7 @@ __device__ inline void tile_forward(const FusionParams& p, const Tile& t, int to
     t.h[(size_t)m * ldF + j] = v;
   }
   __syncthreads();
-  gemm_tile<kF, false>(t.h, ldF, w + O::w2_t, kD, w + O::b2, t.r2h, ldD, rows, kD);     // ff -> r2h buffer
+  gemm_tile<kF, false, 2>(t.h, ldF, w + O::w2_t, kD, w + O::b2, t.r2h, ldD, rows, kD);     // ff -> r2h buffer
   __syncthreads();
 }
 
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(kThreads) fusion_bwd_kernel(const FusionParams
     __syncthreads();
     grad_weights<kD>(t.h, ldF, t.x1, ldD, rows, kF, part + O::w1, part + O::b1);           // dW1 [kF][kD], db1
     __syncthreads();
-    gemm_tile<kF, true>(t.h, ldF, w + O::w1, kD, nullptr, t.g, ldD, rows, kD);             // g = d x1 = d r2 + d h W1
+    gemm_tile<kF, true, 2>(t.h, ldF, w + O::w1, kD, nullptr, t.g, ldD, rows, kD);             // g = d x1 = d r2 + d h W1
     layernorm_backward(t.g, t.r1h, t.rs1, w + O::g1, rows, part + O::g1, part + O::be1);   // g = d r1
     for (int i = threadIdx.x; i < rows * kD; i += kThreads) {                              // g1 = d sa = d r1 * drop1
       const int m = i / kD, j = i - m * kD;
@@ -396,7 +398,7 @@ __global__ void __launch_bounds__(kThreads) fusion_bwd_kernel(const FusionParams
     }
     __syncthreads();
     grad_weights<kD>(t.g1, ldD, t.ctx, ldD, rows, kD, part + O::wo, part + O::bo);         // dWo, dbo
-    gemm_tile<kD, false>(t.g1, ldD, w + O::wo, kD, nullptr, t.dctx, ldD, rows, kD);        // d ctx = d sa Wo
+    gemm_tile<kD, false, 2>(t.g1, ldD, w + O::wo, kD, nullptr, t.dctx, ldD, rows, kD);        // d ctx = d sa Wo
     __syncthreads();
     // ---- attention backward, per token m (query role) and per key token
     // d a'[m][u] = d ctx[m] . v[u]; d a = d a' * drop; d s = a * (d a - sum a d a) / 8
@@ -452,7 +454,7 @@ __global__ void __launch_bounds__(kThreads) fusion_bwd_kernel(const FusionParams
     }
     __syncthreads();
     grad_weights<kD>(t.dqkv, ldQ, t.x, ldD, rows, kQ, part + O::win, part + O::bin);       // dWin, dbin
-    gemm_tile<kQ, true>(t.dqkv, ldQ, w + O::win, kD, nullptr, t.g, ldD, rows, kD);         // g = d x = d r1 + d qkv Win
+    gemm_tile<kQ, true, 2>(t.dqkv, ldQ, w + O::win, kD, nullptr, t.g, ldD, rows, kD);         // g = d x = d r1 + d qkv Win
     __syncthreads();
     for (int i = threadIdx.x; i < rows * (kD / 4); i += kThreads) {
       const int m = i / (kD / 4), c = i - m * (kD / 4);
