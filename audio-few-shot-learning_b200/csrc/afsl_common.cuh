@@ -116,13 +116,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
+      "r"(parity), "r"(0x989680u)       // suspend-time hint: the waiting thread sleeps in hardware until the phase flips
+      : "memory");                      // instead of re-issuing try_wait every ~9 clocks (the spinning issuer warp of the
+                                        // tensor-core head was 10 % of the kernel's instructions, all on one scheduler)
 }
 
 // Stable bucket of rows by label, whole CTA cooperating: on return (after the trailing barrier)

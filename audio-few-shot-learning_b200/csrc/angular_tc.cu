@@ -90,15 +90,6 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
 __device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b) {
   asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
-// 16 consecutive accumulator columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 __device__ __forceinline__ float pick(const float4& t, int u) { return u == 0 ? t.x : u == 1 ? t.y : u == 2 ? t.z : t.w; }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
@@ -466,7 +457,8 @@ __global__ void __launch_bounds__(kThreads, 1) angular_tc_kernel(const AngParams
         const ptrdiff_t dp = (ptrdiff_t)(valid ? ep : 0) * W * kD + d;
         const ptrdiff_t dq = (ptrdiff_t)(valid ? ep : 0) * Nq * kD + d - (ptrdiff_t)W * kD;
         uint32_t o[16];
-        tmem_ld16(tmem + ((uint32_t)(e * 32) << 16) + 256 + h * 64 + (e >> 1) * 32 + half * 16, o);
+        tmem_ld16_nowait(tmem + ((uint32_t)(e * 32) << 16) + 256 + h * 64 + (e >> 1) * 32 + half * 16, o);
+        tmem_ld_wait();
         if (valid) {
 #pragma unroll
           for (int u = 0; u < 16; ++u) {

@@ -29,6 +29,7 @@ struct HeadParams {
   float* d_protos;              // [E,W,D] or null
   float* d_queries;             // [rows,D] or null
   int E, Ns, Nq, W, D;
+  long long* dbg;               // proto_head_tma.cu timeline buffer (AFSL_HEAD_DBG), else null
 };
 
 // proto_head_warp.cu: launches the warp-per-episode kernels when the shape fits them; *handled says whether it did

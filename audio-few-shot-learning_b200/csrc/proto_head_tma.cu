@@ -43,7 +43,8 @@ constexpr int kIssuerWarp = 8;
 constexpr int kLoaderWarp = 9;
 constexpr int kEpiWarp0 = 10;
 constexpr int kEpiWarps = 4;
-constexpr int kTmaThreads = (kEpiWarp0 + kEpiWarps) * 32;       // 448
+constexpr int kBucketWarp = kEpiWarp0 + kEpiWarps;               // 14
+constexpr int kTmaThreads = (kBucketWarp + 1) * 32;             // 480
 constexpr int kTileM = 128;                                     // query rows per accumulator (TMEM lanes)
 constexpr int kTileN = 32;                                      // prototype slots per accumulator (TMEM columns)
 constexpr int kMaxWays = 24;                                    // B tiles hold 24 rows (3 KB); the MMA's slots 24..31 read on into
@@ -54,7 +55,9 @@ constexpr int kBTile = kMaxWays * 128;
 constexpr int kMaxLoRing = 4;
 constexpr int kMaxRing = 9;
 constexpr int kMaxSupportRows = kTileM;
-constexpr uint32_t kIdesc = idesc_tf32(kTileM, kTileN);
+constexpr int kAccN = 2 * kMaxWays;                             // accumulator columns: q.p_hi in 0..23, q.p_lo in 24..47
+constexpr int kAccStride = 64;                                  // TMEM columns between the two accumulators
+constexpr uint32_t kIdesc = idesc_tf32(kTileM, kAccN);
 
 struct TmaBars {
   uint64_t tma_full[kMaxRing];    // stage filled by TMA (transaction bytes)
@@ -63,17 +66,17 @@ struct TmaBars {
   uint64_t lo_free[kMaxLoRing];   // lo tiles of a query stage free again (tcgen05.commit)
   uint64_t b_empty;               // the task's MMAs are done with the prototype tiles
   uint64_t acc_full[2], epi_done[2], meta_full[2];
+  uint64_t bk_full[2], bk_free[2];  // the task's bucket lists are built (bucket warp) / read for the last time (producers)
 };
 
 struct TmaMeta {
   TmaBars bars;
   uint32_t tmem_base;
   float qq[2][kGroups][kTileM];          // |q|^2 partial sums: the k-blocks each producer group handled
-  float pp[2][kGroups][kTileN];
+  float pp[2][kGroups][kTileN];          // |p|^2 partial sums, likewise
   float part[kEpiWarps];
   int hits[kEpiWarps];
   int cnt[2][kTileN];                    // rows per class
-  int warp_cnt[kProducerWarps][kTileN];  // rows per class inside each producer warp's 32-row slice
 };
 
 // waiting roles that are not on the critical path (loader, epilogue) sleep between polls instead of competing with the
@@ -90,8 +93,14 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
   } while (!done);
 }
 
-__device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory"); }
 __device__ __forceinline__ void epilogue_bar() { asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
+
+// timeline of CTA 0 (AFSL_HEAD_DBG=1, tools/head_many_way_bench.py): SM clock at event `ev` of ring stage `c` (all tasks)
+constexpr int kDbgStages = 160, kDbgEvents = 14;
+#define HDBG(c, ev)                                                                                        \
+  do {                                                                                                     \
+    if (p.dbg && blockIdx.x == 0 && (c) < (uint32_t)kDbgStages) p.dbg[(c) * kDbgEvents + (ev)] = clock64(); \
+  } while (0)
 
 template <int kD, int kRing, int kPair, int kLo, bool kOneSup>
 __global__ void __launch_bounds__(kTmaThreads, 1)
@@ -130,6 +139,8 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
       mbar_init(&meta->bars.acc_full[i], 1);
       mbar_init(&meta->bars.epi_done[i], kEpiWarps);
       mbar_init(&meta->bars.meta_full[i], kProducerWarps);
+      mbar_init(&meta->bars.bk_full[i], 1);
+      mbar_init(&meta->bars.bk_free[i], kProducerWarps);
     }
     fence_barrier_init();
     prefetch_tensormap(&map_s);
@@ -137,7 +148,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
   }
   // prototype slots W..23 of every B tile stay zero for the whole launch
   for (int i = tid; i < kKB * 2 * kBTile / 16; i += kTmaThreads) sts4(b_base + i * 16, make_float4(0.f, 0.f, 0.f, 0.f));
-  if (warp == kIssuerWarp) tmem_alloc<64>(&meta->tmem_base);
+  if (warp == kIssuerWarp) tmem_alloc<2 * kAccStride>(&meta->tmem_base);
   fence_async_proxy();
   fence_before();
   __syncthreads();
@@ -159,6 +170,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
           for (int st = 0; st < stages; ++st, ++c) {
             const uint32_t s = c % kRing;
             mbar_wait_relaxed(&meta->bars.empty[s], ((c / kRing) & 1) ^ 1);
+            HDBG(c, 0);
             mbar_arrive_expect_tx(&meta->bars.tma_full[s], (uint32_t)rows * 128u * per);
             for (int i = 0; i < per; ++i)
               tma_load_2d(ring + s * kStageB + i * stride, map, (st * per + i) * kBlockK, e * rows, &meta->bars.tma_full[s]);
@@ -172,44 +184,11 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
     uint32_t c = 0;                        // stages issued so far (all tasks); this group handles those with (kb & 1) == grp
     uint32_t qc = 0;                       // query stages so far -> lo ring slot
     int it = 0;
-    // this thread's support label of the first task (row = tid); the next task's is fetched one task ahead
-    int next_lab = -1;
-    if (tid < sup_rows && blockIdx.x < p.E) next_lab = p.support ? p.s_labels[(size_t)blockIdx.x * p.Ns + tid] : tid;
     for (int e = blockIdx.x; e < p.E; e += gridDim.x, ++it) {
       const int par = it & 1;
-      mbar_wait(&meta->bars.epi_done[par], ((it >> 1) & 1) ^ 1);     // |p|^2, |q|^2, bucket of parity `par` are free
-      // ---------------------------------------------------------- bucket the support rows by class, ascending rows
-      const int my_lab = next_lab;
-      {
-        const int en = e + gridDim.x;
-        next_lab = -1;
-        if (tid < sup_rows && en < p.E) next_lab = p.support ? p.s_labels[(size_t)en * p.Ns + tid] : tid;
-      }
-      uint8_t* rows = rows_base + (size_t)par * W * row_stride;
-      const bool valid = my_lab >= 0 && my_lab < W;                  // other labels are left out, as in the fp32-pipe kernels
-      if (warp * 32 < sup_rows) {
-        for (int w = 0; w < W; ++w) {
-          const unsigned m = __ballot_sync(kFullMask, my_lab == w);
-          if (lane == 0) meta->warp_cnt[warp][w] = __popc(m);
-        }
-      } else if (lane < W) {
-        meta->warp_cnt[warp][lane] = 0;
-      }
-      producer_bar();
-      {
-        const unsigned same = __match_any_sync(kFullMask, my_lab);
-        if (valid) {
-          int pos = __popc(same & ((1u << lane) - 1u));
-          for (int wj = 0; wj < warp; ++wj) pos += meta->warp_cnt[wj][my_lab];
-          rows[my_lab * row_stride + pos] = (uint8_t)tid;
-        }
-        if (tid < W) {
-          int n = 0;
-          for (int wj = 0; wj < kProducerWarps; ++wj) n += meta->warp_cnt[wj][tid];
-          meta->cnt[par][tid] = n;
-        }
-      }
-      producer_bar();
+      mbar_wait(&meta->bars.epi_done[par], ((it >> 1) & 1) ^ 1);     // |p|^2, |q|^2 of parity `par` are free
+      mbar_wait(&meta->bars.bk_full[par], (it >> 1) & 1);            // the bucket warp built this task's class lists
+      const uint8_t* rows = rows_base + (size_t)par * W * row_stride;
       // ---------------------------------------------------------- support stages: prototypes, |p|^2, split prototype tiles
       {
         // item = (class w, 16-byte chunk j): 8 W items over the group's 128 threads, two rounds
@@ -234,10 +213,12 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
           if ((int)(c & 1) != grp) continue;
           const uint32_t s = c % kRing;
           mbar_wait(&meta->bars.tma_full[s], (c / kRing) & 1);
+          if (gtid == 0) HDBG(c, 1);
           if (!tiles_free) {                                                 // previous task's MMAs are done with the tiles
             mbar_wait(&meta->bars.b_empty, (it & 1) ^ 1);
             tiles_free = true;
           }
+          if (gtid == 0) HDBG(c, 2);
 #pragma unroll
           for (int rnd = 0; rnd < 2; ++rnd) {
             const int item = gtid + rnd * kGroupThreads;
@@ -245,34 +226,49 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
             const bool act = w < W;
             const int n = n_it[rnd];
             float sq = 0.f;
+            // the stage's k-blocks two at a time: the row reads of both are in flight together (four rows per step: one
+            // 32-bit read of the row ids, up to eight independent 128-bit reads), then the adds in ascending row order.
+            // One k-block after the other left four dependent load -> add chains per stage (~2300 clocks per stage)
 #pragma unroll
-            for (int i = 0; i < kSupPair; ++i) {
-              const int kb = st * kSupPair + i;
-              const uint32_t stage = ring + s * kStageB + i * kSupStride;
-              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-              // 8 rows per step: one 64-bit read of the row ids, 8 independent 128-bit reads, then the adds in row order
-              for (int i0 = 0; i0 < n; i0 += 8) {
-                const uint2 ids = *reinterpret_cast<const uint2*>(rows_it[rnd] + i0);
-                float4 v[8];
+            for (int ib = 0; ib < kSupPair; ib += 2) {
+              constexpr int kI = kSupPair >= 2 ? 2 : 1;
+              float4 acc[kI];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                  const uint32_t r = ((u < 4 ? ids.x : ids.y) >> (8 * (u & 3))) & 0xffu;
-                  v[u] = lds4(stage + sw128((int)(i0 + u < n ? r : 0u), j));
+              for (int i = 0; i < kI; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              const uint32_t stage0 = ring + s * kStageB + ib * kSupStride;
+              for (int i0 = 0; i0 < n; i0 += 4) {
+                const uint32_t ids = *reinterpret_cast<const uint32_t*>(rows_it[rnd] + i0);
+                float4 v[kI][4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const uint32_t off = sw128((int)((ids >> (8 * u)) & 0xffu), j);
+#pragma unroll
+                  for (int i = 0; i < kI; ++i)
+                    if (i0 + u < n) v[i][u] = lds4(stage0 + i * kSupStride + off);     // predicated: no traffic for missing rows
                 }
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
-                  if (i0 + u < n) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+                for (int u = 0; u < 4; ++u)
+                  if (i0 + u < n) {
+#pragma unroll
+                    for (int i = 0; i < kI; ++i) {
+                      acc[i].x += v[i][u].x; acc[i].y += v[i][u].y; acc[i].z += v[i][u].z; acc[i].w += v[i][u].w;
+                    }
+                  }
               }
               if (act) {
                 const float rc = rcp_it[rnd], fn = fn_it[rnd];
                 auto mean = [&](float sum) { const float q0 = sum * rc; return fmaf(fmaf(-q0, fn, sum), rc, q0); };
-                acc = make_float4(mean(acc.x), mean(acc.y), mean(acc.z), mean(acc.w));
-                if (p.protos_out && p.support)
-                  *reinterpret_cast<float4*>(p.protos_out + ((size_t)e * W + w) * kD + kb * kBlockK + 4 * j) = acc;
-                sq = fmaf(acc.x, acc.x, fmaf(acc.y, acc.y, fmaf(acc.z, acc.z, fmaf(acc.w, acc.w, sq))));
-                const uint32_t off = sw128(w, j);
-                sts4(b_base + (kb * 2 + 0) * kBTile + off, acc);             // hi: the tensor core truncates it itself
-                sts4(b_base + (kb * 2 + 1) * kBTile + off, lo_of_raw(acc));
+#pragma unroll
+                for (int i = 0; i < kI; ++i) {
+                  const int kb = st * kSupPair + ib + i;
+                  const float4 m = make_float4(mean(acc[i].x), mean(acc[i].y), mean(acc[i].z), mean(acc[i].w));
+                  if (p.protos_out && p.support)
+                    *reinterpret_cast<float4*>(p.protos_out + ((size_t)e * W + w) * kD + kb * kBlockK + 4 * j) = m;
+                  sq = fmaf(m.x, m.x, fmaf(m.y, m.y, fmaf(m.z, m.z, fmaf(m.w, m.w, sq))));
+                  const uint32_t off = sw128(w, j);
+                  sts4(b_base + (kb * 2 + 0) * kBTile + off, m);               // hi: the tensor core truncates it itself
+                  sts4(b_base + (kb * 2 + 1) * kBTile + off, lo_of_raw(m));
+                }
               }
             }
             sq += __shfl_xor_sync(kFullMask, sq, 1);
@@ -280,15 +276,20 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
             sq += __shfl_xor_sync(kFullMask, sq, 4);
             pp_acc[rnd] += sq;
           }
+          if (gtid == 0) HDBG(c, 8);
           fence_async_proxy();
+          if (gtid == 0) HDBG(c, 9);
           __syncwarp();
           if (lane == 0) mbar_arrive(&meta->bars.ready[s]);
+          if (gtid == 0) HDBG(c, 3);
         }
 #pragma unroll
         for (int rnd = 0; rnd < 2; ++rnd) {
           const int item = gtid + rnd * kGroupThreads;
           if ((item & 7) == 0 && (item >> 3) < kTileN) meta->pp[par][grp][item >> 3] = pp_acc[rnd];
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&meta->bars.bk_free[par]);                  // done with rows / cnt of parity `par`
       }
       // ---------------------------------------------------------- query stages: lo tile for the raw tile, |q|^2
       {
@@ -302,23 +303,34 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
           if ((int)(c & 1) != grp) continue;
           const uint32_t s = c % kRing, ls = qc % kLo;
           mbar_wait(&meta->bars.tma_full[s], (c / kRing) & 1);
+          if (gtid == 0) HDBG(c, 1);
 #pragma unroll
           for (int i = 0; i < kPair; ++i) {
             const uint32_t src = ring + s * kStageB + i * kTile + off0, dst = lo_base + ls * kStageB + i * kTile + off0;
             // rows >= Nq of the tile were never written by TMA: whatever they hold only reaches accumulator rows nobody reads
+            // (so rows >= Nq are neither read nor split: at Nq = 100 that is a fifth of the tile's shared-memory traffic)
             float4 v[8];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) v[t] = lds4(src + t * 2048);
+            for (int t = 0; t < 8; ++t)
+              if (r0 + 16 * t < Nq) v[t] = lds4(src + t * 2048);
             if (i == 0) mbar_wait(&meta->bars.lo_free[ls], ((qc / kLo) & 1) ^ 1);   // MMAs of query stage qc - kLo are done with the slot
+            if (i == 0 && gtid == 0) HDBG(c, 2);
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-              sts4(dst + t * 2048, lo_of_raw(v[t]));
-              qacc[t] = fmaf(v[t].x, v[t].x, fmaf(v[t].y, v[t].y, fmaf(v[t].z, v[t].z, fmaf(v[t].w, v[t].w, qacc[t]))));
+              if (r0 + 16 * t < Nq) {
+                sts4(dst + t * 2048, lo_of_raw(v[t]));
+                qacc[t] = fmaf(v[t].x, v[t].x, fmaf(v[t].y, v[t].y, fmaf(v[t].z, v[t].z, fmaf(v[t].w, v[t].w, qacc[t]))));
+              }
+              if (t == 0 && gtid == 0) HDBG(c, 10 + 2 * (i & 1));
             }
+            if (gtid == 0) HDBG(c, 11 + 2 * (i & 1));
           }
+          if (gtid == 0) HDBG(c, 8);
           fence_async_proxy();
+          if (gtid == 0) HDBG(c, 9);
           __syncwarp();
           if (lane == 0) mbar_arrive(&meta->bars.ready[s]);
+          if (gtid == 0) HDBG(c, 3);
         }
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
@@ -331,6 +343,51 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&meta->bars.meta_full[par]);
+    }
+  } else if (warp == kBucketWarp) {
+    // =============================================================== bucket warp: class lists of the support rows, one task
+    // ahead of the producers (it used to be a phase of the producers themselves, two 256-thread barriers and ~2000 clocks
+    // per task on their critical path).  rows[w][0 .. cnt[w]) = the rows of class w in ascending order, 32 rows per step:
+    // position inside the step from match.any, the running count of the class from shared memory (one writer per class)
+    uint8_t* rows_w = rows_base;
+    const int chunks = (sup_rows + 31) >> 5;
+    int labs[kMaxSupportRows / 32];
+    auto fetch = [&](int e) {
+#pragma unroll
+      for (int ch = 0; ch < kMaxSupportRows / 32; ++ch) {
+        const int r = ch * 32 + lane;
+        labs[ch] = -1;
+        if (ch < chunks && r < sup_rows && e < p.E) labs[ch] = p.support ? p.s_labels[(size_t)e * p.Ns + r] : r;
+      }
+    };
+    fetch(blockIdx.x);
+    int it = 0;
+    for (int e = blockIdx.x; e < p.E; e += gridDim.x, ++it) {
+      const int par = it & 1;
+      mbar_wait_relaxed(&meta->bars.bk_free[par], ((it >> 1) & 1) ^ 1);
+      int* cnt = meta->cnt[par];
+      uint8_t* rows = rows_w + (size_t)par * W * row_stride;
+      cnt[lane] = 0;
+      __syncwarp();
+#pragma unroll
+      for (int ch = 0; ch < kMaxSupportRows / 32; ++ch) {
+        if (ch < chunks) {
+          const int lab = labs[ch];
+          const bool valid = lab >= 0 && lab < W;                  // other labels are left out, as in the fp32-pipe kernels
+          const unsigned same = __match_any_sync(kFullMask, lab);
+          const int pos = __popc(same & ((1u << lane) - 1u));
+          const int base = valid ? cnt[lab] : 0;
+          __syncwarp();
+          if (valid) {
+            rows[lab * row_stride + base + pos] = (uint8_t)(ch * 32 + lane);
+            if (pos == 0) cnt[lab] = base + __popc(same);
+          }
+          __syncwarp();
+        }
+      }
+      fetch(e + gridDim.x);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&meta->bars.bk_full[par]);
     }
   } else if (warp == kIssuerWarp) {
     // =============================================================== MMA issuer
@@ -348,28 +405,29 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
         if (elect_one()) mbar_arrive(&meta->bars.empty[s]);
       }
       mbar_wait(&meta->bars.epi_done[par], ((it >> 1) & 1) ^ 1);            // accumulator `par` drained (task it-2)
-      const uint32_t acc = tmem + par * kTileN;
+      const uint32_t acc = tmem + par * kAccStride;
 #pragma unroll 1
       for (int st = 0; st < kSt; ++st, ++c, ++qc) {
         const uint32_t s = c % kRing, ls = qc % kLo;
         mbar_wait(&meta->bars.ready[s], (c / kRing) & 1);
         fence_after();
+        if (lane == 0) HDBG(c, 4);
         if (elect_one()) {
 #pragma unroll
           for (int i = 0; i < kPair; ++i) {
             const int kb = st * kPair + i;
             const uint32_t a_hi = desc_lo(ring + s * kStageB + i * kTile), a_lo = desc_lo(lo_base + ls * kStageB + i * kTile);
-            const uint32_t b_hi = desc_lo(b_base + kb * 2 * kBTile), b_lo = desc_lo(b_base + (kb * 2 + 1) * kBTile);
-            // small terms first: lo.lo, lo.hi, hi.lo, hi.hi; a K step of 8 fp32 = 32 bytes = 2 descriptor units
-            mma_tf32_lo(acc, a_lo, b_lo, kIdesc, kb != 0);
+            // the hi and the lo tile of a k-block are adjacent (24 rows each): ONE B operand of 48 rows, so that a pass
+            // over the A tile yields q.p_hi (columns 0..23) and q.p_lo (columns 24..47) at once - two reads of A per
+            // k-block (lo, then hi: small terms first) instead of four.  The shared-memory data pipe was the limiter:
+            // LSU + tensor-core wavefronts ~75 % of its cycles (profiles/r2r_ncu_kernels_summary.txt), 5 KB per
+            // 128 x 32 x 8 MMA; a K step of 8 fp32 = 32 bytes = 2 descriptor units
+            const uint32_t b_hl = desc_lo(b_base + kb * 2 * kBTile);
+            mma_tf32_lo(acc, a_lo, b_hl, kIdesc, kb != 0);
 #pragma unroll
-            for (int k = 1; k < kBlockK / 8; ++k) mma_tf32_lo(acc, a_lo + 2 * k, b_lo + 2 * k, kIdesc, 1u);
+            for (int k = 1; k < kBlockK / 8; ++k) mma_tf32_lo(acc, a_lo + 2 * k, b_hl + 2 * k, kIdesc, 1u);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 8; ++k) mma_tf32_lo(acc, a_lo + 2 * k, b_hi + 2 * k, kIdesc, 1u);
-#pragma unroll
-            for (int k = 0; k < kBlockK / 8; ++k) mma_tf32_lo(acc, a_hi + 2 * k, b_lo + 2 * k, kIdesc, 1u);
-#pragma unroll
-            for (int k = 0; k < kBlockK / 8; ++k) mma_tf32_lo(acc, a_hi + 2 * k, b_hi + 2 * k, kIdesc, 1u);
+            for (int k = 0; k < kBlockK / 8; ++k) mma_tf32_lo(acc, a_hi + 2 * k, b_hl + 2 * k, kIdesc, 1u);
           }
           commit(&meta->bars.empty[s]);
           commit(&meta->bars.lo_free[ls]);
@@ -379,6 +437,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
           }
         }
         __syncwarp();
+        if (lane == 0) HDBG(c, 5);
       }
     }
   } else {
@@ -391,8 +450,19 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
       mbar_wait_relaxed(&meta->bars.meta_full[par], ph);
       mbar_wait_relaxed(&meta->bars.acc_full[par], ph);
       fence_after();
-      uint32_t v[32];
-      tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + par * kTileN, v);
+      if (quad == 0 && lane == 0) HDBG((uint32_t)((it + 1) * (kSupSt + kSt) - 1), 6);
+      // q.p of slot w = column w (q.p_hi) + column 24 + w (q.p_lo)
+      float dot[kMaxWays];
+      {
+        uint32_t v[32], u[16];
+        const uint32_t ta = tmem + ((uint32_t)(quad * 32) << 16) + par * kAccStride;
+        tmem_ld32_nowait(ta, v);
+        tmem_ld16_nowait(ta + 32, u);
+        tmem_ld_wait();
+#pragma unroll
+        for (int w = 0; w < kMaxWays; ++w)
+          dot[w] = __uint_as_float(v[w]) + __uint_as_float(w + kMaxWays < 32 ? v[w + kMaxWays] : u[w + kMaxWays - 32]);
+      }
       const bool live = row < Nq;
       const float qq = meta->qq[par][0][live ? row : 0] + meta->qq[par][1][live ? row : 0];
       const int y = (live && p.q_labels) ? p.q_labels[(size_t)e * Nq + row] : -1;
@@ -406,7 +476,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
           // |q|^2 + |p|^2 - 2 q.p clamped at 0, as at::_euclidean_dist; -sqrt = the score
           const int wc = w < W ? w : 0;
           const float pw2 = meta->pp[par][0][wc] + meta->pp[par][1][wc];
-          const float d2 = fmaxf(fmaf(-2.f, __uint_as_float(v[w]), qq) + pw2, 0.f);
+          const float d2 = fmaxf(fmaf(-2.f, dot[w], qq) + pw2, 0.f);
           const float s = -sqrtf(d2);
           sc[w] = s;
           if (w < W) {
@@ -434,7 +504,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
         for (int w = 0; w < kMaxWays; ++w) {
           const int wc = w < W ? w : 0;
           const float pw2 = meta->pp[par][0][wc] + meta->pp[par][1][wc];
-          const float d2 = fmaxf(fmaf(-2.f, __uint_as_float(v[w]), qq) + pw2, 0.f);
+          const float d2 = fmaxf(fmaf(-2.f, dot[w], qq) + pw2, 0.f);
           if (w < W) {
             if (d2 < best) { best = d2; am = w; }
             if (d2 != d2 && am == 0x7fffffff) am = w;
@@ -465,11 +535,12 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&meta->bars.epi_done[par]);
+      if (quad == 0 && lane == 0) HDBG((uint32_t)((it + 1) * (kSupSt + kSt) - 1), 7);
     }
   }
   fence_before();
   __syncthreads();
-  if (warp == kIssuerWarp) tmem_free<64>(tmem);
+  if (warp == kIssuerWarp) tmem_free<2 * kAccStride>(tmem);
 }
 
 template <int kD, int kRing, int kPair, int kLo, bool kOneSup>
@@ -484,6 +555,29 @@ int launch_variant(const HeadParams& p, const CUtensorMap& ms, const CUtensorMap
   int sms = kNumSMs, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.E < sms ? p.E : sms;
+  if (getenv("AFSL_HEAD_DBG")) {
+    // columns: 0 TMA issued (stage free), 1 producers saw the bytes, 2 producers' tiles free, 3 producers done, 4 issuer saw
+    // the stage, 5 MMAs issued, 6 epilogue saw the accumulator (last stage of a task), 7 epilogue done
+    HeadParams q = p;
+    static long long host[kDbgStages * kDbgEvents];
+    if (cudaMalloc(&q.dbg, sizeof(host)) != cudaSuccess) return AFSL_ECUDA;
+    cudaMemsetAsync(q.dbg, 0, sizeof(host), stream);
+    fn<<<grid, kTmaThreads, bytes, stream>>>(q, ms, mq);
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(host, q.dbg, sizeof(host), cudaMemcpyDeviceToHost);
+    cudaFree(q.dbg);
+    long long t0 = 0;
+    for (long long t : host) if (t && (!t0 || t < t0)) t0 = t;
+    fprintf(stderr, "head_tma timeline D=%d pair=%d (clocks since the first event; rows = ring stages, %d support + %d query per task)\n",
+            kD, kPair, (kOneSup && (kD / kBlockK) * 4096 <= kPair * kTile) ? 1 : kD / kBlockK / kPair, kD / kBlockK / kPair);
+    for (int c = 0; c < kDbgStages; ++c) {
+      fprintf(stderr, "st %3d:", c);
+      for (int ev = 0; ev < kDbgEvents; ++ev) fprintf(stderr, " %7lld", host[c * kDbgEvents + ev] ? host[c * kDbgEvents + ev] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+    AFSL_CHECK_LAUNCH(name);
+    return AFSL_OK;
+  }
   fn<<<grid, kTmaThreads, bytes, stream>>>(p, ms, mq);
   AFSL_CHECK_LAUNCH(name);
   return AFSL_OK;

@@ -84,6 +84,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// the same loads without their wait: several can be in flight before one tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+      "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // ---- split precision: x = hi + lo with hi the TF32 the tensor core itself sees (low 13 mantissa bits dropped) or the
 //      nearest TF32, lo rounded to nearest TF32; hi.hi + hi.lo + lo.hi (+ lo.lo) then carries ~21 bits per product
 __device__ __forceinline__ float rna_tf32(float v) {
@@ -92,9 +112,12 @@ __device__ __forceinline__ float rna_tf32(float v) {
   return __uint_as_float(r);
 }
 __device__ __forceinline__ float trunc_tf32(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+// lo for an operand the TENSOR CORE reads: x - trunc(x) is exact; adding half a TF32 ulp to its bit pattern and letting the
+// MMA drop the low 13 bits is cvt.rna.tf32 (which ptxas expands to compare + add + mask: six instructions per element
+// with the subtraction and the mask, against three here), bit for bit the same operand
+__device__ __forceinline__ float lo_bits(float x) { return __uint_as_float(__float_as_uint(x - trunc_tf32(x)) + 0x1000u); }
 __device__ __forceinline__ float4 lo_of_raw(const float4& v) {      // hi = the raw value as the MMA truncates it
-  return make_float4(rna_tf32(v.x - trunc_tf32(v.x)), rna_tf32(v.y - trunc_tf32(v.y)), rna_tf32(v.z - trunc_tf32(v.z)),
-                     rna_tf32(v.w - trunc_tf32(v.w)));
+  return make_float4(lo_bits(v.x), lo_bits(v.y), lo_bits(v.z), lo_bits(v.w));
 }
 __device__ __forceinline__ void split_rna(const float4& v, float4& hi, float4& lo) {
   hi = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
