@@ -164,8 +164,8 @@ inline int persistent_grid(Kernel fn, int threads, size_t smem_bytes, int work_i
 
 template <typename Kernel>
 inline int opt_in_smem(Kernel fn, size_t bytes, const char* name) {
-  if (bytes > 220 * 1024) {
-    set_error("%s: needs %zu B of shared memory per CTA (limit 220 KB)", name, bytes);
+  if (bytes > 226 * 1024) {
+    set_error("%s: needs %zu B of shared memory per CTA (limit 226 KB)", name, bytes);
     return AFSL_EINVAL;
   }
   if (bytes > 48 * 1024) {

@@ -159,7 +159,22 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
     // =============================================================== loader
     if (lane == 0) {
       uint32_t c = 0;
+      // The ring holds ~3 stages (shared memory is full) and a stage's slot is busy from the TMA issue to the end of its
+      // MMAs; issue -> arrival is 1500-2400 clocks in the timeline.  Optionally the next task's blocks are PREFETCHED INTO
+      // L2 one task ahead (<= 200 KB per SM, 30 MB of the 126 MB L2 over the GPU).  Measured: arrival stays at 1000-2200
+      // clocks even from L2 (the stream runs at ~0.7 of the HBM rate: queueing, not DRAM latency), so the gain is small.
+      const bool l2_prefetch = p.l2_prefetch;
+      auto prefetch_task = [&](int e) {
+        if (!l2_prefetch || e >= p.E) return;
+        // the task's support block and query block are contiguous: two bulk prefetches, so that HBM sees long sequential
+        // reads instead of the boxes' 128-byte pieces at a 4 D-byte stride
+        const float* sup = p.support ? p.support : p.protos_in;
+        bulk_prefetch_l2(sup + (size_t)e * sup_rows * kD, (uint32_t)(sup_rows * kD * 4));
+        bulk_prefetch_l2(p.queries + (size_t)e * Nq * kD, (uint32_t)(Nq * kD * 4));
+      };
+      prefetch_task(blockIdx.x);
       for (int e = blockIdx.x; e < p.E; e += gridDim.x) {
+        prefetch_task(e + gridDim.x);
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
           const CUtensorMap* map = half ? &map_q : &map_s;
@@ -549,7 +564,7 @@ int launch_variant(const HeadParams& p, const CUtensorMap& ms, const CUtensorMap
   auto fn = head_tma_fwd_kernel<kD, kRing, kPair, kLo, kOneSup>;
   const size_t bytes = (size_t)(kRing + kLo) * kPair * kTile + (size_t)(kD / kBlockK) * 2 * kBTile + sizeof(TmaMeta) +
                        2 * (size_t)p.W * ((sup_rows + 7) & ~7) + 1024 + 16;
-  if (bytes > 220 * 1024) return AFSL_OK;          // very long support blocks: the fp32-pipe kernels take the launch
+  if (bytes > 226 * 1024) return AFSL_OK;          // very long support blocks: the fp32-pipe kernels take the launch
   *handled = true;
   if (int rc = opt_in_smem(fn, bytes, name)) return rc;
   int sms = kNumSMs, dev = 0;
@@ -602,11 +617,15 @@ int launch_head_tma(const HeadParams& p, bool bwd, cudaStream_t stream, const ch
   const float* sup = p.support ? p.support : p.protos_in;
   if (int rc = make_tensor_map_f32(&ms, sup, (uint64_t)p.E * sup_rows, (uint64_t)p.D, (uint32_t)sup_rows, name)) return rc;
   if (int rc = make_tensor_map_f32(&mq, p.queries, (uint64_t)p.E * p.Nq, (uint64_t)p.D, (uint32_t)p.Nq, name)) return rc;
-  // ring stages hold two k-blocks at D >= 128 (half as many barrier round trips per task: 0.54 -> 0.61 of HBM at 20w5s
-  // D = 256) and one at D = 64, where a pair would leave one stage per phase and so no overlap between the producer groups
-  // (measured 0.40 against 0.41); AFSL_HEAD_PAIR=1 / 2 forces one / two (the parity tests run both)
+  // ring stages hold two k-blocks (half as many barrier round trips per task: 20w5s D = 256 0.59 -> 0.71 of HBM, 20w5s
+  // D = 64 0.49 -> 0.59, gpurun_out/r2t_hb5_pair*.txt); AFSL_HEAD_PAIR=1 / 2 forces one / two (the parity tests run both)
   const char* pair_env = getenv("AFSL_HEAD_PAIR");
-  const bool pair = pair_env ? atoi(pair_env) == 2 : p.D >= 128;
+  const bool pair = pair_env ? atoi(pair_env) == 2 : true;
+  HeadParams hp = p;
+  const char* pf_env = getenv("AFSL_HEAD_L2PF");
+  // measured (gpurun_out/r2t_hb6_*.txt, r2t_hb7_bulkpf.txt): +0.02 of HBM on the small-support shapes (20w1s D = 256: 0.497 ->
+  // 0.518), within the noise elsewhere (20w5s D = 256: 0.707 / 0.697 / 0.687): on for support blocks of <= 32 rows
+  hp.l2_prefetch = pf_env ? atoi(pf_env) != 0 : sup_rows <= 32;
   // support blocks of at most 32 rows in ONE ring stage: one barrier round trip for the support phase, but one producer
   // group then reduces all k-blocks while the other idles - a small gain at D = 64 (20w1s: 0.975 -> 0.948 ms per 48828
   // tasks), a loss at D = 256 (0.614 -> 0.802 ms per 12207 tasks), so only D = 64 takes it by default; AFSL_HEAD_ONESUP=1 / 0
@@ -614,10 +633,10 @@ int launch_head_tma(const HeadParams& p, bool bwd, cudaStream_t stream, const ch
   const char* one_env = getenv("AFSL_HEAD_ONESUP");
   const bool one = sup_rows <= 32 && (one_env ? atoi(one_env) != 0 : p.D == 64);
 #define AFSL_TMA_VARIANT(D_, R_, P_, L_) \
-  (one ? launch_variant<D_, R_, P_, L_, true>(p, ms, mq, sup_rows, stream, name, handled) \
-       : launch_variant<D_, R_, P_, L_, false>(p, ms, mq, sup_rows, stream, name, handled))
+  (one ? launch_variant<D_, R_, P_, L_, true>(hp, ms, mq, sup_rows, stream, name, handled) \
+       : launch_variant<D_, R_, P_, L_, false>(hp, ms, mq, sup_rows, stream, name, handled))
   if (p.D == 256) return pair ? AFSL_TMA_VARIANT(256, 3, 2, 2) : AFSL_TMA_VARIANT(256, 6, 1, 4);
-  if (p.D == 128) return pair ? AFSL_TMA_VARIANT(128, 3, 2, 2) : AFSL_TMA_VARIANT(128, 7, 1, 4);
+  if (p.D == 128) return pair ? AFSL_TMA_VARIANT(128, 4, 2, 2) : AFSL_TMA_VARIANT(128, 7, 1, 4);
   return pair ? AFSL_TMA_VARIANT(64, 4, 2, 2) : AFSL_TMA_VARIANT(64, 8, 1, 4);
 #undef AFSL_TMA_VARIANT
 }
