@@ -30,6 +30,7 @@ struct HeadParams {
   float* d_queries;             // [rows,D] or null
   int E, Ns, Nq, W, D;
   long long* dbg;               // proto_head_tma.cu timeline buffer (AFSL_HEAD_DBG), else null
+  int tile_rows, ring_stages;   // proto_head_tma.cu: rows per k-block tile of a ring stage, ring depth (set by its launcher)
   int l2_prefetch;              // proto_head_tma.cu: prefetch every box into L2 one task ahead (AFSL_HEAD_L2PF=0 disables)
 };
 

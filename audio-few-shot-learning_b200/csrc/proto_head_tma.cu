@@ -50,7 +50,7 @@ constexpr int kTileN = 32;                                      // prototype slo
 constexpr int kMaxWays = 24;                                    // B tiles hold 24 rows (3 KB); the MMA's slots 24..31 read on into
                                                                 // the next tile / the lo ring: garbage columns nobody looks at
 constexpr int kBlockK = 32;                                     // fp32 per 128-byte swizzle row = one stage's columns
-constexpr int kTile = kTileM * 128;                             // bytes of one [128 x 32] fp32 tile = one ring stage
+constexpr int kTile = kTileM * 128;                             // bytes of a full [128 x 32] fp32 tile: what one MMA reads
 constexpr int kBTile = kMaxWays * 128;
 constexpr int kMaxLoRing = 4;
 constexpr int kMaxRing = 9;
@@ -102,25 +102,32 @@ constexpr int kDbgStages = 160, kDbgEvents = 14;
     if (p.dbg && blockIdx.x == 0 && (c) < (uint32_t)kDbgStages) p.dbg[(c) * kDbgEvents + (ev)] = clock64(); \
   } while (0)
 
-template <int kD, int kRing, int kPair, int kLo, bool kOneSup>
+template <int kD, int kPair, int kLo, bool kOneSup>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_q) {
   constexpr int kKB = kD / kBlockK;
   constexpr int kSt = kKB / kPair;                  // ring stages per phase (support / query) of a task: kPair k-blocks each
-  constexpr int kStageB = kPair * kTile;            // bytes of a ring stage (and of a lo-ring slot)
+  // A k-block tile of a ring stage holds only the rows a task has (its query rows / support rows rounded up to the 8-row
+  // swizzle atom: 13 KB instead of 16 KB at 100 rows), so that one more stage fits the ring: the MMA's M = 128 rows read
+  // on into the following tile, which only reaches accumulator rows nobody looks at.  tile_b / ring_n come from the host.
+  const uint32_t tile_b = (uint32_t)p.tile_rows * 128u;      // bytes of one k-block tile of a stage (a multiple of 1 KB)
+  const uint32_t kStageB = kPair * tile_b;                   // bytes of a ring stage (and of a lo-ring slot)
+  const uint32_t kRing = (uint32_t)p.ring_stages;
   // support blocks of at most 32 rows (20-way 1-shot, given prototypes): ALL their k-blocks share ONE ring stage, 4 KB apart
-  // (8 x 4 KB = a stage at D = 256) - the support phase of a task is one barrier round trip instead of kSt
-  // (one k-block per stage at D = 256 has 16 KB stages: it keeps the per-k-block support stages)
-  constexpr bool kOne = kOneSup && kKB * 4096 <= kStageB;
-  constexpr int kSupSt = kOne ? 1 : kSt, kSupPair = kOne ? kKB : kPair, kSupStride = kOne ? 4096 : kTile;
-  static_assert(kKB % kPair == 0 && kLo <= kMaxLoRing && kRing <= kMaxRing, "bad stage configuration");
+  // - the support phase of a task is one barrier round trip instead of kSt (taken when the k-blocks fit a stage of 32-row
+  // tiles: D = 64 with two k-blocks per stage)
+  constexpr bool kOne = kOneSup && kKB <= kPair;
+  constexpr int kSupSt = kOne ? 1 : kSt, kSupPair = kOne ? kKB : kPair;
+  const uint32_t kSupStride = kOne ? 4096u : tile_b;
+  static_assert(kKB % kPair == 0 && kLo <= kMaxLoRing, "bad stage configuration");
   // the producer group that owns a stage is (global stage index & 1)
   extern __shared__ __align__(1024) uint8_t smem_tma_raw[];
   uint8_t* smem = smem_tma_raw + ((1024u - (smem_u32(smem_tma_raw) & 1023u)) & 1023u);     // 1 KB: swizzle atoms
-  const uint32_t ring = smem_u32(smem);                                        // [kRing][kPair][16 KB] raw rows as TMA wrote them
+  const uint32_t ring = smem_u32(smem);                                        // [ring_n][kPair][tile_b] raw rows as TMA wrote them
   const uint32_t b_base = ring + kRing * kStageB;                                // [kKB][hi, lo][3 KB] split prototypes
   const uint32_t lo_base = b_base + kKB * 2 * kBTile;                          // [kLo][kPair][16 KB] lo tiles of query stages
-  TmaMeta* meta = reinterpret_cast<TmaMeta*>(smem + kRing * kStageB + kKB * 2 * kBTile + kLo * kStageB);
+  // (the last lo tile's MMA reads up to kTile - tile_b bytes past its slot: that much padding before the metadata)
+  TmaMeta* meta = reinterpret_cast<TmaMeta*>(smem + kRing * kStageB + kKB * 2 * kBTile + kLo * kStageB + (kTile - tile_b));
   uint8_t* rows_base = reinterpret_cast<uint8_t*>(meta + 1);                   // [2][W][row_stride]: bucketed support rows
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = p.W, Nq = p.Nq;
@@ -128,7 +135,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
   const int row_stride = (sup_rows + 7) & ~7;                                  // a class's row list is read 8 ids at a time
 
   if (tid == 0) {
-    for (int s = 0; s < kRing; ++s) {
+    for (int s = 0; s < kMaxRing; ++s) {
       mbar_init(&meta->bars.tma_full[s], 1);
       mbar_init(&meta->bars.ready[s], kGroupWarps);
       mbar_init(&meta->bars.empty[s], 1);
@@ -181,7 +188,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
           const int rows = half ? Nq : sup_rows;
 #pragma unroll 1
           const int stages = half ? kSt : kSupSt, per = half ? kPair : kSupPair;
-          const uint32_t stride = half ? kTile : kSupStride;
+          const uint32_t stride = half ? tile_b : kSupStride;
           for (int st = 0; st < stages; ++st, ++c) {
             const uint32_t s = c % kRing;
             mbar_wait_relaxed(&meta->bars.empty[s], ((c / kRing) & 1) ^ 1);
@@ -321,7 +328,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
           if (gtid == 0) HDBG(c, 1);
 #pragma unroll
           for (int i = 0; i < kPair; ++i) {
-            const uint32_t src = ring + s * kStageB + i * kTile + off0, dst = lo_base + ls * kStageB + i * kTile + off0;
+            const uint32_t src = ring + s * kStageB + i * tile_b + off0, dst = lo_base + ls * kStageB + i * tile_b + off0;
             // rows >= Nq of the tile were never written by TMA: whatever they hold only reaches accumulator rows nobody reads
             // (so rows >= Nq are neither read nor split: at Nq = 100 that is a fifth of the tile's shared-memory traffic)
             float4 v[8];
@@ -431,7 +438,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
 #pragma unroll
           for (int i = 0; i < kPair; ++i) {
             const int kb = st * kPair + i;
-            const uint32_t a_hi = desc_lo(ring + s * kStageB + i * kTile), a_lo = desc_lo(lo_base + ls * kStageB + i * kTile);
+            const uint32_t a_hi = desc_lo(ring + s * kStageB + i * tile_b), a_lo = desc_lo(lo_base + ls * kStageB + i * tile_b);
             // the hi and the lo tile of a k-block are adjacent (24 rows each): ONE B operand of 48 rows, so that a pass
             // over the A tile yields q.p_hi (columns 0..23) and q.p_lo (columns 24..47) at once - two reads of A per
             // k-block (lo, then hi: small terms first) instead of four.  The shared-memory data pipe was the limiter:
@@ -558,13 +565,27 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
   if (warp == kIssuerWarp) tmem_free<2 * kAccStride>(tmem);
 }
 
-template <int kD, int kRing, int kPair, int kLo, bool kOneSup>
-int launch_variant(const HeadParams& p, const CUtensorMap& ms, const CUtensorMap& mq, int sup_rows, cudaStream_t stream,
+template <int kD, int kPair, int kLo, bool kOneSup>
+int launch_variant(const HeadParams& p_in, const CUtensorMap& ms, const CUtensorMap& mq, int sup_rows, cudaStream_t stream,
                    const char* name, bool* handled) {
-  auto fn = head_tma_fwd_kernel<kD, kRing, kPair, kLo, kOneSup>;
-  const size_t bytes = (size_t)(kRing + kLo) * kPair * kTile + (size_t)(kD / kBlockK) * 2 * kBTile + sizeof(TmaMeta) +
+  auto fn = head_tma_fwd_kernel<kD, kPair, kLo, kOneSup>;
+  HeadParams p = p_in;
+  // rows per k-block tile of a stage: the longer of the task's two blocks, rounded up to the swizzle atom
+  const int longest = p.Nq > sup_rows ? p.Nq : sup_rows;
+  p.tile_rows = (longest + 7) & ~7;
+  const size_t tile_b = (size_t)p.tile_rows * 128, stage_b = kPair * tile_b;
+  const size_t fixed = (size_t)kLo * stage_b + (size_t)(kD / kBlockK) * 2 * kBTile + (kTile - tile_b) + sizeof(TmaMeta) +
                        2 * (size_t)p.W * ((sup_rows + 7) & ~7) + 1024 + 16;
-  if (bytes > 226 * 1024) return AFSL_OK;          // very long support blocks: the fp32-pipe kernels take the launch
+  const size_t budget = 226 * 1024;
+  if (fixed + 3 * stage_b > budget) return AFSL_OK;   // very long support blocks: the fp32-pipe kernels take the launch
+  size_t ring_n = (budget - fixed) / stage_b;
+  if (ring_n > (size_t)kMaxRing) ring_n = kMaxRing;
+  if (const char* env = getenv("AFSL_HEAD_RING")) {   // fewer stages, for measurements
+    const size_t want = (size_t)atoi(env);
+    if (want >= 2 && want < ring_n) ring_n = want;
+  }
+  p.ring_stages = (int)ring_n;
+  const size_t bytes = fixed + ring_n * stage_b;
   *handled = true;
   if (int rc = opt_in_smem(fn, bytes, name)) return rc;
   int sms = kNumSMs, dev = 0;
@@ -584,7 +605,7 @@ int launch_variant(const HeadParams& p, const CUtensorMap& ms, const CUtensorMap
     long long t0 = 0;
     for (long long t : host) if (t && (!t0 || t < t0)) t0 = t;
     fprintf(stderr, "head_tma timeline D=%d pair=%d (clocks since the first event; rows = ring stages, %d support + %d query per task)\n",
-            kD, kPair, (kOneSup && (kD / kBlockK) * 4096 <= kPair * kTile) ? 1 : kD / kBlockK / kPair, kD / kBlockK / kPair);
+            kD, kPair, (kOneSup && kD / kBlockK <= kPair) ? 1 : kD / kBlockK / kPair, kD / kBlockK / kPair);
     for (int c = 0; c < kDbgStages; ++c) {
       fprintf(stderr, "st %3d:", c);
       for (int ev = 0; ev < kDbgEvents; ++ev) fprintf(stderr, " %7lld", host[c * kDbgEvents + ev] ? host[c * kDbgEvents + ev] - t0 : -1);
@@ -632,12 +653,13 @@ int launch_head_tma(const HeadParams& p, bool bwd, cudaStream_t stream, const ch
   // forces it on / off (the parity test runs both)
   const char* one_env = getenv("AFSL_HEAD_ONESUP");
   const bool one = sup_rows <= 32 && (one_env ? atoi(one_env) != 0 : p.D == 64);
-#define AFSL_TMA_VARIANT(D_, R_, P_, L_) \
-  (one ? launch_variant<D_, R_, P_, L_, true>(hp, ms, mq, sup_rows, stream, name, handled) \
-       : launch_variant<D_, R_, P_, L_, false>(hp, ms, mq, sup_rows, stream, name, handled))
-  if (p.D == 256) return pair ? AFSL_TMA_VARIANT(256, 3, 2, 2) : AFSL_TMA_VARIANT(256, 6, 1, 4);
-  if (p.D == 128) return pair ? AFSL_TMA_VARIANT(128, 4, 2, 2) : AFSL_TMA_VARIANT(128, 7, 1, 4);
-  return pair ? AFSL_TMA_VARIANT(64, 4, 2, 2) : AFSL_TMA_VARIANT(64, 8, 1, 4);
+#define AFSL_TMA_VARIANT(D_, P_, L_) \
+  (one ? launch_variant<D_, P_, L_, true>(hp, ms, mq, sup_rows, stream, name, handled) \
+       : launch_variant<D_, P_, L_, false>(hp, ms, mq, sup_rows, stream, name, handled))
+  // (the ring takes every stage that fits 226 KB of shared memory: 4 stages of 26 KB at D = 256 with 100-row blocks)
+  if (p.D == 256) return pair ? AFSL_TMA_VARIANT(256, 2, 2) : AFSL_TMA_VARIANT(256, 1, 4);
+  if (p.D == 128) return pair ? AFSL_TMA_VARIANT(128, 2, 2) : AFSL_TMA_VARIANT(128, 1, 4);
+  return pair ? AFSL_TMA_VARIANT(64, 2, 2) : AFSL_TMA_VARIANT(64, 1, 4);
 #undef AFSL_TMA_VARIANT
 }
 
