@@ -64,7 +64,7 @@ struct TmaBars {
   uint64_t ready[kMaxRing];       // stage processed by its producer group (4 warps)
   uint64_t empty[kMaxRing];       // stage free again (issuer: plain arrive for support stages, tcgen05.commit for query stages)
   uint64_t lo_free[kMaxLoRing];   // lo tiles of a query stage free again (tcgen05.commit)
-  uint64_t b_empty;               // the task's MMAs are done with the prototype tiles
+  uint64_t b_empty[2];            // the task's MMAs are done with the prototype tiles (of task parity b when double-buffered)
   uint64_t acc_full[2], epi_done[2], meta_full[2];
   uint64_t bk_full[2], bk_free[2];  // the task's bucket lists are built (bucket warp) / read for the last time (producers)
 };
@@ -124,10 +124,15 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
   extern __shared__ __align__(1024) uint8_t smem_tma_raw[];
   uint8_t* smem = smem_tma_raw + ((1024u - (smem_u32(smem_tma_raw) & 1023u)) & 1023u);     // 1 KB: swizzle atoms
   const uint32_t ring = smem_u32(smem);                                        // [ring_n][kPair][tile_b] raw rows as TMA wrote them
-  const uint32_t b_base = ring + kRing * kStageB;                                // [kKB][hi, lo][3 KB] split prototypes
-  const uint32_t lo_base = b_base + kKB * 2 * kBTile;                          // [kLo][kPair][16 KB] lo tiles of query stages
+  // split prototypes [kBBuf][kKB][hi, lo][3 KB]: two sets at D <= 128, so that the support phase of task t + 1 does not
+  // wait for the MMAs of task t (at D = 64 that wait serialised the whole task: support 2200 + MMA 1200 clocks of a 3600
+  // clock period); at D = 256 a second set (48 KB) would cost two ring stages
+  constexpr int kBBuf = kD <= 128 ? 2 : 1;
+  constexpr uint32_t kBSet = kKB * 2 * kBTile;
+  const uint32_t b_base0 = ring + kRing * kStageB;
+  const uint32_t lo_base = b_base0 + kBBuf * kBSet;                            // [kLo][kPair][tile_b] lo tiles of query stages
   // (the last lo tile's MMA reads up to kTile - tile_b bytes past its slot: that much padding before the metadata)
-  TmaMeta* meta = reinterpret_cast<TmaMeta*>(smem + kRing * kStageB + kKB * 2 * kBTile + kLo * kStageB + (kTile - tile_b));
+  TmaMeta* meta = reinterpret_cast<TmaMeta*>(smem + kRing * kStageB + kBBuf * kBSet + kLo * kStageB + (kTile - tile_b));
   uint8_t* rows_base = reinterpret_cast<uint8_t*>(meta + 1);                   // [2][W][row_stride]: bucketed support rows
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = p.W, Nq = p.Nq;
@@ -141,7 +146,8 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
       mbar_init(&meta->bars.empty[s], 1);
     }
     for (int s = 0; s < kLo; ++s) mbar_init(&meta->bars.lo_free[s], 1);
-    mbar_init(&meta->bars.b_empty, 1);
+    mbar_init(&meta->bars.b_empty[0], 1);
+    mbar_init(&meta->bars.b_empty[1], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&meta->bars.acc_full[i], 1);
       mbar_init(&meta->bars.epi_done[i], kEpiWarps);
@@ -154,7 +160,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
     prefetch_tensormap(&map_q);
   }
   // prototype slots W..23 of every B tile stay zero for the whole launch
-  for (int i = tid; i < kKB * 2 * kBTile / 16; i += kTmaThreads) sts4(b_base + i * 16, make_float4(0.f, 0.f, 0.f, 0.f));
+  for (int i = tid; i < kBBuf * kBSet / 16; i += kTmaThreads) sts4(b_base0 + i * 16, make_float4(0.f, 0.f, 0.f, 0.f));
   if (warp == kIssuerWarp) tmem_alloc<2 * kAccStride>(&meta->tmem_base);
   fence_async_proxy();
   fence_before();
@@ -211,6 +217,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
       mbar_wait(&meta->bars.epi_done[par], ((it >> 1) & 1) ^ 1);     // |p|^2, |q|^2 of parity `par` are free
       mbar_wait(&meta->bars.bk_full[par], (it >> 1) & 1);            // the bucket warp built this task's class lists
       const uint8_t* rows = rows_base + (size_t)par * W * row_stride;
+      const uint32_t b_base = b_base0 + (kBBuf == 2 ? par : 0) * kBSet;
       // ---------------------------------------------------------- support stages: prototypes, |p|^2, split prototype tiles
       {
         // item = (class w, 16-byte chunk j): 8 W items over the group's 128 threads, two rounds
@@ -236,10 +243,6 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
           const uint32_t s = c % kRing;
           mbar_wait(&meta->bars.tma_full[s], (c / kRing) & 1);
           if (gtid == 0) HDBG(c, 1);
-          if (!tiles_free) {                                                 // previous task's MMAs are done with the tiles
-            mbar_wait(&meta->bars.b_empty, (it & 1) ^ 1);
-            tiles_free = true;
-          }
           if (gtid == 0) HDBG(c, 2);
 #pragma unroll
           for (int rnd = 0; rnd < 2; ++rnd) {
@@ -276,6 +279,13 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
                       acc[i].x += v[i][u].x; acc[i].y += v[i][u].y; acc[i].z += v[i][u].z; acc[i].w += v[i][u].w;
                     }
                   }
+              }
+              if (!tiles_free) {
+                // the MMAs that last read this set of prototype tiles are done (waited for only here, with the stage's
+                // rows already summed: at D = 256, one set, this hides most of the previous task's last MMAs)
+                if (kBBuf == 2) mbar_wait(&meta->bars.b_empty[par], ((it >> 1) & 1) ^ 1);
+                else mbar_wait(&meta->bars.b_empty[0], (it & 1) ^ 1);
+                tiles_free = true;
               }
               if (act) {
                 const float rc = rcp_it[rnd], fn = fn_it[rnd];
@@ -428,6 +438,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
       }
       mbar_wait(&meta->bars.epi_done[par], ((it >> 1) & 1) ^ 1);            // accumulator `par` drained (task it-2)
       const uint32_t acc = tmem + par * kAccStride;
+      const uint32_t b_base = b_base0 + (kBBuf == 2 ? par : 0) * kBSet;
 #pragma unroll 1
       for (int st = 0; st < kSt; ++st, ++c, ++qc) {
         const uint32_t s = c % kRing, ls = qc % kLo;
@@ -455,7 +466,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
           commit(&meta->bars.lo_free[ls]);
           if (st == kSt - 1) {
             commit(&meta->bars.acc_full[par]);
-            commit(&meta->bars.b_empty);
+            commit(&meta->bars.b_empty[kBBuf == 2 ? par : 0]);
           }
         }
         __syncwarp();
@@ -467,8 +478,16 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
     const int quad = warp & 3;                                              // TMEM lanes 32 quad .. 32 quad + 31
     const int row = quad * 32 + lane;
     int it = 0;
+    // the row's label is fetched ONE TASK AHEAD: read after the barrier waits, its HBM round trip (~1000 clocks under this
+    // load) sat on the epilogue's critical path, a third of its ~3000 clocks per task (the bound of the D = 64 shapes)
+    const bool live = row < Nq;
+    int y_next = -1;
+    if (live && p.q_labels && blockIdx.x < p.E) y_next = p.q_labels[(size_t)blockIdx.x * Nq + row];
     for (int e = blockIdx.x; e < p.E; e += gridDim.x, ++it) {
       const int par = it & 1, ph = (it >> 1) & 1;
+      const int y = y_next;
+      y_next = -1;
+      if (live && p.q_labels && e + (int)gridDim.x < p.E) y_next = p.q_labels[(size_t)(e + gridDim.x) * Nq + row];
       mbar_wait_relaxed(&meta->bars.meta_full[par], ph);
       mbar_wait_relaxed(&meta->bars.acc_full[par], ph);
       fence_after();
@@ -485,9 +504,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
         for (int w = 0; w < kMaxWays; ++w)
           dot[w] = __uint_as_float(v[w]) + __uint_as_float(w + kMaxWays < 32 ? v[w + kMaxWays] : u[w + kMaxWays - 32]);
       }
-      const bool live = row < Nq;
       const float qq = meta->qq[par][0][live ? row : 0] + meta->qq[par][1][live ? row : 0];
-      const int y = (live && p.q_labels) ? p.q_labels[(size_t)e * Nq + row] : -1;
       const bool need_scores = p.scores != nullptr || p.loss != nullptr;
       float m = -INFINITY, vy = 0.f, se = 1.f;
       int am = 0x7fffffff;
@@ -574,7 +591,7 @@ int launch_variant(const HeadParams& p_in, const CUtensorMap& ms, const CUtensor
   const int longest = p.Nq > sup_rows ? p.Nq : sup_rows;
   p.tile_rows = (longest + 7) & ~7;
   const size_t tile_b = (size_t)p.tile_rows * 128, stage_b = kPair * tile_b;
-  const size_t fixed = (size_t)kLo * stage_b + (size_t)(kD / kBlockK) * 2 * kBTile + (kTile - tile_b) + sizeof(TmaMeta) +
+  const size_t fixed = (size_t)kLo * stage_b + (size_t)(kD <= 128 ? 2 : 1) * (kD / kBlockK) * 2 * kBTile + (kTile - tile_b) + sizeof(TmaMeta) +
                        2 * (size_t)p.W * ((sup_rows + 7) & ~7) + 1024 + 16;
   const size_t budget = 226 * 1024;
   if (fixed + 3 * stage_b > budget) return AFSL_OK;   // very long support blocks: the fp32-pipe kernels take the launch

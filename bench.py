@@ -69,7 +69,7 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 500 ms while the timed region runs (rank 0's GPU)."""
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -77,9 +77,11 @@ class ClockSampler:
         self.index, self.proc = index, None
 
     def __enter__(self):
+        if self.index is None:            # ranks other than 0: no sampler (N nvidia-smi pollers contend for the driver)
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "500"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -685,7 +687,7 @@ def run_b200(args):
     barrier()
     launches0 = ops.launch_count()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local if rank == 0 else None) as clocks:
         start.record()
         for i in range(args.steps):
             runner.train_step(resident[i % n_rot])
