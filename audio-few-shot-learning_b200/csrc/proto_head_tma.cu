@@ -214,7 +214,6 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
     int it = 0;
     for (int e = blockIdx.x; e < p.E; e += gridDim.x, ++it) {
       const int par = it & 1;
-      mbar_wait(&meta->bars.epi_done[par], ((it >> 1) & 1) ^ 1);     // |p|^2, |q|^2 of parity `par` are free
       mbar_wait(&meta->bars.bk_full[par], (it >> 1) & 1);            // the bucket warp built this task's class lists
       const uint8_t* rows = rows_base + (size_t)par * W * row_stride;
       const uint32_t b_base = b_base0 + (kBBuf == 2 ? par : 0) * kBSet;
@@ -315,6 +314,10 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
           if (lane == 0) mbar_arrive(&meta->bars.ready[s]);
           if (gtid == 0) HDBG(c, 3);
         }
+        // |p|^2, |q|^2 of parity `par` are free once the epilogue of task it - 2 is done: waited for only here, before the
+        // first write (at the top of the task this wait chained support(t) behind epilogue(t - 2): with one support and
+        // one query stage per task at D = 64 the period was (support + MMAs + epilogue) / 2)
+        mbar_wait(&meta->bars.epi_done[par], ((it >> 1) & 1) ^ 1);
 #pragma unroll
         for (int rnd = 0; rnd < 2; ++rnd) {
           const int item = gtid + rnd * kGroupThreads;
