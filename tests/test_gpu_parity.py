@@ -188,6 +188,54 @@ def test_head_many_way_tensor_core_kernel(ops, monkeypatch, ways, shots, nq, dim
         close(scores, out["0"][3])
 
 
+@pytest.mark.parametrize("ways,ns,nq,dim,e", [(24, 128, 128, 256, 301), (9, 40, 26, 64, 5), (20, 77, 100, 128, 150),
+                                              (16, 16, 128, 256, 149), (8, 128, 27, 64, 297)])
+def test_head_many_way_tensor_core_unbalanced_and_limits(ops, monkeypatch, ways, ns, nq, dim, e):
+    """The TMA + tcgen05 head at the edges of what it takes: the largest blocks (128 support rows, 128 queries, 24 ways),
+    the smallest (26 queries), UNBALANCED classes (1 .. many rows per class, rows of a class scattered over the block:
+    the bucket warp's lists), fewer tasks than SMs and a ragged last wave, every ring depth the launcher may pick, with and
+    without the L2 prefetch - against the fp32-pipe kernel on the same inputs and the oracle on a sample of tasks."""
+    gen = torch.Generator().manual_seed(ways * 1000 + ns + nq + dim)
+    s = torch.randn(e, ns, dim, generator=gen)
+    q = torch.randn(e, nq, dim, generator=gen)
+    sl = torch.randint(0, ways, (e, ns), generator=gen)
+    for i in range(e):                                         # every class has at least one row, somewhere in the block
+        sl[i, torch.randperm(ns, generator=gen)[:ways]] = torch.arange(ways)
+    ql = torch.randint(0, ways, (e, nq), generator=gen)
+    out = {}
+    for tag, env in (("ref", {"AFSL_HEAD_MMA": "0"}), ("tc", {"AFSL_HEAD_MMA": "1"}),
+                     ("tc_pf", {"AFSL_HEAD_MMA": "1", "AFSL_HEAD_L2PF": "1"}), ("tc_nopf", {"AFSL_HEAD_MMA": "1", "AFSL_HEAD_L2PF": "0"}),
+                     ("tc_ring2", {"AFSL_HEAD_MMA": "1", "AFSL_HEAD_RING": "2"}),
+                     ("tc_single", {"AFSL_HEAD_MMA": "1", "AFSL_HEAD_PAIR": "1", "AFSL_HEAD_RING": "3"})):
+        for k in ("AFSL_HEAD_MMA", "AFSL_HEAD_L2PF", "AFSL_HEAD_RING", "AFSL_HEAD_PAIR"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        pred, post, correct, scores = ops.proto_eval(s.cuda(), sl.cuda(), q.cuda(), ql.cuda(), n_way=ways, want_scores=True)
+        pred2, post2, correct2, _ = ops.proto_eval(s.cuda(), sl.cuda(), q.cuda(), ql.cuda(), n_way=ways)     # evaluation-only epilogue
+        loss, protos, _ = ops.proto_head(s.cuda(), sl.cuda(), q.cuda(), ql.cuda(), n_way=ways)
+        torch.cuda.synchronize()
+        out[tag] = [x.cpu() for x in (pred, post, correct, scores, loss, protos, pred2, post2, correct2)]
+    ref = out["ref"]
+    for tag in ("tc", "tc_pf", "tc_nopf", "tc_ring2", "tc_single"):
+        pred, post, correct, scores, loss, protos, pred2, post2, correct2 = out[tag]
+        close(scores, ref[3])
+        close(post, ref[1])
+        close(post2, ref[1])
+        close(loss, ref[4])
+        close(protos, ref[5])
+        assert torch.equal(pred, pred2) and torch.equal(correct, correct2)
+        assert float((pred == ref[0]).float().mean()) > 0.9999
+        if tag != "tc_single":                                 # ring depth and prefetch do not touch the arithmetic
+            assert torch.equal(scores, out["tc"][3]) and torch.equal(pred, out["tc"][0])
+    for i in range(0, e, max(1, e // 7)):
+        pr = ohead.prototypes(s[i], sl[i])
+        sc = ohead.l2_scores(q[i], pr)
+        close(out["tc"][5][i], pr)
+        close(out["tc"][3].view(e, nq, ways)[i], sc)
+        close(out["tc"][4][i], ohead.fsl_loss(pr, q[i], ql[i]))
+
+
 @pytest.mark.parametrize("ways,shots,dim,wide", [(5, 5, 64, 1), (20, 5, 256, 1), (20, 5, 256, 0), (20, 1, 64, 1), (20, 1, 64, 0),
                                                  (13, 3, 128, 1)])
 def test_head_ragged_tasks(ops, monkeypatch, ways, shots, dim, wide):
