@@ -51,6 +51,7 @@ SIGNATURES = {
     "afsl_stage1_dw_f32": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _D, _I, _P, _P, _P, _P, _P],
     "afsl_eval_vote_i32": [_P, _P, _P, _P, _P, _I, _P, _P, _I, _P],
     "afsl_logmel_f32": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P],
+    "afsl_transpose_f32": [_P, _P, _I, _I, _I, _P],
     "afsl_linear_fwd_f32": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "afsl_linear_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
 }

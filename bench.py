@@ -595,40 +595,49 @@ def eval_throughput(runner, device, world, rank, tasks_per_step, steps):
     return out
 
 
-def tf32_variant(args, device, world, rank, episodes, host, barrier):
-    """Second, LABELLED line: the same step with cuDNN TF32 convolutions allowed (PyTorch's default, i.e. what the
-    reference itself would run on this GPU).  Fresh model with the headline's initial weights; reports throughput with
-    device-resident inputs and the first step's loss next to the fp32 run's for the same batch and seeds."""
+def conv_variant(args, device, world, rank, episodes, host, barrier, kind):
+    """A second, LABELLED line: the same step with another convolution arithmetic than the fp32 channels-last headline.
+    ``kind`` "tf32": cuDNN TF32 convolutions allowed (PyTorch's default, i.e. what the reference itself would run on this
+    GPU).  ``kind`` "nchw": still fp32, but blocks 2-4 on NCHW tensors, where cuDNN picks faster, less exact kernels
+    (embeddings 1e-5 from the channels-last ones, projection-head gradients 1e-2 from the fp32 oracle: outside the parity
+    suite's bounds, hence not the headline).  Fresh model with the headline's initial weights; reports throughput with
+    device-resident inputs and the first step's loss next to the headline arithmetic's for the same batch and seeds."""
     import random
     import numpy as np
     import torch.distributed as dist
+    import afsl_b200.models.main_modules as mm
     from afsl_b200 import parallel
     from afsl_b200.episodes import EpisodeRunner
-    out = {}
+
+    def arithmetic(on):
+        torch.backends.cudnn.allow_tf32 = on and kind == "tf32"
+        mm.NCHW_FP32_CONVS = on and kind == "nchw"
+
     first = {}
-    for allow in (False, True):
-        torch.backends.cudnn.allow_tf32 = allow
+    for on in (False, True):
+        arithmetic(on)
         model = build_model(device)
         for m in model.modules():
             if isinstance(m, torch.nn.Dropout):
                 m.p = 0.0
         torch.manual_seed(4321); np.random.seed(4321); random.seed(4321)
         runner = EpisodeRunner(model, EXPERIMENT_CONFIG, None, replay_reference_rng=False, use_cuda_graph=False)
-        first[allow] = runner.train_step(host[0])["loss"].double().cpu()
+        first[on] = runner.train_step(host[0])["loss"].double().cpu()
     dev_loss = float(((first[True] - first[False]).abs() / first[False].abs()).max())
-    torch.backends.cudnn.allow_tf32 = True
+    arithmetic(True)
     model = build_model(device)
     opt = torch.optim.Adam(model.parameters(), lr=EXPERIMENT_CONFIG["lr"])
     runner = EpisodeRunner(model, EXPERIMENT_CONFIG, opt, replay_reference_rng=False, use_cuda_graph=not args.no_graph)
     dp = parallel.EpisodeDataParallel(model)
     runner.grad_sync = dp.sync_gradients if world > 1 else None
     resident = [b.to(device) for b in host]
+    steps = min(args.steps, 30)
     for i in range(args.warmup):
         runner.train_step(resident[i % len(resident)])
     barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for i in range(args.steps):
+    for i in range(steps):
         runner.train_step(resident[i % len(resident)])
     b.record()
     barrier()
@@ -636,10 +645,12 @@ def tf32_variant(args, device, world, rank, episodes, host, barrier):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    torch.backends.cudnn.allow_tf32 = False
-    return {"label": "cuDNN TF32 convolutions allowed (NOT the headline; parity suite validates fp32 only)",
-            "dtype": "tf32-conv", "value": world * episodes * args.steps / (ms * 1e-3), "unit": "episodes/s",
-            "ms_per_step": ms / args.steps,
+    arithmetic(False)
+    label = {"tf32": "cuDNN TF32 convolutions allowed (NOT the headline; parity suite validates fp32 only)",
+             "nchw": "fp32, convolution blocks 2-4 on NCHW tensors: faster, less exact cuDNN kernels (NOT the headline: "
+                     "gradients leave the parity suite's bounds)"}[kind]
+    return {"label": label, "dtype": "tf32-conv" if kind == "tf32" else "f32-nchw-conv",
+            "value": world * episodes * steps / (ms * 1e-3), "unit": "episodes/s", "ms_per_step": ms / steps, "steps": steps,
             "max_rel_loss_deviation_vs_fp32_first_step": dev_loss}
 
 
@@ -723,9 +734,10 @@ def run_b200(args):
     e2e_value = world * E * args.steps / (e2e_ms * 1e-3)
     h2d_bytes = host[0].nbytes() * world            # whole job, like `value`
 
-    tf32_line = None
+    tf32_line = nchw_line = None
     if not args.skip_tf32:
-        tf32_line = tf32_variant(args, device, world, rank, E, host, barrier)
+        tf32_line = conv_variant(args, device, world, rank, E, host, barrier, "tf32")
+        nchw_line = conv_variant(args, device, world, rank, E, host, barrier, "nchw")
     del host
     evals = eval_throughput(runner, device, world, rank, args.eval_tasks, max(2, args.steps // 2)) if not args.skip_eval else {}
 
@@ -771,7 +783,7 @@ def run_b200(args):
         "kernels": roofs,
         "cpu_baseline": cpu,
         "baselines": baselines,
-        "extra_metrics": dict(evals, **({"tf32_conv_variant": tf32_line} if tf32_line else {})),
+        "extra_metrics": dict(evals, **({"tf32_conv_variant": tf32_line, "nchw_conv_variant": nchw_line} if tf32_line else {})),
     }
     emit(line)
     if world > 1:
@@ -798,7 +810,7 @@ def main():
     ap.add_argument("--skip-eval", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-kernels", action="store_true")
-    ap.add_argument("--skip-tf32", action="store_true", help="skip the labelled TF32-convolution variant")
+    ap.add_argument("--skip-tf32", action="store_true", help="skip the labelled TF32 / NCHW convolution variants")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

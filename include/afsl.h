@@ -316,6 +316,14 @@ int afsl_stage1_dw_f32(const float* partial, int parts, int G, const double* S, 
                        void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Layout switch of the encoder wrapper: y[n][B][A] = x[n][A][B].  With A = H*W, B = C it turns the
+ * channels-last output of the fused first block into the NCHW tensor on which cuDNN's fp32 (TF32 off) convolutions
+ * of the following conv_blocks (models/main_modules.py:43-60) run fastest on sm_100; with A = C, B = H*W it is its
+ * backward.  Replaces Tensor.contiguous() (3.7 ms for the 3.6 GB stage-1 output of a 32-episode step).
+ * ------------------------------------------------------------------------- */
+int afsl_transpose_f32(const float* x, float* y, int n, int A, int B, void* stream);
+
+/* ---------------------------------------------------------------------------
  * F2: the Linear layers of ProjectionHead (models/main_modules.py:231-255: fc1 -> ReLU -> fc2 -> L2 normalise;
  * the closing normalisation is afsl_l2_normalize_*).  Replaces torch.nn.functional.linear / cuBLAS on this path.
  * fwd: y[M,N] = x[M,K] . w[N,K]^T + bias[N] [opt], ReLU when relu != 0.

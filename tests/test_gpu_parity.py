@@ -188,6 +188,24 @@ def test_head_many_way_tensor_core_kernel(ops, monkeypatch, ways, shots, nq, dim
         close(scores, out["0"][3])
 
 
+@pytest.mark.parametrize("n,a,b", [(7, 2184, 64), (7, 64, 2184), (3, 37, 5), (2, 4, 4), (5, 238, 64), (1, 130, 68)])
+def test_layout_transpose(ops, n, a, b):
+    """afsl_transpose_f32 (the channels-last -> NCHW switch in front of the fp32 convolutions) is a pure data movement:
+    bit-equal to torch, vector and scalar paths, ragged tiles; nhwc_to_nchw and its backward against Tensor.contiguous()."""
+    x = torch.randn(n, a, b, device="cuda")
+    y = ops._Transpose.apply(x)
+    assert y.shape == (n, b, a) and y.is_contiguous() and torch.equal(y, x.transpose(1, 2).contiguous())
+    if b % 4 == 0:
+        h = 2 if a % 2 == 0 else 1
+        img = torch.randn(n, b, h, a // h, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        out = ops.nhwc_to_nchw(img)
+        assert out.is_contiguous() and torch.equal(out, img.detach().contiguous())
+        g = torch.randn_like(out)
+        out.backward(g)
+        assert torch.equal(img.grad, g)
+        assert img.grad.is_contiguous(memory_format=torch.channels_last) or img.grad.is_contiguous()
+
+
 @pytest.mark.parametrize("ways,ns,nq,dim,e", [(24, 128, 128, 256, 301), (9, 40, 26, 64, 5), (20, 77, 100, 128, 150),
                                               (16, 16, 128, 256, 149), (8, 128, 27, 64, 297)])
 def test_head_many_way_tensor_core_unbalanced_and_limits(ops, monkeypatch, ways, ns, nq, dim, e):
@@ -966,6 +984,11 @@ def test_training_epoch_and_validation_vs_reference_loops(ops):
         msg = training_epoch(net, ds, opt, 2, "cuda", FSL_Loss(), None, 0.0, False, False, 5, 5, 5, None, False, False)
         random.seed(99)
         val_mean, val_std = evaluate_single_segment(net, ds, 3, "cuda", 5, 5, 5, None, False)
+        after = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        # the same validation with the REFERENCE's post-training weights: identical weights -> identical accuracies
+        net.load_state_dict({k[len("after_"):]: t(v) for k, v in g.items() if k.startswith("after_")})
+        random.seed(99)
+        ref_mean, ref_std = evaluate_single_segment(net, ds, 3, "cuda", 5, 5, 5, None, False)
     finally:
         torch.backends.cudnn.allow_tf32 = tf32
     # the first episode does not go through the optimizer: tight.  The second one follows an Adam step, whose
@@ -975,8 +998,11 @@ def test_training_epoch_and_validation_vs_reference_loops(ops):
     assert abs(msg["loss"] - float(g["loss"])) <= 1e-3 * abs(float(g["loss"]))
     assert abs(msg["fsl_loss"] - float(g["fsl_loss"])) <= 1e-3 * abs(float(g["fsl_loss"]))
     assert np.isnan(msg["cpl_loss"])
-    assert abs(val_mean - float(g["val_mean"])) < 1e-9 and abs(val_std - float(g["val_std"])) < 1e-9
-    after = net.state_dict()
+    assert abs(ref_mean - float(g["val_mean"])) < 1e-9 and abs(ref_std - float(g["val_std"])) < 1e-9
+    # with the weights trained HERE (two Adam steps away from the reference's by +-lr in entries whose near-zero gradient
+    # changes sign in the last bit, see below) a near-tie among the 75 validation queries may fall the other way
+    print(f"validation accuracy with the weights trained here: {val_mean:.6f} (reference's run: {float(g['val_mean']):.6f})")
+    assert abs(val_mean - float(g["val_mean"])) <= 3.0 / 75 + 1e-9
     for k, v in g.items():
         if k.startswith("after_") and "num_batches_tracked" not in k:
             # two Adam steps: +-lr per step where a near-zero gradient's sign differs in the last bit
@@ -1299,12 +1325,65 @@ def test_eval_step_batched_single_segment_vs_oracle(ops):
         torch.backends.cudnn.allow_tf32 = tf32
 
 
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_encoder_nchw_path_equals_channels_last(ops, mode):
+    """The OPTIONAL fp32 path (AFSL_NCHW_FP32=1, bench.py's labelled nchw_conv_variant): convolutions of blocks 2-4 on NCHW
+    tensors (afsl_transpose_f32 after the fused first block, the NCHW family of the BatchNorm/ReLU/pool kernels) against the
+    default channels-last path on the same weights and
+    inputs, two groups of 25 samples: embeddings 1e-5, running statistics 1e-6, every parameter gradient 2e-3 in L2
+    (observed: <= 6e-5 for most, 5e-4 for the first block's weights - the two convolution algorithms round differently,
+    so a few pooling windows of blocks 2-4 pick another winner and route their gradient to a neighbouring tap)."""
+    import afsl_b200.models.main_modules as mm
+    from afsl_b200.models.main_modules import StandardCNN
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    flag = mm.NCHW_FP32_CONVS
+    try:
+        enc = StandardCNN(1, (1, 1, 128, 157), 64, [3, 3], 64).cuda()
+        for m in enc.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+            if hasattr(m, "group_size"):
+                m.group_size = 25
+        x = torch.randn(50, 1, 128, 157, device="cuda")
+        wts = torch.linspace(-1, 1, 50 * 64, device="cuda").view(50, 64)
+        init = {k: v.clone() for k, v in enc.state_dict().items()}
+        res = {}
+        for nchw in (True, False):
+            mm.NCHW_FP32_CONVS = nchw
+            enc.load_state_dict(init)
+            enc.train(mode == "train")
+            enc.zero_grad()
+            y = enc(x)
+            grads = {}
+            if mode == "train":
+                (y * wts).sum().backward()
+                grads = {n: p.grad.clone() for n, p in enc.named_parameters()}
+            res[nchw] = (y.detach().clone(), grads, {k: v.clone() for k, v in enc.state_dict().items() if "running" in k})
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+        mm.NCHW_FP32_CONVS = flag
+    close(res[True][0], res[False][0], rtol=1e-5)
+    for k, v in res[True][2].items():
+        close(v, res[False][2][k], rtol=1e-6)
+    for n, ga in res[True][1].items():
+        gb = res[False][1][n]
+        if float(gb.abs().max()) == 0.0:
+            assert float(ga.abs().max()) == 0.0
+            continue
+        rel = float((ga - gb).norm() / gb.norm())
+        record_observed(rel, 2e-3)
+        assert rel < 2e-3 or float((ga - gb).abs().max()) < 1e-4, (n, rel)
+
+
 @pytest.mark.parametrize("graph", [False, True])
 def test_train_step_batched_vs_oracle(ops, graph):
     """EpisodeRunner.train_step on E = 3 episodes at once (config 2: views, fusion, projection, CPL with sampled negatives;
     eager and CUDA-graph replay) against oracle.episode.train_step episode by episode on the same weights and seeds:
     per-episode losses within 2e-5, the step's gradient (mean over episodes) within 1e-3 relative in L2 norm per parameter
-    (elementwise 5e-3 of max|grad|)."""
+    (elementwise 5e-3 of max|grad|; observed 5e-4).  The optional NCHW convolution path (AFSL_NCHW_FP32=1) does NOT meet
+    these bounds (projection-head gradients 9e-3, attention norm2.bias 7e-3, first block 1.1e-3), which is why it is off
+    by default; test_encoder_nchw_path_equals_channels_last states what it does meet."""
     import random
     from afsl_b200.episodes import EpisodeRunner
     from oracle import episode as oep
