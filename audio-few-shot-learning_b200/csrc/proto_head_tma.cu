@@ -35,7 +35,6 @@ using namespace tc;
 
 constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kProducerWarps = 8;
-constexpr int kProducers = kProducerWarps * 32;
 constexpr int kGroups = 2;                                      // producer groups taking alternate stages
 constexpr int kGroupWarps = kProducerWarps / kGroups;
 constexpr int kGroupThreads = kGroupWarps * 32;                 // 128
@@ -59,6 +58,12 @@ constexpr int kAccN = 2 * kMaxWays;                             // accumulator c
 constexpr int kAccStride = 64;                                  // TMEM columns between the two accumulators
 constexpr uint32_t kIdesc = idesc_tf32(kTileM, kAccN);
 
+// bucket lists of kBk tasks: the bucket warp runs up to kBk - 1 tasks ahead.  With two sets, the lists of task t could only be
+// built once EVERY producer warp was done with those of task t - 2 - and the first warp of a group, which alone has items in
+// the second round of a support stage (classes 16-19 of 20), finishes ~2500 clocks after the others: the chain
+// slowest warp (t - 2) -> bucket warp (+ an exposed label fetch) -> start of support (t) set the period at D = 64
+constexpr int kBk = 4;
+
 struct TmaBars {
   uint64_t tma_full[kMaxRing];    // stage filled by TMA (transaction bytes)
   uint64_t ready[kMaxRing];       // stage processed by its producer group (4 warps)
@@ -66,17 +71,17 @@ struct TmaBars {
   uint64_t lo_free[kMaxLoRing];   // lo tiles of a query stage free again (tcgen05.commit)
   uint64_t b_empty[2];            // the task's MMAs are done with the prototype tiles (of task parity b when double-buffered)
   uint64_t acc_full[2], epi_done[2], meta_full[2];
-  uint64_t bk_full[2], bk_free[2];  // the task's bucket lists are built (bucket warp) / read for the last time (producers)
+  uint64_t bk_full[kBk], bk_free[kBk];  // the task's bucket lists are built (bucket warp) / read for the last time (producers)
 };
 
 struct TmaMeta {
   TmaBars bars;
   uint32_t tmem_base;
-  float qq[2][kGroups][kTileM];          // |q|^2 partial sums: the k-blocks each producer group handled
-  float pp[2][kGroups][kTileN];          // |p|^2 partial sums, likewise
+  alignas(16) float qq[2][kGroups][kTileM];   // |q|^2 partial sums: the k-blocks each producer group handled
+  alignas(16) float pp[2][kGroups][kTileN];   // |p|^2 partial sums, likewise (read 128 bits at a time by the epilogue)
   float part[kEpiWarps];
   int hits[kEpiWarps];
-  int cnt[2][kTileN];                    // rows per class
+  int cnt[kBk][kTileN];                  // rows per class
 };
 
 // waiting roles that are not on the critical path (loader, epilogue) sleep between polls instead of competing with the
@@ -96,7 +101,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
 __device__ __forceinline__ void epilogue_bar() { asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 
 // timeline of CTA 0 (AFSL_HEAD_DBG=1, tools/head_many_way_bench.py): SM clock at event `ev` of ring stage `c` (all tasks)
-constexpr int kDbgStages = 160, kDbgEvents = 14;
+constexpr int kDbgStages = 160, kDbgEvents = 22;
 #define HDBG(c, ev)                                                                                        \
   do {                                                                                                     \
     if (p.dbg && blockIdx.x == 0 && (c) < (uint32_t)kDbgStages) p.dbg[(c) * kDbgEvents + (ev)] = clock64(); \
@@ -133,7 +138,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
   const uint32_t lo_base = b_base0 + kBBuf * kBSet;                            // [kLo][kPair][tile_b] lo tiles of query stages
   // (the last lo tile's MMA reads up to kTile - tile_b bytes past its slot: that much padding before the metadata)
   TmaMeta* meta = reinterpret_cast<TmaMeta*>(smem + kRing * kStageB + kBBuf * kBSet + kLo * kStageB + (kTile - tile_b));
-  uint8_t* rows_base = reinterpret_cast<uint8_t*>(meta + 1);                   // [2][W][row_stride]: bucketed support rows
+  uint8_t* rows_base = reinterpret_cast<uint8_t*>(meta + 1);                   // [kBk][W][row_stride]: bucketed support rows
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = p.W, Nq = p.Nq;
   const int sup_rows = p.support ? p.Ns : W;                                   // given prototypes: one "support row" per class
@@ -152,6 +157,8 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
       mbar_init(&meta->bars.acc_full[i], 1);
       mbar_init(&meta->bars.epi_done[i], kEpiWarps);
       mbar_init(&meta->bars.meta_full[i], kProducerWarps);
+    }
+    for (int i = 0; i < kBk; ++i) {
       mbar_init(&meta->bars.bk_full[i], 1);
       mbar_init(&meta->bars.bk_free[i], kProducerWarps);
     }
@@ -161,6 +168,9 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
   }
   // prototype slots W..23 of every B tile stay zero for the whole launch
   for (int i = tid; i < kBBuf * kBSet / 16; i += kTmaThreads) sts4(b_base0 + i * 16, make_float4(0.f, 0.f, 0.f, 0.f));
+  // a group that handles no support (query) stage of a task never writes its |p|^2 (|q|^2) partials: they stay zero
+  for (int i = tid; i < 2 * kGroups * kTileM; i += kTmaThreads) (&meta->qq[0][0][0])[i] = 0.f;
+  for (int i = tid; i < 2 * kGroups * kTileN; i += kTmaThreads) (&meta->pp[0][0][0])[i] = 0.f;
   if (warp == kIssuerWarp) tmem_alloc<2 * kAccStride>(&meta->tmem_base);
   fence_async_proxy();
   fence_before();
@@ -214,9 +224,12 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
     int it = 0;
     for (int e = blockIdx.x; e < p.E; e += gridDim.x, ++it) {
       const int par = it & 1;
-      mbar_wait(&meta->bars.bk_full[par], (it >> 1) & 1);            // the bucket warp built this task's class lists
-      const uint8_t* rows = rows_base + (size_t)par * W * row_stride;
+      const int bq = it & (kBk - 1);
+      mbar_wait(&meta->bars.bk_full[bq], (it / kBk) & 1);            // the bucket warp built this task's class lists
+      const uint8_t* rows = rows_base + (size_t)bq * W * row_stride;
       const uint32_t b_base = b_base0 + (kBBuf == 2 ? par : 0) * kBSet;
+      constexpr bool kFixedRoles = ((kSupSt + kSt) & 1) == 0;       // the same group takes the same stages of every task
+      bool did_sup = false, did_qry = false, epi_ok = false;
       // ---------------------------------------------------------- support stages: prototypes, |p|^2, split prototype tiles
       {
         // item = (class w, 16-byte chunk j): 8 W items over the group's 128 threads, two rounds
@@ -227,7 +240,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
 #pragma unroll
         for (int rnd = 0; rnd < 2; ++rnd) {
           const int w = (gtid + rnd * kGroupThreads) >> 3;
-          n_it[rnd] = w < W ? meta->cnt[par][w] : 0;
+          n_it[rnd] = w < W ? meta->cnt[bq][w] : 0;
           rows_it[rnd] = rows + (w < W ? w : 0) * row_stride;
           // mean = sum / n through a refined reciprocal and one residual correction (the division's own fast path, without
           // its per-element reciprocal): n == 0 gives 0 * inf = NaN, as the reference's empty mean
@@ -239,73 +252,90 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
 #pragma unroll 1
         for (int st = 0; st < kSupSt; ++st, ++c) {
           if ((int)(c & 1) != grp) continue;
+          did_sup = true;
           const uint32_t s = c % kRing;
           mbar_wait(&meta->bars.tma_full[s], (c / kRing) & 1);
           if (gtid == 0) HDBG(c, 1);
+          if (gtid == 32) HDBG(c, 18);
+          if (gtid == 96) HDBG(c, 20);
           if (gtid == 0) HDBG(c, 2);
+          // A thread's two items (item = gtid and gtid + 128: classes 16.. belong to the first warp only) and the stage's
+          // k-blocks two at a time are reduced TOGETHER: two rows per step, one 16-bit read of the row ids per item, up to
+          // eight independent 128-bit reads in flight, then the adds in ascending row order.  One item after the other made
+          // the first warp of a group - the only one with second items at 20 ways - finish every support stage ~800
+          // clocks after the others (profiles/r2u_head_timeline_16.txt), and a stage is ready when its last warp is.
+          float sq[2] = {0.f, 0.f};
+          const int nmax = n_it[0] > n_it[1] ? n_it[0] : n_it[1];
 #pragma unroll
-          for (int rnd = 0; rnd < 2; ++rnd) {
-            const int item = gtid + rnd * kGroupThreads;
-            const int w = item >> 3, j = item & 7;
-            const bool act = w < W;
-            const int n = n_it[rnd];
-            float sq = 0.f;
-            // the stage's k-blocks two at a time: the row reads of both are in flight together (four rows per step: one
-            // 32-bit read of the row ids, up to eight independent 128-bit reads), then the adds in ascending row order.
-            // One k-block after the other left four dependent load -> add chains per stage (~2300 clocks per stage)
+          for (int ib = 0; ib < kSupPair; ib += 2) {
+            constexpr int kI = kSupPair >= 2 ? 2 : 1;
+            float4 acc[2][kI];
 #pragma unroll
-            for (int ib = 0; ib < kSupPair; ib += 2) {
-              constexpr int kI = kSupPair >= 2 ? 2 : 1;
-              float4 acc[kI];
+            for (int rnd = 0; rnd < 2; ++rnd)
 #pragma unroll
-              for (int i = 0; i < kI; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              const uint32_t stage0 = ring + s * kStageB + ib * kSupStride;
-              for (int i0 = 0; i0 < n; i0 += 4) {
-                const uint32_t ids = *reinterpret_cast<const uint32_t*>(rows_it[rnd] + i0);
-                float4 v[kI][4];
+              for (int i = 0; i < kI; ++i) acc[rnd][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const uint32_t stage0 = ring + s * kStageB + ib * kSupStride;
+            for (int i0 = 0; i0 < nmax; i0 += 2) {
+              float4 v[2][kI][2];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+              for (int rnd = 0; rnd < 2; ++rnd) {
+                const uint32_t ids = *reinterpret_cast<const uint16_t*>(rows_it[rnd] + i0);
+                const int j = (gtid + rnd * kGroupThreads) & 7;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
                   const uint32_t off = sw128((int)((ids >> (8 * u)) & 0xffu), j);
 #pragma unroll
                   for (int i = 0; i < kI; ++i)
-                    if (i0 + u < n) v[i][u] = lds4(stage0 + i * kSupStride + off);     // predicated: no traffic for missing rows
+                    if (i0 + u < n_it[rnd]) v[rnd][i][u] = lds4(stage0 + i * kSupStride + off);   // predicated: no traffic for missing rows
                 }
+              }
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                  if (i0 + u < n) {
+              for (int rnd = 0; rnd < 2; ++rnd)
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+                  if (i0 + u < n_it[rnd]) {
 #pragma unroll
                     for (int i = 0; i < kI; ++i) {
-                      acc[i].x += v[i][u].x; acc[i].y += v[i][u].y; acc[i].z += v[i][u].z; acc[i].w += v[i][u].w;
+                      acc[rnd][i].x += v[rnd][i][u].x; acc[rnd][i].y += v[rnd][i][u].y;
+                      acc[rnd][i].z += v[rnd][i][u].z; acc[rnd][i].w += v[rnd][i][u].w;
                     }
                   }
-              }
-              if (!tiles_free) {
-                // the MMAs that last read this set of prototype tiles are done (waited for only here, with the stage's
-                // rows already summed: at D = 256, one set, this hides most of the previous task's last MMAs)
-                if (kBBuf == 2) mbar_wait(&meta->bars.b_empty[par], ((it >> 1) & 1) ^ 1);
-                else mbar_wait(&meta->bars.b_empty[0], (it & 1) ^ 1);
-                tiles_free = true;
-              }
-              if (act) {
+            }
+            if (!tiles_free) {
+              // the MMAs that last read this set of prototype tiles are done (waited for only here, with the stage's
+              // rows already summed: at D = 256, one set, this hides most of the previous task's last MMAs)
+              if (kBBuf == 2) mbar_wait(&meta->bars.b_empty[par], ((it >> 1) & 1) ^ 1);
+              else mbar_wait(&meta->bars.b_empty[0], (it & 1) ^ 1);
+              tiles_free = true;
+            }
+#pragma unroll
+            for (int rnd = 0; rnd < 2; ++rnd) {
+              const int item = gtid + rnd * kGroupThreads;
+              const int w = item >> 3, j = item & 7;
+              if (w < W) {
                 const float rc = rcp_it[rnd], fn = fn_it[rnd];
                 auto mean = [&](float sum) { const float q0 = sum * rc; return fmaf(fmaf(-q0, fn, sum), rc, q0); };
 #pragma unroll
                 for (int i = 0; i < kI; ++i) {
                   const int kb = st * kSupPair + ib + i;
-                  const float4 m = make_float4(mean(acc[i].x), mean(acc[i].y), mean(acc[i].z), mean(acc[i].w));
+                  const float4 m = make_float4(mean(acc[rnd][i].x), mean(acc[rnd][i].y), mean(acc[rnd][i].z), mean(acc[rnd][i].w));
                   if (p.protos_out && p.support)
                     *reinterpret_cast<float4*>(p.protos_out + ((size_t)e * W + w) * kD + kb * kBlockK + 4 * j) = m;
-                  sq = fmaf(m.x, m.x, fmaf(m.y, m.y, fmaf(m.z, m.z, fmaf(m.w, m.w, sq))));
+                  sq[rnd] = fmaf(m.x, m.x, fmaf(m.y, m.y, fmaf(m.z, m.z, fmaf(m.w, m.w, sq[rnd]))));
                   const uint32_t off = sw128(w, j);
                   sts4(b_base + (kb * 2 + 0) * kBTile + off, m);               // hi: the tensor core truncates it itself
                   sts4(b_base + (kb * 2 + 1) * kBTile + off, lo_of_raw(m));
                 }
               }
             }
-            sq += __shfl_xor_sync(kFullMask, sq, 1);
-            sq += __shfl_xor_sync(kFullMask, sq, 2);
-            sq += __shfl_xor_sync(kFullMask, sq, 4);
-            pp_acc[rnd] += sq;
+          }
+#pragma unroll
+          for (int rnd = 0; rnd < 2; ++rnd) {
+            float x = sq[rnd];
+            x += __shfl_xor_sync(kFullMask, x, 1);
+            x += __shfl_xor_sync(kFullMask, x, 2);
+            x += __shfl_xor_sync(kFullMask, x, 4);
+            pp_acc[rnd] += x;
           }
           if (gtid == 0) HDBG(c, 8);
           fence_async_proxy();
@@ -313,18 +343,26 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
           __syncwarp();
           if (lane == 0) mbar_arrive(&meta->bars.ready[s]);
           if (gtid == 0) HDBG(c, 3);
+          if (gtid == 32) HDBG(c, 19);
+          if (gtid == 96) HDBG(c, 21);
         }
         // |p|^2, |q|^2 of parity `par` are free once the epilogue of task it - 2 is done: waited for only here, before the
         // first write (at the top of the task this wait chained support(t) behind epilogue(t - 2): with one support and
         // one query stage per task at D = 64 the period was (support + MMAs + epilogue) / 2)
-        mbar_wait(&meta->bars.epi_done[par], ((it >> 1) & 1) ^ 1);
+        // (a group that took no support stage of this task has nothing to write - with an even number of stages per task
+        // the groups' roles never change and its partials stay zero - and does not wait here: at D = 64 that wait held the
+        // QUERY group's stage of task t behind the epilogue of task t - 2)
+        if (did_sup || !kFixedRoles) {
+          mbar_wait(&meta->bars.epi_done[par], ((it >> 1) & 1) ^ 1);
+          epi_ok = true;
 #pragma unroll
-        for (int rnd = 0; rnd < 2; ++rnd) {
-          const int item = gtid + rnd * kGroupThreads;
-          if ((item & 7) == 0 && (item >> 3) < kTileN) meta->pp[par][grp][item >> 3] = pp_acc[rnd];
+          for (int rnd = 0; rnd < 2; ++rnd) {
+            const int item = gtid + rnd * kGroupThreads;
+            if ((item & 7) == 0 && (item >> 3) < kTileN) meta->pp[par][grp][item >> 3] = pp_acc[rnd];
+          }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&meta->bars.bk_free[par]);                  // done with rows / cnt of parity `par`
+        if (lane == 0) mbar_arrive(&meta->bars.bk_free[bq]);                   // done with rows / cnt of this task
       }
       // ---------------------------------------------------------- query stages: lo tile for the raw tile, |q|^2
       {
@@ -336,9 +374,12 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
 #pragma unroll 1
         for (int st = 0; st < kSt; ++st, ++c, ++qc) {
           if ((int)(c & 1) != grp) continue;
+          did_qry = true;
           const uint32_t s = c % kRing, ls = qc % kLo;
           mbar_wait(&meta->bars.tma_full[s], (c / kRing) & 1);
           if (gtid == 0) HDBG(c, 1);
+          if (gtid == 32) HDBG(c, 18);
+          if (gtid == 96) HDBG(c, 20);
 #pragma unroll
           for (int i = 0; i < kPair; ++i) {
             const uint32_t src = ring + s * kStageB + i * tile_b + off0, dst = lo_base + ls * kStageB + i * tile_b + off0;
@@ -366,14 +407,19 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
           __syncwarp();
           if (lane == 0) mbar_arrive(&meta->bars.ready[s]);
           if (gtid == 0) HDBG(c, 3);
+          if (gtid == 32) HDBG(c, 19);
+          if (gtid == 96) HDBG(c, 21);
         }
+        if (did_qry || !kFixedRoles) {
+          if (!epi_ok) mbar_wait(&meta->bars.epi_done[par], ((it >> 1) & 1) ^ 1);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          float x = qacc[t];
-          x += __shfl_xor_sync(kFullMask, x, 1);
-          x += __shfl_xor_sync(kFullMask, x, 2);
-          x += __shfl_xor_sync(kFullMask, x, 4);
-          if (j == 0) meta->qq[par][grp][r0 + 16 * t] = x;
+          for (int t = 0; t < 8; ++t) {
+            float x = qacc[t];
+            x += __shfl_xor_sync(kFullMask, x, 1);
+            x += __shfl_xor_sync(kFullMask, x, 2);
+            x += __shfl_xor_sync(kFullMask, x, 4);
+            if (j == 0) meta->qq[par][grp][r0 + 16 * t] = x;
+          }
         }
       }
       __syncwarp();
@@ -398,10 +444,10 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
     fetch(blockIdx.x);
     int it = 0;
     for (int e = blockIdx.x; e < p.E; e += gridDim.x, ++it) {
-      const int par = it & 1;
-      mbar_wait_relaxed(&meta->bars.bk_free[par], ((it >> 1) & 1) ^ 1);
-      int* cnt = meta->cnt[par];
-      uint8_t* rows = rows_w + (size_t)par * W * row_stride;
+      const int bq = it & (kBk - 1);
+      mbar_wait_relaxed(&meta->bars.bk_free[bq], ((it / kBk) & 1) ^ 1);
+      int* cnt = meta->cnt[bq];
+      uint8_t* rows = rows_w + (size_t)bq * W * row_stride;
       cnt[lane] = 0;
       __syncwarp();
 #pragma unroll
@@ -422,7 +468,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
       }
       fetch(e + gridDim.x);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&meta->bars.bk_full[par]);
+      if (lane == 0) mbar_arrive(&meta->bars.bk_full[bq]);
     }
   } else if (warp == kIssuerWarp) {
     // =============================================================== MMA issuer
@@ -503,11 +549,28 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
         tmem_ld32_nowait(ta, v);
         tmem_ld16_nowait(ta + 32, u);
         tmem_ld_wait();
+        if (quad == 0 && lane == 0) HDBG((uint32_t)((it + 1) * (kSupSt + kSt) - 1), 14);
 #pragma unroll
         for (int w = 0; w < kMaxWays; ++w)
           dot[w] = __uint_as_float(v[w]) + __uint_as_float(w + kMaxWays < 32 ? v[w + kMaxWays] : u[w + kMaxWays - 32]);
       }
       const float qq = meta->qq[par][0][live ? row : 0] + meta->qq[par][1][live ? row : 0];
+      // |p|^2 of every slot, twelve 128-bit reads issued together (48 scalar reads inside the loops below, each waiting for
+      // its own shared-memory round trip behind the producers' traffic, made the score loop 1900 of the epilogue's 2900
+      // clocks per task: the bound of the D = 64 shapes, whose tasks have one stage per phase)
+      float pw2s[kMaxWays];
+      {
+        const float4* pa = reinterpret_cast<const float4*>(meta->pp[par][0]);
+        const float4* pb = reinterpret_cast<const float4*>(meta->pp[par][1]);
+        float4 xa[kMaxWays / 4], xb[kMaxWays / 4];
+#pragma unroll
+        for (int k = 0; k < kMaxWays / 4; ++k) { xa[k] = pa[k]; xb[k] = pb[k]; }
+#pragma unroll
+        for (int k = 0; k < kMaxWays / 4; ++k) {
+          pw2s[4 * k] = xa[k].x + xb[k].x; pw2s[4 * k + 1] = xa[k].y + xb[k].y;
+          pw2s[4 * k + 2] = xa[k].z + xb[k].z; pw2s[4 * k + 3] = xa[k].w + xb[k].w;
+        }
+      }
       const bool need_scores = p.scores != nullptr || p.loss != nullptr;
       float m = -INFINITY, vy = 0.f, se = 1.f;
       int am = 0x7fffffff;
@@ -516,9 +579,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
 #pragma unroll
         for (int w = 0; w < kMaxWays; ++w) {
           // |q|^2 + |p|^2 - 2 q.p clamped at 0, as at::_euclidean_dist; -sqrt = the score
-          const int wc = w < W ? w : 0;
-          const float pw2 = meta->pp[par][0][wc] + meta->pp[par][1][wc];
-          const float d2 = fmaxf(fmaf(-2.f, dot[w], qq) + pw2, 0.f);
+          const float d2 = fmaxf(fmaf(-2.f, dot[w], qq) + pw2s[w], 0.f);
           const float s = -sqrtf(d2);
           sc[w] = s;
           if (w < W) {
@@ -544,9 +605,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
         float best = INFINITY;
 #pragma unroll
         for (int w = 0; w < kMaxWays; ++w) {
-          const int wc = w < W ? w : 0;
-          const float pw2 = meta->pp[par][0][wc] + meta->pp[par][1][wc];
-          const float d2 = fmaxf(fmaf(-2.f, dot[w], qq) + pw2, 0.f);
+          const float d2 = fmaxf(fmaf(-2.f, dot[w], qq) + pw2s[w], 0.f);
           if (w < W) {
             if (d2 < best) { best = d2; am = w; }
             if (d2 != d2 && am == 0x7fffffff) am = w;
@@ -554,6 +613,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
         }
         m = -sqrtf(best);
       }
+      if (quad == 0 && lane == 0) HDBG((uint32_t)((it + 1) * (kSupSt + kSt) - 1), 15);
       float nll = 0.f;
       int hit = 0;
       if (live) {
@@ -563,6 +623,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
         if (p.loss && y >= 0 && y < W) nll = -((vy - m) - logf(se));        // log_softmax then NLL
         hit = (am == y);
       }
+      if (quad == 0 && lane == 0) HDBG((uint32_t)((it + 1) * (kSupSt + kSt) - 1), 16);
       if (p.loss || p.correct) {
         nll = warp_sum(nll);
         for (int o = 16; o > 0; o >>= 1) hit += __shfl_xor_sync(kFullMask, hit, o);
@@ -574,6 +635,7 @@ head_tma_fwd_kernel(const HeadParams p, const __grid_constant__ CUtensorMap map_
         }
         epilogue_bar();
       }
+      if (quad == 0 && lane == 0) HDBG((uint32_t)((it + 1) * (kSupSt + kSt) - 1), 17);
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&meta->bars.epi_done[par]);
@@ -595,7 +657,7 @@ int launch_variant(const HeadParams& p_in, const CUtensorMap& ms, const CUtensor
   p.tile_rows = (longest + 7) & ~7;
   const size_t tile_b = (size_t)p.tile_rows * 128, stage_b = kPair * tile_b;
   const size_t fixed = (size_t)kLo * stage_b + (size_t)(kD <= 128 ? 2 : 1) * (kD / kBlockK) * 2 * kBTile + (kTile - tile_b) + sizeof(TmaMeta) +
-                       2 * (size_t)p.W * ((sup_rows + 7) & ~7) + 1024 + 16;
+                       kBk * (size_t)p.W * ((sup_rows + 7) & ~7) + 1024 + 16;
   const size_t budget = 226 * 1024;
   if (fixed + 3 * stage_b > budget) return AFSL_OK;   // very long support blocks: the fp32-pipe kernels take the launch
   size_t ring_n = (budget - fixed) / stage_b;
